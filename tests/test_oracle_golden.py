@@ -78,9 +78,11 @@ def test_variants(golden):
     rp, rc = [-1.0, 0.2, 0.3], [0.4, 0.3]
     hz = [1, 50, 150]
 
-    def run(b, horizons, check):
+    def run(b, horizons, check, controls=None):
         done = 0
         for k, h in enumerate(horizons):
+            if controls is not None:  # controls are per call: one row per step of this call
+                b.set_controls(controls[done:h, None, :])
             b.rollout(0.01, h - done)
             done = h
             check(k, b)
@@ -113,36 +115,33 @@ def test_variants(golden):
 
     # bicycle + per-step controls
     b = _crowd_batch(poses, table, rp, [0.0, 0.0], robot=orc.ROBOT_BICYCLE)
-    b.set_controls(g["bicycle_controls"][:, None, :])
 
     def chk_bi(k, b):
         assert np.allclose(b.robot_pose[0], g["bicycle_robot_pose"][k], atol=1e-12)
         assert np.allclose(b.robot_vel[0], g["bicycle_robot_vel"][k], atol=0)
         assert rel_err(b.poses[0], g["bicycle_poses"][k]) < 1e-11
         assert (b.det_mask[0] == g["bicycle_det_mask"][k]).all()
-    run(b, hz, chk_bi)
+    run(b, hz, chk_bi, g["bicycle_controls"])
 
     b = _crowd_batch(poses, table, rp, [0.0, 0.0], robot=orc.ROBOT_UNICYCLE)
-    b.set_controls(g["unictrl_controls"][:, None, :] if "unictrl_controls" in g else g["bicycle_controls"][:, None, :])
 
     def chk_uni(k, b):
         assert np.allclose(b.robot_pose[0], g["unictrl_robot_pose"][k], atol=1e-12)
         assert np.allclose(b.robot_vel[0], g["unictrl_robot_vel"][k], atol=1e-12)
         assert rel_err(b.poses[0], g["unictrl_poses"][k]) < 1e-11
         assert (b.coll_mask[0] == g["unictrl_coll_mask"][k]).all()
-    run(b, hz, chk_uni)
+    run(b, hz, chk_uni, g["bicycle_controls"])
 
     # map veto
     b = _crowd_batch(poses, table, [-1.0, 0.2, 0.0], [0.0, 0.0])
     b.set_map(orc.MAP_CIRCLES, g["blocked_circles"])
-    b.set_controls(g["blocked_controls"][:, None, :])
 
     def chk_blk(k, b):
         assert np.allclose(b.robot_pose[0], g["blocked_robot_pose"][k], atol=1e-12)
         assert np.allclose(b.robot_vel[0], g["blocked_robot_vel"][k], atol=1e-12)
         assert b.robot_world_collision[0] == g["blocked_robot_world_collision"][k]
         assert rel_err(b.poses[0], g["blocked_poses"][k]) < 1e-11
-    run(b, [1, 60, 120, 200], chk_blk)
+    run(b, [1, 60, 120, 200], chk_blk, g["blocked_controls"])
     assert g["blocked_robot_world_collision"].any()
 
 
