@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- HSFM pedestrian-updates/s of the fused B200 path (BASELINE.json metric).
+
+A bench "step" = one pass of the hot path over one batch of synthetic worlds: `--sim-steps` fused
+simulation steps (robot -> HSFM forces + Euler -> waypoints -> collision list + detector) of
+`--worlds` worlds x `--peds` pedestrians per GPU.  Default workload = BASELINE config C4
+(4096 worlds x 64 pedestrians + detector, dt = 0.01, 1000 simulation steps) per GPU.
+
+  value : whole-job pedestrian-updates/s with state resident in HBM (CUDA events around the kernel,
+          L2 flushed between timed steps, max over ranks).
+  e2e   : the same metric through the public API with HOST buffers: pinned H2D upload of the initial
+          state, the fused launch, D2H of final state + detector reading + statistics, every step.
+  roofline    : FP32 pipe, algorithmic FLOPs (30 per directed pair, 30*N + 120 per pedestrian-update,
+                SURVEY.md 8d) / kernel time vs the FP32 peak measured live by an FMA-chain kernel.
+  cpu_baseline: the CPU oracle (C port of the reference's algorithm) on all host cores, bounded sample.
+
+`--impl reference` times only that CPU port (the reference is Python/numba and cannot travel to the
+GPU box) and prints the same JSON line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hsfm_pedestrian_updates_per_sec"
+UNIT = "pedestrian-updates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU (weak scaling)")
+    ap.add_argument("--peds", type=int, default=64)
+    ap.add_argument("--sim-steps", type=int, default=1000, help="fused simulation steps per bench step")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "mixed", "fp64"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--j-split", type=int, default=0)
+    ap.add_argument("--wpc", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time mixed / fp64 / single-step launches")
+    return ap.parse_args()
+
+
+def flops_per_update(n_peds: int) -> float:
+    return 30.0 * n_peds + 120.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(args, n_steps_timed: int, warmup: int):
+    """Bounded sample of the workload on the CPU oracle, all host cores."""
+    from oracle import oracle as orc
+    from pyminisim_b200.scenarios import make_crowd
+    cores = os.cpu_count() or 1
+    sample_worlds = min(args.worlds, max(2 * cores, 16))
+    sample_steps = min(args.sim_steps, 100)
+    sc = make_crowd(sample_worlds, args.peds)
+
+    def fresh():
+        b = orc.OracleBatch(sc.poses, vels=sc.vels, vmag=sc.vmag)
+        b.set_waypoints_fixed(sc.table, loop=True)
+        b.set_robot(orc.ROBOT_UNICYCLE, sc.robot_pose, control=sc.robot_control)
+        b.set_detector(5.0, np.deg2rad(120.0), orc.DET_POLAR)
+        return b
+
+    for _ in range(warmup):
+        fresh().rollout(0.01, sample_steps, n_threads=cores)
+    t_total = 0.0
+    for _ in range(n_steps_timed):
+        b = fresh()
+        t0 = time.perf_counter()
+        b.rollout(0.01, sample_steps, n_threads=cores)
+        t_total += time.perf_counter() - t0
+    updates = sample_worlds * args.peds * sample_steps * n_steps_timed
+    return {"value": updates / t_total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_worlds} worlds x {args.peds} peds x {sample_steps} sim-steps per step, "
+                      f"{n_steps_timed} steps, C oracle (fp64), pthreads over worlds",
+            "ms_per_step": 1e3 * t_total / n_steps_timed}
+
+
+def config_dict(args, world_size):
+    return {"workload": f"C4: {args.worlds} worlds x {args.peds} pedestrians per GPU, HSFM + unicycle robot + "
+                        f"pedestrian detector (5 m, 120 deg) + collision list, {args.sim_steps} fused sim-steps "
+                        f"of dt=0.01 per bench step",
+            "worlds_per_gpu": args.worlds, "peds_per_world": args.peds, "sim_steps_per_step": args.sim_steps,
+            "dt": 0.01, "precision": args.precision, "parallelism": f"worlds sharded over {world_size} GPU(s), "
+            "no collective on the step path", "l2": "256 MiB L2 flush between timed steps (state is 16 MB and "
+            "lives on-chip during a step)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_run(args, max(1, args.steps), max(0, min(args.warmup, 2)))
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, args.gpus),
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference is Python+numba and cannot travel to the GPU box; this arm is the C port of its "
+                    "algorithm (oracle/), pinned to the live reference by tests/golden, on all host cores"}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pyminisim_b200 import _capi as capi
+    from pyminisim_b200.batched import BatchedSimulation
+    from pyminisim_b200.scenarios import make_crowd
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    worlds = args.worlds if args.scaling == "weak" else max(1, args.worlds // world_size)
+    sc = make_crowd(worlds, args.peds, first_world=rank * worlds)
+    W, N, K = worlds, args.peds, args.sim_steps
+
+    sim = BatchedSimulation(W, N, precision=args.precision, device=local_rank)
+    if args.j_split or args.wpc:
+        sim.set_tuning(args.j_split, args.wpc)
+    # pinned host buffers for the end-to-end leg
+    h_poses = capi.pinned_array((W, N, 3)); h_poses[:] = sc.poses
+    h_vels = capi.pinned_array((W, N, 3)); h_vels[:] = sc.vels
+    o_poses = capi.pinned_array((W, N, 3)); o_vels = capi.pinned_array((W, N, 3))
+    sim.set_state(h_poses, h_vels)
+    sim.set_speeds(sc.vmag)
+    sim.set_waypoints_fixed(sc.table, loop=True)
+    sim.set_robot(capi.ROBOT_UNICYCLE, sc.robot_pose, control=sc.robot_control)
+    sim.set_detector(5.0, np.deg2rad(120.0), capi.DET_POLAR)
+    sim.snapshot_save()
+
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_device_steps(n, n_sim, collect=True):
+        total_ms = 0.0
+        for _ in range(n):
+            sim.snapshot_restore()
+            with torch.cuda.stream(stream):
+                flush.zero_()                                   # L2 flush, outside the timed events
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                sim.step_async(0.01, n_sim)
+                e1.record(stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        return total_ms
+
+    # ---- warm-up ----
+    timed_device_steps(max(args.warmup, 3), K)
+    fp32_peak = capi.load().pms_measure_fp32_tflops(local_rank)
+
+    # ---- device-resident throughput (value) ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches_before = sim.launch_info()["kernel_launches"]
+    ms = timed_device_steps(args.steps, K)
+    launches = sim.launch_info()["kernel_launches"] - launches_before
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    updates_per_rank = float(W) * N * K * args.steps
+    value = updates_per_rank * world_size / (ms_max * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers ----
+    def e2e_step():
+        sim.snapshot_restore()                 # robot / tracker / statistics back to t = 0 (device-side)
+        sim.set_state(h_poses, h_vels)          # H2D from pinned memory
+        sim.step(0.01, K)
+        sim.get_state(o_poses, o_vels)          # D2H
+        mask, vals = sim.get_detector()
+        coll = sim.get_collisions()
+        stats = sim.get_stats()
+        return mask, vals, coll, stats
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mask, vals, coll, stats = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = updates_per_rank * world_size / float(te.item())
+    h2d = h_poses.nbytes + h_vels.nbytes
+    d2h = o_poses.nbytes + o_vels.nbytes + mask.nbytes + vals.nbytes + coll.nbytes + sum(s.nbytes for s in stats)
+
+    # ---- episode statistics: the only collective (NCCL all-reduce of a few numbers) ----
+    det, col, nf = stats
+    st = torch.tensor([float(det.sum()), float(col.sum()), float((nf != 0).sum()),
+                       float(np.linalg.norm(o_vels[..., :2], axis=-1).mean())], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    episode = {"detections": int(st[0].item()), "robot_ped_collisions": int(st[1].item()),
+               "nonfinite_worlds": int(st[2].item()), "mean_speed": float(st[3].item()) / world_size}
+
+    extra = {}
+    if args.extra and rank == 0:
+        for prec in ("mixed", "fp64"):
+            s2 = BatchedSimulation(W, N, precision=prec, device=local_rank)
+            s2.set_state(sc.poses, sc.vels); s2.set_speeds(sc.vmag); s2.set_waypoints_fixed(sc.table, loop=True)
+            s2.set_robot(capi.ROBOT_UNICYCLE, sc.robot_pose, control=sc.robot_control)
+            s2.set_detector(5.0, np.deg2rad(120.0), capi.DET_POLAR)
+            s2.snapshot_save()
+            st2 = torch.cuda.ExternalStream(s2.stream)
+            best = 0.0
+            for rep in range(3):
+                s2.snapshot_restore()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(st2); s2.step_async(0.01, K); e1.record(st2); e1.synchronize()
+                if rep:
+                    best = max(best, W * N * K / (e0.elapsed_time(e1) * 1e-3))
+            extra[f"value_{prec}"] = best
+            s2.close()
+        # launch-per-step mode (state round-trips HBM every simulation step)
+        sim.snapshot_restore()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(200):
+            sim.step_async(0.01, 1)
+        e1.record(stream); e1.synchronize()
+        extra["value_one_sim_step_per_launch"] = W * N * 200 / (e0.elapsed_time(e1) * 1e-3)
+
+    if rank == 0:
+        info = sim.launch_info()
+        kernel_ms = ms / max(launches, 1)
+        achieved_tflops = float(W) * N * K * flops_per_update(N) / (kernel_ms * 1e-3) / 1e12
+        peak = fp32_peak if fp32_peak and fp32_peak > 0 else 148 * 128 * 2 * 1.965e9 / 1e12
+        cpu = None
+        if not args.no_cpu_baseline:
+            res = cpu_reference_run(args, 3, 1)
+            cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": {"fp32": "f32", "mixed": "f32/f64", "fp64": "f64"}[args.precision],
+            "data": "synthetic", "config": config_dict(args, world_size),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved_tflops / peak, "traffic": None,
+                         "peak_source": "FP32 FMA-chain microbenchmark measured in this run (pms_measure_fp32_tflops); "
+                                        "MEASURED_PEAKS.json has no non-tensor FP32 figure",
+                         "kernel": "hsfm_small_kernel", "flops_per_pedestrian_update": flops_per_update(N),
+                         "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu, "clocks": clocks, "launch": info, "episode_stats": episode,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    sim.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

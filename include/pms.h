@@ -1,0 +1,181 @@
+/*
+ * pms.h -- C ABI of libpms_b200: the B200-native (sm_100a) pedestrian-dynamics hot path of
+ * TimeEscaper/pyminisim, batched over independent worlds.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the duck-typed Python
+ * interface  AbstractPedestriansModel.step(dt, robot_pose, robot_velocity)
+ * (pyminisim/core/_pedestrians_model.py:34-47), AbstractSensor.get_reading(world_state, world_map)
+ * (core/_sensor.py:16-38) and Simulation.step / _get_world_state / _update_sensors_state
+ * (core/_simulation.py:60-73,138-185).  Each entry point below names the reference code it
+ * replaces.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions: plain C, opaque handle, every call returns 0 on success or a negative pms_status
+ * (message via pms_last_error()).  All host arrays are caller-owned, row-major, float64 unless
+ * stated, and world-major: "(W,N,3)" is poses[w][i][0..2].  One handle per device; a handle is
+ * not thread-safe (one host thread per GPU).  No exceptions cross the boundary.
+ */
+#ifndef PMS_H
+#define PMS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pms_sim pms_sim;
+
+typedef enum {
+    PMS_OK = 0,
+    PMS_ERR_INVALID = -1,   /* bad argument (AssertionError / ValueError in the reference) */
+    PMS_ERR_CUDA = -2,      /* CUDA runtime failure */
+    PMS_ERR_STATE = -3,     /* call order / configuration error (RuntimeError in the reference) */
+    PMS_ERR_UNSUPPORTED = -4
+} pms_status;
+
+/* Arithmetic mode of the HSFM kernels.
+ *   PMS_FP32  : state, pair forces and per-pedestrian math in fp32 (north-star production mode).
+ *   PMS_MIXED : fp64 state and per-pedestrian math; pair forces in fp32 from hi/lo-split
+ *               positions (differences exact to fp64).
+ *   PMS_FP64  : everything fp64 -- verification mode, algorithmically identical to the reference.
+ * Robot pose, detector and collision predicates are evaluated in fp64 in every mode. */
+typedef enum { PMS_FP32 = 0, PMS_MIXED = 1, PMS_FP64 = 2 } pms_precision;
+
+typedef enum { PMS_ROBOT_NONE = 0, PMS_ROBOT_EXTERNAL = 1, PMS_ROBOT_UNICYCLE = 2, PMS_ROBOT_BICYCLE = 3 } pms_robot_model;
+typedef enum { PMS_MAP_EMPTY = 0, PMS_MAP_CIRCLES = 1, PMS_MAP_AABB = 2 } pms_map_kind;
+typedef enum { PMS_DET_POLAR = 0, PMS_DET_RELATIVE_ROTATED = 1, PMS_DET_RELATIVE = 2, PMS_DET_ABSOLUTE = 3 } pms_det_return;
+
+/* HSFMParams (pedestrians/_hsfm.py:20-42) + constructor constants (:198-208,235-239). */
+typedef struct {
+    double tau, A, B, k_1, k_2, k_o, k_d, k_lambda, alpha;
+    double pedestrian_mass;   /* 70.0 */
+    double pedestrian_radius; /* core/_constants.py:2 = 0.3 */
+    double robot_radius;      /* HSFM ctor robot_radius = 0.35: used in the robot force term only */
+} pms_hsfm_params;
+
+/* ORCAParams (pedestrians/_orca.py:13-21) + PyRVOSimulator ctor (:73-79). */
+typedef struct {
+    double time_step, neighbor_dist;
+    int max_neighbors;
+    double time_horizon, radius, goal_reaching_threshold;
+} pms_orca_params;
+
+const char *pms_last_error(void);
+int pms_version(void);
+void pms_default_hsfm_params(pms_hsfm_params *out);   /* HSFMParams.create_default(), _hsfm.py:31-42 */
+void pms_default_orca_params(pms_orca_params *out);   /* ORCAParams(), _orca.py:13-21; time_step 0.01 */
+
+/* ---- lifetime ---- */
+/* Replaces HeadedSocialForceModelPolicy.__init__ (_hsfm.py:198-244) for n_worlds independent
+ * simulations of n_peds pedestrians each.  Fails (PMS_ERR_CUDA) when no CUDA device is present:
+ * there is no CPU fallback. */
+int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hsfm_params *params, pms_sim **out);
+int pms_destroy(pms_sim *h);
+int pms_n_worlds(const pms_sim *h);
+int pms_n_peds(const pms_sim *h);
+
+/* ---- pedestrian state: AbstractPedestriansModelState.poses / .velocities
+ *      (core/_pedestrians_model.py:9-31) and reset_to_state (_hsfm.py:308-310) ---- */
+int pms_set_ped_state(pms_sim *h, const double *poses /*(W,N,3)*/, const double *vels /*(W,N,3)*/);
+int pms_get_ped_state(pms_sim *h, double *poses /*(W,N,3)*/, double *vels /*(W,N,3)*/);
+int pms_set_ped_speeds(pms_sim *h, const double *vmag /*(W,N)*/); /* pedestrian_linear_velocity_magnitude */
+/* device-side snapshot of the complete simulation state (checkpoint / resume) */
+int pms_snapshot_save(pms_sim *h);
+int pms_snapshot_restore(pms_sim *h);
+
+/* ---- waypoint trackers ---- */
+/* FixedWaypointTracker (pedestrians/_fixed_waypoint_tracker.py:28-98).  table holds n_rows rows
+ * per pedestrian with the initial position at row 0 (:45); start_index NULL -> 1 (:59). */
+int pms_set_waypoints_fixed(pms_sim *h, const double *table /*(W,N,n_rows,2)*/, int n_rows,
+                            const int32_t *start_index /*(W,N) or NULL*/, double reach_distance, int loop);
+/* RandomWaypointTracker (pedestrians/_random_waypoint_tracker.py:66-91): the device pops
+ * current <- queue front on reach and logs an event; the host draws the new tail with the global
+ * numpy RNG while replaying the event log in order, then appends it. */
+int pms_set_waypoint_queue(pms_sim *h, const double *current /*(W,N,2)*/, const double *queue /*(W,N,q_len,2)*/,
+                           int q_len, double reach_distance);
+int pms_append_waypoints(pms_sim *h, int n, const int32_t *world_ped /*(n,2)*/, const double *points /*(n,2)*/);
+int pms_pop_waypoint_events(pms_sim *h, int32_t *events /*(cap,3): step,world,ped*/, int cap, int *n_out);
+int pms_get_waypoints(pms_sim *h, double *current /*(W,N,2)*/, int32_t *index /*(W,N) or NULL*/);
+
+/* ---- robot: AbstractRobotMotionModel (core/_motion.py:10-32) ---- */
+/* model EXTERNAL: pose/velocity supplied by the caller are what AbstractPedestriansModel.step
+ * receives (held for all steps of the next pms_hsfm_step call).  UNICYCLE / BICYCLE integrate on
+ * the device exactly like robot/_unicycle.py:53-69 and robot/_bicycle.py:71-95 including the map
+ * collision veto (core/_world_map.py:35-62).  `radius` is AbstractRobotMotionModel.radius
+ * (collision list, veto); `visible` is HSFM's robot_visible (_hsfm.py:279). */
+int pms_set_robot(pms_sim *h, int model, const double *pose /*(W,3)*/, const double *velocity /*(W,3) EXTERNAL only, else NULL*/,
+                  const double *control /*(W,2) or NULL*/, double radius, double wheel_base, int visible);
+/* controls for the next pms_hsfm_step call: row s drives step s; the last row is held. NULL/0 clears. */
+int pms_set_robot_controls(pms_sim *h, const double *controls /*(n_rows,W,2)*/, int n_rows);
+int pms_get_robot(pms_sim *h, double *pose /*(W,3)*/, double *velocity /*(W,3)*/, int32_t *world_collision /*(W) or NULL*/);
+
+/* ---- world map: world_map/_circles_world.py, _aabb_world.py, _empty_world.py ---- */
+int pms_set_map(pms_sim *h, int kind, const double *data /*circles (C,3) | aabb (C,4); per-world: (W,C,.)*/,
+                int count, int per_world);
+
+/* ---- sensors ---- */
+/* PedestrianDetector (sensors/_pedestrian_detector.py:78-134); fov in radians. */
+int pms_detector_config(pms_sim *h, int enabled, double max_dist, double fov, int return_type);
+
+/* ---- the hot path ---- */
+/* n_steps fused iterations of Simulation._make_steps + _get_world_state + detector
+ * (core/_simulation.py:119-160; pedestrians/_hsfm.py:250-306): robot step -> HSFM forces and
+ * explicit-Euler integration -> waypoint hand-off / freeze -> collision list + detector. */
+int pms_hsfm_step(pms_sim *h, double dt, int n_steps);
+/* same, asynchronous on the handle's stream (no host synchronisation); pair with pms_sync */
+int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps);
+int pms_sync(pms_sim *h);
+/* CUDA stream of the handle as an opaque pointer (cudaStream_t), for event timing by the caller */
+void *pms_stream(pms_sim *h);
+/* evaluate collision list + detector on the current state without stepping (Simulation.__init__
+ * runs the sensor pass once, core/_simulation.py:37) */
+int pms_sense(pms_sim *h);
+
+/* readings for the latest state */
+int pms_get_detector(pms_sim *h, uint32_t *mask /*(W,ceil(N/32))*/, double *values /*(W,N,2)*/);
+int pms_get_collisions(pms_sim *h, uint32_t *mask /*(W,ceil(N/32))*/);
+/* per-world episode statistics accumulated over all steps since the last pms_reset_stats */
+int pms_get_stats(pms_sim *h, int64_t *detections /*(W)*/, int64_t *collisions /*(W)*/, int32_t *first_nonfinite_step /*(W)*/);
+int pms_reset_stats(pms_sim *h);
+
+/* LidarSensor (sensors/_lidar.py:105-129) against the map; hit_index = index of the first
+ * occupied sample along the beam or -1; points are absolute. */
+int pms_lidar_scan(pms_sim *h, int n_beams, double max_dist, double resolution,
+                   int32_t *hit_index /*(W,n_beams)*/, double *points /*(W,n_beams,2)*/);
+/* OmniObstacleDetector (sensors/_omni_obstacle_detector.py:58-62): min distance robot -> map */
+int pms_omni_scan(pms_sim *h, double *min_dist /*(W)*/);
+
+/* ---- ORCA (pedestrians/_orca.py:95-127 around rvo2.doStep) ---- */
+int pms_orca_create(int device, int n_worlds, int n_agents, const pms_orca_params *params, pms_sim **out);
+int pms_orca_set_agents(pms_sim *h, const double *positions /*(W,N,2)*/, const double *velocities /*(W,N,2)*/,
+                        const double *max_speeds /*(W,N)*/, const double *pref_speeds /*(W,N)*/);
+/* FixedWaypointTracker for the ORCA agents (same semantics as pms_set_waypoints_fixed; the steady
+ * flag is ignored like _orca.py:106-107 does) */
+int pms_orca_set_waypoints_fixed(pms_sim *h, const double *table /*(W,N,n_rows,2)*/, int n_rows,
+                                 const int32_t *start_index /*(W,N) or NULL*/, double reach_distance, int loop);
+int pms_orca_step(pms_sim *h, int n_steps);
+int pms_orca_get_agents(pms_sim *h, double *poses /*(W,N,3)*/, double *velocities /*(W,N,3)*/);
+
+/* ---- launch introspection (bench / tests) ---- */
+typedef struct {
+    int kernel;            /* 0 = small-world fused kernel, 1 = large-crowd kernel */
+    int threads_per_block, blocks, worlds_per_block, j_split;
+    int smem_bytes;
+    int64_t kernel_launches; /* cumulative count of kernels launched by this handle */
+} pms_launch_info;
+int pms_get_launch_info(pms_sim *h, pms_launch_info *out);
+/* tuning overrides; 0 = automatic */
+int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block);
+
+/* measured FP32 FMA-pipe peak (TFLOP/s, FMA = 2 FLOP) of `device`: the roofline denominator of the
+ * pairwise kernel (MEASURED_PEAKS.json holds only HBM and tensor-core peaks) */
+double pms_measure_fp32_tflops(int device);
+
+/* pinned host memory helpers (for callers without their own allocator) */
+void *pms_host_alloc(uint64_t bytes);
+void pms_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMS_H */

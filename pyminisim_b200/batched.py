@@ -1,0 +1,218 @@
+"""Batched world API over libpms_b200: W independent worlds of N pedestrians on one GPU.
+
+This is new surface (the reference has no batching concept); the single-world
+drop-in classes in ``pyminisim_b200.pedestrians`` / ``.sensors`` / ``.core`` are thin views over it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import check, dptr, f64, iptr, lptr, uptr
+
+
+@dataclass
+class HSFMParams:
+    """Same fields and defaults as pyminisim.pedestrians.HSFMParams (_hsfm.py:20-42)."""
+    tau: float = 0.2
+    A: float = 2000
+    B: float = 0.08
+    k_1: float = 1.2 * 10 ** 5
+    k_2: float = 2.4 * 10 ** 5
+    k_o: float = 1.
+    k_d: float = 500.
+    k_lambda: float = 0.3
+    alpha: float = 3.
+
+    @staticmethod
+    def create_default() -> "HSFMParams":
+        return HSFMParams()
+
+
+class BatchedSimulation:
+    """W worlds x N pedestrians, HSFM dynamics + robot + detector/collision pass fused on the GPU."""
+
+    def __init__(self, n_worlds: int, n_peds: int, precision: str = "fp32", device: int = 0,
+                 hsfm_params: Optional[HSFMParams] = None, pedestrian_mass: float = 70.0,
+                 pedestrian_radius: float = 0.3, hsfm_robot_radius: float = 0.35):
+        self._lib = capi.load()
+        self.W, self.N = int(n_worlds), int(n_peds)
+        self.words = (self.N + 31) // 32
+        self.precision = precision
+        p = hsfm_params or HSFMParams()
+        cp = capi.HsfmParamsC(float(p.tau), float(p.A), float(p.B), float(p.k_1), float(p.k_2), float(p.k_o),
+                              float(p.k_d), float(p.k_lambda), float(p.alpha), float(pedestrian_mass),
+                              float(pedestrian_radius), float(hsfm_robot_radius))
+        self._h = C.c_void_p()
+        check(self._lib.pms_create(int(device), self.W, self.N, capi.PRECISIONS[precision], C.byref(cp), C.byref(self._h)))
+        self.robot_model = capi.ROBOT_NONE
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.pms_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state ----------------------------------------------------------------------------------
+    def set_state(self, poses, velocities=None):
+        poses = f64(poses, (self.W, self.N, 3))
+        vels = None if velocities is None else f64(velocities, (self.W, self.N, 3))
+        check(self._lib.pms_set_ped_state(self._h, dptr(poses), dptr(vels)))
+
+    def get_state(self, out_poses=None, out_vels=None) -> Tuple[np.ndarray, np.ndarray]:
+        poses = np.empty((self.W, self.N, 3)) if out_poses is None else out_poses
+        vels = np.empty((self.W, self.N, 3)) if out_vels is None else out_vels
+        check(self._lib.pms_get_ped_state(self._h, dptr(poses), dptr(vels)))
+        return poses, vels
+
+    def set_speeds(self, vmag):
+        check(self._lib.pms_set_ped_speeds(self._h, dptr(f64(vmag, (self.W, self.N)))))
+
+    def snapshot_save(self):
+        check(self._lib.pms_snapshot_save(self._h))
+
+    def snapshot_restore(self):
+        check(self._lib.pms_snapshot_restore(self._h))
+
+    # ---- trackers -------------------------------------------------------------------------------
+    def set_waypoints_fixed(self, table, start_index=None, reach_distance: float = 0.3, loop: bool = False):
+        table = np.asarray(table, dtype=np.float64)
+        n_rows = table.shape[-2]
+        table = f64(table, (self.W, self.N, n_rows, 2))
+        si = None
+        if start_index is not None:
+            si = np.ascontiguousarray(np.broadcast_to(np.asarray(start_index, dtype=np.int32), (self.W, self.N)))
+        check(self._lib.pms_set_waypoints_fixed(self._h, dptr(table), n_rows, iptr(si), float(reach_distance), int(bool(loop))))
+
+    def set_waypoint_queue(self, current, queue, reach_distance: float = 0.3):
+        queue = np.asarray(queue, dtype=np.float64)
+        q_len = queue.shape[-2]
+        check(self._lib.pms_set_waypoint_queue(self._h, dptr(f64(current, (self.W, self.N, 2))),
+                                               dptr(f64(queue, (self.W, self.N, q_len, 2))), q_len, float(reach_distance)))
+
+    def append_waypoints(self, world_ped, points):
+        wp = np.ascontiguousarray(world_ped, dtype=np.int32).reshape(-1, 2)
+        pts = f64(points).reshape(-1, 2)
+        check(self._lib.pms_append_waypoints(self._h, len(wp), iptr(wp), dptr(pts)))
+
+    def pop_waypoint_events(self, cap: int = 1 << 16) -> np.ndarray:
+        ev = np.zeros((cap, 3), dtype=np.int32)
+        n = C.c_int(0)
+        check(self._lib.pms_pop_waypoint_events(self._h, iptr(ev), cap, C.byref(n)))
+        ev = ev[:n.value]
+        if len(ev):
+            ev = ev[np.lexsort((ev[:, 2], ev[:, 1], ev[:, 0]))]  # (step, world, ped) order = reference order
+        return ev
+
+    def get_waypoints(self) -> Tuple[np.ndarray, np.ndarray]:
+        cur = np.empty((self.W, self.N, 2))
+        idx = np.empty((self.W, self.N), dtype=np.int32)
+        check(self._lib.pms_get_waypoints(self._h, dptr(cur), iptr(idx)))
+        return cur, idx
+
+    # ---- robot / map / sensors --------------------------------------------------------------------
+    def set_robot(self, model: int, pose=None, velocity=None, control=None, radius: float = 0.35,
+                  wheel_base: float = 1.0, visible: bool = True):
+        self.robot_model = int(model)
+        pose_a = None if pose is None else f64(pose, (self.W, 3))
+        vel_a = None if velocity is None else f64(velocity, (self.W, 3))
+        ctl_a = None if control is None else f64(control, (self.W, 2))
+        check(self._lib.pms_set_robot(self._h, int(model), dptr(pose_a), dptr(vel_a), dptr(ctl_a), float(radius),
+                                      float(wheel_base), int(bool(visible))))
+
+    def set_robot_controls(self, controls):
+        if controls is None:
+            check(self._lib.pms_set_robot_controls(self._h, None, 0))
+            return
+        c = f64(controls).reshape(-1, self.W, 2)
+        check(self._lib.pms_set_robot_controls(self._h, dptr(c), c.shape[0]))
+
+    def get_robot(self):
+        pose = np.empty((self.W, 3))
+        vel = np.empty((self.W, 3))
+        wc = np.empty(self.W, dtype=np.int32)
+        check(self._lib.pms_get_robot(self._h, dptr(pose), dptr(vel), iptr(wc)))
+        return pose, vel, wc
+
+    def set_map(self, kind: int, data=None):
+        if data is None or kind == capi.MAP_EMPTY:
+            check(self._lib.pms_set_map(self._h, capi.MAP_EMPTY, None, 0, 0))
+            return
+        data = f64(data)
+        per_world = data.ndim == 3
+        check(self._lib.pms_set_map(self._h, int(kind), dptr(data), data.shape[-2], int(per_world)))
+
+    def set_detector(self, max_dist: float = 3.0, fov: float = np.deg2rad(30.0), return_type: int = capi.DET_POLAR,
+                     enabled: bool = True):
+        check(self._lib.pms_detector_config(self._h, int(bool(enabled)), float(max_dist), float(fov), int(return_type)))
+
+    # ---- hot path ---------------------------------------------------------------------------------
+    def step(self, dt: float = 0.01, n_steps: int = 1):
+        check(self._lib.pms_hsfm_step(self._h, float(dt), int(n_steps)))
+
+    def step_async(self, dt: float = 0.01, n_steps: int = 1):
+        check(self._lib.pms_hsfm_step_async(self._h, float(dt), int(n_steps)))
+
+    def sync(self):
+        check(self._lib.pms_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.pms_stream(self._h) or 0)
+
+    def sense(self):
+        check(self._lib.pms_sense(self._h))
+
+    def get_detector(self) -> Tuple[np.ndarray, np.ndarray]:
+        mask = np.empty((self.W, self.words), dtype=np.uint32)
+        vals = np.empty((self.W, self.N, 2))
+        check(self._lib.pms_get_detector(self._h, uptr(mask), dptr(vals)))
+        return mask, vals
+
+    def get_collisions(self) -> np.ndarray:
+        mask = np.empty((self.W, self.words), dtype=np.uint32)
+        check(self._lib.pms_get_collisions(self._h, uptr(mask)))
+        return mask
+
+    def get_stats(self):
+        det = np.empty(self.W, dtype=np.int64)
+        col = np.empty(self.W, dtype=np.int64)
+        nf = np.empty(self.W, dtype=np.int32)
+        check(self._lib.pms_get_stats(self._h, lptr(det), lptr(col), iptr(nf)))
+        return det, col, nf
+
+    def reset_stats(self):
+        check(self._lib.pms_reset_stats(self._h))
+
+    def lidar_scan(self, n_beams: int = 100, max_dist: float = 8.0, resolution: float = 0.01):
+        hit = np.empty((self.W, n_beams), dtype=np.int32)
+        pts = np.empty((self.W, n_beams, 2))
+        check(self._lib.pms_lidar_scan(self._h, int(n_beams), float(max_dist), float(resolution), iptr(hit), dptr(pts)))
+        return hit, pts
+
+    def omni_scan(self) -> np.ndarray:
+        out = np.empty(self.W)
+        check(self._lib.pms_omni_scan(self._h, dptr(out)))
+        return out
+
+    def launch_info(self) -> dict:
+        info = capi.LaunchInfoC()
+        check(self._lib.pms_get_launch_info(self._h, C.byref(info)))
+        return {n: getattr(info, n) for n, _ in capi.LaunchInfoC._fields_}
+
+    def set_tuning(self, j_split: int = 0, worlds_per_block: int = 0):
+        check(self._lib.pms_set_tuning(self._h, int(j_split), int(worlds_per_block)))
+
+    # ---- helpers mirroring the reference's dict outputs ---------------------------------------------
+    @staticmethod
+    def mask_to_ids(mask_row: np.ndarray, n: int) -> List[int]:
+        return [i for i in range(n) if (int(mask_row[i >> 5]) >> (i & 31)) & 1]

@@ -1,0 +1,910 @@
+// pms_api.cu -- C ABI of libpms_b200 (see include/pms.h).  Host-side handle management, state
+// marshalling (fp64 host arrays <-> native structure-of-arrays in HBM), launch configuration and the
+// extern "C" entry points.  All compute is in the CUDA kernels included below; there is no CPU path.
+#include "../../include/pms.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hsfm_small.cuh"
+#include "hsfm_large.cuh"
+#include "sensors.cuh"
+#include "orca.cuh"
+
+using namespace pms;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(PMS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+template <typename T> cudaError_t dalloc(T **p, size_t n)
+{
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+// ---- marshalling kernels: host layout (W,N,3) fp64 <-> native SoA --------------------------------
+template <typename ST>
+__global__ void pack_state_kernel(size_t n, const double *poses, const double *vels, HsfmArgs a)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    using ST2 = typename Vec2<ST>::type;
+    store_pv(a, g, (ST)poses[3 * g], (ST)poses[3 * g + 1], (ST)vels[3 * g], (ST)vels[3 * g + 1]);
+    ST2 t; t.x = (ST)poses[3 * g + 2]; t.y = (ST)vels[3 * g + 2];
+    reinterpret_cast<ST2 *>(a.th)[g] = t;
+}
+template <typename ST>
+__global__ void unpack_state_kernel(size_t n, double *poses, double *vels, HsfmArgs a)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    using ST2 = typename Vec2<ST>::type;
+    ST x, y, vx, vy;
+    load_pv(a, g, x, y, vx, vy);
+    const ST2 t = reinterpret_cast<const ST2 *>(a.th)[g];
+    poses[3 * g] = (double)x; poses[3 * g + 1] = (double)y; poses[3 * g + 2] = (double)t.x;
+    vels[3 * g] = (double)vx; vels[3 * g + 1] = (double)vy; vels[3 * g + 2] = (double)t.y;
+}
+template <typename ST>
+__global__ void convert_array_kernel(size_t n, const double *src, ST *dst)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g < n) dst[g] = (ST)src[g];
+}
+template <typename ST>
+__global__ void convert_back_kernel(size_t n, const ST *src, double *dst)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g < n) dst[g] = (double)src[g];
+}
+// current waypoint <- table[index] (FixedWaypointTracker._get_current_waypoints)
+template <typename ST>
+__global__ void gather_waypoints_kernel(size_t n, int n_table, const ST *table, const int *index, ST *wp)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    wp[2 * g] = table[(g * n_table + index[g]) * 2];
+    wp[2 * g + 1] = table[(g * n_table + index[g]) * 2 + 1];
+}
+template <typename ST>
+__global__ void append_queue_kernel(int n, const int *world_ped, const double *pts, int N, int q_cap, ST *queue,
+                                    const int *q_head, int *q_count, int *overflow)
+{
+    // sequential: several appends may target the same pedestrian and must keep their order
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int k = 0; k < n; ++k) {
+        const size_t g = (size_t)world_ped[2 * k] * N + world_ped[2 * k + 1];
+        if (q_count[g] >= q_cap) { *overflow = 1; continue; }
+        const int slot = (q_head[g] + q_count[g]) % q_cap;
+        queue[(g * q_cap + slot) * 2] = (ST)pts[2 * k];
+        queue[(g * q_cap + slot) * 2 + 1] = (ST)pts[2 * k + 1];
+        q_count[g]++;
+    }
+}
+__global__ void fill_int_kernel(size_t n, int *p, int v)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g < n) p[g] = v;
+}
+
+inline unsigned nblk(size_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct pms_sim {
+    int kind = 0;          // 0 = HSFM simulation, 1 = ORCA
+    int device = 0;
+    int W = 0, N = 0, Np = 0, words = 0;
+    int precision = PMS_FP32;
+    size_t esz = 4;        // bytes of one state scalar
+    cudaStream_t stream = nullptr;
+    HsfmArgs a{};          // device pointers + configuration (the kernel argument block)
+    // staging (device, fp64) for host <-> device marshalling
+    double *stage = nullptr;
+    size_t stage_elems = 0;
+    double *controls_dev = nullptr;
+    size_t controls_cap = 0;
+    double *map_dev = nullptr;
+    size_t map_cap = 0;
+    int *overflow_dev = nullptr;
+    // snapshot
+    std::vector<std::pair<void *, size_t>> snap_src;
+    std::vector<void *> snap_dst;
+    long long snap_steps = 0;
+    bool has_snapshot = false;
+    // tuning / introspection
+    int tune_S = 0, tune_wpc = 0;
+    pms_launch_info info{};
+    bool waypoints_set = false;
+    // large-crowd path scratch
+    LargeScratch large{};
+    // ORCA
+    OrcaState orca{};
+};
+
+namespace {
+
+int ensure_stage(pms_sim *h, size_t elems)
+{
+    if (elems <= h->stage_elems) return 0;
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_elems = 0;
+    CK(cudaMalloc((void **)&h->stage, elems * sizeof(double)));
+    h->stage_elems = elems;
+    return 0;
+}
+
+struct Guard {
+    int prev = -1;
+    explicit Guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename F> int by_state(pms_sim *h, F &&f)
+{
+    if (h->precision == PMS_FP32) return f(float{});
+    return f(double{});
+}
+
+// ---- launch of the small-world fused kernel ----
+template <typename PT, typename ST, bool SPLIT, int S>
+int launch_small_t(pms_sim *h, int wpc, bool big)
+{
+    const size_t smem = SmallSmem<PT, ST, SPLIT>::bytes(h->Np, S) * wpc;
+    const int threads = wpc * S * h->Np + 32;
+    const int blocks = (h->W + wpc - 1) / wpc;
+    h->a.wpc = wpc;
+    auto kern = big ? hsfm_small_kernel_big<PT, ST, SPLIT, S> : hsfm_small_kernel<PT, ST, SPLIT, S>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, threads, smem, h->stream>>>(h->a);
+    CK(cudaGetLastError());
+    h->info.kernel = 0;
+    h->info.threads_per_block = threads;
+    h->info.blocks = blocks;
+    h->info.worlds_per_block = wpc;
+    h->info.j_split = S;
+    h->info.smem_bytes = (int)smem;
+    h->info.kernel_launches++;
+    return 0;
+}
+
+template <int S> int launch_small_s(pms_sim *h, int wpc, bool big)
+{
+    switch (h->precision) {
+    case PMS_FP32: return launch_small_t<float, float, false, S>(h, wpc, big);
+    case PMS_MIXED: return launch_small_t<float, double, true, S>(h, wpc, big);
+    default: return launch_small_t<double, double, false, S>(h, wpc, big);
+    }
+}
+
+int launch_small(pms_sim *h)
+{
+    const int Np = h->Np;
+    int S = h->tune_S;
+    if (S <= 0) {
+        // enough threads to fill 148 SMs; every slice keeps >= 8 pairs for ILP
+        const long long target = 148LL * 1536;
+        S = 1;
+        while (S < 8 && (long long)h->W * Np * S * 2 <= target && h->N / (S * 2) >= 8) S *= 2;
+    }
+    while (S > 1 && S * Np + 32 > 1024) S /= 2;
+    if (S != 1 && S != 2 && S != 4 && S != 8) return fail(PMS_ERR_INVALID, "j_split must be 1, 2, 4 or 8");
+    int wpc = h->tune_wpc;
+    if (wpc <= 0) wpc = 256 / (S * Np);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 32) wpc = 32;
+    if (wpc > h->W) wpc = h->W;
+    while (wpc > 1 && wpc * S * Np + 32 > 1024) --wpc;
+    const bool big = wpc * S * Np + 32 > 288;
+    switch (S) {
+    case 1: return launch_small_s<1>(h, wpc, big);
+    case 2: return launch_small_s<2>(h, wpc, big);
+    case 4: return launch_small_s<4>(h, wpc, big);
+    default: return launch_small_s<8>(h, wpc, big);
+    }
+}
+
+int clear_sensor_outputs(pms_sim *h)
+{
+    CK(cudaMemsetAsync(h->a.det_mask, 0, sizeof(uint32_t) * (size_t)h->W * h->words, h->stream));
+    CK(cudaMemsetAsync(h->a.coll_mask, 0, sizeof(uint32_t) * (size_t)h->W * h->words, h->stream));
+    return 0;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *pms_last_error(void) { return g_err.c_str(); }
+int pms_version(void) { return 100; }
+
+void pms_default_hsfm_params(pms_hsfm_params *p)
+{
+    if (!p) return;
+    p->tau = 0.2; p->A = 2000.0; p->B = 0.08; p->k_1 = 1.2e5; p->k_2 = 2.4e5; p->k_o = 1.0; p->k_d = 500.0;
+    p->k_lambda = 0.3; p->alpha = 3.0; p->pedestrian_mass = 70.0; p->pedestrian_radius = 0.3; p->robot_radius = 0.35;
+}
+
+void pms_default_orca_params(pms_orca_params *p)
+{
+    if (!p) return;
+    p->time_step = 0.01; p->neighbor_dist = 1.0; p->max_neighbors = 10; p->time_horizon = 2.0; p->radius = 0.3;
+    p->goal_reaching_threshold = 0.2;
+}
+
+int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hsfm_params *params, pms_sim **out)
+{
+    if (!out) return fail(PMS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_worlds < 1 || n_peds < 1) return fail(PMS_ERR_INVALID, "n_worlds and n_peds must be >= 1");
+    if (precision < PMS_FP32 || precision > PMS_FP64) return fail(PMS_ERR_INVALID, "unknown precision");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PMS_ERR_CUDA, std::string("no CUDA device available (libpms_b200 has no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(PMS_ERR_INVALID, "device index out of range");
+    Guard gd(device);
+    pms_hsfm_params p;
+    if (params) p = *params; else pms_default_hsfm_params(&p);
+    pms_sim *h = new pms_sim();
+    h->device = device;
+    h->W = n_worlds; h->N = n_peds; h->Np = (n_peds + 31) & ~31; h->words = (n_peds + 31) / 32;
+    h->precision = precision;
+    h->esz = precision == PMS_FP32 ? 4 : 8;
+    const size_t n = (size_t)n_worlds * n_peds;
+    HsfmArgs &a = h->a;
+    a.W = n_worlds; a.N = n_peds; a.Np = h->Np; a.wpc = 1;
+    a.tau = p.tau; a.A = p.A; a.B = p.B; a.k1 = p.k_1; a.k2 = p.k_2; a.ko = p.k_o; a.kd = p.k_d;
+    a.k_lambda = p.k_lambda; a.alpha = p.alpha; a.mass = p.pedestrian_mass; a.ped_radius = p.pedestrian_radius;
+    a.hsfm_robot_radius = p.robot_radius;
+    a.robot_radius = 0.35; a.wheel_base = 1.0; a.robot_visible = 1; a.robot_model = ROBOT_NONE;
+    a.reach = 0.3; a.tracker_kind = TRACKER_FIXED; a.n_table = 1;
+    a.det_enabled = 0; a.det_max_dist = 3.0; a.det_half_fov = 0.5 * (30.0 * PMS_PI / 180.0); a.det_type = DET_POLAR;
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            pms_destroy(h);                                                                        \
+            return fail(PMS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+        }                                                                                          \
+    } while (0)
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t e2 = h->esz * 2;
+    unsigned char *raw;
+    CKC(dalloc(&raw, n * (precision == PMS_FP32 ? 16 : 16))); a.pos = raw;
+    CKC(dalloc(&raw, n * 16)); a.vel = raw;
+    CKC(dalloc(&raw, n * e2)); a.th = raw;
+    CKC(dalloc(&raw, n * e2)); a.wp = raw;
+    CKC(dalloc(&raw, n * h->esz)); a.vmag = raw;
+    CKC(dalloc(&a.wp_index, n));
+    CKC(dalloc(&a.q_head, n));
+    CKC(dalloc(&a.q_count, n));
+    a.ev_cap = 1 << 16;
+    CKC(dalloc(&a.events, (size_t)a.ev_cap * 3));
+    CKC(dalloc(&a.ev_count, 1));
+    CKC(dalloc(&a.robot_pose, (size_t)n_worlds * 3));
+    CKC(dalloc(&a.robot_vel, (size_t)n_worlds * 3));
+    CKC(dalloc(&a.robot_ctrl, (size_t)n_worlds * 2));
+    CKC(dalloc(&a.robot_rear, (size_t)n_worlds * 3));
+    CKC(dalloc(&a.robot_world_collision, (size_t)n_worlds));
+    CKC(dalloc(&a.det_mask, (size_t)n_worlds * h->words));
+    CKC(dalloc(&a.coll_mask, (size_t)n_worlds * h->words));
+    CKC(dalloc(&a.det_vals, n));
+    CKC(dalloc(&a.det_count, (size_t)n_worlds));
+    CKC(dalloc(&a.coll_count, (size_t)n_worlds));
+    CKC(dalloc(&a.nonfinite, (size_t)n_worlds));
+    CKC(dalloc(&h->overflow_dev, 1));
+    fill_int_kernel<<<nblk(n_worlds), 256, 0, h->stream>>>((size_t)n_worlds, a.nonfinite, 0x7fffffff);
+    // default speed 1.5 (_hsfm.py:205) and a waypoint table of one row (set properly by the caller)
+    {
+        std::vector<double> v(n, 1.5);
+        if (ensure_stage(h, n * 6)) { pms_destroy(h); return PMS_ERR_CUDA; }
+        CKC(cudaMemcpyAsync(h->stage, v.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (precision == PMS_FP32) convert_array_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, (float *)a.vmag);
+        else convert_array_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, (double *)a.vmag);
+        CKC(cudaStreamSynchronize(h->stream));
+    }
+#undef CKC
+    *out = h;
+    return PMS_OK;
+}
+
+int pms_destroy(pms_sim *h)
+{
+    if (!h) return PMS_OK;
+    Guard gd(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    HsfmArgs &a = h->a;
+    void *ptrs[] = {a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
+                    a.events, a.ev_count, a.robot_pose, a.robot_vel, a.robot_ctrl, a.robot_rear,
+                    a.robot_world_collision, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
+                    a.nonfinite, h->stage, h->controls_dev, h->map_dev, h->overflow_dev};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : h->snap_dst) if (p) cudaFree(p);
+    large_free(h->large);
+    orca_free(h->orca);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PMS_OK;
+}
+
+int pms_n_worlds(const pms_sim *h) { return h ? h->W : 0; }
+int pms_n_peds(const pms_sim *h) { return h ? h->N : 0; }
+
+#define HCHECK(h)                                                     \
+    if (!(h)) return fail(PMS_ERR_INVALID, "handle is NULL");         \
+    if ((h)->kind != 0) return fail(PMS_ERR_STATE, "not an HSFM handle"); \
+    Guard gd__((h)->device)
+
+int pms_set_ped_state(pms_sim *h, const double *poses, const double *vels)
+{
+    HCHECK(h);
+    if (!poses) return fail(PMS_ERR_INVALID, "poses is NULL");
+    const size_t n = (size_t)h->W * h->N;
+    if (ensure_stage(h, n * 6)) return PMS_ERR_CUDA;
+    CK(cudaMemcpyAsync(h->stage, poses, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (vels) CK(cudaMemcpyAsync(h->stage + n * 3, vels, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->stage + n * 3, 0, n * 3 * sizeof(double), h->stream));
+    if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
+    else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_get_ped_state(pms_sim *h, double *poses, double *vels)
+{
+    HCHECK(h);
+    const size_t n = (size_t)h->W * h->N;
+    if (ensure_stage(h, n * 6)) return PMS_ERR_CUDA;
+    if (h->precision == PMS_FP32) unpack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
+    else unpack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
+    CK(cudaGetLastError());
+    if (poses) CK(cudaMemcpyAsync(poses, h->stage, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (vels) CK(cudaMemcpyAsync(vels, h->stage + n * 3, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+static int upload_converted(pms_sim *h, const double *src, size_t n, void *dst)
+{
+    if (ensure_stage(h, n)) return PMS_ERR_CUDA;
+    CK(cudaMemcpyAsync(h->stage, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->precision == PMS_FP32) convert_array_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, (float *)dst);
+    else convert_array_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, (double *)dst);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_set_ped_speeds(pms_sim *h, const double *vmag)
+{
+    HCHECK(h);
+    if (!vmag) return fail(PMS_ERR_INVALID, "vmag is NULL");
+    return upload_converted(h, vmag, (size_t)h->W * h->N, h->a.vmag);
+}
+
+int pms_set_waypoints_fixed(pms_sim *h, const double *table, int n_rows, const int32_t *start_index, double reach, int loop)
+{
+    HCHECK(h);
+    if (!table || n_rows < 1) return fail(PMS_ERR_INVALID, "table is NULL or n_rows < 1");
+    const size_t n = (size_t)h->W * h->N;
+    HsfmArgs &a = h->a;
+    if (a.table) { cudaFree((void *)a.table); a.table = nullptr; }
+    unsigned char *raw;
+    CK(dalloc(&raw, n * n_rows * 2 * h->esz));
+    a.table = raw;
+    int rc = upload_converted(h, table, n * n_rows * 2, raw);
+    if (rc) return rc;
+    if (start_index) {
+        for (size_t k = 0; k < n; ++k)
+            if (start_index[k] < 0 || start_index[k] >= n_rows) return fail(PMS_ERR_INVALID, "start_index out of range");
+        CK(cudaMemcpyAsync(a.wp_index, start_index, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        fill_int_kernel<<<nblk(n), 256, 0, h->stream>>>(n, a.wp_index, n_rows > 1 ? 1 : 0);
+    }
+    a.tracker_kind = TRACKER_FIXED; a.n_table = n_rows; a.reach = reach; a.loop = loop ? 1 : 0;
+    if (h->precision == PMS_FP32)
+        gather_waypoints_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, n_rows, (const float *)a.table, a.wp_index, (float *)a.wp);
+    else
+        gather_waypoints_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, n_rows, (const double *)a.table, a.wp_index, (double *)a.wp);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->waypoints_set = true;
+    return PMS_OK;
+}
+
+int pms_set_waypoint_queue(pms_sim *h, const double *current, const double *queue, int q_len, double reach)
+{
+    HCHECK(h);
+    if (!current || !queue || q_len < 1) return fail(PMS_ERR_INVALID, "current/queue NULL or q_len < 1");
+    const size_t n = (size_t)h->W * h->N;
+    HsfmArgs &a = h->a;
+    if (a.queue) { cudaFree((void *)a.queue); a.queue = nullptr; }
+    unsigned char *raw;
+    CK(dalloc(&raw, n * q_len * 2 * h->esz));
+    a.queue = raw;
+    int rc = upload_converted(h, queue, n * q_len * 2, raw);
+    if (rc) return rc;
+    rc = upload_converted(h, current, n * 2, a.wp);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(a.q_head, 0, n * sizeof(int), h->stream));
+    fill_int_kernel<<<nblk(n), 256, 0, h->stream>>>(n, a.q_count, q_len);
+    CK(cudaMemsetAsync(a.ev_count, 0, sizeof(int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    a.tracker_kind = TRACKER_QUEUE; a.q_cap = q_len; a.reach = reach;
+    h->waypoints_set = true;
+    return PMS_OK;
+}
+
+int pms_append_waypoints(pms_sim *h, int n, const int32_t *world_ped, const double *points)
+{
+    HCHECK(h);
+    if (h->a.tracker_kind != TRACKER_QUEUE) return fail(PMS_ERR_STATE, "waypoint queue is not configured");
+    if (n <= 0) return PMS_OK;
+    if (!world_ped || !points) return fail(PMS_ERR_INVALID, "world_ped/points NULL");
+    for (int k = 0; k < n; ++k)
+        if (world_ped[2 * k] < 0 || world_ped[2 * k] >= h->W || world_ped[2 * k + 1] < 0 || world_ped[2 * k + 1] >= h->N)
+            return fail(PMS_ERR_INVALID, "world/ped index out of range");
+    if (ensure_stage(h, (size_t)n * 3 + 2)) return PMS_ERR_CUDA;
+    int *wp_dev = reinterpret_cast<int *>(h->stage + (size_t)n * 2);
+    CK(cudaMemcpyAsync(h->stage, points, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(wp_dev, world_ped, (size_t)n * 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->overflow_dev, 0, sizeof(int), h->stream));
+    if (h->precision == PMS_FP32)
+        append_queue_kernel<float><<<1, 1, 0, h->stream>>>(n, wp_dev, h->stage, h->N, h->a.q_cap, (float *)h->a.queue, h->a.q_head, h->a.q_count, h->overflow_dev);
+    else
+        append_queue_kernel<double><<<1, 1, 0, h->stream>>>(n, wp_dev, h->stage, h->N, h->a.q_cap, (double *)h->a.queue, h->a.q_head, h->a.q_count, h->overflow_dev);
+    int ov = 0;
+    CK(cudaMemcpyAsync(&ov, h->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ov) return fail(PMS_ERR_STATE, "waypoint queue overflow");
+    return PMS_OK;
+}
+
+int pms_pop_waypoint_events(pms_sim *h, int32_t *events, int cap, int *n_out)
+{
+    HCHECK(h);
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, h->a.ev_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (cnt > h->a.ev_cap) return fail(PMS_ERR_STATE, "waypoint event log overflowed (too many steps per call)");
+    const int n = cnt < cap ? cnt : cap;
+    if (n > 0 && events) CK(cudaMemcpyAsync(events, h->a.events, (size_t)n * 3 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemsetAsync(h->a.ev_count, 0, sizeof(int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_out) *n_out = n;
+    if (cnt > cap) return fail(PMS_ERR_INVALID, "event buffer too small");
+    return PMS_OK;
+}
+
+int pms_get_waypoints(pms_sim *h, double *current, int32_t *index)
+{
+    HCHECK(h);
+    const size_t n = (size_t)h->W * h->N;
+    if (current) {
+        if (ensure_stage(h, n * 2)) return PMS_ERR_CUDA;
+        if (h->precision == PMS_FP32) convert_back_kernel<float><<<nblk(n * 2), 256, 0, h->stream>>>(n * 2, (const float *)h->a.wp, h->stage);
+        else convert_back_kernel<double><<<nblk(n * 2), 256, 0, h->stream>>>(n * 2, (const double *)h->a.wp, h->stage);
+        CK(cudaMemcpyAsync(current, h->stage, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (index) CK(cudaMemcpyAsync(index, h->a.wp_index, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_set_robot(pms_sim *h, int model, const double *pose, const double *velocity, const double *control,
+                  double radius, double wheel_base, int visible)
+{
+    HCHECK(h);
+    if (model < PMS_ROBOT_NONE || model > PMS_ROBOT_BICYCLE) return fail(PMS_ERR_INVALID, "unknown robot model");
+    HsfmArgs &a = h->a;
+    a.robot_model = model;
+    a.robot_visible = visible ? 1 : 0;
+    if (model == PMS_ROBOT_NONE) return PMS_OK;
+    if (!pose) return fail(PMS_ERR_INVALID, "pose is NULL");
+    if (!(radius > 0.0)) return fail(PMS_ERR_INVALID, "robot radius must be > 0");   // core/_motion.py:15
+    if (model == PMS_ROBOT_BICYCLE && !(wheel_base > 0.0)) return fail(PMS_ERR_INVALID, "wheel_base must be > 0");
+    a.robot_radius = radius; a.wheel_base = wheel_base;
+    const int W = h->W;
+    std::vector<double> vel((size_t)W * 3, 0.0), ctrl((size_t)W * 2, 0.0), rear((size_t)W * 3, 0.0);
+    if (control) std::memcpy(ctrl.data(), control, sizeof(double) * W * 2);
+    for (int w = 0; w < W; ++w) {
+        const double th = pose[3 * w + 2];
+        if (model == PMS_ROBOT_EXTERNAL && velocity) {
+            vel[3 * w] = velocity[3 * w]; vel[3 * w + 1] = velocity[3 * w + 1]; vel[3 * w + 2] = velocity[3 * w + 2];
+        } else if (model == PMS_ROBOT_UNICYCLE) {   // UnicycleRobotModelState.velocity
+            vel[3 * w] = ctrl[2 * w] * std::cos(th); vel[3 * w + 1] = ctrl[2 * w] * std::sin(th); vel[3 * w + 2] = ctrl[2 * w + 1];
+        }
+        // BicycleRobotModel.__init__: rear-axle pose (robot/_bicycle.py:58-62)
+        rear[3 * w] = pose[3 * w] - (wheel_base / 2.0) * std::cos(th);
+        rear[3 * w + 1] = pose[3 * w + 1] - (wheel_base / 2.0) * std::sin(th);
+        rear[3 * w + 2] = th;
+    }
+    CK(cudaMemcpyAsync(a.robot_pose, pose, sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(a.robot_vel, vel.data(), sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(a.robot_ctrl, ctrl.data(), sizeof(double) * W * 2, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(a.robot_rear, rear.data(), sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(a.robot_world_collision, 0, sizeof(int) * W, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_set_robot_controls(pms_sim *h, const double *controls, int n_rows)
+{
+    HCHECK(h);
+    if (!controls || n_rows <= 0) { h->a.controls = nullptr; h->a.n_controls = 0; return PMS_OK; }
+    const size_t n = (size_t)n_rows * h->W * 2;
+    if (n > h->controls_cap) {
+        if (h->controls_dev) cudaFree(h->controls_dev);
+        h->controls_dev = nullptr; h->controls_cap = 0;
+        CK(cudaMalloc((void **)&h->controls_dev, n * sizeof(double)));
+        h->controls_cap = n;
+    }
+    CK(cudaMemcpyAsync(h->controls_dev, controls, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->a.controls = h->controls_dev; h->a.n_controls = n_rows;
+    return PMS_OK;
+}
+
+int pms_get_robot(pms_sim *h, double *pose, double *velocity, int32_t *world_collision)
+{
+    HCHECK(h);
+    const int W = h->W;
+    if (pose) CK(cudaMemcpyAsync(pose, h->a.robot_pose, sizeof(double) * W * 3, cudaMemcpyDeviceToHost, h->stream));
+    if (velocity) CK(cudaMemcpyAsync(velocity, h->a.robot_vel, sizeof(double) * W * 3, cudaMemcpyDeviceToHost, h->stream));
+    if (world_collision) CK(cudaMemcpyAsync(world_collision, h->a.robot_world_collision, sizeof(int) * W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_set_map(pms_sim *h, int kind, const double *data, int count, int per_world)
+{
+    HCHECK(h);
+    if (kind < PMS_MAP_EMPTY || kind > PMS_MAP_AABB) return fail(PMS_ERR_INVALID, "unknown map kind");
+    HsfmArgs &a = h->a;
+    if (kind == PMS_MAP_EMPTY || count <= 0) { a.map_kind = kind; a.map_count = 0; a.map_data = nullptr; a.map_stride = 0; return PMS_OK; }
+    if (!data) return fail(PMS_ERR_INVALID, "map data is NULL");
+    const int k = kind == PMS_MAP_CIRCLES ? 3 : 4;
+    const size_t n = (size_t)count * k * (per_world ? h->W : 1);
+    if (n > h->map_cap) {
+        if (h->map_dev) cudaFree(h->map_dev);
+        h->map_dev = nullptr; h->map_cap = 0;
+        CK(cudaMalloc((void **)&h->map_dev, n * sizeof(double)));
+        h->map_cap = n;
+    }
+    CK(cudaMemcpyAsync(h->map_dev, data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    a.map_kind = kind; a.map_count = count; a.map_data = h->map_dev; a.map_stride = per_world ? count * k : 0;
+    return PMS_OK;
+}
+
+int pms_detector_config(pms_sim *h, int enabled, double max_dist, double fov, int return_type)
+{
+    HCHECK(h);
+    if (return_type < PMS_DET_POLAR || return_type > PMS_DET_ABSOLUTE)
+        return fail(PMS_ERR_INVALID, "unknown detector return type");   // _pedestrian_detector.py:29-32
+    h->a.det_enabled = enabled ? 1 : 0; h->a.det_max_dist = max_dist; h->a.det_half_fov = fov / 2.0; h->a.det_type = return_type;
+    return PMS_OK;
+}
+
+int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
+{
+    HCHECK(h);
+    if (n_steps < 0) return fail(PMS_ERR_INVALID, "n_steps < 0");
+    if (n_steps == 0) return PMS_OK;
+    if (!h->waypoints_set) return fail(PMS_ERR_STATE, "Waypoint tracker is not initialized");
+    h->a.dt = dt; h->a.n_steps = n_steps;
+    fill_consts(h->a);
+    int rc;
+    if (h->a.robot_model == ROBOT_NONE && (rc = clear_sensor_outputs(h))) return rc;
+    if (h->Np + 32 <= 1024) rc = launch_small(h);
+    else rc = launch_large(h, h->large, h->a, h->precision, h->stream, &h->info);
+    if (rc) return rc;
+    h->a.steps_done += n_steps;
+    return PMS_OK;
+}
+
+int pms_sync(pms_sim *h)
+{
+    if (!h) return fail(PMS_ERR_INVALID, "handle is NULL");
+    Guard gd(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_hsfm_step(pms_sim *h, double dt, int n_steps)
+{
+    int rc = pms_hsfm_step_async(h, dt, n_steps);
+    if (rc) return rc;
+    return pms_sync(h);
+}
+
+void *pms_stream(pms_sim *h) { return h ? (void *)h->stream : nullptr; }
+
+int pms_sense(pms_sim *h)
+{
+    HCHECK(h);
+    int rc = clear_sensor_outputs(h);
+    if (rc) return rc;
+    fill_consts(h->a);
+    if (h->a.robot_model != ROBOT_NONE) {
+        if (h->precision == PMS_FP32) sense_kernel<float><<<h->W, h->Np, 0, h->stream>>>(h->a);
+        else sense_kernel<double><<<h->W, h->Np, 0, h->stream>>>(h->a);
+        CK(cudaGetLastError());
+        h->info.kernel_launches++;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_get_detector(pms_sim *h, uint32_t *mask, double *values)
+{
+    HCHECK(h);
+    const size_t n = (size_t)h->W * h->N;
+    if (mask) CK(cudaMemcpyAsync(mask, h->a.det_mask, sizeof(uint32_t) * h->W * h->words, cudaMemcpyDeviceToHost, h->stream));
+    if (values) CK(cudaMemcpyAsync(values, h->a.det_vals, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_get_collisions(pms_sim *h, uint32_t *mask)
+{
+    HCHECK(h);
+    if (mask) CK(cudaMemcpyAsync(mask, h->a.coll_mask, sizeof(uint32_t) * h->W * h->words, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_get_stats(pms_sim *h, int64_t *detections, int64_t *collisions, int32_t *first_nonfinite_step)
+{
+    HCHECK(h);
+    const int W = h->W;
+    if (detections) CK(cudaMemcpyAsync(detections, h->a.det_count, sizeof(int64_t) * W, cudaMemcpyDeviceToHost, h->stream));
+    if (collisions) CK(cudaMemcpyAsync(collisions, h->a.coll_count, sizeof(int64_t) * W, cudaMemcpyDeviceToHost, h->stream));
+    if (first_nonfinite_step) CK(cudaMemcpyAsync(first_nonfinite_step, h->a.nonfinite, sizeof(int) * W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (first_nonfinite_step)
+        for (int w = 0; w < W; ++w) if (first_nonfinite_step[w] == 0x7fffffff) first_nonfinite_step[w] = 0;
+    return PMS_OK;
+}
+
+int pms_reset_stats(pms_sim *h)
+{
+    HCHECK(h);
+    CK(cudaMemsetAsync(h->a.det_count, 0, sizeof(int64_t) * h->W, h->stream));
+    CK(cudaMemsetAsync(h->a.coll_count, 0, sizeof(int64_t) * h->W, h->stream));
+    fill_int_kernel<<<nblk(h->W), 256, 0, h->stream>>>((size_t)h->W, h->a.nonfinite, 0x7fffffff);
+    CK(cudaStreamSynchronize(h->stream));
+    h->a.steps_done = 0;
+    return PMS_OK;
+}
+
+// ---- snapshot ----
+static void snapshot_regions(pms_sim *h, std::vector<std::pair<void *, size_t>> &r)
+{
+    const HsfmArgs &a = h->a;
+    const size_t n = (size_t)h->W * h->N, W = h->W;
+    r = {{a.pos, n * 16}, {a.vel, n * 16}, {a.th, n * h->esz * 2}, {a.wp, n * h->esz * 2},
+         {a.wp_index, n * 4}, {a.q_head, n * 4}, {a.q_count, n * 4},
+         {a.robot_pose, W * 24}, {a.robot_vel, W * 24}, {a.robot_ctrl, W * 16}, {a.robot_rear, W * 24},
+         {a.robot_world_collision, W * 4}, {a.det_count, W * 8}, {a.coll_count, W * 8}, {a.nonfinite, W * 4}};
+    if (a.queue) r.push_back({(void *)a.queue, n * a.q_cap * 2 * h->esz});
+}
+
+int pms_snapshot_save(pms_sim *h)
+{
+    HCHECK(h);
+    std::vector<std::pair<void *, size_t>> r;
+    snapshot_regions(h, r);
+    for (void *p : h->snap_dst) if (p) cudaFree(p);
+    h->snap_dst.assign(r.size(), nullptr);
+    for (size_t k = 0; k < r.size(); ++k) {
+        CK(cudaMalloc(&h->snap_dst[k], r[k].second ? r[k].second : 1));
+        CK(cudaMemcpyAsync(h->snap_dst[k], r[k].first, r[k].second, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->snap_src = r;
+    h->snap_steps = h->a.steps_done;
+    h->has_snapshot = true;
+    return PMS_OK;
+}
+
+int pms_snapshot_restore(pms_sim *h)
+{
+    HCHECK(h);
+    if (!h->has_snapshot) return fail(PMS_ERR_STATE, "no snapshot saved");
+    for (size_t k = 0; k < h->snap_src.size(); ++k)
+        CK(cudaMemcpyAsync(h->snap_src[k].first, h->snap_dst[k], h->snap_src[k].second, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemsetAsync(h->a.ev_count, 0, sizeof(int), h->stream));
+    h->a.steps_done = h->snap_steps;
+    return PMS_OK;
+}
+
+// ---- lidar / omni ----
+int pms_lidar_scan(pms_sim *h, int n_beams, double max_dist, double resolution, int32_t *hit_index, double *points)
+{
+    HCHECK(h);
+    if (n_beams <= 0) return fail(PMS_ERR_INVALID, "n_beams must be > 0");                          // _lidar.py:15
+    if (!(max_dist > resolution && resolution > 0.0)) return fail(PMS_ERR_INVALID, "need max_dist > resolution > 0"); // :16
+    if (h->a.robot_model == ROBOT_NONE) return fail(PMS_ERR_STATE, "no robot configured");
+    const size_t nb = (size_t)h->W * n_beams;
+    // np.linspace(0, 2*pi, n_beams) and np.arange(0, max_dist, resolution): _lidar.py:111-112
+    std::vector<double> dirs((size_t)n_beams * 2);
+    for (int k = 0; k < n_beams; ++k) {
+        double ang;
+        if (n_beams == 1) ang = 0.0;
+        else if (k == n_beams - 1) ang = 2.0 * PMS_PI;
+        else ang = (double)k * ((2.0 * PMS_PI - 0.0) / (double)(n_beams - 1)) + 0.0;
+        dirs[2 * k] = std::cos(ang); dirs[2 * k + 1] = std::sin(ang);
+    }
+    const int n_samples = (int)std::ceil((max_dist - 0.0) / resolution);
+    // stage layout: dirs | points(double2) | hit(int)
+    const size_t need = (size_t)n_beams * 2 + nb * 2 + (nb + 1) / 2 + 2;
+    if (ensure_stage(h, need)) return PMS_ERR_CUDA;
+    double *d_dirs = h->stage;
+    double2 *d_pts = reinterpret_cast<double2 *>(h->stage + (size_t)n_beams * 2);
+    int32_t *d_hit = reinterpret_cast<int32_t *>(h->stage + (size_t)n_beams * 2 + nb * 2);
+    CK(cudaMemcpyAsync(d_dirs, dirs.data(), dirs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LidarArgs la{h->W, n_beams, n_samples, resolution, h->a.robot_pose, d_dirs, h->a.map_kind, h->a.map_count,
+                 h->a.map_stride, h->a.map_data, d_hit, d_pts};
+    lidar_kernel<<<nblk(nb, 128), 128, 0, h->stream>>>(la);
+    CK(cudaGetLastError());
+    h->info.kernel_launches++;
+    if (hit_index) CK(cudaMemcpyAsync(hit_index, d_hit, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (points) CK(cudaMemcpyAsync(points, d_pts, nb * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_omni_scan(pms_sim *h, double *min_dist)
+{
+    HCHECK(h);
+    if (h->a.robot_model == ROBOT_NONE) return fail(PMS_ERR_STATE, "no robot configured");
+    if (ensure_stage(h, (size_t)h->W)) return PMS_ERR_CUDA;
+    omni_kernel<<<nblk(h->W, 128), 128, 0, h->stream>>>(h->W, h->a.robot_pose, h->a.map_kind, h->a.map_count,
+                                                        h->a.map_stride, h->a.map_data, h->stage);
+    CK(cudaGetLastError());
+    h->info.kernel_launches++;
+    if (min_dist) CK(cudaMemcpyAsync(min_dist, h->stage, sizeof(double) * h->W, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_get_launch_info(pms_sim *h, pms_launch_info *out)
+{
+    if (!h || !out) return fail(PMS_ERR_INVALID, "NULL argument");
+    *out = h->info;
+    return PMS_OK;
+}
+
+int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block)
+{
+    if (!h) return fail(PMS_ERR_INVALID, "handle is NULL");
+    h->tune_S = j_split; h->tune_wpc = worlds_per_block;
+    return PMS_OK;
+}
+
+// FP32 FMA-pipe peak of the current device, measured with 8 independent FMA chains per thread.
+__global__ void fma_peak_kernel(float *out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 1e-3f;
+    for (int k = 0; k < iters; ++k) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+double pms_measure_fp32_tflops(int device)
+{
+    Guard gd(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 4096;
+    float *buf = nullptr;
+    if (cudaMalloc((void **)&buf, sizeof(float) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<blocks, threads>>>(buf, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        if (rep >= 1 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    return best;
+}
+
+void *pms_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void pms_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- ORCA ----
+int pms_orca_create(int device, int n_worlds, int n_agents, const pms_orca_params *params, pms_sim **out)
+{
+    if (!out) return fail(PMS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_worlds < 1 || n_agents < 1) return fail(PMS_ERR_INVALID, "n_worlds and n_agents must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PMS_ERR_CUDA, std::string("no CUDA device available (libpms_b200 has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(PMS_ERR_INVALID, "device index out of range");
+    Guard gd(device);
+    pms_orca_params p;
+    if (params) p = *params; else pms_default_orca_params(&p);
+    if (p.max_neighbors < 0 || p.max_neighbors > ORCA_MAX_NEIGHBORS)
+        return fail(PMS_ERR_UNSUPPORTED, "max_neighbors must be in [0, 16]");
+    pms_sim *h = new pms_sim();
+    h->kind = 1; h->device = device; h->W = n_worlds; h->N = n_agents;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(PMS_ERR_CUDA, "stream"); }
+    int rc = orca_alloc(h->orca, n_worlds, n_agents, p.time_step, p.neighbor_dist, p.max_neighbors, p.time_horizon,
+                        p.radius, p.goal_reaching_threshold);
+    if (rc) { pms_destroy(h); return fail(PMS_ERR_CUDA, "ORCA allocation failed"); }
+    *out = h;
+    return PMS_OK;
+}
+
+} // extern "C"
+
+extern "C" {
+int pms_orca_set_agents(pms_sim *h, const double *, const double *, const double *, const double *)
+{
+    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
+    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+}
+int pms_orca_set_waypoints_fixed(pms_sim *h, const double *, int, const int32_t *, double, int)
+{
+    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
+    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+}
+int pms_orca_step(pms_sim *h, int)
+{
+    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
+    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+}
+int pms_orca_get_agents(pms_sim *h, double *, double *)
+{
+    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
+    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+}
+}

@@ -1,0 +1,298 @@
+// pms_common.cuh -- shared types and device math for libpms_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#define PMS_PI 3.14159265358979323846
+#define PMS_TWO_PI 6.28318530717958647692
+#define PMS_PED_RADIUS_CONST 0.3  // core/_constants.py:2 -- the collision list always uses this radius
+
+namespace pms {
+
+// Model constants pre-converted on the host to the arithmetic type that consumes them, so the SASS
+// reads them as constant-bank operands instead of pinning registers for the whole step loop.
+template <typename T> struct PairK {
+    T rij;      // radius_i + radius_j
+    T cexp;     // fp32: log2(e)/B ; fp64: B itself (the division of the reference is kept)
+    T A, k1, k2;
+};
+template <typename T> struct PedConsts {
+    T m, tau, ko, kd, kl, alpha, I, dt, inv_m, inv_tau, inv_alpha, one_alpha, m_over_tau, reach;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernel argument block (passed by value as a __grid_constant__).
+// ---------------------------------------------------------------------------------------------
+struct HsfmArgs {
+    int W, N, Np, wpc;          // worlds, peds/world, padded peds (multiple of 32), worlds per CTA
+    int n_steps;
+    long long steps_done;       // cumulative steps before this launch (non-finite bookkeeping)
+    // pedestrian state, structure-of-arrays, world-major (element g = w*N + i)
+    void *pos;                  // FP32: float4 {x,y,vx,vy}   | fp64 state: double2 {x,y}
+    void *vel;                  // FP32: unused               | fp64 state: double2 {vx,vy}
+    void *th;                   // {theta, omega}  float2 | double2
+    void *wp;                   // current waypoint float2 | double2
+    void *vmag;                 // float | double
+    int *wp_index;
+    // waypoint tracker
+    int tracker_kind, loop, n_table, q_cap;
+    double reach;
+    const void *table;          // (W*N*n_table) float2 | double2
+    const void *queue;          // (W*N*q_cap) float2 | double2 ring
+    int *q_head, *q_count;
+    int *events, *ev_count;     // (ev_cap,3) step, world, ped
+    int ev_cap;
+    // robot (always fp64)
+    int robot_model, robot_visible;
+    double robot_radius, wheel_base;
+    double *robot_pose, *robot_vel, *robot_ctrl, *robot_rear;
+    const double *controls;     // (n_controls, W, 2)
+    int n_controls;
+    int *robot_world_collision;
+    // map
+    int map_kind, map_count, map_stride;
+    const double *map_data;
+    // detector + collision list
+    int det_enabled, det_type;
+    double det_max_dist, det_half_fov;
+    uint32_t *det_mask, *coll_mask;
+    double2 *det_vals;
+    unsigned long long *det_count, *coll_count;
+    int *nonfinite;
+    // model constants (fp64 masters; kernels down-convert once)
+    double dt;
+    double tau, A, B, k1, k2, ko, kd, k_lambda, alpha, mass, ped_radius, hsfm_robot_radius;
+    // derived blocks, filled by fill_consts() on the host before every launch
+    PairK<float> kpp_f, kpr_f;       // ped-ped, ped-robot
+    PairK<double> kpp_d, kpr_d;
+    PedConsts<float> kc_f;
+    PedConsts<double> kc_d;
+    double sense_lim2;               // squared cheap-reject radius of the sensor pass
+};
+
+template <typename T> __host__ __device__ inline void fill_pair(PairK<T> &k, const HsfmArgs &a, double radius_j)
+{
+    k.rij = (T)(a.ped_radius + radius_j);
+    k.cexp = sizeof(T) == 4 ? (T)(1.4426950408889634 / a.B) : (T)a.B;
+    k.A = (T)a.A; k.k1 = (T)a.k1; k.k2 = (T)a.k2;
+}
+template <typename T> __host__ __device__ inline void fill_ped(PedConsts<T> &c, const HsfmArgs &a)
+{
+    c.m = (T)a.mass; c.tau = (T)a.tau; c.ko = (T)a.ko; c.kd = (T)a.kd; c.kl = (T)a.k_lambda;
+    c.alpha = (T)a.alpha; c.I = (T)(0.5 * (a.ped_radius * a.ped_radius)); c.dt = (T)a.dt;
+    c.inv_m = (T)(1.0 / a.mass); c.inv_tau = (T)(1.0 / a.tau); c.inv_alpha = (T)(1.0 / a.alpha);
+    c.one_alpha = (T)(1.0 + a.alpha); c.m_over_tau = (T)(a.mass / a.tau); c.reach = (T)a.reach;
+}
+inline void fill_consts(HsfmArgs &a)
+{
+    fill_pair(a.kpp_f, a, a.ped_radius); fill_pair(a.kpr_f, a, a.hsfm_robot_radius);
+    fill_pair(a.kpp_d, a, a.ped_radius); fill_pair(a.kpr_d, a, a.hsfm_robot_radius);
+    fill_ped(a.kc_f, a); fill_ped(a.kc_d, a);
+    const double coll_r = a.robot_radius + PMS_PED_RADIUS_CONST;
+    const double lim = (a.det_enabled ? (a.det_max_dist > coll_r ? a.det_max_dist : coll_r) : coll_r) * 1.001 + 1e-3;
+    a.sense_lim2 = lim * lim;
+}
+__device__ __forceinline__ const PairK<float> &kpp_of(const HsfmArgs &a, float) { return a.kpp_f; }
+__device__ __forceinline__ const PairK<double> &kpp_of(const HsfmArgs &a, double) { return a.kpp_d; }
+__device__ __forceinline__ const PairK<float> &kpr_of(const HsfmArgs &a, float) { return a.kpr_f; }
+__device__ __forceinline__ const PairK<double> &kpr_of(const HsfmArgs &a, double) { return a.kpr_d; }
+__device__ __forceinline__ const PedConsts<float> &kc_of(const HsfmArgs &a, float) { return a.kc_f; }
+__device__ __forceinline__ const PedConsts<double> &kc_of(const HsfmArgs &a, double) { return a.kc_d; }
+
+enum { ROBOT_NONE = 0, ROBOT_EXTERNAL = 1, ROBOT_UNICYCLE = 2, ROBOT_BICYCLE = 3 };
+enum { TRACKER_FIXED = 0, TRACKER_QUEUE = 1 };
+enum { MAP_EMPTY = 0, MAP_CIRCLES = 1, MAP_AABB = 2 };
+enum { DET_POLAR = 0, DET_RELATIVE_ROTATED = 1, DET_RELATIVE = 2, DET_ABSOLUTE = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// Overloaded scalar math (float / double) so the per-pedestrian code is written once.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float m_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double m_atan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ void m_sincos(float a, float *s, float *c) { sincosf(a, s, c); }
+__device__ __forceinline__ void m_sincos(double a, double *s, double *c) { sincos(a, s, c); }
+__device__ __forceinline__ float m_fmod(float a, float b) { return fmodf(a, b); }
+__device__ __forceinline__ double m_fmod(double a, double b) { return fmod(a, b); }
+__device__ __forceinline__ float m_exp(float a) { return expf(a); }
+__device__ __forceinline__ double m_exp(double a) { return exp(a); }
+__device__ __forceinline__ float m_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double m_max(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ bool m_finite(float a) { return isfinite(a); }
+__device__ __forceinline__ bool m_finite(double a) { return isfinite(a); }
+
+// Python / numpy float modulo (sign of the divisor): _hsfm.py:98,189, util/_util.py:6.
+template <typename T>
+__device__ __forceinline__ T py_mod(T a, T b)
+{
+    T m = m_fmod(a, b);
+    if (m != T(0)) {
+        if ((b < T(0)) != (m < T(0))) m += b;
+    } else {
+        m = copysign(T(0), b);
+    }
+    return m;
+}
+template <typename T>
+__device__ __forceinline__ T wrap_angle(T a)
+{
+    return py_mod(a + T(PMS_PI), T(PMS_TWO_PI)) - T(PMS_PI);
+}
+
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+// ---------------------------------------------------------------------------------------------
+// State I/O: FP32 state is one float4 {x,y,vx,vy} per pedestrian (one coalesced 16-byte load per
+// lane); fp64 state is two double2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_pv(const HsfmArgs &a, size_t g, float &x, float &y, float &vx, float &vy)
+{
+    float4 p = reinterpret_cast<const float4 *>(a.pos)[g];
+    x = p.x; y = p.y; vx = p.z; vy = p.w;
+}
+__device__ __forceinline__ void load_pv(const HsfmArgs &a, size_t g, double &x, double &y, double &vx, double &vy)
+{
+    double2 p = reinterpret_cast<const double2 *>(a.pos)[g];
+    double2 v = reinterpret_cast<const double2 *>(a.vel)[g];
+    x = p.x; y = p.y; vx = v.x; vy = v.y;
+}
+__device__ __forceinline__ void store_pv(const HsfmArgs &a, size_t g, float x, float y, float vx, float vy)
+{
+    reinterpret_cast<float4 *>(a.pos)[g] = make_float4(x, y, vx, vy);
+}
+__device__ __forceinline__ void store_pv(const HsfmArgs &a, size_t g, double x, double y, double vx, double vy)
+{
+    reinterpret_cast<double2 *>(a.pos)[g] = make_double2(x, y);
+    reinterpret_cast<double2 *>(a.vel)[g] = make_double2(vx, vy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pair force  F(i <- j)  (pedestrians/_hsfm.py:113-134).
+// ---------------------------------------------------------------------------------------------
+// Single-instruction MUFU forms (the library rsqrtf/exp2f add denormal fix-ups we do not need).
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_ex2(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// fp32: 1 MUFU.RSQ + 1 MUFU.EX2; the sqrt is refined to ~0.5 ulp because its error is amplified
+// by d/B (~7.5x) inside the exponential.  `self` zeroes the j == i term exactly.
+__device__ __forceinline__ void pair_accum(const PairK<float> &k, float dx, float dy, float dvx, float dvy,
+                                           bool self, float &fx, float &fy)
+{
+    const float d2 = fmaf(dx, dx, dy * dy);
+    float inv = fast_rsqrt(d2);
+    inv = self ? 0.0f : inv;
+    float d = d2 * inv;
+    const float err = fmaf(-d, d, d2);
+    d = fmaf(err, 0.5f * inv, d);
+    const float s = k.rij - d;
+    const float e = fast_ex2(s * k.cexp);
+    const float g = fmaxf(s, 0.0f);
+    const float nx = dx * inv, ny = dy * inv;
+    const float dvt = fmaf(dvy, nx, -dvx * ny); // (v_j - v_i) . t,  t = (-n_y, n_x)
+    const float cn = fmaf(k.A, e, k.k1 * g);
+    const float ct = k.k2 * g * dvt;
+    fx += fmaf(cn, nx, -ct * ny);
+    fy += fmaf(cn, ny, ct * nx);
+}
+
+// fp64: same operation order as the reference.
+__device__ __forceinline__ void pair_accum(const PairK<double> &k, double dx, double dy, double dvx, double dvy,
+                                           bool self, double &fx, double &fy)
+{
+    if (self) return;
+    const double d = sqrt(dx * dx + dy * dy);
+    const double nx = dx / d, ny = dy / d;
+    const double tx = -ny, ty = nx;
+    const double dvt = dvx * tx + dvy * ty;
+    double g = k.rij - d;
+    if (!(g > 0.0)) g = 0.0;
+    const double cn = k.A * exp((k.rij - d) / k.cexp) + k.k1 * g;
+    double px = cn * nx, py = cn * ny;
+    const double ct = k.k2 * g * dvt;
+    px += ct * tx;
+    py += ct * ty;
+    fx += px;
+    fy += py;
+}
+
+// ---------------------------------------------------------------------------------------------
+// World map predicates (fp64), shared by the robot veto, lidar and omni kernels.
+// world_map/_circles_world.py:29-50, _aabb_world.py:98-113,135-156, util/_geometry.py:4-42.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool map_occupied(int kind, int count, const double *m, double x, double y)
+{
+    if (kind == MAP_CIRCLES) {
+        for (int c = 0; c < count; ++c) {
+            const double dx = x - m[3 * c], dy = y - m[3 * c + 1];
+            if (sqrt(dx * dx + dy * dy) - m[3 * c + 2] <= 0.0) return true;
+        }
+    } else if (kind == MAP_AABB) {
+        for (int c = 0; c < count; ++c) {
+            const double tlx = m[4 * c], tly = m[4 * c + 1], bw = m[4 * c + 2], bh = m[4 * c + 3];
+            if (x <= tlx && x >= (tlx - bh) && y >= tly && y <= (tly + bw)) return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ double seg_dist(double px, double py, double x1, double y1, double x2, double y2)
+{
+    const double ex = x2 - x1, ey = y2 - y1;
+    const double ox = px - x1, oy = py - y1;
+    double t = (ox * ex + oy * ey) / (ex * ex + ey * ey);
+    t = t < 0.0 ? 0.0 : t;   // NaN (degenerate segment) falls through both clamps like np.clip
+    t = t > 1.0 ? 1.0 : t;
+    const double qx = x1 + t * ex, qy = y1 + t * ey;
+    const double dx = px - qx, dy = py - qy;
+    return sqrt(dx * dx + dy * dy);
+}
+
+__device__ __forceinline__ double map_closest(int kind, int count, const double *m, double x, double y)
+{
+    double best = CUDART_INF;
+    if (kind == MAP_CIRCLES) {
+        for (int c = 0; c < count; ++c) {
+            const double dx = x - m[3 * c], dy = y - m[3 * c + 1];
+            const double d = sqrt(dx * dx + dy * dy) - m[3 * c + 2];
+            if (d < best || d != d) best = d;
+        }
+    } else if (kind == MAP_AABB) {
+        for (int c = 0; c < count; ++c) {
+            const double tlx = m[4 * c], tly = m[4 * c + 1], bw = m[4 * c + 2], bh = m[4 * c + 3];
+            double d;
+            d = seg_dist(x, y, tlx, tly, tlx, tly + bw);            if (d < best || d != d) best = d;
+            d = seg_dist(x, y, tlx - bh, tly, tlx - bh, tly + bw);  if (d < best || d != d) best = d;
+            d = seg_dist(x, y, tlx, tly, tlx - bh, tly);            if (d < best || d != d) best = d;
+            d = seg_dist(x, y, tlx, tly + bw, tlx - bh, tly + bw);  if (d < best || d != d) best = d;
+        }
+    }
+    return best;
+}
+
+// core/_world_map.py:35-62 with eps_margin = 0.05
+__device__ __forceinline__ bool map_is_collision(int kind, int count, const double *m, double x, double y, double radius)
+{
+    if (kind == MAP_EMPTY || count == 0) return false;
+    const bool occ = map_occupied(kind, count, m, x, y);
+    const double dist = map_closest(kind, count, m, x, y) - radius + 0.05;
+    return occ || (dist <= 0.0);
+}
+
+} // namespace pms

@@ -1,0 +1,60 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/pms.h declares,
+and fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from helpers import cuda_available
+from pyminisim_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pms.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pms_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pyminisim_b200 import build
+    build.build()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pms.h but not exported"
+    # the Python binding covers the same surface
+    assert set(declared) == set(_capi.PROTOTYPES)
+
+
+def test_defaults_match_reference_constants():
+    lib = _capi.load()
+    p = _capi.HsfmParamsC()
+    lib.pms_default_hsfm_params(ctypes.byref(p))
+    # HSFMParams.create_default (_hsfm.py:31-42), ctor defaults (:198-208), core/_constants.py
+    assert (p.tau, p.A, p.B, p.k_1, p.k_2, p.k_o, p.k_d, p.k_lambda, p.alpha) == (0.2, 2000.0, 0.08, 1.2e5, 2.4e5, 1.0, 500.0, 0.3, 3.0)
+    assert (p.pedestrian_mass, p.pedestrian_radius, p.robot_radius) == (70.0, 0.3, 0.35)
+    o = _capi.OrcaParamsC()
+    lib.pms_default_orca_params(ctypes.byref(o))
+    assert (o.neighbor_dist, o.max_neighbors, o.time_horizon, o.radius, o.goal_reaching_threshold) == (1.0, 10, 2.0, 0.3, 0.2)
+
+
+@pytest.mark.skipif(cuda_available(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    from pyminisim_b200.batched import BatchedSimulation
+    with pytest.raises(_capi.PmsError) as ei:
+        BatchedSimulation(2, 4)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pyminisim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                for needle in ("import oracle", "from oracle", "pms_oracle", "liboracle", "orc_"):
+                    assert needle not in src, f"{f} references the oracle ({needle})"

@@ -1,0 +1,307 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances are max-abs error / max-abs value (conftest.rel_err), stated per horizon because the HSFM
+dynamics amplify rounding noise roughly 1e6x over 1000 steps:
+  fp64  : <= 1e-12 @1, 1e-10 @100, 1e-9 @300, 1e-6 @1000   (algorithmic identity)
+  mixed : <= 1e-6 @1 (vel), 1e-5 @100, 1e-4 @300
+  fp32  : <= 1e-6 @1, 1e-5 @100, 1e-4 @300                 (positions; velocities 10x looser)
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from helpers import make_cuda, make_oracle
+from oracle import oracle as orc
+from pyminisim_b200.scenarios import make_crowd
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = {
+    "fp64": {1: 1e-12, 100: 1e-10, 300: 1e-9, 1000: 1e-6},
+    "mixed": {1: 1e-7, 100: 1e-5, 300: 1e-4},
+    "fp32": {1: 1e-6, 100: 1e-5, 300: 1e-4},
+}
+
+
+@pytest.mark.parametrize("precision", ["fp64", "mixed", "fp32"])
+@pytest.mark.parametrize("n", [8, 32, 64])
+def test_rollout_vs_oracle(precision, n):
+    sc = make_crowd(6, n)
+    o = make_oracle(sc)
+    c = make_cuda(sc, precision)
+    done = 0
+    for h, tol in POS_TOL[precision].items():
+        o.rollout(0.01, h - done, n_threads=4)
+        c.step(0.01, h - done)
+        done = h
+        poses, vels = c.get_state()
+        ep, ev = rel_err(poses, o.poses), rel_err(vels, o.vels)
+        assert ep < tol, (precision, n, h, ep)
+        assert ev < tol * 20, (precision, n, h, ev)
+        rp, rv, _ = c.get_robot()
+        assert np.allclose(rp, o.robot_pose, atol=1e-11)
+        assert np.allclose(rv, o.robot_vel, atol=1e-11)
+    det, col, nf = c.get_stats()
+    assert (nf == 0).all()
+    if precision == "fp64":
+        _, idx = c.get_waypoints()
+        assert (idx == o.wp_index).all()
+        assert (det == o.det_count).all() and (col == o.coll_count).all()
+        mask, vals = c.get_detector()
+        assert (mask == o.det_mask).all()
+        assert np.allclose(vals, o.det_vals, atol=1e-6)
+        assert (c.get_collisions() == o.coll_mask).all()
+
+
+@pytest.mark.parametrize("n", [8, 32, 64])
+def test_fp64_vs_golden(golden, n):
+    """fp64 mode against fixtures generated from the live reference."""
+    g = golden(f"crowd_n{n}")
+    W = g["poses"].shape[0]
+    sc = make_crowd(W, n)
+    c = make_cuda(sc, "fp64")
+    done = 0
+    tol = {1: 1e-12, 100: 1e-10, 300: 1e-9, 1000: 1e-6}
+    for k, h in enumerate(g["horizons"]):
+        c.step(0.01, int(h) - done)
+        done = int(h)
+        poses, vels = c.get_state()
+        assert rel_err(poses, g["poses"][:, k]) < tol[int(h)]
+        assert rel_err(vels, g["vels"][:, k]) < tol[int(h)] * 20
+        mask, _ = c.get_detector()
+        assert (mask == g["det_mask"][:, k]).all()
+        assert (c.get_collisions() == g["coll_mask"][:, k]).all()
+        det, col, _ = c.get_stats()
+        assert (det == g["det_count"][:, k]).all()
+        assert (col == g["coll_count"][:, k]).all()
+        _, idx = c.get_waypoints()
+        assert (idx == g["wp_index"][:, k]).all()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "mixed", "fp32"])
+def test_kat2(golden, precision):
+    from pyminisim_b200.batched import BatchedSimulation
+    g = golden("kat2")
+    sim = BatchedSimulation(1, 3, precision=precision)
+    sim.set_state(g["init_poses"][None])
+    sim.set_waypoints_fixed(g["table"][None], loop=True)
+    sim.set_robot(2, [[0., 0., 0.]], control=[[0.5, 0.2]])
+    sim.set_detector(5.0, np.deg2rad(120.0), 0)
+    tol = {"fp64": 1e-10, "mixed": 1e-5, "fp32": 1e-4}[precision]
+    done = 0
+    for k, h in enumerate(g["horizons"]):
+        sim.step(0.01, int(h) - done)
+        done = int(h)
+        poses, vels = sim.get_state()
+        assert rel_err(poses[0], g["poses"][k]) < tol
+        mask, vals = sim.get_detector()
+        assert (mask[0] == g["det_mask"][k]).all()
+        assert np.allclose(vals[0], g["det_vals"][k], atol=tol * 10)
+        assert (sim.get_collisions()[0] == g["coll_mask"][k]).all()
+
+
+def test_variants_golden(golden):
+    """Return types, invisible / absent robot, non-loop freeze, bicycle, control sequences, map veto."""
+    from pyminisim_b200.batched import BatchedSimulation
+    g = golden("variants")
+    poses, table = g["init_poses"][None], g["table"][None]
+
+    def new(loop=True, tbl=table, vmag=None):
+        sim = BatchedSimulation(1, poses.shape[1], precision="fp64")
+        sim.set_state(poses)
+        sim.set_waypoints_fixed(tbl, loop=loop)
+        if vmag is not None:
+            sim.set_speeds(vmag[None])
+        return sim
+
+    def run(sim, horizons, check, controls=None):
+        done = 0
+        for k, h in enumerate(horizons):
+            sim.set_robot_controls(None if controls is None else controls[done:h, None, :])
+            sim.step(0.01, h - done)
+            done = h
+            check(k, sim)
+
+    rp, rc, hz = [[-1.0, 0.2, 0.3]], [[0.4, 0.3]], [1, 50, 150]
+    for t, name in enumerate(["polar", "relative_rotated", "relative", "absolute"]):
+        sim = new()
+        sim.set_robot(2, rp, control=rc)
+        sim.set_detector(4.0, np.deg2rad(200.0), t)
+
+        def chk(k, sim, name=name):
+            p, _ = sim.get_state()
+            assert rel_err(p[0], g[f"rt_{name}_poses"][k]) < 1e-10
+            mask, vals = sim.get_detector()
+            assert (mask[0] == g[f"rt_{name}_det_mask"][k]).all()
+            assert np.allclose(vals[0], g[f"rt_{name}_det_vals"][k], atol=1e-9)
+        run(sim, hz, chk)
+
+    sim = new()
+    sim.set_robot(2, rp, control=rc, visible=False)
+    run(sim, hz, lambda k, s: np.testing.assert_array_less(rel_err(s.get_state()[0][0], g["invisible_poses"][k]), 1e-10))
+    sim = new()
+    run(sim, hz, lambda k, s: np.testing.assert_array_less(rel_err(s.get_state()[1][0], g["norobot_vels"][k]), 1e-9))
+
+    sim = new(loop=False, tbl=table[:, :, :2], vmag=g["freeze_vmag"])
+    sim.set_robot(2, [[-4.0, 0.0, 0.0]], control=[[0.3, 0.0]])
+    sim.set_detector(5.0, np.deg2rad(120.0), 0)
+
+    def chk_freeze(k, sim):
+        p, v = sim.get_state()
+        assert rel_err(p[0], g["freeze_poses"][k]) < 1e-9
+        assert np.abs(v[0] - g["freeze_vels"][k]).max() < 1e-8
+        assert (sim.get_waypoints()[1][0] == g["freeze_wp_index"][k]).all()
+        assert (sim.get_detector()[0][0] == g["freeze_det_mask"][k]).all()
+    run(sim, [1, 200, 400, 700], chk_freeze)
+
+    sim = new()
+    sim.set_robot(3, rp, control=[[0.0, 0.0]], wheel_base=0.324)
+    sim.set_detector(5.0, np.deg2rad(120.0), 0)
+
+    def chk_bi(k, sim):
+        pose, vel, _ = sim.get_robot()
+        assert np.allclose(pose[0], g["bicycle_robot_pose"][k], atol=1e-11)
+        assert np.allclose(vel[0], 0.0)
+        assert rel_err(sim.get_state()[0][0], g["bicycle_poses"][k]) < 1e-10
+        assert (sim.get_detector()[0][0] == g["bicycle_det_mask"][k]).all()
+    run(sim, hz, chk_bi, g["bicycle_controls"])
+
+    sim = new()
+    sim.set_robot(2, [[-1.0, 0.2, 0.0]], control=[[0.0, 0.0]])
+    sim.set_map(1, g["blocked_circles"])
+
+    def chk_blk(k, sim):
+        pose, vel, wc = sim.get_robot()
+        assert np.allclose(pose[0], g["blocked_robot_pose"][k], atol=1e-11)
+        assert np.allclose(vel[0], g["blocked_robot_vel"][k], atol=1e-11)
+        assert wc[0] == g["blocked_robot_world_collision"][k]
+        assert rel_err(sim.get_state()[0][0], g["blocked_poses"][k]) < 1e-10
+    run(sim, [1, 60, 120, 200], chk_blk, g["blocked_controls"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_sensor_predicates_bit_exact_on_identical_state(precision):
+    """Detector membership / collision flags are integer outputs: bit-exact on identical input state."""
+    rng = np.random.default_rng(5)
+    W, N = 64, 48
+    poses = np.zeros((W, N, 3))
+    poses[..., :2] = rng.uniform(-6, 6, (W, N, 2))
+    poses[..., 2] = rng.uniform(-np.pi, np.pi, (W, N))
+    if precision == "fp32":   # identical input state = fp32-representable values on both sides
+        poses = poses.astype(np.float32).astype(np.float64)
+    robot = np.concatenate([rng.uniform(-2, 2, (W, 2)), rng.uniform(-np.pi, np.pi, (W, 1))], axis=1)
+    from pyminisim_b200.batched import BatchedSimulation
+    for rt in range(4):
+        sim = BatchedSimulation(W, N, precision=precision)
+        sim.set_state(poses)
+        sim.set_robot(1, robot, velocity=np.zeros((W, 3)))
+        sim.set_detector(4.0, np.deg2rad(100.0), rt)
+        sim.sense()
+        o = orc.OracleBatch(poses)
+        o.set_robot(orc.ROBOT_EXTERNAL, robot)
+        o.set_detector(4.0, np.deg2rad(100.0), rt)
+        o.sense()
+        mask, vals = sim.get_detector()
+        assert o.det_mask.any() and (mask == o.det_mask).all()
+        assert (sim.get_collisions() == o.coll_mask).all()
+        assert np.allclose(vals, o.det_vals, atol=1e-12)
+
+
+def test_batched_equals_single_world_and_jsplit():
+    sc = make_crowd(5, 32)
+    ref = make_cuda(sc, "fp64")
+    ref.step(0.01, 200)
+    p_ref, v_ref = ref.get_state()
+    for w in range(5):
+        one = make_cuda(sc, "fp64", worlds=slice(w, w + 1))
+        one.step(0.01, 200)
+        p, v = one.get_state()
+        assert rel_err(p[0], p_ref[w]) < 1e-10
+    for S, wpc in ((1, 1), (2, 2), (4, 1), (8, 1), (1, 8)):
+        alt = make_cuda(sc, "fp64")
+        alt.set_tuning(S, wpc)
+        alt.step(0.01, 200)
+        info = alt.launch_info()
+        assert info["j_split"] == S and info["worlds_per_block"] == min(wpc, 5)
+        p, v = alt.get_state()
+        assert rel_err(p, p_ref) < 1e-10, (S, wpc)
+
+
+def test_properties_permutation_translation_invisible():
+    sc = make_crowd(3, 32)
+    base = make_cuda(sc, "fp64", robot=0)
+    base.step(0.01, 100)
+    p0, v0 = base.get_state()
+    # permutation equivariance
+    perm = np.random.default_rng(1).permutation(32)
+    sc2 = make_crowd(3, 32)
+    sc2.poses, sc2.table, sc2.vmag, sc2.vels = sc.poses[:, perm], sc.table[:, perm], sc.vmag[:, perm], sc.vels[:, perm]
+    pm = make_cuda(sc2, "fp64", robot=0)
+    pm.step(0.01, 100)
+    p1, _ = pm.get_state()
+    assert rel_err(p1, p0[:, perm]) < 1e-9
+    # translation invariance
+    sc3 = make_crowd(3, 32)
+    shift = np.array([7.0, -3.0])
+    sc3.poses[..., :2] += shift
+    sc3.table += shift
+    tr = make_cuda(sc3, "fp64", robot=0)
+    tr.step(0.01, 100)
+    p2, _ = tr.get_state()
+    p2[..., :2] -= shift
+    assert rel_err(p2, p0) < 1e-9
+    # robot_visible=False == no robot for the dynamics (_hsfm.py:279-284)
+    inv = make_cuda(sc, "fp64", robot=2, visible=False)
+    inv.step(0.01, 100)
+    p3, _ = inv.get_state()
+    assert rel_err(p3, p0) < 1e-12
+
+
+def test_one_step_forces_antisymmetry_fp32():
+    """Two pedestrians, equal radii: f_ij = -f_ji exactly, so the momentum change is the goal force only."""
+    from pyminisim_b200.batched import BatchedSimulation
+    poses = np.array([[[0.0, 0.0, 0.3], [0.5, 0.1, -2.0]]])
+    table = np.concatenate([poses[:, :, None, :2], poses[:, :, None, :2] + np.array([5.0, 0.0])], axis=2)
+    o = orc.OracleBatch(poses)
+    o.set_waypoints_fixed(table, loop=True)
+    o.rollout(0.01, 1)
+    for prec, tol in (("fp32", 2e-6), ("mixed", 1e-6), ("fp64", 1e-12)):
+        sim = BatchedSimulation(1, 2, precision=prec)
+        sim.set_state(poses)
+        sim.set_waypoints_fixed(table, loop=True)
+        sim.step(0.01, 1)
+        p, v = sim.get_state()
+        assert rel_err(v, o.vels) < tol, prec
+
+
+def test_snapshot_restore_and_nonfinite_flag():
+    sc = make_crowd(4, 32)
+    sim = make_cuda(sc, "fp32")
+    sim.snapshot_save()
+    sim.step(0.01, 50)
+    a, _ = sim.get_state()
+    sim.snapshot_restore()
+    sim.step(0.01, 50)
+    b, _ = sim.get_state()
+    assert np.array_equal(a, b)          # deterministic
+    # two coincident pedestrians -> 0/0 like the reference (_hsfm.py:125-126): flagged, not clamped
+    bad = make_crowd(2, 8)
+    bad.poses[1, 1, :2] = bad.poses[1, 0, :2]
+    sim = make_cuda(bad, "fp32")
+    sim.step(0.01, 3)
+    _, _, nf = sim.get_stats()
+    assert nf[0] == 0 and nf[1] == 1
+
+
+def test_error_paths():
+    from pyminisim_b200.batched import BatchedSimulation
+    from pyminisim_b200._capi import PmsError
+    with pytest.raises(PmsError):
+        BatchedSimulation(0, 4)
+    sim = BatchedSimulation(1, 4)
+    with pytest.raises(PmsError):   # tracker not initialised (RuntimeError in the reference)
+        sim.step(0.01, 1)
+    with pytest.raises(PmsError):
+        sim.set_detector(3.0, 1.0, 7)
+    with pytest.raises(PmsError):
+        sim.lidar_scan(0)
