@@ -102,11 +102,11 @@ class ClockSampler:
 def cpu_reference_run(args, n_steps_timed: int, warmup: int):
     """Bounded sample of the workload on the CPU oracle, all host cores."""
     from oracle import oracle as orc
-    from pyminisim_b200.scenarios import make_crowd
+    from pyminisim_b200.scenarios import make_bench_crowd
     cores = os.cpu_count() or 1
     sample_worlds = min(args.worlds, max(2 * cores, 16))
     sample_steps = min(args.sim_steps, 100)
-    sc = make_crowd(sample_worlds, args.peds)
+    sc = make_bench_crowd(sample_worlds, args.peds)
 
     def fresh():
         b = orc.OracleBatch(sc.poses, vels=sc.vels, vmag=sc.vmag)
@@ -132,7 +132,8 @@ def cpu_reference_run(args, n_steps_timed: int, warmup: int):
 
 def config_dict(args, world_size):
     return {"workload": f"C4: {args.worlds} worlds x {args.peds} pedestrians per GPU, HSFM + unicycle robot + "
-                        f"pedestrian detector (5 m, 120 deg) + collision list, {args.sim_steps} fused sim-steps "
+                        f"pedestrian detector (5 m, 120 deg) + collision list, jittered grid with local looped goals "
+                        f"(scenarios.make_bench_crowd), {args.sim_steps} fused sim-steps "
                         f"of dt=0.01 per bench step",
             "worlds_per_gpu": args.worlds, "peds_per_world": args.peds, "sim_steps_per_step": args.sim_steps,
             "dt": 0.01, "precision": args.precision, "parallelism": f"worlds sharded over {world_size} GPU(s), "
@@ -167,7 +168,7 @@ def main():
     import torch.distributed as dist
     from pyminisim_b200 import _capi as capi
     from pyminisim_b200.batched import BatchedSimulation
-    from pyminisim_b200.scenarios import make_crowd
+    from pyminisim_b200.scenarios import make_bench_crowd
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +180,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     worlds = args.worlds if args.scaling == "weak" else max(1, args.worlds // world_size)
-    sc = make_crowd(worlds, args.peds, first_world=rank * worlds)
+    sc = make_bench_crowd(worlds, args.peds, first_world=rank * worlds)
     W, N, K = worlds, args.peds, args.sim_steps
 
     sim = BatchedSimulation(W, N, precision=args.precision, device=local_rank)

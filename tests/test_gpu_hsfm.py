@@ -12,7 +12,7 @@ import pytest
 from conftest import rel_err
 from helpers import make_cuda, make_oracle
 from oracle import oracle as orc
-from pyminisim_b200.scenarios import make_crowd
+from pyminisim_b200.scenarios import make_bench_crowd, make_crowd
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,7 @@ POS_TOL = {
 @pytest.mark.parametrize("precision", ["fp64", "mixed", "fp32"])
 @pytest.mark.parametrize("n", [8, 32, 64])
 def test_rollout_vs_oracle(precision, n):
-    sc = make_crowd(6, n)
+    sc = make_bench_crowd(6, n)
     o = make_oracle(sc)
     c = make_cuda(sc, precision)
     done = 0
