@@ -36,7 +36,7 @@ class OrcaParamsC(C.Structure):
 class LaunchInfoC(C.Structure):
     _fields_ = [("kernel", C.c_int), ("threads_per_block", C.c_int), ("blocks", C.c_int),
                 ("worlds_per_block", C.c_int), ("j_split", C.c_int), ("smem_bytes", C.c_int),
-                ("kernel_launches", C.c_int64)]
+                ("n_chunks", C.c_int), ("blocks_per_sm", C.c_int), ("kernel_launches", C.c_int64)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -87,7 +87,7 @@ PROTOTYPES = {
     "pms_orca_step": (C.c_int, [_h, C.c_int]),
     "pms_orca_get_agents": (C.c_int, [_h, _dp, _dp]),
     "pms_get_launch_info": (C.c_int, [_h, C.POINTER(LaunchInfoC)]),
-    "pms_set_tuning": (C.c_int, [_h, C.c_int, C.c_int]),
+    "pms_set_tuning": (C.c_int, [_h, C.c_int, C.c_int, C.c_int]),
     "pms_measure_fp32_tflops": (C.c_double, [C.c_int]),
     "pms_host_alloc": (C.c_void_p, [C.c_uint64]),
     "pms_host_free": (None, [C.c_void_p]),

@@ -31,17 +31,25 @@ struct RobotRegs {
 
 // Shared-memory image of one world.  The owner state lives here between steps (not in registers) so
 // that nothing but the force accumulators is live across the pair loop.
-//   st0 {x,y,vx,vy}  st1 {theta,omega,wp_x,wp_y}  st2 {speed,cos,sin,wp_index}   in state precision ST
-//   pv  {x,y,vx,vy} in pair precision PT (aliases st0 when PT == ST), lo = low parts of x,y (MIXED)
+//   spos {x,y}  svel {vx,vy}  st1 {theta,omega,wp_x,wp_y}  st2 {speed,cos,sin,wp_index}   state precision ST
+//   ppos {x,y}  pvel {vx,vy}  in pair precision PT (alias spos/svel when PT == ST); plo = low parts of x,y (MIXED)
+// Positions and velocities are separate arrays: the pair loop reads only positions (one LDS.64 per
+// pair); velocities are touched only on body contact.
 template <typename PT, typename ST, bool SPLIT>
 struct SmallSmem {
     static constexpr bool ALIAS = sizeof(PT) == sizeof(ST);
-    __host__ __device__ static size_t off_st1(int Np) { return sizeof(typename Vec4<ST>::type) * Np; }
-    __host__ __device__ static size_t off_st2(int Np) { return 2 * off_st1(Np); }
-    __host__ __device__ static size_t off_pv(int Np) { return ALIAS ? 0 : 3 * off_st1(Np); }
-    __host__ __device__ static size_t off_lo(int Np) { return 3 * off_st1(Np) + (ALIAS ? 0 : sizeof(typename Vec4<PT>::type) * Np); }
-    __host__ __device__ static size_t off_part(int Np) { return off_lo(Np) + (SPLIT ? sizeof(float2) * Np : 0); }
-    __host__ __device__ static size_t off_robot(int Np, int S) { return off_part(Np) + (S > 1 ? sizeof(typename Vec2<PT>::type) * Np * S : 0); }
+    using ST2 = typename Vec2<ST>::type;
+    using ST4 = typename Vec4<ST>::type;
+    using PT2 = typename Vec2<PT>::type;
+    __host__ __device__ static size_t off_svel(int Np) { return sizeof(ST2) * Np; }
+    __host__ __device__ static size_t off_st1(int Np) { return 2 * sizeof(ST2) * Np; }
+    __host__ __device__ static size_t off_st2(int Np) { return off_st1(Np) + sizeof(ST4) * Np; }
+    __host__ __device__ static size_t end_state(int Np) { return off_st2(Np) + sizeof(ST4) * Np; }
+    __host__ __device__ static size_t off_ppos(int Np) { return ALIAS ? 0 : end_state(Np); }
+    __host__ __device__ static size_t off_pvel(int Np) { return ALIAS ? off_svel(Np) : end_state(Np) + sizeof(PT2) * Np; }
+    __host__ __device__ static size_t off_plo(int Np) { return end_state(Np) + (ALIAS ? 0 : 2 * sizeof(PT2) * Np); }
+    __host__ __device__ static size_t off_part(int Np) { return off_plo(Np) + (SPLIT ? sizeof(float2) * Np : 0); }
+    __host__ __device__ static size_t off_robot(int Np, int S) { return off_part(Np) + (S > 1 ? sizeof(PT2) * Np * S : 0); }
     __host__ __device__ static size_t bytes(int Np, int S)
     {
         return (off_robot(Np, S) + 2 * sizeof(RobotSlot) + sizeof(RobotRegs) + 15) & ~size_t(15);
@@ -123,14 +131,18 @@ __device__ __forceinline__ void ped_integrate(const PedConsts<ST> &k, ST fx, ST 
                                               ST &x, ST &y, ST &vx, ST &vy, ST &th, ST &om, ST &c, ST &s)
 {
     const ST ddx = wx - x, ddy = wy - y;
-    const ST dn = m_sqrt(ddx * ddx + ddy * ddy);
-    ST vdx, vdy, f0x, f0y, klf, komega, dom, dvbx, dvby;
+    ST vdx, vdy, f0x, f0y, klf, komega, dom, dvbx, dvby, werr;
     if constexpr (sizeof(ST) == 8) {
         // fp64: reference operation order (divisions kept)
+        const ST dn = m_sqrt(ddx * ddx + ddy * ddy);
         vdx = ddx / dn * vm; vdy = ddy / dn * vm;
         f0x = k.m * (vdx - vx) / k.tau; f0y = k.m * (vdy - vy) / k.tau;
     } else {
-        const ST sc = vm / dn;
+        // fp32: 1/|w - r| from MUFU.RSQ + one Newton step (no IEEE divide / sqrt sequences)
+        const ST n2 = ddx * ddx + ddy * ddy;
+        ST ri = fast_rsqrt(n2);
+        ri = ri * fmaf(-0.5f * n2 * ri, ri, 1.5f);
+        const ST sc = vm * ri;
         vdx = ddx * sc; vdy = ddy * sc;
         f0x = k.m_over_tau * (vdx - vx); f0y = k.m_over_tau * (vdy - vy);
     }
@@ -138,8 +150,14 @@ __device__ __forceinline__ void ped_integrate(const PedConsts<ST> &k, ST fx, ST 
     const ST uf = (f0x + fx) * c + (f0y + fy) * s;
     const ST uo = k.ko * (fx * (-s) + fy * c) - k.kd * vo;
     klf = k.kl * m_sqrt(f0x * f0x + f0y * f0y);
-    const ST th0 = py_mod(m_atan2(vdy, vdx), ST(PMS_TWO_PI));
-    const ST werr = wrap_angle(th - th0);
+    if constexpr (sizeof(ST) == 8) {
+        const ST th0 = py_mod(m_atan2(vdy, vdx), ST(PMS_TWO_PI));
+        werr = wrap_angle(th - th0);
+    } else {
+        // wrap(theta - atan2(v_d)) == atan2(sin(theta - theta_0), cos(theta - theta_0)) built from the cached
+        // (cos, sin) of theta: one atan2f, no fmod (differs from the reference only at exactly +-pi)
+        werr = m_atan2(s * vdx - c * vdy, c * vdx + s * vdy);
+    }
     if constexpr (sizeof(ST) == 8) {
         const ST ktheta = k.I * klf;
         komega = k.I * k.one_alpha * m_sqrt(klf / k.alpha);
@@ -210,10 +228,11 @@ __device__ __forceinline__ SenseOut sense_ped(const HsfmArgs &a, const RobotSlot
 // same hardware barrier from different instructions (warp-specialised producer / consumer).
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 
+// One chunk of simulation steps [t_begin, t_end) for the wpc worlds of `group`.  Every thread of the
+// CTA (pedestrian warps and the robot warp) executes the same sequence of CTA barriers.
 template <typename PT, typename ST, bool SPLIT, int S>
-__device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
+__device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, const int t_begin, const int t_end)
 {
-    using PT4 = typename Vec4<PT>::type;
     using PT2 = typename Vec2<PT>::type;
     using ST2 = typename Vec2<ST>::type;
     using ST4 = typename Vec4<ST>::type;
@@ -229,20 +248,23 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
     const int r = tid - wl * per_world;
     const int s = r / Np;
     const int i = r - s * Np;
-    const int w = blockIdx.x * a.wpc + wl;
+    const int w = group * a.wpc + wl;
     const bool world_ok = (wl < a.wpc) && (w < a.W);
-    const bool active = !is_robot_warp && world_ok && i < N;
+    const bool pair_warp = !is_robot_warp && world_ok;              // warp-uniform
+    const bool active = pair_warp && i < N;
     const bool owner = active && s == 0;
-    const bool owner_warp = !is_robot_warp && world_ok && s == 0;   // warp-uniform
+    const bool owner_warp = pair_warp && s == 0;                     // warp-uniform
     const bool has_robot = a.robot_model != ROBOT_NONE;
 
     // carve the shared memory of local world wl
     unsigned char *base = smem_raw + (size_t)(wl < a.wpc ? wl : 0) * L::bytes(Np, S);
-    ST4 *st0 = reinterpret_cast<ST4 *>(base);
+    ST2 *spos = reinterpret_cast<ST2 *>(base);
+    ST2 *svel = reinterpret_cast<ST2 *>(base + L::off_svel(Np));
     ST4 *st1 = reinterpret_cast<ST4 *>(base + L::off_st1(Np));
     ST4 *st2 = reinterpret_cast<ST4 *>(base + L::off_st2(Np));
-    PT4 *pv = reinterpret_cast<PT4 *>(base + L::off_pv(Np));
-    float2 *lo = reinterpret_cast<float2 *>(base + L::off_lo(Np));
+    PT2 *ppos = reinterpret_cast<PT2 *>(base + L::off_ppos(Np));
+    PT2 *pvel = reinterpret_cast<PT2 *>(base + L::off_pvel(Np));
+    float2 *plo = reinterpret_cast<float2 *>(base + L::off_plo(Np));
     PT2 *part = reinterpret_cast<PT2 *>(base + L::off_part(Np));
     RobotSlot *rslot = reinterpret_cast<RobotSlot *>(base + L::off_robot(Np, S));
     RobotRegs &rr = *reinterpret_cast<RobotRegs *>(base + L::off_robot(Np, S) + 2 * sizeof(RobotSlot));
@@ -256,25 +278,32 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
     auto publish = [&](ST x, ST y, ST vx, ST vy) {
         if constexpr (SPLIT) {
             const float xh = (float)x, yh = (float)y;
-            pv[i] = make_float4(xh, yh, (float)vx, (float)vy);
-            lo[i] = make_float2((float)(x - (double)xh), (float)(y - (double)yh));
+            ppos[i] = make_float2(xh, yh);
+            pvel[i] = make_float2((float)vx, (float)vy);
+            plo[i] = make_float2((float)(x - (double)xh), (float)(y - (double)yh));
         } else if constexpr (!L::ALIAS) {
-            PT4 p; p.x = (PT)x; p.y = (PT)y; p.z = (PT)vx; p.w = (PT)vy;
-            pv[i] = p;
+            PT2 p; p.x = (PT)x; p.y = (PT)y; ppos[i] = p;
+            PT2 v; v.x = (PT)vx; v.y = (PT)vy; pvel[i] = v;
         }
     };
 
     if (owner) {
-        ST4 q0, q1, q2;
-        load_pv(a, g, q0.x, q0.y, q0.z, q0.w);
-        const ST2 t = reinterpret_cast<const ST2 *>(a.th)[g];
-        const ST2 q = reinterpret_cast<const ST2 *>(a.wp)[g];
+        ST2 p0, v0; ST4 q1, q2;
+        load_pv(a, g, p0.x, p0.y, v0.x, v0.y);
+        const ST2 t = __ldcg(reinterpret_cast<const ST2 *>(a.th) + g);
+        const ST2 q = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
         q1.x = t.x; q1.y = t.y; q1.z = q.x; q1.w = q.y;
         q2.x = reinterpret_cast<const ST *>(a.vmag)[g];
         m_sincos(t.x, &q2.z, &q2.y);
-        q2.w = (ST)a.wp_index[g];                 // small integer, exact in fp32
-        st0[i] = q0; st1[i] = q1; st2[i] = q2;
-        publish(q0.x, q0.y, q0.z, q0.w);
+        q2.w = (ST)__ldcg(a.wp_index + g);        // small integer, exact in fp32
+        spos[i] = p0; svel[i] = v0; st1[i] = q1; st2[i] = q2;
+        publish(p0.x, p0.y, v0.x, v0.y);
+    } else if (pair_warp && s == 0) {
+        // padding lanes (N <= i < Np) run the pair loop for warp-uniform votes: park them far away
+        PT2 far; far.x = (PT)1e18; far.y = (PT)(1e18 + 1e15 * i);
+        PT2 z; z.x = 0; z.y = 0;
+        ppos[i] = far; pvel[i] = z;
+        if constexpr (SPLIT) plo[i] = make_float2(0.f, 0.f);
     }
 
     // ---- robot warp: its own loop (same barrier sequence), one step ahead of the pedestrians ----
@@ -282,12 +311,12 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
         const bool robot_lane = world_ok && has_robot;
         if (robot_lane) {
             robot_load(a, w, rr);
-            robot_step(a, w, 0, rr);
-            rslot[0] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
+            robot_step(a, w, t_begin, rr);
+            rslot[t_begin & 1] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
         }
-        for (int t = 0; t < a.n_steps; ++t) {
+        for (int t = t_begin; t < t_end; ++t) {
             cta_barrier();   // A
-            if (robot_lane && t + 1 < a.n_steps) {
+            if (robot_lane && t + 1 < t_end) {
                 robot_step(a, w, t + 1, rr);
                 rslot[(t + 1) & 1] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
             }
@@ -301,36 +330,57 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
     int first_bad = 0;
     const int lane = tid & 31;
 
-    for (int t = 0; t < a.n_steps; ++t) {
+    for (int t = t_begin; t < t_end; ++t) {
         cta_barrier();     // A: state t and robot slot t&1 are visible
         const RobotSlot &rb = rslot[t & 1];
         PT fx = 0, fy = 0;
-        if (active) {
-            const PT4 me = pv[i];
+        if (pair_warp) {
+            const PT2 me = ppos[i];
             float2 melo = make_float2(0.f, 0.f);
-            if constexpr (SPLIT) melo = lo[i];
+            if constexpr (SPLIT) melo = plo[i];
             PT fx1 = 0, fy1 = 0;
             int j = s;
-#pragma unroll 2
-            for (; j + S < N; j += 2 * S) {
-                const PT4 o0 = pv[j], o1 = pv[j + S];
-                PT dx0 = me.x - o0.x, dy0 = me.y - o0.y, dx1 = me.x - o1.x, dy1 = me.y - o1.y;
-                if constexpr (SPLIT) {
-                    const float2 l0 = lo[j], l1 = lo[j + S];
-                    dx0 += melo.x - l0.x; dy0 += melo.y - l0.y;
-                    dx1 += melo.x - l1.x; dy1 += melo.y - l1.y;
+            if constexpr (sizeof(PT) == 4) {
+                // fp32 pair loop, 4 pairs per trip; one warp vote decides whether anybody is in contact
+                for (; j + 3 * S < N; j += 4 * S) {
+                    float dx[4], dy[4], inv[4], sg[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 o = ppos[j + q * S];
+                        dx[q] = me.x - o.x; dy[q] = me.y - o.y;
+                        if constexpr (SPLIT) { const float2 l = plo[j + q * S]; dx[q] += melo.x - l.x; dy[q] += melo.y - l.y; }
+                    }
+                    pair_far(kpp, dx[0], dy[0], j == i, inv[0], sg[0], fx, fy);
+                    pair_far(kpp, dx[1], dy[1], j + S == i, inv[1], sg[1], fx1, fy1);
+                    pair_far(kpp, dx[2], dy[2], j + 2 * S == i, inv[2], sg[2], fx, fy);
+                    pair_far(kpp, dx[3], dy[3], j + 3 * S == i, inv[3], sg[3], fx1, fy1);
+                    const float smax = fmaxf(fmaxf(sg[0], sg[1]), fmaxf(sg[2], sg[3]));
+                    if (__any_sync(0xffffffffu, smax > 0.0f)) {
+                        const float2 mv = pvel[i];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 ov = pvel[j + q * S];
+                            pair_contact(kpp, dx[q], dy[q], ov.x - mv.x, ov.y - mv.y, inv[q], sg[q], fx, fy);
+                        }
+                    }
                 }
-                pair_accum(kpp, dx0, dy0, o0.z - me.z, o0.w - me.w, j == i, fx, fy);
-                pair_accum(kpp, dx1, dy1, o1.z - me.z, o1.w - me.w, j + S == i, fx1, fy1);
-            }
-            if (j < N) {
-                const PT4 o0 = pv[j];
-                PT dx0 = me.x - o0.x, dy0 = me.y - o0.y;
-                if constexpr (SPLIT) { const float2 l0 = lo[j]; dx0 += melo.x - l0.x; dy0 += melo.y - l0.y; }
-                pair_accum(kpp, dx0, dy0, o0.z - me.z, o0.w - me.w, j == i, fx, fy);
+                for (; j < N; j += S) {
+                    const float2 o = ppos[j];
+                    float dx0 = me.x - o.x, dy0 = me.y - o.y;
+                    if constexpr (SPLIT) { const float2 l = plo[j]; dx0 += melo.x - l.x; dy0 += melo.y - l.y; }
+                    const float2 mv = pvel[i], ov = pvel[j];
+                    pair_accum(kpp, dx0, dy0, ov.x - mv.x, ov.y - mv.y, j == i, fx, fy);
+                }
+            } else {
+                const PT2 mv = pvel[i];
+                for (; j < N; j += S) {
+                    const PT2 o = ppos[j], ov = pvel[j];
+                    pair_accum(kpp, me.x - o.x, me.y - o.y, ov.x - mv.x, ov.y - mv.y, j == i, fx, fy);
+                }
             }
             fx += fx1; fy += fy1;
             if (s == S - 1 && has_robot && a.robot_visible) {   // robot term (_hsfm.py:80-82)
+                const PT2 mv = pvel[i];
                 PT dx, dy;
                 if constexpr (SPLIT) {
                     const float rxh = (float)rb.x, ryh = (float)rb.y;
@@ -339,25 +389,26 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
                 } else {
                     dx = me.x - (PT)rb.x; dy = me.y - (PT)rb.y;
                 }
-                pair_accum(kpr, dx, dy, (PT)rb.vx - me.z, (PT)rb.vy - me.w, false, fx, fy);
+                pair_accum(kpr, dx, dy, (PT)rb.vx - mv.x, (PT)rb.vy - mv.y, false, fx, fy);
             }
             if (S > 1) { PT2 p; p.x = fx; p.y = fy; part[s * Np + i] = p; }
         }
         cta_barrier();     // B: all reads of state t done; slice partials visible
         if (owner_warp) {
             SenseOut so{false, false, 0.0, 0.0};
-            const bool last = (t == a.n_steps - 1);
+            const bool last = (t == a.n_steps - 1);   // last step of the launch
             if (owner) {
                 if (S > 1) {
                     fx = 0; fy = 0;
 #pragma unroll
                     for (int q = 0; q < S; ++q) { const PT2 p = part[q * Np + i]; fx += p.x; fy += p.y; }
                 }
-                ST4 q0 = st0[i], q1 = st1[i], q2 = st2[i];
-                const ST x0 = q0.x, y0 = q0.y, th0 = q1.x;
-                ped_integrate<ST>(kc, (ST)fx, (ST)fy, q1.z, q1.w, q2.x, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q2.y, q2.z);
+                ST2 p0 = spos[i], v0 = svel[i];
+                ST4 q1 = st1[i], q2 = st2[i];
+                const ST x0 = p0.x, y0 = p0.y, th0 = q1.x;
+                ped_integrate<ST>(kc, (ST)fx, (ST)fy, q1.z, q1.w, q2.x, p0.x, p0.y, v0.x, v0.y, q1.x, q1.y, q2.y, q2.z);
                 // ---- waypoint tracker on the NEW pose (_hsfm.py:301) ----
-                const ST ex = q1.z - q0.x, ey = q1.w - q0.y;
+                const ST ex = q1.z - p0.x, ey = q1.w - p0.y;
                 if (m_sqrt(ex * ex + ey * ey) <= kc.reach) {
                     if (a.tracker_kind == TRACKER_FIXED) {       // _fixed_waypoint_tracker.py:68-87
                         int ni = (int)q2.w + 1;
@@ -369,7 +420,7 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
                         const ST2 nw = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
                         q1.z = nw.x; q1.w = nw.y;
                         if (steady) {                            // _hsfm.py:302-304
-                            q0.x = x0; q0.y = y0; q1.x = th0; q0.z = 0; q0.w = 0; q1.y = 0;
+                            p0.x = x0; p0.y = y0; q1.x = th0; v0.x = 0; v0.y = 0; q1.y = 0;
                             m_sincos(q1.x, &q2.z, &q2.y);
                         }
                     } else {                                     // _random_waypoint_tracker.py:66-91
@@ -387,11 +438,11 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
                         }
                     }
                 }
-                st0[i] = q0; st1[i] = q1; st2[i] = q2;
-                publish(q0.x, q0.y, q0.z, q0.w);
-                if (!first_bad && !m_finite(q0.x + q0.y + q0.z + q0.w + q1.x + q1.y)) first_bad = (int)(a.steps_done + t + 1);
+                spos[i] = p0; svel[i] = v0; st1[i] = q1; st2[i] = q2;
+                publish(p0.x, p0.y, v0.x, v0.y);
+                if (!first_bad && !m_finite(p0.x + p0.y + v0.x + v0.y + q1.x + q1.y)) first_bad = (int)(a.steps_done + t + 1);
                 // ---- collision list + detector on the new state ----
-                if (has_robot) so = sense_ped<ST>(a, rb, q0.x, q0.y, last);
+                if (has_robot) so = sense_ped<ST>(a, rb, p0.x, p0.y, last);
                 if (last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
             }
             if (has_robot) {   // owner warps are whole warps: ballots are safe
@@ -412,8 +463,9 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
 
     // ---- write back (owners read their own shared-memory entries: no barrier needed) ----
     if (owner) {
-        const ST4 q0 = st0[i], q1 = st1[i], q2 = st2[i];
-        store_pv(a, g, q0.x, q0.y, q0.z, q0.w);
+        const ST2 p0 = spos[i], v0 = svel[i];
+        const ST4 q1 = st1[i], q2 = st2[i];
+        store_pv(a, g, p0.x, p0.y, v0.x, v0.y);
         ST2 t2; t2.x = q1.x; t2.y = q1.y;
         reinterpret_cast<ST2 *>(a.th)[g] = t2;
         ST2 w2; w2.x = q1.z; w2.y = q1.w;
@@ -424,6 +476,48 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
     if (owner_warp && has_robot && lane == 0) {
         if (det_acc) atomicAdd(&a.det_count[w], (unsigned long long)det_acc);
         if (coll_acc) atomicAdd(&a.coll_count[w], (unsigned long long)coll_acc);
+    }
+}
+
+// Work distribution.  Static: CTA b runs all steps of group b.  Dynamic (n_chunks > 1): persistent CTAs
+// pull (chunk, group) items in chunk-major order from a global counter; an item waits for the previous
+// chunk of its group (already held by a running CTA, so the wait cannot deadlock).  With thousands of
+// equal-length worlds this removes the partial last wave of a static grid (e.g. 1024 CTAs on 296 slots
+// = 3.46 waves run as 4) at the price of one state round trip through HBM per chunk.
+template <typename PT, typename ST, bool SPLIT, int S>
+__device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
+{
+    if (a.n_chunks <= 1) {
+        small_chunk<PT, ST, SPLIT, S>(a, blockIdx.x, 0, a.n_steps);
+        return;
+    }
+    __shared__ int s_item;
+    const int n_groups = (a.W + a.wpc - 1) / a.wpc;
+    const int total = n_groups * a.n_chunks;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.work_counter, 1);
+        cta_barrier();
+        const int item = s_item;
+        cta_barrier();
+        if (item >= total) break;
+        const int chunk = item / n_groups, group = item - chunk * n_groups;
+        if (chunk > 0) {
+            if (threadIdx.x == 0) {
+                int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(a.group_done + group) : "memory");
+                    if (seen < chunk) __nanosleep(200);
+                } while (seen < chunk);
+            }
+            cta_barrier();
+        }
+        const int t_begin = chunk * a.chunk_steps;
+        const int t_end = min(a.n_steps, t_begin + a.chunk_steps);
+        small_chunk<PT, ST, SPLIT, S>(a, group, t_begin, t_end);
+        __threadfence();
+        cta_barrier();
+        if (threadIdx.x == 0)
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(a.group_done + group), "r"(chunk + 1) : "memory");
     }
 }
 

@@ -133,7 +133,9 @@ struct pms_sim {
     long long snap_steps = 0;
     bool has_snapshot = false;
     // tuning / introspection
-    int tune_S = 0, tune_wpc = 0;
+    int tune_S = 0, tune_wpc = 0, tune_chunks = 0;
+    int sm_count = 148;
+    int sched_cap = 0;
     pms_launch_info info{};
     bool waypoints_set = false;
     // large-crowd path scratch
@@ -173,10 +175,34 @@ int launch_small_t(pms_sim *h, int wpc, bool big)
 {
     const size_t smem = SmallSmem<PT, ST, SPLIT>::bytes(h->Np, S) * wpc;
     const int threads = wpc * S * h->Np + 32;
-    const int blocks = (h->W + wpc - 1) / wpc;
+    const int groups = (h->W + wpc - 1) / wpc;
+    int blocks = groups;
     h->a.wpc = wpc;
     auto kern = big ? hsfm_small_kernel_big<PT, ST, SPLIT, S> : hsfm_small_kernel<PT, ST, SPLIT, S>;
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // dynamic (chunk, group) scheduling when a static grid would leave a partial last wave
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    const int slots = occ * h->sm_count;
+    h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
+    int want = h->tune_chunks;
+    if (want == 0 && groups > slots && h->a.n_steps >= 64) want = h->a.n_steps / 32 < 8 ? h->a.n_steps / 32 : 8;
+    if (want > 1 && slots > 0) {
+        h->a.chunk_steps = (h->a.n_steps + want - 1) / want;
+        h->a.n_chunks = (h->a.n_steps + h->a.chunk_steps - 1) / h->a.chunk_steps;
+    }
+    if (h->a.n_chunks > 1) {
+        if (groups > h->sched_cap) {
+            if (h->a.group_done) cudaFree(h->a.group_done);
+            h->a.group_done = nullptr; h->sched_cap = 0;
+            CK(cudaMalloc((void **)&h->a.group_done, sizeof(int) * (size_t)groups));
+            h->sched_cap = groups;
+        }
+        CK(cudaMemsetAsync(h->a.group_done, 0, sizeof(int) * (size_t)groups, h->stream));
+        CK(cudaMemsetAsync(h->a.work_counter, 0, sizeof(int), h->stream));
+        const long long total = (long long)groups * h->a.n_chunks;
+        blocks = (int)(total < slots ? total : slots);
+    }
     kern<<<blocks, threads, smem, h->stream>>>(h->a);
     CK(cudaGetLastError());
     h->info.kernel = 0;
@@ -185,6 +211,8 @@ int launch_small_t(pms_sim *h, int wpc, bool big)
     h->info.worlds_per_block = wpc;
     h->info.j_split = S;
     h->info.smem_bytes = (int)smem;
+    h->info.n_chunks = h->a.n_chunks;
+    h->info.blocks_per_sm = occ;
     h->info.kernel_launches++;
     return 0;
 }
@@ -317,6 +345,12 @@ int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hs
     CKC(dalloc(&a.coll_count, (size_t)n_worlds));
     CKC(dalloc(&a.nonfinite, (size_t)n_worlds));
     CKC(dalloc(&h->overflow_dev, 1));
+    CKC(dalloc(&a.work_counter, 1));
+    {
+        cudaDeviceProp prop;
+        CKC(cudaGetDeviceProperties(&prop, device));
+        h->sm_count = prop.multiProcessorCount;
+    }
     fill_int_kernel<<<nblk(n_worlds), 256, 0, h->stream>>>((size_t)n_worlds, a.nonfinite, 0x7fffffff);
     // default speed 1.5 (_hsfm.py:205) and a waypoint table of one row (set properly by the caller)
     {
@@ -341,7 +375,7 @@ int pms_destroy(pms_sim *h)
     void *ptrs[] = {a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
                     a.events, a.ev_count, a.robot_pose, a.robot_vel, a.robot_ctrl, a.robot_rear,
                     a.robot_world_collision, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
-                    a.nonfinite, h->stage, h->controls_dev, h->map_dev, h->overflow_dev};
+                    a.nonfinite, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->snap_dst) if (p) cudaFree(p);
     large_free(h->large);
@@ -801,10 +835,10 @@ int pms_get_launch_info(pms_sim *h, pms_launch_info *out)
     return PMS_OK;
 }
 
-int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block)
+int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks)
 {
     if (!h) return fail(PMS_ERR_INVALID, "handle is NULL");
-    h->tune_S = j_split; h->tune_wpc = worlds_per_block;
+    h->tune_S = j_split; h->tune_wpc = worlds_per_block; h->tune_chunks = n_chunks;
     return PMS_OK;
 }
 

@@ -27,6 +27,8 @@ template <typename T> struct PedConsts {
 struct HsfmArgs {
     int W, N, Np, wpc;          // worlds, peds/world, padded peds (multiple of 32), worlds per CTA
     int n_steps;
+    int n_chunks, chunk_steps;  // dynamic (chunk, group) scheduling when n_chunks > 1
+    int *work_counter, *group_done;
     long long steps_done;       // cumulative steps before this launch (non-finite bookkeeping)
     // pedestrian state, structure-of-arrays, world-major (element g = w*N + i)
     void *pos;                  // FP32: float4 {x,y,vx,vy}   | fp64 state: double2 {x,y}
@@ -154,13 +156,13 @@ template <> struct Vec4<double> { using type = double4; };
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_pv(const HsfmArgs &a, size_t g, float &x, float &y, float &vx, float &vy)
 {
-    float4 p = reinterpret_cast<const float4 *>(a.pos)[g];
+    float4 p = __ldcg(reinterpret_cast<const float4 *>(a.pos) + g);
     x = p.x; y = p.y; vx = p.z; vy = p.w;
 }
 __device__ __forceinline__ void load_pv(const HsfmArgs &a, size_t g, double &x, double &y, double &vx, double &vy)
 {
-    double2 p = reinterpret_cast<const double2 *>(a.pos)[g];
-    double2 v = reinterpret_cast<const double2 *>(a.vel)[g];
+    double2 p = __ldcg(reinterpret_cast<const double2 *>(a.pos) + g);
+    double2 v = __ldcg(reinterpret_cast<const double2 *>(a.vel) + g);
     x = p.x; y = p.y; vx = v.x; vy = v.y;
 }
 __device__ __forceinline__ void store_pv(const HsfmArgs &a, size_t g, float x, float y, float vx, float vy)
@@ -190,26 +192,44 @@ __device__ __forceinline__ float fast_ex2(float x)
     return r;
 }
 
-// fp32: 1 MUFU.RSQ + 1 MUFU.EX2; the sqrt is refined to ~0.5 ulp because its error is amplified
-// by d/B (~7.5x) inside the exponential.  `self` zeroes the j == i term exactly.
-__device__ __forceinline__ void pair_accum(const PairK<float> &k, float dx, float dy, float dvx, float dvy,
-                                           bool self, float &fx, float &fy)
+// fp32 pair force, split in two parts so that the common case (no body contact, g = 0) costs
+// 14 FMA-pipe + 2 MUFU instructions:
+//   pair_far     : exponential repulsion  A exp((r_ij - d)/B) n   (always)
+//   pair_contact : k_1 g n + k_2 g dv_t t                          (only when some lane has g > 0)
+// The sqrt is refined to ~0.5 ulp because its error is amplified by d/B (~7.5x) inside the
+// exponential.  `self` zeroes the j == i term exactly (inv = 0 => every product below is 0).
+__device__ __forceinline__ void pair_far(const PairK<float> &k, float dx, float dy, bool self,
+                                         float &inv, float &s, float &fx, float &fy)
 {
     const float d2 = fmaf(dx, dx, dy * dy);
-    float inv = fast_rsqrt(d2);
+    inv = fast_rsqrt(d2);
     inv = self ? 0.0f : inv;
     float d = d2 * inv;
     const float err = fmaf(-d, d, d2);
     d = fmaf(err, 0.5f * inv, d);
-    const float s = k.rij - d;
+    s = k.rij - d;
     const float e = fast_ex2(s * k.cexp);
+    const float a = e * (k.A * inv);             // A e / d : multiplies (dx,dy) directly
+    fx = fmaf(a, dx, fx);
+    fy = fmaf(a, dy, fy);
+}
+__device__ __forceinline__ void pair_contact(const PairK<float> &k, float dx, float dy, float dvx, float dvy,
+                                             float inv, float s, float &fx, float &fy)
+{
     const float g = fmaxf(s, 0.0f);
-    const float nx = dx * inv, ny = dy * inv;
-    const float dvt = fmaf(dvy, nx, -dvx * ny); // (v_j - v_i) . t,  t = (-n_y, n_x)
-    const float cn = fmaf(k.A, e, k.k1 * g);
-    const float ct = k.k2 * g * dvt;
-    fx += fmaf(cn, nx, -ct * ny);
-    fy += fmaf(cn, ny, ct * nx);
+    const float w = fmaf(dvy, dx, -dvx * dy);    // d * (v_j - v_i) . t
+    const float gi = g * inv;
+    const float a = k.k1 * gi;                   // k_1 g / d
+    const float b = k.k2 * gi * inv * w;         // k_2 g dv_t / d
+    fx = fmaf(a, dx, fx); fx = fmaf(-b, dy, fx);
+    fy = fmaf(a, dy, fy); fy = fmaf(b, dx, fy);
+}
+__device__ __forceinline__ void pair_accum(const PairK<float> &k, float dx, float dy, float dvx, float dvy,
+                                           bool self, float &fx, float &fy)
+{
+    float inv, s;
+    pair_far(k, dx, dy, self, inv, s, fx, fy);
+    pair_contact(k, dx, dy, dvx, dvy, inv, s, fx, fy);
 }
 
 // fp64: same operation order as the reference.

@@ -227,6 +227,23 @@ def test_batched_equals_single_world_and_jsplit():
         assert rel_err(p, p_ref) < 1e-10, (S, wpc)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "mixed", "fp64"])
+def test_dynamic_chunk_scheduler_is_bit_identical(precision):
+    """Persistent (chunk, group) scheduling only re-orders work: results equal the static grid bit for bit."""
+    sc = make_bench_crowd(300, 32)
+    outs = []
+    for chunks, wpc in ((1, 0), (4, 0), (7, 2), (3, 1)):
+        sim = make_cuda(sc, precision)
+        sim.set_tuning(0, wpc, chunks)
+        sim.step(0.01, 150)
+        info = sim.launch_info()
+        assert info["n_chunks"] == chunks
+        outs.append(sim.get_state() + sim.get_detector() + (sim.get_collisions(),) + sim.get_stats() + sim.get_robot())
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+
+
 def test_properties_permutation_translation_invisible():
     sc = make_crowd(3, 32)
     base = make_cuda(sc, "fp64", robot=0)
