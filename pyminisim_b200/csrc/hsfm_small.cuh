@@ -14,6 +14,7 @@
 //   * the robot warp runs ONE STEP AHEAD (the robot does not depend on pedestrians), double-buffered in
 //     shared memory, so its fp64 trigonometry never sits on the critical path of a step.
 #pragma once
+#include <type_traits>
 #include "pms_common.cuh"
 
 namespace pms {
@@ -29,30 +30,31 @@ struct RobotRegs {
     int world_collision;
 };
 
-// Shared-memory image of one world.  The owner state lives here between steps (not in registers) so
-// that nothing but the force accumulators is live across the pair loop.
-//   spos {x,y}  svel {vx,vy}  st1 {theta,omega,wp_x,wp_y}  st2 {speed,cos,sin,wp_index}   state precision ST
-//   ppos {x,y}  pvel {vx,vy}  in pair precision PT (alias spos/svel when PT == ST); plo = low parts of x,y (MIXED)
-// Positions and velocities are separate arrays: the pair loop reads only positions (one LDS.64 per
-// pair); velocities are touched only on body contact.
+// Shared-memory image of one world: structure-of-arrays, one scalar array per field (conflict-free
+// scalar access by owners, 16-byte vector access along j in the pair loop).
+//   owner state (ST):  x y vx vy theta omega wp_x wp_y speed cos sin  + int wp_index
+//   pair view   (PT):  xs ys vxs vys   (alias the owner x y vx vy when PT == ST)
+//   MIXED only       :  xlo ylo  = low parts of the fp64 position (x = (float)x + lo)
+//   S > 1            :  slice partial forces fxp[S][Np], fyp[S][Np]
+//   robot            :  ring of ROBOT_RING RobotSlots written ahead by the robot warp + its registers
+// The owner state lives here between steps (not in registers) so that nothing but the force
+// accumulators is live across the pair loop.
+constexpr int ROBOT_RING = 32;    // slots; the robot warp runs up to ROBOT_BLOCK steps ahead
+constexpr int ROBOT_BLOCK = 16;
+
 template <typename PT, typename ST, bool SPLIT>
 struct SmallSmem {
     static constexpr bool ALIAS = sizeof(PT) == sizeof(ST);
-    using ST2 = typename Vec2<ST>::type;
-    using ST4 = typename Vec4<ST>::type;
-    using PT2 = typename Vec2<PT>::type;
-    __host__ __device__ static size_t off_svel(int Np) { return sizeof(ST2) * Np; }
-    __host__ __device__ static size_t off_st1(int Np) { return 2 * sizeof(ST2) * Np; }
-    __host__ __device__ static size_t off_st2(int Np) { return off_st1(Np) + sizeof(ST4) * Np; }
-    __host__ __device__ static size_t end_state(int Np) { return off_st2(Np) + sizeof(ST4) * Np; }
-    __host__ __device__ static size_t off_ppos(int Np) { return ALIAS ? 0 : end_state(Np); }
-    __host__ __device__ static size_t off_pvel(int Np) { return ALIAS ? off_svel(Np) : end_state(Np) + sizeof(PT2) * Np; }
-    __host__ __device__ static size_t off_plo(int Np) { return end_state(Np) + (ALIAS ? 0 : 2 * sizeof(PT2) * Np); }
-    __host__ __device__ static size_t off_part(int Np) { return off_plo(Np) + (SPLIT ? sizeof(float2) * Np : 0); }
-    __host__ __device__ static size_t off_robot(int Np, int S) { return off_part(Np) + (S > 1 ? sizeof(PT2) * Np * S : 0); }
+    static constexpr int N_OWNER = 11;
+    __host__ __device__ static size_t off_widx(int Np) { return sizeof(ST) * N_OWNER * Np; }
+    __host__ __device__ static size_t off_pair(int Np) { return ALIAS ? 0 : off_widx(Np) + sizeof(int) * Np; }
+    __host__ __device__ static size_t end_pair(int Np) { return off_widx(Np) + sizeof(int) * Np + (ALIAS ? 0 : 4 * sizeof(PT) * Np); }
+    __host__ __device__ static size_t off_lo(int Np) { return end_pair(Np); }
+    __host__ __device__ static size_t off_part(int Np) { return off_lo(Np) + (SPLIT ? 2 * sizeof(float) * Np : 0); }
+    __host__ __device__ static size_t off_robot(int Np, int S) { return (off_part(Np) + (S > 1 ? 2 * sizeof(PT) * Np * S : 0) + 15) & ~size_t(15); }
     __host__ __device__ static size_t bytes(int Np, int S)
     {
-        return (off_robot(Np, S) + 2 * sizeof(RobotSlot) + sizeof(RobotRegs) + 15) & ~size_t(15);
+        return (off_robot(Np, S) + ROBOT_RING * sizeof(RobotSlot) + sizeof(RobotRegs) + 15) & ~size_t(15);
     }
 };
 
@@ -228,14 +230,38 @@ __device__ __forceinline__ SenseOut sense_ped(const HsfmArgs &a, const RobotSlot
 // same hardware barrier from different instructions (warp-specialised producer / consumer).
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-// One chunk of simulation steps [t_begin, t_end) for the wpc worlds of `group`.  Every thread of the
-// CTA (pedestrian warps and the robot warp) executes the same sequence of CTA barriers.
+// Barrier over the S*Np threads of one world (named barrier 1 + wl; a single warp just re-converges).
+__device__ __forceinline__ void world_barrier(int wl, int count)
+{
+    if (count == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" :: "r"(wl + 1), "r"(count) : "memory");
+}
+
+// fp32 far-field pair force for TWO pairs at once on the Blackwell packed-FP32 pipe (FFMA2 / FMUL2 /
+// FADD2): 11 packed FMA-pipe instructions + 4 MUFU for 2 pairs.  Same arithmetic as pair_far.
+__device__ __forceinline__ void pair_far2(const PairK<float> &k, float2 dx, float2 dy, float2 &inv, float2 &sg,
+                                          float2 &fx, float2 &fy)
+{
+    const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+    inv.x = fast_rsqrt(d2.x); inv.y = fast_rsqrt(d2.y);
+    float2 d = __fmul2_rn(d2, inv);
+    const float2 err = __ffma2_rn(make_float2(-d.x, -d.y), d, d2);
+    d = __ffma2_rn(err, __fmul2_rn(inv, make_float2(0.5f, 0.5f)), d);
+    sg = __fadd2_rn(make_float2(k.rij, k.rij), make_float2(-d.x, -d.y));
+    const float2 arg = __fmul2_rn(sg, make_float2(k.cexp, k.cexp));
+    float2 e; e.x = fast_ex2(arg.x); e.y = fast_ex2(arg.y);
+    const float2 a = __fmul2_rn(e, __fmul2_rn(inv, make_float2(k.A, k.A)));
+    fx = __ffma2_rn(a, dx, fx);
+    fy = __ffma2_rn(a, dy, fy);
+}
+
+// One chunk of simulation steps [t_begin, t_end) for the wpc worlds of `group`.
+// Synchronisation: the warps of one world meet twice per step at that world's named barrier; the robot
+// warp fills the robot ring ROBOT_BLOCK steps ahead and everybody meets at CTA barrier 0 once per block.
 template <typename PT, typename ST, bool SPLIT, int S>
 __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, const int t_begin, const int t_end)
 {
-    using PT2 = typename Vec2<PT>::type;
     using ST2 = typename Vec2<ST>::type;
-    using ST4 = typename Vec4<ST>::type;
     using L = SmallSmem<PT, ST, SPLIT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -258,16 +284,18 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
 
     // carve the shared memory of local world wl
     unsigned char *base = smem_raw + (size_t)(wl < a.wpc ? wl : 0) * L::bytes(Np, S);
-    ST2 *spos = reinterpret_cast<ST2 *>(base);
-    ST2 *svel = reinterpret_cast<ST2 *>(base + L::off_svel(Np));
-    ST4 *st1 = reinterpret_cast<ST4 *>(base + L::off_st1(Np));
-    ST4 *st2 = reinterpret_cast<ST4 *>(base + L::off_st2(Np));
-    PT2 *ppos = reinterpret_cast<PT2 *>(base + L::off_ppos(Np));
-    PT2 *pvel = reinterpret_cast<PT2 *>(base + L::off_pvel(Np));
-    float2 *plo = reinterpret_cast<float2 *>(base + L::off_plo(Np));
-    PT2 *part = reinterpret_cast<PT2 *>(base + L::off_part(Np));
-    RobotSlot *rslot = reinterpret_cast<RobotSlot *>(base + L::off_robot(Np, S));
-    RobotRegs &rr = *reinterpret_cast<RobotRegs *>(base + L::off_robot(Np, S) + 2 * sizeof(RobotSlot));
+    ST *o_x = reinterpret_cast<ST *>(base);
+    ST *o_y = o_x + Np, *o_vx = o_x + 2 * Np, *o_vy = o_x + 3 * Np, *o_th = o_x + 4 * Np, *o_om = o_x + 5 * Np;
+    ST *o_wx = o_x + 6 * Np, *o_wy = o_x + 7 * Np, *o_vm = o_x + 8 * Np, *o_c = o_x + 9 * Np, *o_s = o_x + 10 * Np;
+    int *o_widx = reinterpret_cast<int *>(base + L::off_widx(Np));
+    PT *xs = reinterpret_cast<PT *>(base + L::off_pair(Np));
+    PT *ys = xs + Np, *vxs = xs + 2 * Np, *vys = xs + 3 * Np;
+    float *xlo = reinterpret_cast<float *>(base + L::off_lo(Np));
+    float *ylo = xlo + Np;
+    PT *fxp = reinterpret_cast<PT *>(base + L::off_part(Np));
+    PT *fyp = fxp + S * Np;
+    RobotSlot *ring = reinterpret_cast<RobotSlot *>(base + L::off_robot(Np, S));
+    RobotRegs &rr = *reinterpret_cast<RobotRegs *>(base + L::off_robot(Np, S) + ROBOT_RING * sizeof(RobotSlot));
 
     const PairK<PT> &kpp = kpp_of(a, PT{});
     const PairK<PT> &kpr = kpr_of(a, PT{});
@@ -278,50 +306,48 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
     auto publish = [&](ST x, ST y, ST vx, ST vy) {
         if constexpr (SPLIT) {
             const float xh = (float)x, yh = (float)y;
-            ppos[i] = make_float2(xh, yh);
-            pvel[i] = make_float2((float)vx, (float)vy);
-            plo[i] = make_float2((float)(x - (double)xh), (float)(y - (double)yh));
+            xs[i] = xh; ys[i] = yh; vxs[i] = (float)vx; vys[i] = (float)vy;
+            xlo[i] = (float)(x - (double)xh); ylo[i] = (float)(y - (double)yh);
         } else if constexpr (!L::ALIAS) {
-            PT2 p; p.x = (PT)x; p.y = (PT)y; ppos[i] = p;
-            PT2 v; v.x = (PT)vx; v.y = (PT)vy; pvel[i] = v;
+            xs[i] = (PT)x; ys[i] = (PT)y; vxs[i] = (PT)vx; vys[i] = (PT)vy;
         }
     };
 
     if (owner) {
-        ST2 p0, v0; ST4 q1, q2;
-        load_pv(a, g, p0.x, p0.y, v0.x, v0.y);
+        ST x, y, vx, vy, c, sn;
+        load_pv(a, g, x, y, vx, vy);
         const ST2 t = __ldcg(reinterpret_cast<const ST2 *>(a.th) + g);
         const ST2 q = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
-        q1.x = t.x; q1.y = t.y; q1.z = q.x; q1.w = q.y;
-        q2.x = reinterpret_cast<const ST *>(a.vmag)[g];
-        m_sincos(t.x, &q2.z, &q2.y);
-        q2.w = (ST)__ldcg(a.wp_index + g);        // small integer, exact in fp32
-        spos[i] = p0; svel[i] = v0; st1[i] = q1; st2[i] = q2;
-        publish(p0.x, p0.y, v0.x, v0.y);
-    } else if (pair_warp && s == 0) {
-        // padding lanes (N <= i < Np) run the pair loop for warp-uniform votes: park them far away
-        PT2 far; far.x = (PT)1e18; far.y = (PT)(1e18 + 1e15 * i);
-        PT2 z; z.x = 0; z.y = 0;
-        ppos[i] = far; pvel[i] = z;
-        if constexpr (SPLIT) plo[i] = make_float2(0.f, 0.f);
+        m_sincos(t.x, &sn, &c);
+        o_x[i] = x; o_y[i] = y; o_vx[i] = vx; o_vy[i] = vy; o_th[i] = t.x; o_om[i] = t.y;
+        o_wx[i] = q.x; o_wy[i] = q.y; o_vm[i] = reinterpret_cast<const ST *>(a.vmag)[g]; o_c[i] = c; o_s[i] = sn;
+        o_widx[i] = __ldcg(a.wp_index + g);
+        publish(x, y, vx, vy);
+    } else if (owner_warp) {
+        // padding lanes (N <= i < Np) run the pair loop so that warp votes stay uniform, and padded j
+        // entries are read by the 4-wide pair loop: park them far away (their force underflows to 0)
+        xs[i] = (PT)1e18; ys[i] = (PT)(1e18 + 1e15 * (i + 1)); vxs[i] = 0; vys[i] = 0;
+        if constexpr (SPLIT) { xlo[i] = 0.f; ylo[i] = 0.f; }
     }
 
-    // ---- robot warp: its own loop (same barrier sequence), one step ahead of the pedestrians ----
+    // ---- robot warp: fills the ring one block ahead of the pedestrians ----
     if (is_robot_warp) {
         const bool robot_lane = world_ok && has_robot;
-        if (robot_lane) {
-            robot_load(a, w, rr);
-            robot_step(a, w, t_begin, rr);
-            rslot[t_begin & 1] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
-        }
-        for (int t = t_begin; t < t_end; ++t) {
-            cta_barrier();   // A
-            if (robot_lane && t + 1 < t_end) {
-                robot_step(a, w, t + 1, rr);
-                rslot[(t + 1) & 1] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
+        int filled = t_begin;                  // ring holds steps < filled
+        auto fill = [&](int upto) {
+            if (!robot_lane) return;
+            for (; filled < upto; ++filled) {
+                robot_step(a, w, filled, rr);
+                ring[(filled - t_begin) & (ROBOT_RING - 1)] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
             }
-            cta_barrier();   // B
+        };
+        if (robot_lane) robot_load(a, w, rr);
+        fill(min(t_end, t_begin + ROBOT_BLOCK));
+        for (int tb = t_begin; tb < t_end; tb += ROBOT_BLOCK) {
+            cta_barrier();                     // block tb is complete; block tb - ROBOT_BLOCK is consumed
+            fill(min(t_end, tb + 2 * ROBOT_BLOCK));
         }
+        cta_barrier();                         // matches the pedestrians' final barrier
         if (robot_lane) robot_store(a, w, rr);
         return;
     }
@@ -329,71 +355,86 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
     unsigned det_acc = 0, coll_acc = 0;   // per owner warp
     int first_bad = 0;
     const int lane = tid & 31;
+    // contiguous j-slice of this thread: [j_lo, j_hi), multiples of 4
+    const int N4 = (N + 3) & ~3;
+    const int slice = (((N4 + S - 1) / S) + 3) & ~3;
+    const int j_lo = min(N4, s * slice), j_hi = min(N4, j_lo + slice);
+    const int i0 = i & ~31;               // first pedestrian of this warp: groups in [i0, i0+32) may hold j == i
 
     for (int t = t_begin; t < t_end; ++t) {
-        cta_barrier();     // A: state t and robot slot t&1 are visible
-        const RobotSlot &rb = rslot[t & 1];
+        if (((t - t_begin) & (ROBOT_BLOCK - 1)) == 0) cta_barrier();   // robot block hand-off
+        if (pair_warp) world_barrier(wl, per_world);                    // A: state t visible to the world
+        const RobotSlot &rb = ring[(t - t_begin) & (ROBOT_RING - 1)];
         PT fx = 0, fy = 0;
         if (pair_warp) {
-            const PT2 me = ppos[i];
-            float2 melo = make_float2(0.f, 0.f);
-            if constexpr (SPLIT) melo = plo[i];
-            PT fx1 = 0, fy1 = 0;
-            int j = s;
+            const PT mx = xs[i], my = ys[i];
+            float mlx = 0.f, mly = 0.f;
+            if constexpr (SPLIT) { mlx = xlo[i]; mly = ylo[i]; }
             if constexpr (sizeof(PT) == 4) {
-                // fp32 pair loop, 4 pairs per trip; one warp vote decides whether anybody is in contact
-                for (; j + 3 * S < N; j += 4 * S) {
-                    float dx[4], dy[4], inv[4], sg[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 o = ppos[j + q * S];
-                        dx[q] = me.x - o.x; dy[q] = me.y - o.y;
-                        if constexpr (SPLIT) { const float2 l = plo[j + q * S]; dx[q] += melo.x - l.x; dy[q] += melo.y - l.y; }
-                    }
-                    pair_far(kpp, dx[0], dy[0], j == i, inv[0], sg[0], fx, fy);
-                    pair_far(kpp, dx[1], dy[1], j + S == i, inv[1], sg[1], fx1, fy1);
-                    pair_far(kpp, dx[2], dy[2], j + 2 * S == i, inv[2], sg[2], fx, fy);
-                    pair_far(kpp, dx[3], dy[3], j + 3 * S == i, inv[3], sg[3], fx1, fy1);
-                    const float smax = fmaxf(fmaxf(sg[0], sg[1]), fmaxf(sg[2], sg[3]));
-                    if (__any_sync(0xffffffffu, smax > 0.0f)) {
-                        const float2 mv = pvel[i];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 ov = pvel[j + q * S];
-                            pair_contact(kpp, dx[q], dy[q], ov.x - mv.x, ov.y - mv.y, inv[q], sg[q], fx, fy);
+                // ---- fp32 pair loop: 4 pairs per trip as two packed (f32x2) pairs ----
+                float2 fxa = make_float2(0.f, 0.f), fya = fxa, fxb = fxa, fyb = fxa;
+                auto groups = [&](int jb, const int je, auto masked) {
+                    for (; jb < je; jb += 4) {
+                        const float4 X = *reinterpret_cast<const float4 *>(xs + jb);
+                        const float4 Y = *reinterpret_cast<const float4 *>(ys + jb);
+                        const float2 m2x = make_float2(mx, mx), m2y = make_float2(my, my);
+                        float2 dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
+                        float2 dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
+                        if constexpr (SPLIT) {
+                            const float4 XL = *reinterpret_cast<const float4 *>(xlo + jb);
+                            const float4 YL = *reinterpret_cast<const float4 *>(ylo + jb);
+                            const float2 l2x = make_float2(mlx, mlx), l2y = make_float2(mly, mly);
+                            dxa = __fadd2_rn(dxa, __fadd2_rn(l2x, make_float2(-XL.x, -XL.y)));
+                            dxb = __fadd2_rn(dxb, __fadd2_rn(l2x, make_float2(-XL.z, -XL.w)));
+                            dya = __fadd2_rn(dya, __fadd2_rn(l2y, make_float2(-YL.x, -YL.y)));
+                            dyb = __fadd2_rn(dyb, __fadd2_rn(l2y, make_float2(-YL.z, -YL.w)));
+                        }
+                        if constexpr (decltype(masked)::value) {
+                            // j == i: move the partner far away => its term is exactly 0 (exp underflows)
+                            const int k = i - jb;
+                            dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
+                            dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
+                        }
+                        float2 inva, invb, sa, sb;
+                        pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
+                        pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
+                        const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
+                        if (__any_sync(0xffffffffu, smax > 0.0f)) {      // somebody in the warp touches somebody
+                            const float mvx = vxs[i], mvy = vys[i];
+                            const float4 VX = *reinterpret_cast<const float4 *>(vxs + jb);
+                            const float4 VY = *reinterpret_cast<const float4 *>(vys + jb);
+                            pair_contact(kpp, dxa.x, dya.x, VX.x - mvx, VY.x - mvy, inva.x, sa.x, fx, fy);
+                            pair_contact(kpp, dxa.y, dya.y, VX.y - mvx, VY.y - mvy, inva.y, sa.y, fx, fy);
+                            pair_contact(kpp, dxb.x, dyb.x, VX.z - mvx, VY.z - mvy, invb.x, sb.x, fx, fy);
+                            pair_contact(kpp, dxb.y, dyb.y, VX.w - mvx, VY.w - mvy, invb.y, sb.y, fx, fy);
                         }
                     }
-                }
-                for (; j < N; j += S) {
-                    const float2 o = ppos[j];
-                    float dx0 = me.x - o.x, dy0 = me.y - o.y;
-                    if constexpr (SPLIT) { const float2 l = plo[j]; dx0 += melo.x - l.x; dy0 += melo.y - l.y; }
-                    const float2 mv = pvel[i], ov = pvel[j];
-                    pair_accum(kpp, dx0, dy0, ov.x - mv.x, ov.y - mv.y, j == i, fx, fy);
-                }
+                };
+                const int m_lo = max(j_lo, min(j_hi, i0)), m_hi = min(j_hi, max(j_lo, i0 + 32));
+                groups(j_lo, m_lo, std::false_type{});
+                groups(m_lo, m_hi, std::true_type{});
+                groups(m_hi, j_hi, std::false_type{});
+                fx += (fxa.x + fxa.y) + (fxb.x + fxb.y);
+                fy += (fya.x + fya.y) + (fyb.x + fyb.y);
             } else {
-                const PT2 mv = pvel[i];
-                for (; j < N; j += S) {
-                    const PT2 o = ppos[j], ov = pvel[j];
-                    pair_accum(kpp, me.x - o.x, me.y - o.y, ov.x - mv.x, ov.y - mv.y, j == i, fx, fy);
-                }
+                const PT mvx = vxs[i], mvy = vys[i];
+                for (int j = j_lo; j < min(j_hi, N); ++j)
+                    pair_accum(kpp, mx - xs[j], my - ys[j], vxs[j] - mvx, vys[j] - mvy, j == i, fx, fy);
             }
-            fx += fx1; fy += fy1;
             if (s == S - 1 && has_robot && a.robot_visible) {   // robot term (_hsfm.py:80-82)
-                const PT2 mv = pvel[i];
                 PT dx, dy;
                 if constexpr (SPLIT) {
                     const float rxh = (float)rb.x, ryh = (float)rb.y;
-                    dx = (me.x - rxh) + (melo.x - (float)(rb.x - (double)rxh));
-                    dy = (me.y - ryh) + (melo.y - (float)(rb.y - (double)ryh));
+                    dx = (mx - rxh) + (mlx - (float)(rb.x - (double)rxh));
+                    dy = (my - ryh) + (mly - (float)(rb.y - (double)ryh));
                 } else {
-                    dx = me.x - (PT)rb.x; dy = me.y - (PT)rb.y;
+                    dx = mx - (PT)rb.x; dy = my - (PT)rb.y;
                 }
-                pair_accum(kpr, dx, dy, (PT)rb.vx - mv.x, (PT)rb.vy - mv.y, false, fx, fy);
+                pair_accum(kpr, dx, dy, (PT)rb.vx - vxs[i], (PT)rb.vy - vys[i], false, fx, fy);
             }
-            if (S > 1) { PT2 p; p.x = fx; p.y = fy; part[s * Np + i] = p; }
+            if (S > 1) { fxp[s * Np + i] = fx; fyp[s * Np + i] = fy; }
+            world_barrier(wl, per_world);                               // B: reads of state t done; partials visible
         }
-        cta_barrier();     // B: all reads of state t done; slice partials visible
         if (owner_warp) {
             SenseOut so{false, false, 0.0, 0.0};
             const bool last = (t == a.n_steps - 1);   // last step of the launch
@@ -401,27 +442,30 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
                 if (S > 1) {
                     fx = 0; fy = 0;
 #pragma unroll
-                    for (int q = 0; q < S; ++q) { const PT2 p = part[q * Np + i]; fx += p.x; fy += p.y; }
+                    for (int q = 0; q < S; ++q) { fx += fxp[q * Np + i]; fy += fyp[q * Np + i]; }
                 }
-                ST2 p0 = spos[i], v0 = svel[i];
-                ST4 q1 = st1[i], q2 = st2[i];
-                const ST x0 = p0.x, y0 = p0.y, th0 = q1.x;
-                ped_integrate<ST>(kc, (ST)fx, (ST)fy, q1.z, q1.w, q2.x, p0.x, p0.y, v0.x, v0.y, q1.x, q1.y, q2.y, q2.z);
+                ST x = o_x[i], y = o_y[i], vx = o_vx[i], vy = o_vy[i], th = o_th[i], om = o_om[i];
+                ST wx = o_wx[i], wy = o_wy[i], c = o_c[i], sn = o_s[i];
+                const ST x0 = x, y0 = y, th0 = th;
+                ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn);
                 // ---- waypoint tracker on the NEW pose (_hsfm.py:301) ----
-                const ST ex = q1.z - p0.x, ey = q1.w - p0.y;
-                if (m_sqrt(ex * ex + ey * ey) <= kc.reach) {
+                const ST ex = wx - x, ey = wy - y;
+                bool reached;
+                if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
+                else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
+                if (reached) {
                     if (a.tracker_kind == TRACKER_FIXED) {       // _fixed_waypoint_tracker.py:68-87
-                        int ni = (int)q2.w + 1;
+                        int ni = o_widx[i] + 1;
                         bool steady = false;
                         if (ni >= a.n_table) {
                             if (a.loop) ni = 0; else { ni = a.n_table - 1; steady = true; }
                         }
-                        q2.w = (ST)ni;
+                        o_widx[i] = ni;
                         const ST2 nw = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
-                        q1.z = nw.x; q1.w = nw.y;
+                        wx = nw.x; wy = nw.y;
                         if (steady) {                            // _hsfm.py:302-304
-                            p0.x = x0; p0.y = y0; q1.x = th0; v0.x = 0; v0.y = 0; q1.y = 0;
-                            m_sincos(q1.x, &q2.z, &q2.y);
+                            x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0;
+                            m_sincos(th, &sn, &c);
                         }
                     } else {                                     // _random_waypoint_tracker.py:66-91
                         const int cnt = a.q_count[g];
@@ -429,7 +473,7 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
                         if (cnt > 0) {
                             const int head = a.q_head[g];
                             const ST2 nw = reinterpret_cast<const ST2 *>(a.queue)[g * a.q_cap + head];
-                            q1.z = nw.x; q1.w = nw.y;
+                            wx = nw.x; wy = nw.y;
                             a.q_head[g] = (head + 1) % a.q_cap;
                             a.q_count[g] = cnt - 1;
                             if (slot < a.ev_cap) { a.events[3 * slot] = t; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i; }
@@ -437,12 +481,13 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
                             a.events[3 * slot] = -1 - t; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i;
                         }
                     }
+                    o_wx[i] = wx; o_wy[i] = wy;
                 }
-                spos[i] = p0; svel[i] = v0; st1[i] = q1; st2[i] = q2;
-                publish(p0.x, p0.y, v0.x, v0.y);
-                if (!first_bad && !m_finite(p0.x + p0.y + v0.x + v0.y + q1.x + q1.y)) first_bad = (int)(a.steps_done + t + 1);
+                o_x[i] = x; o_y[i] = y; o_vx[i] = vx; o_vy[i] = vy; o_th[i] = th; o_om[i] = om; o_c[i] = c; o_s[i] = sn;
+                publish(x, y, vx, vy);
+                if (!first_bad && !m_finite(x + y + vx + vy + th + om)) first_bad = (int)(a.steps_done + t + 1);
                 // ---- collision list + detector on the new state ----
-                if (has_robot) so = sense_ped<ST>(a, rb, p0.x, p0.y, last);
+                if (has_robot) so = sense_ped<ST>(a, rb, x, y, last);
                 if (last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
             }
             if (has_robot) {   // owner warps are whole warps: ballots are safe
@@ -460,17 +505,16 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
             }
         }
     }
+    cta_barrier();   // pairs with the robot warp's final barrier (robot ring may be re-used by the next chunk)
 
     // ---- write back (owners read their own shared-memory entries: no barrier needed) ----
     if (owner) {
-        const ST2 p0 = spos[i], v0 = svel[i];
-        const ST4 q1 = st1[i], q2 = st2[i];
-        store_pv(a, g, p0.x, p0.y, v0.x, v0.y);
-        ST2 t2; t2.x = q1.x; t2.y = q1.y;
+        store_pv(a, g, o_x[i], o_y[i], o_vx[i], o_vy[i]);
+        ST2 t2; t2.x = o_th[i]; t2.y = o_om[i];
         reinterpret_cast<ST2 *>(a.th)[g] = t2;
-        ST2 w2; w2.x = q1.z; w2.y = q1.w;
+        ST2 w2; w2.x = o_wx[i]; w2.y = o_wy[i];
         reinterpret_cast<ST2 *>(a.wp)[g] = w2;
-        a.wp_index[g] = (int)q2.w;
+        a.wp_index[g] = o_widx[i];
         if (first_bad) atomicMin(&a.nonfinite[w], first_bad);
     }
     if (owner_warp && has_robot && lane == 0) {

@@ -241,7 +241,8 @@ int launch_small(pms_sim *h)
     int wpc = h->tune_wpc;
     if (wpc <= 0) wpc = 256 / (S * Np);
     if (wpc < 1) wpc = 1;
-    if (wpc > 32) wpc = 32;
+    const int wpc_max = (S * Np == 32) ? 31 : 15;   // named barriers 1..15 (single-warp worlds need none)
+    if (wpc > wpc_max) wpc = wpc_max;
     if (wpc > h->W) wpc = h->W;
     while (wpc > 1 && wpc * S * Np + 32 > 1024) --wpc;
     const bool big = wpc * S * Np + 32 > 288;
