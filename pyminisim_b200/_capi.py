@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpms_b200.so")
+LIB_PATH = os.environ.get("PMS_LIB", os.path.join(HERE, "libpms_b200.so"))  # PMS_LIB: experiment builds only
 
 PMS_FP32, PMS_MIXED, PMS_FP64 = 0, 1, 2
 ROBOT_NONE, ROBOT_EXTERNAL, ROBOT_UNICYCLE, ROBOT_BICYCLE = 0, 1, 2, 3

@@ -238,18 +238,24 @@ __device__ __forceinline__ void world_barrier(int wl, int count)
 }
 
 // fp32 far-field pair force for TWO pairs at once on the Blackwell packed-FP32 pipe (FFMA2 / FMUL2 /
-// FADD2): 11 packed FMA-pipe instructions + 4 MUFU for 2 pairs.  Same arithmetic as pair_far.
+// FADD2): 8 packed FMA-pipe instructions + 4 MUFU for 2 pairs.  Same arithmetic as pair_far.
 __device__ __forceinline__ void pair_far2(const PairK<float> &k, float2 dx, float2 dy, float2 &inv, float2 &sg,
                                           float2 &fx, float2 &fy)
 {
     const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
     inv.x = fast_rsqrt(d2.x); inv.y = fast_rsqrt(d2.y);
     float2 d = __fmul2_rn(d2, inv);
+#ifdef PMS_REFINE_SQRT   // off: measured to make no difference to parity (profiles/parity_r1.md), costs 9 %
     const float2 err = __ffma2_rn(make_float2(-d.x, -d.y), d, d2);
     d = __ffma2_rn(err, __fmul2_rn(inv, make_float2(0.5f, 0.5f)), d);
+#endif
     sg = __fadd2_rn(make_float2(k.rij, k.rij), make_float2(-d.x, -d.y));
     const float2 arg = __fmul2_rn(sg, make_float2(k.cexp, k.cexp));
+#ifdef PMS_EXP_NOEX2
+    float2 e = __ffma2_rn(arg, make_float2(1e-9f, 1e-9f), make_float2(1e-9f, 1e-9f));   // experiment only: no MUFU.EX2
+#else
     float2 e; e.x = fast_ex2(arg.x); e.y = fast_ex2(arg.y);
+#endif
     const float2 a = __fmul2_rn(e, __fmul2_rn(inv, make_float2(k.A, k.A)));
     fx = __ffma2_rn(a, dx, fx);
     fy = __ffma2_rn(a, dy, fy);
@@ -373,41 +379,63 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
             if constexpr (sizeof(PT) == 4) {
                 // ---- fp32 pair loop: 4 pairs per trip as two packed (f32x2) pairs ----
                 float2 fxa = make_float2(0.f, 0.f), fya = fxa, fxb = fxa, fyb = fxa;
+                const float2 m2x = make_float2(mx, mx), m2y = make_float2(my, my);
+                const float2 l2x = make_float2(mlx, mlx), l2y = make_float2(mly, mly);
+                // one group = 4 consecutive j: differences (MIXED: hi + lo), optional self mask
+                auto load_group = [&](int jb, auto masked, float2 &dxa, float2 &dya, float2 &dxb, float2 &dyb) {
+                    const float4 X = *reinterpret_cast<const float4 *>(xs + jb);
+                    const float4 Y = *reinterpret_cast<const float4 *>(ys + jb);
+                    dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)); dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
+                    dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)); dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
+                    if constexpr (SPLIT) {
+                        const float4 XL = *reinterpret_cast<const float4 *>(xlo + jb);
+                        const float4 YL = *reinterpret_cast<const float4 *>(ylo + jb);
+                        dxa = __fadd2_rn(dxa, __fadd2_rn(l2x, make_float2(-XL.x, -XL.y)));
+                        dxb = __fadd2_rn(dxb, __fadd2_rn(l2x, make_float2(-XL.z, -XL.w)));
+                        dya = __fadd2_rn(dya, __fadd2_rn(l2y, make_float2(-YL.x, -YL.y)));
+                        dyb = __fadd2_rn(dyb, __fadd2_rn(l2y, make_float2(-YL.z, -YL.w)));
+                    }
+                    if constexpr (decltype(masked)::value) {
+                        // j == i: move the partner far away => its term is exactly 0 (exp underflows)
+                        const int k = i - jb;
+                        dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
+                        dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
+                    }
+                };
+                auto contact_group = [&](int jb, float2 dxa, float2 dya, float2 dxb, float2 dyb, float2 inva, float2 invb,
+                                         float2 sa, float2 sb) {
+                    const float mvx = vxs[i], mvy = vys[i];
+                    const float4 VX = *reinterpret_cast<const float4 *>(vxs + jb);
+                    const float4 VY = *reinterpret_cast<const float4 *>(vys + jb);
+                    pair_contact(kpp, dxa.x, dya.x, VX.x - mvx, VY.x - mvy, inva.x, sa.x, fx, fy);
+                    pair_contact(kpp, dxa.y, dya.y, VX.y - mvx, VY.y - mvy, inva.y, sa.y, fx, fy);
+                    pair_contact(kpp, dxb.x, dyb.x, VX.z - mvx, VY.z - mvy, invb.x, sb.x, fx, fy);
+                    pair_contact(kpp, dxb.y, dyb.y, VX.w - mvx, VY.w - mvy, invb.y, sb.y, fx, fy);
+                };
                 auto groups = [&](int jb, const int je, auto masked) {
+                    // 8 pairs per trip (four independent packed chains), then a 4-pair tail
+                    for (; jb + 8 <= je; jb += 8) {
+                        float2 dxa, dya, dxb, dyb, dxc, dyc, dxd, dyd, inva, invb, invc, invd, sa, sb, sc, sd;
+                        load_group(jb, masked, dxa, dya, dxb, dyb);
+                        load_group(jb + 4, masked, dxc, dyc, dxd, dyd);
+                        pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
+                        pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
+                        pair_far2(kpp, dxc, dyc, invc, sc, fxa, fya);
+                        pair_far2(kpp, dxd, dyd, invd, sd, fxb, fyb);
+                        const float smax = fmaxf(fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y)),
+                                                 fmaxf(fmaxf(sc.x, sc.y), fmaxf(sd.x, sd.y)));
+                        if (__any_sync(0xffffffffu, smax > 0.0f)) {      // somebody in the warp touches somebody
+                            contact_group(jb, dxa, dya, dxb, dyb, inva, invb, sa, sb);
+                            contact_group(jb + 4, dxc, dyc, dxd, dyd, invc, invd, sc, sd);
+                        }
+                    }
                     for (; jb < je; jb += 4) {
-                        const float4 X = *reinterpret_cast<const float4 *>(xs + jb);
-                        const float4 Y = *reinterpret_cast<const float4 *>(ys + jb);
-                        const float2 m2x = make_float2(mx, mx), m2y = make_float2(my, my);
-                        float2 dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
-                        float2 dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
-                        if constexpr (SPLIT) {
-                            const float4 XL = *reinterpret_cast<const float4 *>(xlo + jb);
-                            const float4 YL = *reinterpret_cast<const float4 *>(ylo + jb);
-                            const float2 l2x = make_float2(mlx, mlx), l2y = make_float2(mly, mly);
-                            dxa = __fadd2_rn(dxa, __fadd2_rn(l2x, make_float2(-XL.x, -XL.y)));
-                            dxb = __fadd2_rn(dxb, __fadd2_rn(l2x, make_float2(-XL.z, -XL.w)));
-                            dya = __fadd2_rn(dya, __fadd2_rn(l2y, make_float2(-YL.x, -YL.y)));
-                            dyb = __fadd2_rn(dyb, __fadd2_rn(l2y, make_float2(-YL.z, -YL.w)));
-                        }
-                        if constexpr (decltype(masked)::value) {
-                            // j == i: move the partner far away => its term is exactly 0 (exp underflows)
-                            const int k = i - jb;
-                            dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
-                            dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
-                        }
-                        float2 inva, invb, sa, sb;
+                        float2 dxa, dya, dxb, dyb, inva, invb, sa, sb;
+                        load_group(jb, masked, dxa, dya, dxb, dyb);
                         pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
                         pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
                         const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
-                        if (__any_sync(0xffffffffu, smax > 0.0f)) {      // somebody in the warp touches somebody
-                            const float mvx = vxs[i], mvy = vys[i];
-                            const float4 VX = *reinterpret_cast<const float4 *>(vxs + jb);
-                            const float4 VY = *reinterpret_cast<const float4 *>(vys + jb);
-                            pair_contact(kpp, dxa.x, dya.x, VX.x - mvx, VY.x - mvy, inva.x, sa.x, fx, fy);
-                            pair_contact(kpp, dxa.y, dya.y, VX.y - mvx, VY.y - mvy, inva.y, sa.y, fx, fy);
-                            pair_contact(kpp, dxb.x, dyb.x, VX.z - mvx, VY.z - mvy, invb.x, sb.x, fx, fy);
-                            pair_contact(kpp, dxb.y, dyb.y, VX.w - mvx, VY.w - mvy, invb.y, sb.y, fx, fy);
-                        }
+                        if (__any_sync(0xffffffffu, smax > 0.0f)) contact_group(jb, dxa, dya, dxb, dyb, inva, invb, sa, sb);
                     }
                 };
                 const int m_lo = max(j_lo, min(j_hi, i0)), m_hi = min(j_hi, max(j_lo, i0 + 32));

@@ -196,8 +196,9 @@ __device__ __forceinline__ float fast_ex2(float x)
 // 14 FMA-pipe + 2 MUFU instructions:
 //   pair_far     : exponential repulsion  A exp((r_ij - d)/B) n   (always)
 //   pair_contact : k_1 g n + k_2 g dv_t t                          (only when some lane has g > 0)
-// The sqrt is refined to ~0.5 ulp because its error is amplified by d/B (~7.5x) inside the
-// exponential.  `self` zeroes the j == i term exactly (inv = 0 => every product below is 0).
+// d = d2 * rsqrt(d2) (MUFU.RSQ, ~2 ulp).  -DPMS_REFINE_SQRT adds one Newton step; measured to make no
+// difference to parity with the reference because fp32 state rounding dominates.
+// `self` zeroes the j == i term exactly (inv = 0 => every product below is 0).
 __device__ __forceinline__ void pair_far(const PairK<float> &k, float dx, float dy, bool self,
                                          float &inv, float &s, float &fx, float &fy)
 {
@@ -205,8 +206,10 @@ __device__ __forceinline__ void pair_far(const PairK<float> &k, float dx, float 
     inv = fast_rsqrt(d2);
     inv = self ? 0.0f : inv;
     float d = d2 * inv;
+#ifdef PMS_REFINE_SQRT
     const float err = fmaf(-d, d, d2);
     d = fmaf(err, 0.5f * inv, d);
+#endif
     s = k.rij - d;
     const float e = fast_ex2(s * k.cexp);
     const float a = e * (k.A * inv);             // A e / d : multiplies (dx,dy) directly
