@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--j-split", type=int, default=0)
     ap.add_argument("--wpc", type=int, default=0)
     ap.add_argument("--chunks", type=int, default=0)
+    ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time mixed / fp64 / single-step launches")
     return ap.parse_args()
@@ -185,8 +186,8 @@ def main():
     W, N, K = worlds, args.peds, args.sim_steps
 
     sim = BatchedSimulation(W, N, precision=args.precision, device=local_rank)
-    if args.j_split or args.wpc or args.chunks:
-        sim.set_tuning(args.j_split, args.wpc, args.chunks)
+    if args.j_split or args.wpc or args.chunks or args.cluster:
+        sim.set_tuning(args.j_split, args.wpc, args.chunks, args.cluster)
     # pinned host buffers for the end-to-end leg
     h_poses = capi.pinned_array((W, N, 3)); h_poses[:] = sc.poses
     h_vels = capi.pinned_array((W, N, 3)); h_vels[:] = sc.vels

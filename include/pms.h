@@ -159,15 +159,16 @@ int pms_orca_get_agents(pms_sim *h, double *poses /*(W,N,3)*/, double *velocitie
 /* ---- launch introspection (bench / tests) ---- */
 typedef struct {
     int kernel;            /* 0 = small-world fused kernel, 1 = large-crowd kernel */
-    int threads_per_block, blocks, worlds_per_block, j_split;
+    int threads_per_block, blocks, worlds_per_block, j_split; /* large kernel: j_split = cluster size */
     int smem_bytes;
     int n_chunks;          /* > 1: persistent CTAs pull (chunk, world-group) items dynamically */
     int blocks_per_sm;     /* resident CTAs per SM (occupancy API) */
     int64_t kernel_launches; /* cumulative count of kernels launched by this handle */
 } pms_launch_info;
 int pms_get_launch_info(pms_sim *h, pms_launch_info *out);
-/* tuning overrides; 0 = automatic.  n_chunks = 1 forces the static grid. */
-int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks);
+/* tuning overrides; 0 = automatic.  n_chunks = 1 forces the static grid.  cluster_size (1,2,4,8) is the
+ * multicast width of the large-crowd kernel; a negative value also forces that kernel for small N. */
+int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, int cluster_size);
 
 /* measured FP32 FMA-pipe peak (TFLOP/s, FMA = 2 FLOP) of `device`: the roofline denominator of the
  * pairwise kernel (MEASURED_PEAKS.json holds only HBM and tensor-core peaks) */

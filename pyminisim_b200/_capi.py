@@ -87,7 +87,7 @@ PROTOTYPES = {
     "pms_orca_step": (C.c_int, [_h, C.c_int]),
     "pms_orca_get_agents": (C.c_int, [_h, _dp, _dp]),
     "pms_get_launch_info": (C.c_int, [_h, C.POINTER(LaunchInfoC)]),
-    "pms_set_tuning": (C.c_int, [_h, C.c_int, C.c_int, C.c_int]),
+    "pms_set_tuning": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pms_measure_fp32_tflops": (C.c_double, [C.c_int]),
     "pms_host_alloc": (C.c_void_p, [C.c_uint64]),
     "pms_host_free": (None, [C.c_void_p]),

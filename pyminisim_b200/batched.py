@@ -209,8 +209,8 @@ class BatchedSimulation:
         check(self._lib.pms_get_launch_info(self._h, C.byref(info)))
         return {n: getattr(info, n) for n, _ in capi.LaunchInfoC._fields_}
 
-    def set_tuning(self, j_split: int = 0, worlds_per_block: int = 0, n_chunks: int = 0):
-        check(self._lib.pms_set_tuning(self._h, int(j_split), int(worlds_per_block), int(n_chunks)))
+    def set_tuning(self, j_split: int = 0, worlds_per_block: int = 0, n_chunks: int = 0, cluster_size: int = 0):
+        check(self._lib.pms_set_tuning(self._h, int(j_split), int(worlds_per_block), int(n_chunks), int(cluster_size)))
 
     # ---- helpers mirroring the reference's dict outputs ---------------------------------------------
     @staticmethod

@@ -1,10 +1,419 @@
-// hsfm_large.cuh -- large single crowds (N > 992): placeholder until the cluster-tiled kernel lands.
+// hsfm_large.cuh -- HSFM step for crowds that do not fit one CTA (N > 992, up to millions).
+//
+// One launch per simulation step (the step needs every pedestrian's state at time t, so the state is
+// double-buffered in HBM and the launch boundary is the grid-wide barrier):
+//   robot_step_kernel   : one thread per world, fp64 (tiny)
+//   hsfm_large_kernel   : grid = worlds x i-tiles.  A CTA owns TI pedestrians (one per thread) and streams
+//                         the whole world's "pair view" (structure-of-arrays x, y, vx, vy [, xlo, ylo])
+//                         through shared memory in j-tiles of TJ with cp.async.bulk (TMA 1-D bulk copy)
+//                         completing on an mbarrier, double-buffered.  CTAs are launched in clusters; each
+//                         CTA of a cluster fetches 1/C of every j-tile and MULTICASTS it into the shared
+//                         memory of all C CTAs, so a tile is read from L2 once per cluster.  Buffer reuse is
+//                         guarded by a split cluster barrier (arrive after compute, wait before refill).
+// The pair math is the same packed-FP32 (FFMA2) code as the small-world kernel.
 #pragma once
 #include "hsfm_small.cuh"
-struct pms_launch_info_fwd;
+
 namespace pms {
-struct LargeScratch { void *buf = nullptr; };
-inline void large_free(LargeScratch &s) { if (s.buf) cudaFree(s.buf); s.buf = nullptr; }
-template <typename Info>
-inline int launch_large(void *, LargeScratch &, HsfmArgs &, int, cudaStream_t, Info *) { return -4; }
+
+constexpr int LARGE_TI = 128;        // pedestrians (threads) per CTA
+constexpr int LARGE_TJ = 512;        // pedestrians per streamed j-tile
+
+struct LargeArgs {
+    // ping-pong state (element g = w*N + i); src is read, dst is written
+    void *pos_src, *vel_src, *th_src, *pos_dst, *vel_dst, *th_dst;
+    // pair view, structure-of-arrays of PT: arrays x, y, vx, vy (+ float xlo, ylo), each Npad long per world
+    const void *view_src;
+    void *view_dst;
+    size_t view_stride;              // elements between consecutive arrays ( = W * Npad )
+    int Npad;                        // N rounded up to a multiple of LARGE_TJ
+    int tiles_i, tiles_j;
+    int cluster;                     // CTAs per cluster (multicast width)
+    int step;                        // global step index of this launch (events, controls)
+    int last;                        // 1 if this is the last step of the pms_hsfm_step call
+    const RobotSlot *robot_slot;     // (W) robot state for this step
+};
+
+struct LargeScratch {
+    void *pos2 = nullptr, *vel2 = nullptr, *th2 = nullptr;
+    void *view[2] = {nullptr, nullptr};
+    RobotSlot *robot_slot = nullptr;
+    RobotRegs *robot_regs = nullptr;
+    int Npad = 0;
+    int parity = 0;                  // which view buffer holds the current state
+    bool view_valid = false;
+    size_t view_bytes = 0;
+};
+
+inline void large_free(LargeScratch &s)
+{
+    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs};
+    for (void *q : p) if (q) cudaFree(q);
+    s = LargeScratch{};
+}
+
+// ---- PTX helpers: mbarrier, bulk copy (TMA), cluster barrier ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_multicast(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                                    uint16_t cta_mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// ---- robot: one thread per world ---------------------------------------------------------------------
+__global__ void robot_step_kernel(const __grid_constant__ HsfmArgs a, RobotRegs *regs, RobotSlot *slot, int step, int first, int last)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.W || a.robot_model == ROBOT_NONE) return;
+    RobotRegs r;
+    if (first) robot_load(a, w, r); else r = regs[w];
+    robot_step(a, w, step, r);
+    regs[w] = r;
+    slot[w] = RobotSlot{r.x, r.y, r.th, r.vx, r.vy};
+    if (last) robot_store(a, w, r);
+}
+
+// ---- pair view initialisation from the state (first step of a call) --------------------------------------
+template <typename PT, typename ST, bool SPLIT>
+__global__ void large_view_kernel(const __grid_constant__ HsfmArgs a, PT *view, size_t stride, int Npad)
+{
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)a.W * Npad) return;
+    const int w = (int)(idx / Npad), i = (int)(idx - (size_t)w * Npad);
+    PT x, y, vx = 0, vy = 0;
+    float xl = 0.f, yl = 0.f;
+    if (i < a.N) {
+        ST sx, sy, svx, svy;
+        load_pv(a, (size_t)w * a.N + i, sx, sy, svx, svy);
+        if constexpr (SPLIT) {
+            x = (float)sx; y = (float)sy; xl = (float)(sx - (double)x); yl = (float)(sy - (double)y);
+        } else { x = (PT)sx; y = (PT)sy; }
+        vx = (PT)svx; vy = (PT)svy;
+    } else {   // padding: far away, contributes exactly 0
+        x = (PT)1e18; y = (PT)(1e18 + 1e15 * ((i - a.N) % 1024 + 1));
+    }
+    view[idx] = x; view[stride + idx] = y; view[2 * stride + idx] = vx; view[3 * stride + idx] = vy;
+    if constexpr (SPLIT) {
+        float *lo = reinterpret_cast<float *>(view + 4 * stride);
+        lo[idx] = xl; lo[stride + idx] = yl;
+    }
+}
+
+// ---- the step kernel --------------------------------------------------------------------------------
+template <typename PT, typename ST, bool SPLIT>
+__global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
+{
+    using ST2 = typename Vec2<ST>::type;
+    constexpr int NARR = SPLIT ? 6 : 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [2 stages][NARR arrays][TJ] of PT (lo arrays are float == PT in MIXED), then 2 mbarriers
+    PT *tiles = reinterpret_cast<PT *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 2 * NARR * LARGE_TJ * sizeof(PT));
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = blockIdx.x / la.tiles_i, it = blockIdx.x - w * la.tiles_i;
+    const int i = it * LARGE_TI + tid;
+    const int N = a.N;
+    const bool valid = i < N;
+    const size_t g = (size_t)w * N + (valid ? i : 0);
+    const uint32_t crank = la.cluster > 1 ? cluster_ctarank() : 0;
+    const PT *vsrc = reinterpret_cast<const PT *>(la.view_src) + (size_t)w * la.Npad;
+    const size_t vs = la.view_stride;
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_arrive();
+    cluster_wait();          // every CTA of the cluster has initialised its barriers
+
+    constexpr uint32_t kTileBytes = NARR * LARGE_TJ * sizeof(PT);
+    auto issue = [&](int jt) {   // thread 0 only
+        const int b = jt & 1;
+        PT *dst = tiles + (size_t)b * NARR * LARGE_TJ;
+        mbar_expect_tx(&full[b], kTileBytes);
+        const int C = la.cluster;
+        const int part = LARGE_TJ / C;                      // elements fetched by this CTA per array
+        const uint16_t mask = (uint16_t)((1u << C) - 1u);
+#pragma unroll
+        for (int arr = 0; arr < NARR; ++arr) {
+            const PT *src = vsrc + (size_t)arr * vs + (size_t)jt * LARGE_TJ + (size_t)crank * part;
+            PT *d = dst + arr * LARGE_TJ + crank * part;
+            if (C > 1) bulk_copy_multicast(d, src, part * sizeof(PT), &full[b], mask);
+            else bulk_copy(d, src, part * sizeof(PT), &full[b]);
+        }
+    };
+
+    // my own pedestrian (pair view of the source state)
+    const int iv = valid ? i : 0;
+    const PT mx = vsrc[iv], my = vsrc[vs + iv], mvx = vsrc[2 * vs + iv], mvy = vsrc[3 * vs + iv];
+    float mlx = 0.f, mly = 0.f;
+    if constexpr (SPLIT) { mlx = (float)vsrc[4 * vs + iv]; mly = (float)vsrc[5 * vs + iv]; }
+    const PairK<PT> &kpp = kpp_of(a, PT{});
+    const PairK<PT> &kpr = kpr_of(a, PT{});
+
+    PT fx = 0, fy = 0;
+    float2 fxa = make_float2(0.f, 0.f), fya = fxa, fxb = fxa, fyb = fxa;
+    const int i0 = i & ~31;
+    const int T = la.tiles_j;
+    if (tid == 0) issue(0);
+    for (int jt = 0; jt < T; ++jt) {
+        if (jt >= 1) cluster_wait();                 // everybody is done with the buffer tile jt+1 will overwrite
+        if (jt + 1 < T && tid == 0) issue(jt + 1);
+        mbar_wait(&full[jt & 1], (jt >> 1) & 1);
+        const PT *xs = tiles + (size_t)(jt & 1) * NARR * LARGE_TJ;
+        const PT *ys = xs + LARGE_TJ, *vxs = xs + 2 * LARGE_TJ, *vys = xs + 3 * LARGE_TJ;
+        const int jbase = jt * LARGE_TJ;
+        if constexpr (sizeof(PT) == 4) {
+            const float *xlo = reinterpret_cast<const float *>(xs + 4 * LARGE_TJ), *ylo = xlo + LARGE_TJ;
+            const float2 m2x = make_float2(mx, mx), m2y = make_float2(my, my);
+            const float2 l2x = make_float2(mlx, mlx), l2y = make_float2(mly, mly);
+            auto group = [&](int jl, auto masked) {
+                const float4 X = *reinterpret_cast<const float4 *>(xs + jl);
+                const float4 Y = *reinterpret_cast<const float4 *>(ys + jl);
+                float2 dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
+                float2 dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
+                if constexpr (SPLIT) {
+                    const float4 XL = *reinterpret_cast<const float4 *>(xlo + jl);
+                    const float4 YL = *reinterpret_cast<const float4 *>(ylo + jl);
+                    dxa = __fadd2_rn(dxa, __fadd2_rn(l2x, make_float2(-XL.x, -XL.y)));
+                    dxb = __fadd2_rn(dxb, __fadd2_rn(l2x, make_float2(-XL.z, -XL.w)));
+                    dya = __fadd2_rn(dya, __fadd2_rn(l2y, make_float2(-YL.x, -YL.y)));
+                    dyb = __fadd2_rn(dyb, __fadd2_rn(l2y, make_float2(-YL.z, -YL.w)));
+                }
+                if constexpr (decltype(masked)::value) {
+                    const int k = i - (jbase + jl);
+                    dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
+                    dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
+                }
+                float2 inva, invb, sa, sb;
+                pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
+                pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
+                const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
+                if (__any_sync(0xffffffffu, smax > 0.0f)) {
+                    const float4 VX = *reinterpret_cast<const float4 *>(vxs + jl);
+                    const float4 VY = *reinterpret_cast<const float4 *>(vys + jl);
+                    pair_contact(kpp, dxa.x, dya.x, VX.x - mvx, VY.x - mvy, inva.x, sa.x, fx, fy);
+                    pair_contact(kpp, dxa.y, dya.y, VX.y - mvx, VY.y - mvy, inva.y, sa.y, fx, fy);
+                    pair_contact(kpp, dxb.x, dyb.x, VX.z - mvx, VY.z - mvy, invb.x, sb.x, fx, fy);
+                    pair_contact(kpp, dxb.y, dyb.y, VX.w - mvx, VY.w - mvy, invb.y, sb.y, fx, fy);
+                }
+            };
+            // groups that may contain j == i: [i0, i0+32) if it falls inside this tile
+            const int m_lo = min(LARGE_TJ, max(0, i0 - jbase)), m_hi = min(LARGE_TJ, max(0, i0 + 32 - jbase));
+            for (int jl = 0; jl < m_lo; jl += 4) group(jl, std::false_type{});
+            for (int jl = m_lo; jl < m_hi; jl += 4) group(jl, std::true_type{});
+            for (int jl = m_hi; jl < LARGE_TJ; jl += 4) group(jl, std::false_type{});
+        } else {
+            const int jn = min(LARGE_TJ, N - jbase);
+            for (int jl = 0; jl < jn; ++jl)
+                pair_accum(kpp, mx - xs[jl], my - ys[jl], vxs[jl] - mvx, vys[jl] - mvy, jbase + jl == i, fx, fy);
+        }
+        cluster_arrive();                            // done reading buffer jt & 1
+    }
+    cluster_wait();
+    if constexpr (sizeof(PT) == 4) {
+        fx += (fxa.x + fxa.y) + (fxb.x + fxb.y);
+        fy += (fya.x + fya.y) + (fyb.x + fyb.y);
+    }
+
+    // ---- robot term, O(1) dynamics, tracker, sensors: identical to the small-world owner phase ----
+    const bool has_robot = a.robot_model != ROBOT_NONE;
+    RobotSlot rb{0, 0, 0, 0, 0};
+    if (has_robot) rb = la.robot_slot[w];
+    SenseOut so{false, false, 0.0, 0.0};
+    PT *vdst = reinterpret_cast<PT *>(la.view_dst) + (size_t)w * la.Npad;
+    if (valid) {
+        if (has_robot && a.robot_visible) {
+            PT dx, dy;
+            if constexpr (SPLIT) {
+                const float rxh = (float)rb.x, ryh = (float)rb.y;
+                dx = (mx - rxh) + (mlx - (float)(rb.x - (double)rxh));
+                dy = (my - ryh) + (mly - (float)(rb.y - (double)ryh));
+            } else { dx = mx - (PT)rb.x; dy = my - (PT)rb.y; }
+            pair_accum(kpr, dx, dy, (PT)rb.vx - mvx, (PT)rb.vy - mvy, false, fx, fy);
+        }
+        const PedConsts<ST> &kc = kc_of(a, ST{});
+        ST x, y, vx, vy;
+        if constexpr (sizeof(ST) == 4) {
+            const float4 p = __ldcg(reinterpret_cast<const float4 *>(la.pos_src) + g);
+            x = p.x; y = p.y; vx = p.z; vy = p.w;
+        } else {
+            const double2 p = __ldcg(reinterpret_cast<const double2 *>(la.pos_src) + g);
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(la.vel_src) + g);
+            x = p.x; y = p.y; vx = v.x; vy = v.y;
+        }
+        const ST2 tw = __ldcg(reinterpret_cast<const ST2 *>(la.th_src) + g);
+        ST th = tw.x, om = tw.y, c, sn;
+        m_sincos(th, &sn, &c);
+        ST2 wp = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
+        const ST vm = reinterpret_cast<const ST *>(a.vmag)[g];
+        const ST x0 = x, y0 = y, th0 = th;
+        ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn);
+        const ST ex = wp.x - x, ey = wp.y - y;
+        bool reached;
+        if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
+        else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
+        if (reached) {
+            if (a.tracker_kind == TRACKER_FIXED) {
+                int ni = a.wp_index[g] + 1;
+                bool steady = false;
+                if (ni >= a.n_table) { if (a.loop) ni = 0; else { ni = a.n_table - 1; steady = true; } }
+                a.wp_index[g] = ni;
+                wp = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
+                if (steady) { x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0; }
+            } else {
+                const int cnt = a.q_count[g];
+                const int slot = atomicAdd(a.ev_count, 1);
+                if (cnt > 0) {
+                    const int head = a.q_head[g];
+                    wp = reinterpret_cast<const ST2 *>(a.queue)[g * a.q_cap + head];
+                    a.q_head[g] = (head + 1) % a.q_cap;
+                    a.q_count[g] = cnt - 1;
+                    if (slot < a.ev_cap) { a.events[3 * slot] = la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i; }
+                } else if (slot < a.ev_cap) {
+                    a.events[3 * slot] = -1 - la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i;
+                }
+            }
+            reinterpret_cast<ST2 *>(a.wp)[g] = wp;
+        }
+        // new state -> destination buffers + destination pair view
+        if constexpr (sizeof(ST) == 4) {
+            reinterpret_cast<float4 *>(la.pos_dst)[g] = make_float4(x, y, vx, vy);
+        } else {
+            reinterpret_cast<double2 *>(la.pos_dst)[g] = make_double2(x, y);
+            reinterpret_cast<double2 *>(la.vel_dst)[g] = make_double2(vx, vy);
+        }
+        ST2 t2; t2.x = th; t2.y = om;
+        reinterpret_cast<ST2 *>(la.th_dst)[g] = t2;
+        if constexpr (SPLIT) {
+            const float xh = (float)x, yh = (float)y;
+            vdst[i] = xh; vdst[vs + i] = yh; vdst[2 * vs + i] = (float)vx; vdst[3 * vs + i] = (float)vy;
+            vdst[4 * vs + i] = (float)(x - (double)xh); vdst[5 * vs + i] = (float)(y - (double)yh);
+        } else {
+            vdst[i] = (PT)x; vdst[vs + i] = (PT)y; vdst[2 * vs + i] = (PT)vx; vdst[3 * vs + i] = (PT)vy;
+        }
+        if (!m_finite(x + y + vx + vy + th + om)) atomicMin(&a.nonfinite[w], (int)(a.steps_done + la.step + 1));
+        if (has_robot) so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+        if (la.last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
+    }
+    if (has_robot) {
+        const unsigned dm = __ballot_sync(0xffffffffu, so.det);
+        const unsigned cm = __ballot_sync(0xffffffffu, so.coll);
+        if (lane == 0) {
+            if (dm) atomicAdd(&a.det_count[w], (unsigned long long)__popc(dm));
+            if (cm) atomicAdd(&a.coll_count[w], (unsigned long long)__popc(cm));
+            const int words = (N + 31) >> 5;
+            if (la.last && (i >> 5) < words) {
+                a.det_mask[(size_t)w * words + (i >> 5)] = dm;
+                a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
+            }
+        }
+    }
+}
+
+// ---- host-side launch of n_steps large-crowd steps ---------------------------------------------------
+template <typename PT, typename ST, bool SPLIT>
+inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, cudaStream_t stream, long long *launches, int *out_blocks,
+                          int *out_smem)
+{
+    constexpr int NARR = SPLIT ? 6 : 4;
+    const int Npad = (a.N + LARGE_TJ - 1) / LARGE_TJ * LARGE_TJ;
+    const size_t n = (size_t)a.W * a.N, nv = (size_t)a.W * Npad;
+    const size_t e2 = sizeof(ST) * 2;
+    cudaError_t e;
+    if (!s.pos2 || s.Npad != Npad) {
+        void *keep[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs};
+        for (void *q : keep) if (q) cudaFree(q);
+        s = LargeScratch{};
+        if ((e = cudaMalloc(&s.pos2, n * 16)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc(&s.vel2, n * 16)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc(&s.th2, n * e2)) != cudaSuccess) return -2;
+        s.view_bytes = nv * NARR * sizeof(PT);
+        if ((e = cudaMalloc(&s.view[0], s.view_bytes)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc(&s.view[1], s.view_bytes)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc((void **)&s.robot_slot, sizeof(RobotSlot) * a.W)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc((void **)&s.robot_regs, sizeof(RobotRegs) * a.W)) != cudaSuccess) return -2;
+        s.Npad = Npad;
+    }
+    // the pair view is rebuilt from the state at the start of every call (the host may have changed it)
+    large_view_kernel<PT, ST, SPLIT><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(a, reinterpret_cast<PT *>(s.view[0]), nv, Npad);
+    large_view_kernel<PT, ST, SPLIT><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(a, reinterpret_cast<PT *>(s.view[1]), nv, Npad);
+    *launches += 2;
+
+    const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ;
+    // grid must be a multiple of the cluster size and a cluster must stay inside one world
+    while (cluster > 1 && (tiles_i % cluster != 0 || LARGE_TJ % cluster != 0)) cluster >>= 1;
+    const size_t smem = 2 * NARR * LARGE_TJ * sizeof(PT) + 2 * sizeof(uint64_t);
+    auto kern = hsfm_large_kernel<PT, ST, SPLIT>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+
+    void *pos[2] = {a.pos, s.pos2}, *vel[2] = {a.vel, s.vel2}, *th[2] = {a.th, s.th2};
+    for (int t = 0; t < a.n_steps; ++t) {
+        const int src = t & 1, dst = src ^ 1;
+        if (a.robot_model != ROBOT_NONE) {
+            robot_step_kernel<<<(a.W + 127) / 128, 128, 0, stream>>>(a, s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
+            ++*launches;
+        }
+        LargeArgs la{};
+        la.pos_src = pos[src]; la.vel_src = vel[src]; la.th_src = th[src];
+        la.pos_dst = pos[dst]; la.vel_dst = vel[dst]; la.th_dst = th[dst];
+        la.view_src = s.view[src]; la.view_dst = s.view[dst];
+        la.view_stride = nv; la.Npad = Npad; la.tiles_i = tiles_i; la.tiles_j = tiles_j; la.cluster = cluster;
+        la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = s.robot_slot;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(a.W * tiles_i)); cfg.blockDim = dim3(LARGE_TI); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if ((e = cudaLaunchKernelEx(&cfg, kern, a, la)) != cudaSuccess) return -2;
+        ++*launches;
+    }
+    // an odd number of steps leaves the newest state in the scratch buffers: copy it home
+    if (a.n_steps & 1) {
+        cudaMemcpyAsync(a.pos, s.pos2, n * 16, cudaMemcpyDeviceToDevice, stream);
+        if (sizeof(ST) == 8) cudaMemcpyAsync(a.vel, s.vel2, n * 16, cudaMemcpyDeviceToDevice, stream);
+        cudaMemcpyAsync(a.th, s.th2, n * e2, cudaMemcpyDeviceToDevice, stream);
+    }
+    *out_blocks = a.W * tiles_i;
+    *out_smem = (int)smem;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 } // namespace pms

@@ -133,7 +133,8 @@ struct pms_sim {
     long long snap_steps = 0;
     bool has_snapshot = false;
     // tuning / introspection
-    int tune_S = 0, tune_wpc = 0, tune_chunks = 0;
+    int tune_S = 0, tune_wpc = 0, tune_chunks = 0, tune_cluster = 0;
+    bool force_large = false;
     int sm_count = 148;
     int sched_cap = 0;
     pms_launch_info info{};
@@ -252,6 +253,31 @@ int launch_small(pms_sim *h)
     case 4: return launch_small_s<4>(h, wpc, big);
     default: return launch_small_s<8>(h, wpc, big);
     }
+}
+
+// large crowds: one launch per step, cluster-multicast j-tiles (hsfm_large.cuh)
+int launch_large(pms_sim *h)
+{
+    int cluster = h->tune_cluster > 0 ? h->tune_cluster : 4;
+    if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return fail(PMS_ERR_INVALID, "cluster size must be 1, 2, 4 or 8");
+    int blocks = 0, smem = 0, rc;
+    long long launches = 0;
+    switch (h->precision) {
+    case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, h->stream, &launches, &blocks, &smem); break;
+    case PMS_MIXED: rc = launch_large_t<float, double, true>(h->large, h->a, cluster, h->stream, &launches, &blocks, &smem); break;
+    default: rc = launch_large_t<double, double, false>(h->large, h->a, cluster, h->stream, &launches, &blocks, &smem); break;
+    }
+    if (rc) return fail(PMS_ERR_CUDA, std::string("large-crowd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->info.kernel = 1;
+    h->info.threads_per_block = LARGE_TI;
+    h->info.blocks = blocks;
+    h->info.worlds_per_block = 0;
+    h->info.j_split = cluster;
+    h->info.smem_bytes = smem;
+    h->info.n_chunks = 1;
+    h->info.blocks_per_sm = 0;
+    h->info.kernel_launches += launches;
+    return 0;
 }
 
 int clear_sensor_outputs(pms_sim *h)
@@ -656,8 +682,8 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     fill_consts(h->a);
     int rc;
     if (h->a.robot_model == ROBOT_NONE && (rc = clear_sensor_outputs(h))) return rc;
-    if (h->Np + 32 <= 1024) rc = launch_small(h);
-    else rc = launch_large(h, h->large, h->a, h->precision, h->stream, &h->info);
+    if (h->Np + 32 <= 1024 && !h->force_large) rc = launch_small(h);
+    else rc = launch_large(h);
     if (rc) return rc;
     h->a.steps_done += n_steps;
     return PMS_OK;
@@ -836,10 +862,12 @@ int pms_get_launch_info(pms_sim *h, pms_launch_info *out)
     return PMS_OK;
 }
 
-int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks)
+int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, int cluster_size)
 {
     if (!h) return fail(PMS_ERR_INVALID, "handle is NULL");
     h->tune_S = j_split; h->tune_wpc = worlds_per_block; h->tune_chunks = n_chunks;
+    h->force_large = cluster_size < 0;               // negative: force the large-crowd kernel (tests)
+    h->tune_cluster = cluster_size < 0 ? -cluster_size : cluster_size;
     return PMS_OK;
 }
 

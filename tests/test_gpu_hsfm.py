@@ -322,3 +322,44 @@ def test_error_paths():
         sim.set_detector(3.0, 1.0, 7)
     with pytest.raises(PmsError):
         sim.lidar_scan(0)
+
+
+# ---------------- large-crowd kernel (cluster-multicast j-tiles) ----------------
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("precision", ["fp64", "mixed", "fp32"])
+def test_large_kernel_forced_on_small_worlds(precision, cluster):
+    """Same worlds through the small fused kernel and the large streaming kernel (forced)."""
+    sc = make_bench_crowd(3, 64)
+    o = make_oracle(sc)
+    o.rollout(0.01, 60, n_threads=4)
+    c = make_cuda(sc, precision)
+    c.set_tuning(0, 0, 0, -cluster)
+    c.step(0.01, 25)
+    c.step(0.01, 35)          # odd and even step counts: ping-pong buffers come home
+    assert c.launch_info()["kernel"] == 1
+    p, v = c.get_state()
+    tol = {"fp64": 1e-11, "mixed": 1e-7, "fp32": 1e-5}[precision]
+    assert rel_err(p, o.poses) < tol
+    assert rel_err(v, o.vels) < tol * 20
+    rp, _, _ = c.get_robot()
+    assert np.allclose(rp, o.robot_pose, atol=1e-11)
+    if precision == "fp64":
+        det, col, nf = c.get_stats()
+        assert (det == o.det_count).all() and (col == o.coll_count).all() and (nf == 0).all()
+        assert (c.get_detector()[0] == o.det_mask).all()
+        assert (c.get_waypoints()[1] == o.wp_index).all()
+
+
+@pytest.mark.parametrize("n,steps", [(1500, 12), (4096, 4)])
+def test_large_crowd_vs_oracle(n, steps):
+    sc = make_crowd(1, n, side=2.0 * np.sqrt(n), local_goals=5.0)
+    o = make_oracle(sc)
+    o.rollout(0.01, steps, n_threads=8)
+    for precision, tol in (("fp64", 1e-11), ("mixed", 1e-9), ("fp32", 2e-6)):
+        c = make_cuda(sc, precision)
+        c.step(0.01, steps)
+        assert c.launch_info()["kernel"] == 1
+        p, v = c.get_state()
+        assert rel_err(p, o.poses) < tol, (precision, rel_err(p, o.poses))
+        assert np.abs(v - o.vels).max() < tol * 1e4
