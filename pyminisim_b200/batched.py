@@ -216,3 +216,70 @@ class BatchedSimulation:
     @staticmethod
     def mask_to_ids(mask_row: np.ndarray, n: int) -> List[int]:
         return [i for i in range(n) if (int(mask_row[i >> 5]) >> (i & 31)) & 1]
+
+
+@dataclass
+class ORCAParams:
+    """Same fields and defaults as pyminisim.pedestrians.ORCAParams (_orca.py:13-21)."""
+    neighbor_dist: float = 1.
+    max_neighbors: int = 10
+    time_horizon: float = 2.
+    time_horizon_obst: float = 2.
+    radius = 0.3
+    default_max_speed: float = 1.7
+    goal_reaching_threshold: float = 0.2
+
+
+class BatchedOrca:
+    """W worlds x N ORCA agents (the rvo2 doStep + adapter of _orca.py:95-127) on one GPU."""
+
+    def __init__(self, dt: float, n_worlds: int, n_agents: int, params: Optional[ORCAParams] = None, device: int = 0):
+        self._lib = capi.load()
+        self.W, self.N = int(n_worlds), int(n_agents)
+        p = params or ORCAParams()
+        self.params = p
+        cp = capi.OrcaParamsC(float(dt), float(p.neighbor_dist), int(p.max_neighbors), float(p.time_horizon),
+                              float(p.radius), float(p.goal_reaching_threshold))
+        self._h = C.c_void_p()
+        check(self._lib.pms_orca_create(int(device), self.W, self.N, C.byref(cp), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.pms_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_agents(self, positions, velocities=None, max_speeds=None, pref_speeds=None):
+        pos = f64(np.asarray(positions, dtype=np.float64)[..., :2], (self.W, self.N, 2))
+        vel = None if velocities is None else f64(np.asarray(velocities, dtype=np.float64)[..., :2], (self.W, self.N, 2))
+        ms = f64(self.params.default_max_speed if max_speeds is None else max_speeds, (self.W, self.N))
+        ps = None if pref_speeds is None else f64(pref_speeds, (self.W, self.N))
+        check(self._lib.pms_orca_set_agents(self._h, dptr(pos), dptr(vel), dptr(ms), dptr(ps)))
+
+    def set_waypoints_fixed(self, table, start_index=None, reach_distance: float = 0.3, loop: bool = False):
+        table = np.asarray(table, dtype=np.float64)
+        n_rows = table.shape[-2]
+        table = f64(table, (self.W, self.N, n_rows, 2))
+        si = None
+        if start_index is not None:
+            si = np.ascontiguousarray(np.broadcast_to(np.asarray(start_index, dtype=np.int32), (self.W, self.N)))
+        check(self._lib.pms_orca_set_waypoints_fixed(self._h, dptr(table), n_rows, iptr(si), float(reach_distance), int(bool(loop))))
+
+    def step(self, n_steps: int = 1):
+        check(self._lib.pms_orca_step(self._h, int(n_steps)))
+
+    def get_agents(self) -> Tuple[np.ndarray, np.ndarray]:
+        poses = np.empty((self.W, self.N, 3))
+        vels = np.empty((self.W, self.N, 3))
+        check(self._lib.pms_orca_get_agents(self._h, dptr(poses), dptr(vels)))
+        return poses, vels
+
+    def launch_info(self) -> dict:
+        info = capi.LaunchInfoC()
+        check(self._lib.pms_get_launch_info(self._h, C.byref(info)))
+        return {n: getattr(info, n) for n, _ in capi.LaunchInfoC._fields_}

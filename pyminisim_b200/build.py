@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpms_b200.so")
-SOURCES = ["pms_api.cu"]
+SOURCES = ["pms_api.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
 HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
 
 
@@ -30,14 +30,19 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
     if not force and out == LIB and not is_stale():
         return LIB
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", out] + [f"-D{d}" for d in defines] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+    nvcc = nvcc_path()
+    common = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"] + \
+             [f"-D{d}" for d in defines]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    env = dict(os.environ)
-    # the image exports CC=/opt/gcc/bin/gcc; let nvcc pick the system host compiler it was validated with
-    subprocess.run(cmd, check=True, env=env)
+        common.insert(0, "-Xptxas=-v")
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + (".o" if out == LIB else ".exp.o"))
+        extra = ["-fmad=false"] if src == "orca.cu" else []
+        subprocess.run([nvcc] + common + extra + ["-c", os.path.join(CSRC, src), "-o", obj], check=True)
+        objs.append(obj)
+    subprocess.run([nvcc, "-shared", "-o", out] + objs, check=True)
+    return out
     return LIB
 
 

@@ -937,12 +937,14 @@ int pms_orca_create(int device, int n_worlds, int n_agents, const pms_orca_param
     if (params) p = *params; else pms_default_orca_params(&p);
     if (p.max_neighbors < 0 || p.max_neighbors > ORCA_MAX_NEIGHBORS)
         return fail(PMS_ERR_UNSUPPORTED, "max_neighbors must be in [0, 16]");
+    if (n_agents > 256) return fail(PMS_ERR_UNSUPPORTED, "ORCA worlds are limited to 256 agents");
     pms_sim *h = new pms_sim();
     h->kind = 1; h->device = device; h->W = n_worlds; h->N = n_agents;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(PMS_ERR_CUDA, "stream"); }
     int rc = orca_alloc(h->orca, n_worlds, n_agents, p.time_step, p.neighbor_dist, p.max_neighbors, p.time_horizon,
                         p.radius, p.goal_reaching_threshold);
     if (rc) { pms_destroy(h); return fail(PMS_ERR_CUDA, "ORCA allocation failed"); }
+    h->info = pms_launch_info{};
     *out = h;
     return PMS_OK;
 }
@@ -950,24 +952,59 @@ int pms_orca_create(int device, int n_worlds, int n_agents, const pms_orca_param
 } // extern "C"
 
 extern "C" {
-int pms_orca_set_agents(pms_sim *h, const double *, const double *, const double *, const double *)
+#define OCHECK(h)                                                                  \
+    if (!(h)) return fail(PMS_ERR_INVALID, "handle is NULL");                      \
+    if ((h)->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");          \
+    Guard gd__((h)->device)
+
+int pms_orca_set_agents(pms_sim *h, const double *positions, const double *velocities, const double *max_speeds,
+                        const double *pref_speeds)
 {
-    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
-    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+    OCHECK(h);
+    if (!positions || !max_speeds) return fail(PMS_ERR_INVALID, "positions / max_speeds is NULL");
+    const size_t n = (size_t)h->W * h->N;
+    for (size_t k = 0; k < n; ++k) {   // _orca.py:56-62
+        if (velocities) {
+            const double sp = std::sqrt(velocities[2 * k] * velocities[2 * k] + velocities[2 * k + 1] * velocities[2 * k + 1]);
+            if (!(sp <= max_speeds[k])) return fail(PMS_ERR_INVALID, "Initial speeds must be <= all corresponding max_speeds");
+        }
+        if (pref_speeds && !(pref_speeds[k] <= max_speeds[k]))
+            return fail(PMS_ERR_INVALID, "All preferred_speeds must be <= corresponding max_speeds");
+    }
+    if (orca_set_agents(h->orca, positions, velocities, max_speeds, pref_speeds, h->stream)) return fail(PMS_ERR_CUDA, "orca_set_agents failed");
+    return PMS_OK;
 }
-int pms_orca_set_waypoints_fixed(pms_sim *h, const double *, int, const int32_t *, double, int)
+
+int pms_orca_set_waypoints_fixed(pms_sim *h, const double *table, int n_rows, const int32_t *start_index, double reach, int loop)
 {
-    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
-    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+    OCHECK(h);
+    if (!table || n_rows < 1) return fail(PMS_ERR_INVALID, "table is NULL or n_rows < 1");
+    if (start_index)
+        for (size_t k = 0; k < (size_t)h->W * h->N; ++k)
+            if (start_index[k] < 0 || start_index[k] >= n_rows) return fail(PMS_ERR_INVALID, "start_index out of range");
+    if (orca_set_waypoints(h->orca, table, n_rows, start_index, reach, loop, h->stream)) return fail(PMS_ERR_CUDA, "orca_set_waypoints failed");
+    return PMS_OK;
 }
-int pms_orca_step(pms_sim *h, int)
+
+int pms_orca_step(pms_sim *h, int n_steps)
 {
-    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
-    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+    OCHECK(h);
+    if (n_steps < 0) return fail(PMS_ERR_INVALID, "n_steps < 0");
+    if (!h->orca.agents_set) return fail(PMS_ERR_STATE, "agents are not set");
+    if (!h->orca.waypoints_set) return fail(PMS_ERR_STATE, "Waypoint tracker is not initialized");
+    if (n_steps == 0) return PMS_OK;
+    long long launches = 0;
+    if (orca_step(h->orca, n_steps, h->stream, &launches)) return fail(PMS_ERR_CUDA, std::string("orca launch: ") + cudaGetErrorString(cudaGetLastError()));
+    h->info.kernel = 2;
+    h->info.kernel_launches += launches;
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
 }
-int pms_orca_get_agents(pms_sim *h, double *, double *)
+
+int pms_orca_get_agents(pms_sim *h, double *poses, double *velocities)
 {
-    if (!h || h->kind != 1) return fail(PMS_ERR_STATE, "not an ORCA handle");
-    return fail(PMS_ERR_UNSUPPORTED, "ORCA kernel not built yet");
+    OCHECK(h);
+    if (orca_get_agents(h->orca, poses, velocities, nullptr, h->stream)) return fail(PMS_ERR_CUDA, "orca_get_agents failed");
+    return PMS_OK;
 }
 }
