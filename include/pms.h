@@ -113,6 +113,11 @@ int pms_get_robot(pms_sim *h, double *pose /*(W,3)*/, double *velocity /*(W,3)*/
 int pms_set_map(pms_sim *h, int kind, const double *data /*circles (C,3) | aabb (C,4); per-world: (W,C,.)*/,
                 int count, int per_world);
 
+/* HSFM acceleration noise (noise_std, _hsfm.py:288-289): `noise` (W,N,2) is added to the body-frame
+ * acceleration dv_b in every step of the following pms_hsfm_step calls; the caller draws it (the
+ * reference uses the global numpy RNG).  NULL switches it off. */
+int pms_set_accel_noise(pms_sim *h, const double *noise /*(W,N,2) or NULL*/);
+
 /* ---- sensors ---- */
 /* PedestrianDetector (sensors/_pedestrian_detector.py:78-134); fov in radians. */
 int pms_detector_config(pms_sim *h, int enabled, double max_dist, double fov, int return_type);

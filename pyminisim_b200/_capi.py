@@ -69,6 +69,7 @@ PROTOTYPES = {
     "pms_set_robot_controls": (C.c_int, [_h, _dp, C.c_int]),
     "pms_get_robot": (C.c_int, [_h, _dp, _dp, _ip]),
     "pms_set_map": (C.c_int, [_h, C.c_int, _dp, C.c_int, C.c_int]),
+    "pms_set_accel_noise": (C.c_int, [_h, _dp]),
     "pms_detector_config": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, C.c_int]),
     "pms_hsfm_step": (C.c_int, [_h, C.c_double, C.c_int]),
     "pms_hsfm_step_async": (C.c_int, [_h, C.c_double, C.c_int]),

@@ -151,6 +151,9 @@ class BatchedSimulation:
         per_world = data.ndim == 3
         check(self._lib.pms_set_map(self._h, int(kind), dptr(data), data.shape[-2], int(per_world)))
 
+    def set_accel_noise(self, noise):
+        check(self._lib.pms_set_accel_noise(self._h, None if noise is None else dptr(f64(noise, (self.W, self.N, 2)))))
+
     def set_detector(self, max_dist: float = 3.0, fov: float = np.deg2rad(30.0), return_type: int = capi.DET_POLAR,
                      enabled: bool = True):
         check(self._lib.pms_detector_config(self._h, int(bool(enabled)), float(max_dist), float(fov), int(return_type)))

@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         ST2 wp = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
         const ST vm = reinterpret_cast<const ST *>(a.vmag)[g];
         const ST x0 = x, y0 = y, th0 = th;
-        ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn);
+        ST nzx = 0, nzy = 0;
+        if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
+        ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
         const ST ex = wp.x - x, ey = wp.y - y;
         bool reached;
         if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;

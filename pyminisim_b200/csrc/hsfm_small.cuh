@@ -130,7 +130,8 @@ __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, RobotRe
 // previous step (R(theta') of step t is R(theta) of step t+1).
 template <typename ST>
 __device__ __forceinline__ void ped_integrate(const PedConsts<ST> &k, ST fx, ST fy, ST wx, ST wy, ST vm,
-                                              ST &x, ST &y, ST &vx, ST &vy, ST &th, ST &om, ST &c, ST &s)
+                                              ST &x, ST &y, ST &vx, ST &vy, ST &th, ST &om, ST &c, ST &s,
+                                              ST noise_x = ST(0), ST noise_y = ST(0))
 {
     const ST ddx = wx - x, ddy = wy - y;
     ST vdx, vdy, f0x, f0y, klf, komega, dom, dvbx, dvby, werr;
@@ -172,6 +173,7 @@ __device__ __forceinline__ void ped_integrate(const PedConsts<ST> &k, ST fx, ST 
         dom = -klf * werr - komega * om;
         dvbx = k.inv_m * uf; dvby = k.inv_m * uo;
     }
+    dvbx += noise_x; dvby += noise_y;
     x = x + vx * k.dt;
     y = y + vy * k.dt;
     th = th + om * k.dt;
@@ -475,7 +477,9 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
                 ST x = o_x[i], y = o_y[i], vx = o_vx[i], vy = o_vy[i], th = o_th[i], om = o_om[i];
                 ST wx = o_wx[i], wy = o_wy[i], c = o_c[i], sn = o_s[i];
                 const ST x0 = x, y0 = y, th0 = th;
-                ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn);
+                ST nzx = 0, nzy = 0;
+                if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
+                ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, nzx, nzy);
                 // ---- waypoint tracker on the NEW pose (_hsfm.py:301) ----
                 const ST ex = wx - x, ey = wy - y;
                 bool reached;

@@ -127,6 +127,7 @@ struct pms_sim {
     double *map_dev = nullptr;
     size_t map_cap = 0;
     int *overflow_dev = nullptr;
+    double *noise_dev = nullptr;
     // snapshot
     std::vector<std::pair<void *, size_t>> snap_src;
     std::vector<void *> snap_dst;
@@ -402,7 +403,7 @@ int pms_destroy(pms_sim *h)
     void *ptrs[] = {a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
                     a.events, a.ev_count, a.robot_pose, a.robot_vel, a.robot_ctrl, a.robot_rear,
                     a.robot_world_collision, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
-                    a.nonfinite, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done};
+                    a.nonfinite, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done, h->noise_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->snap_dst) if (p) cudaFree(p);
     large_free(h->large);
@@ -660,6 +661,18 @@ int pms_set_map(pms_sim *h, int kind, const double *data, int count, int per_wor
     CK(cudaMemcpyAsync(h->map_dev, data, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     a.map_kind = kind; a.map_count = count; a.map_data = h->map_dev; a.map_stride = per_world ? count * k : 0;
+    return PMS_OK;
+}
+
+int pms_set_accel_noise(pms_sim *h, const double *noise)
+{
+    HCHECK(h);
+    const size_t n = (size_t)h->W * h->N * 2;
+    if (!noise) { h->a.accel_noise = nullptr; return PMS_OK; }
+    if (!h->noise_dev) CK(cudaMalloc((void **)&h->noise_dev, n * sizeof(double)));
+    CK(cudaMemcpyAsync(h->noise_dev, noise, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->a.accel_noise = h->noise_dev;
     return PMS_OK;
 }
 

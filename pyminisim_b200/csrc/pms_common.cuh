@@ -62,6 +62,7 @@ struct HsfmArgs {
     double2 *det_vals;
     unsigned long long *det_count, *coll_count;
     int *nonfinite;
+    const double *accel_noise;  // (W,N,2) added to the body-frame acceleration dv_b, or NULL (_hsfm.py:288-289)
     // model constants (fp64 masters; kernels down-convert once)
     double dt;
     double tau, A, B, k1, k2, ko, kd, k_lambda, alpha, mass, ped_radius, hsfm_robot_radius;

@@ -1,0 +1,390 @@
+"""Drop-in mirror of ``pyminisim.pedestrians`` for the accelerated path.
+
+``HeadedSocialForceModelPolicy`` and ``ORCAPedestriansModel`` keep the reference's constructor signature
+and ``state`` / ``step`` / ``reset_to_state`` contract (pedestrians/_hsfm.py:196-313, _orca.py:28-127) but
+every step runs in libpms_b200 on the GPU (one world = a batch of one).  The waypoint trackers hold the
+host-side state the reference exposes; the reach test, index hand-off and queue pop happen on the device.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import _capi as capi
+from .batched import BatchedOrca, BatchedSimulation, HSFMParams, ORCAParams
+from .core import (DEFAULT_ROBOT_RADIUS, PEDESTRIAN_RADIUS, AbstractPedestriansModel, AbstractPedestriansModelState,
+                   AbstractWaypointTracker, AbstractWaypointTrackerState)
+
+__all__ = ["HSFMParams", "HeadedSocialForceModelPolicy", "RandomWaypointTracker", "FixedWaypointTracker",
+           "ORCAParams", "ORCAPedestriansModel", "HSFMState", "ORCAState"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# FixedWaypointTracker (pedestrians/_fixed_waypoint_tracker.py)
+# ---------------------------------------------------------------------------------------------------------
+class FixedWaypointTrackerState(AbstractWaypointTrackerState):
+    def __init__(self, current_waypoints: Dict[int, np.ndarray], current_indices: Optional[Dict[int, int]] = None):
+        if current_indices is None:
+            current_indices = {k: 0 for k in current_waypoints.keys()}
+        else:
+            assert current_waypoints.keys() == current_indices.keys()
+        super().__init__(current_waypoints)
+        self._current_indices = current_indices
+
+    @property
+    def current_indices(self) -> Dict[int, int]:
+        return self._current_indices
+
+
+class FixedWaypointTracker(AbstractWaypointTracker):
+    def __init__(self, initial_positions, waypoints, reach_distance=0.3, loop: bool = False):
+        self._reach_distance, self._loop = reach_distance, loop
+        if isinstance(waypoints, np.ndarray):
+            assert isinstance(initial_positions, np.ndarray), "Initial positions must have same type as waypoints"
+            assert initial_positions.ndim == 2 and initial_positions.shape[1] == 2, \
+                f"Initial positions must have shape of (n_pedestrians, 2) the {initial_positions.shape} array is given"
+            assert initial_positions.shape[0] == waypoints.shape[0], "Initial positions and waypoints must have same number of pedestrians"
+            assert waypoints.ndim == 3 and waypoints.shape[2] == 2, "Waypoints must have shape of (n_pedestrians, n_points, 2)"
+            ids = range(waypoints.shape[0])
+        else:
+            assert isinstance(initial_positions, dict), "Initial positions must have same type as waypoints"
+            for k, v in waypoints.items():
+                assert k in initial_positions, f"Pedestrian {k} doesn't have initial position"
+                assert initial_positions[k].shape == (2,)
+                assert v.ndim == 2 and v.shape[1] == 2
+            ids = waypoints.keys()
+        # row 0 of every table is the initial position; tracking starts at row 1 (:45,59)
+        self._all_waypoints = {k: np.concatenate((np.asarray(initial_positions[k], dtype=float)[None, :],
+                                                   np.asarray(waypoints[k], dtype=float)), axis=0) for k in ids}
+        self._current_indices = {k: 1 for k in self._all_waypoints}
+
+    # -- device hand-off helpers --
+    @property
+    def reach_distance(self):
+        return self._reach_distance
+
+    @property
+    def loop(self):
+        return self._loop
+
+    def table(self) -> Tuple[List[int], np.ndarray]:
+        ids = list(self._all_waypoints.keys())
+        rows = {self._all_waypoints[k].shape[0] for k in ids}
+        assert len(rows) == 1, "the accelerated path needs the same number of waypoints for every pedestrian"
+        return ids, np.stack([self._all_waypoints[k] for k in ids])
+
+    def _set_indices(self, idx):
+        self._current_indices = {k: int(i) for k, i in zip(self._all_waypoints.keys(), idx)}
+
+    @property
+    def state(self) -> FixedWaypointTrackerState:
+        return FixedWaypointTrackerState(self._current(), self._current_indices)
+
+    def resample_all(self, agents_poses):
+        return self._current()
+
+    def update_waypoints(self, agents_poses):
+        assert agents_poses.keys() == self._all_waypoints.keys()
+        out = {}
+        for k, pose in agents_poses.items():
+            tab, idx = self._all_waypoints[k], self._current_indices[k]
+            if np.linalg.norm(tab[idx] - pose[:2]) <= self._reach_distance:
+                nxt, steady = idx + 1, False
+                if nxt >= tab.shape[0]:
+                    nxt, steady = (0, False) if self._loop else (tab.shape[0] - 1, True)
+                self._current_indices[k] = nxt
+                out[k] = (tab[nxt], steady)
+        return out
+
+    def reset_to_state(self, state: FixedWaypointTrackerState):
+        self._current_indices = state.current_indices
+
+    def sample_independent_points(self, n_points: int, min_cross_distance: Optional[float] = None):
+        pass
+
+    def _current(self):
+        return {k: self._all_waypoints[k][i, :] for k, i in self._current_indices.items()}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# RandomWaypointTracker (pedestrians/_random_waypoint_tracker.py): global numpy RNG, same draw order
+# ---------------------------------------------------------------------------------------------------------
+class RandomWaypointTrackerState(AbstractWaypointTrackerState):
+    def __init__(self, current_waypoints: Dict[int, np.ndarray], next_waypoints: Dict[int, np.ndarray]):
+        super().__init__(current_waypoints)
+        self._next_waypoints = next_waypoints
+
+    @property
+    def next_waypoints(self) -> Dict[int, np.ndarray]:
+        return self._next_waypoints
+
+
+class RandomWaypointTracker(AbstractWaypointTracker):
+    def __init__(self, world_size: Tuple[float, float], min_sample_distance=3.0, max_sample_trials=100,
+                 reach_distance=0.3, n_next_waypoints: int = 10):
+        assert len(world_size) == 2
+        assert n_next_waypoints >= 1
+        self._world_size = world_size
+        self._min_sample_distance, self._max_sample_trials = min_sample_distance, max_sample_trials
+        self._reach_distance, self._n_next_waypoints = reach_distance, n_next_waypoints
+        self._state: Optional[RandomWaypointTrackerState] = None
+
+    @property
+    def reach_distance(self):
+        return self._reach_distance
+
+    @property
+    def min_sample_distance(self):
+        return self._min_sample_distance
+
+    @property
+    def state(self) -> RandomWaypointTrackerState:
+        return self._state
+
+    def _draw(self) -> np.ndarray:
+        half = self._world_size[0] / 2.       # both axes use world_size[0], like the reference (:101-102,112-113)
+        return np.random.uniform(low=np.array([-half, -half]), high=np.array([half, half]))
+
+    def sample_waypoint(self, others: np.ndarray, min_distance: float) -> np.ndarray:
+        """Rejection sampling against one point or a set of points (_random_waypoint_tracker.py:110-123)."""
+        for _ in range(self._max_sample_trials):
+            cand = self._draw()
+            if others.ndim == 1:
+                dist = np.linalg.norm(others - cand)
+            elif others.ndim == 2:
+                dist = np.min(np.linalg.norm(others - cand, axis=1))
+            else:
+                raise RuntimeError("Unsupported agents positions shape")
+            if dist < min_distance:
+                continue
+            return cand
+        raise RuntimeError("Failed to sample waypoint")
+
+    def resample_all(self, agents_poses):
+        keys = sorted(agents_poses.keys())
+        start = np.stack([agents_poses[k] for k in keys], axis=0)[:, :2]
+        chain = np.zeros((len(keys), self._n_next_waypoints + 1, 2))
+        chain[:, 0] = np.stack([self.sample_waypoint(p, self._min_sample_distance) for p in start])
+        for j in range(1, self._n_next_waypoints + 1):     # column by column: every pedestrian, then the next column
+            chain[:, j] = np.stack([self.sample_waypoint(p, self._min_sample_distance) for p in chain[:, j - 1]])
+        cur = {k: chain[n, 0] for n, k in enumerate(keys)}
+        nxt = {k: chain[n, 1:] for n, k in enumerate(keys)}
+        self._state = RandomWaypointTrackerState(cur, nxt)
+        return cur
+
+    def update_waypoints(self, agents_poses):
+        if self._state is None:
+            raise RuntimeError("Waypoint tracker is not initialized")
+        assert agents_poses.keys() == self._state.current_waypoints.keys()
+        cur, nxt = self._state.current_waypoints, self._state.next_waypoints
+        new_cur, new_nxt = {}, {}
+        for k, pose in agents_poses.items():
+            if np.linalg.norm(cur[k] - pose[:2]) <= self._reach_distance:
+                new_cur[k], new_nxt[k] = self.advance(nxt[k])
+            else:
+                new_cur[k], new_nxt[k] = cur[k].copy(), nxt[k].copy()
+        self._state = RandomWaypointTrackerState(new_cur, new_nxt)
+        return {k: (v.copy(), False) for k, v in new_cur.items()}
+
+    def advance(self, queue: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Pop the queue front and draw a new tail >= min_sample_distance from the old tail (:83-87)."""
+        shifted = np.zeros_like(queue)
+        shifted[:-1] = queue[1:]
+        shifted[-1] = self.sample_waypoint(queue[-1], self._min_sample_distance)
+        return queue[0], shifted
+
+    def reset_to_state(self, state: RandomWaypointTrackerState):
+        self._state = state
+
+    def sample_independent_points(self, n_points: int, min_cross_distance: Optional[float] = None):
+        assert n_points > 0
+        if min_cross_distance is None:
+            min_cross_distance = -np.inf
+        pts = self._draw().reshape(1, -1)
+        for _ in range(1, n_points):
+            pts = np.vstack([pts, self.sample_waypoint(pts, min_cross_distance).reshape(1, -1)])
+        return pts
+
+
+# ---------------------------------------------------------------------------------------------------------
+# HSFM
+# ---------------------------------------------------------------------------------------------------------
+class HSFMState(AbstractPedestriansModelState):
+    pass
+
+
+def _initial_arrays(tracker, n, initial_poses, initial_velocities):
+    if initial_poses is None:   # _hsfm.py:210-214 / _orca.py:41-45: positions from the tracker, headings ~ U(-pi, pi)
+        positions = tracker.sample_independent_points(n, 0.5)
+        headings = np.random.uniform(-np.pi, np.pi, size=n)
+        initial_poses = np.hstack([positions, headings.reshape(-1, 1)])
+    else:
+        assert initial_poses.shape[0] == n
+    if initial_velocities is None:
+        initial_velocities = np.zeros((n, 3))
+    else:
+        assert initial_velocities.shape[0] == n
+    return np.asarray(initial_poses, dtype=np.float64), np.asarray(initial_velocities, dtype=np.float64)
+
+
+class _TrackerLink:
+    """Keeps a host tracker object and the device-side tracker state of one world in sync."""
+
+    def __init__(self, tracker: AbstractWaypointTracker, n: int):
+        self.tracker, self.n = tracker, n
+        self.random = isinstance(tracker, RandomWaypointTracker)
+        if not self.random and not isinstance(tracker, FixedWaypointTracker):
+            raise TypeError("the accelerated path supports FixedWaypointTracker and RandomWaypointTracker")
+
+    def upload(self, sim):
+        st = self.tracker.state
+        if self.random:
+            cur = np.stack([st.current_waypoints[i] for i in range(self.n)])[None]
+            queue = np.stack([st.next_waypoints[i] for i in range(self.n)])[None]
+            sim.set_waypoint_queue(cur, queue, reach_distance=self.tracker.reach_distance)
+        else:
+            ids, table = self.tracker.table()
+            assert ids == list(range(self.n)), "pedestrian ids must be 0..n-1"
+            idx = np.array([st.current_indices[i] for i in range(self.n)], dtype=np.int32)[None]
+            sim.set_waypoints_fixed(table[None], start_index=idx, reach_distance=self.tracker.reach_distance, loop=self.tracker.loop)
+
+    def after_step(self, sim):
+        if self.random:
+            events = sim.pop_waypoint_events()
+            if len(events) == 0:
+                return
+            st = self.tracker.state
+            cur, nxt = dict(st.current_waypoints), dict(st.next_waypoints)
+            appended_ids, appended_pts = [], []
+            for step, _, ped in events:          # (step, world, ped) order == the reference's draw order
+                if step < 0:
+                    raise RuntimeError("waypoint queue starved on the device (too many steps per call)")
+                cur[ped], nxt[ped] = self.tracker.advance(nxt[ped])
+                appended_ids.append((0, int(ped)))
+                appended_pts.append(nxt[ped][-1])
+            self.tracker.reset_to_state(RandomWaypointTrackerState(cur, nxt))
+            sim.append_waypoints(np.array(appended_ids, dtype=np.int32), np.array(appended_pts))
+        else:
+            _, idx = sim.get_waypoints()
+            self.tracker._set_indices(idx[0])
+
+
+class HeadedSocialForceModelPolicy(AbstractPedestriansModel):
+    """GPU-backed HSFM with the constructor of pedestrians/_hsfm.py:198-208.  ``precision`` selects the
+    arithmetic mode of the kernel ("fp64" reproduces the reference to ~1e-15 per step)."""
+
+    def __init__(self, waypoint_tracker: AbstractWaypointTracker, n_pedestrians: int,
+                 initial_poses: Optional[np.ndarray] = None, initial_velocities: Optional[np.ndarray] = None,
+                 hsfm_params: HSFMParams = HSFMParams.create_default(), pedestrian_mass: float = 70.0,
+                 pedestrian_linear_velocity_magnitude: Union[float, np.ndarray] = 1.5, robot_visible: bool = True,
+                 robot_radius: float = DEFAULT_ROBOT_RADIUS, noise_std: Optional[float] = None,
+                 precision: str = "fp64", device: int = 0):
+        poses, vels = _initial_arrays(waypoint_tracker, n_pedestrians, initial_poses, initial_velocities)
+        self._n = poses.shape[0]
+        if isinstance(pedestrian_linear_velocity_magnitude, np.ndarray):
+            assert pedestrian_linear_velocity_magnitude.shape == (n_pedestrians,), \
+                "Linear velocity magnitude must be float or (n_pedestrians,) shape ndarray"
+            vmag = pedestrian_linear_velocity_magnitude.astype(np.float64)
+        else:
+            vmag = np.repeat(float(pedestrian_linear_velocity_magnitude), self._n)
+        self._tracker = waypoint_tracker
+        if self._tracker.state is None:
+            self._tracker.resample_all({i: poses[i] for i in range(self._n)})
+        self._robot_visible, self._robot_radius, self._noise_std = robot_visible, robot_radius, noise_std
+        self._sim = BatchedSimulation(1, self._n, precision=precision, device=device, hsfm_params=hsfm_params,
+                                      pedestrian_mass=pedestrian_mass, pedestrian_radius=PEDESTRIAN_RADIUS,
+                                      hsfm_robot_radius=robot_radius)
+        self._sim.set_speeds(vmag[None])
+        self._sim.set_state(poses[None], vels[None])
+        self._link = _TrackerLink(self._tracker, self._n)
+        self._link.upload(self._sim)
+        self._state = HSFMState({i: (poses[i].copy(), vels[i].copy()) for i in range(self._n)}, self._tracker.state)
+
+    @property
+    def state(self) -> HSFMState:
+        return self._state
+
+    def step(self, dt: float, robot_pose: Optional[np.ndarray], robot_velocity: Optional[np.ndarray]):
+        if robot_pose is None:
+            assert robot_velocity is None
+        elif robot_velocity is None:
+            assert robot_pose is None
+        if robot_pose is not None and self._robot_visible:     # _hsfm.py:279-284
+            self._sim.set_robot(capi.ROBOT_EXTERNAL, np.asarray(robot_pose, dtype=np.float64)[None],
+                                velocity=np.asarray(robot_velocity, dtype=np.float64)[None], radius=self._robot_radius)
+        else:
+            self._sim.set_robot(capi.ROBOT_NONE)
+        if self._noise_std is not None:                        # :288-289, same global RNG draw
+            self._sim.set_accel_noise(np.random.normal(0, self._noise_std, (self._n, 2))[None])
+        self._sim.step(dt, 1)
+        _, _, nonfinite = self._sim.get_stats()
+        if nonfinite[0]:   # the reference's numba inverse raises on non-finite headings
+            raise np.linalg.LinAlgError("Array must not contain infs or NaNs")
+        self._link.after_step(self._sim)
+        poses, vels = self._sim.get_state()
+        self._state = HSFMState({i: (poses[0, i].copy(), vels[0, i].copy()) for i in range(self._n)}, self._tracker.state)
+
+    def reset_to_state(self, state: HSFMState):
+        self._state = state
+        self._tracker.reset_to_state(state.waypoints)
+        poses, vels = state.poses, state.velocities
+        self._sim.set_state(np.stack([poses[i] for i in range(self._n)])[None], np.stack([vels[i] for i in range(self._n)])[None])
+        self._sim.reset_stats()
+        self._link.upload(self._sim)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ORCA
+# ---------------------------------------------------------------------------------------------------------
+class ORCAState(AbstractPedestriansModelState):
+    pass
+
+
+class ORCAPedestriansModel(AbstractPedestriansModel):
+    """GPU-backed ORCA with the constructor of pedestrians/_orca.py:30-39.  dt, robot_pose and
+    robot_velocity passed to step() are ignored, like in the reference (:95-98)."""
+
+    def __init__(self, dt: float, waypoint_tracker: AbstractWaypointTracker, n_pedestrians: int, params=ORCAParams(),
+                 initial_poses: Optional[np.ndarray] = None, initial_velocities: Optional[np.ndarray] = None,
+                 preferred_speeds: Optional[np.ndarray] = None, max_speeds: Optional[np.ndarray] = None,
+                 robot_visible: bool = False, device: int = 0):
+        poses, vels = _initial_arrays(waypoint_tracker, n_pedestrians, initial_poses, initial_velocities)
+        if max_speeds is None:
+            max_speeds = np.array([params.default_max_speed for _ in range(n_pedestrians)])
+        else:
+            assert max_speeds.shape == (n_pedestrians,), f"max_speeds must have shape (n_pedestrians,), got shape {max_speeds.shape}"
+        assert (np.linalg.norm(vels[:, :2], axis=1) <= max_speeds).all(), "Initial speeds must be <= all corresponding max_speeds"
+        if preferred_speeds is not None:
+            assert preferred_speeds.shape == (n_pedestrians,), f"preferred_speeds must have shape (n_pedestrians,), got shape {preferred_speeds.shape}"
+            assert (preferred_speeds <= max_speeds).all(), "All preferred_speeds must be <= corresponding max_speeds"
+        else:
+            preferred_speeds = max_speeds.copy()
+        self._n = poses.shape[0]
+        self._tracker = waypoint_tracker
+        if not isinstance(waypoint_tracker, FixedWaypointTracker):
+            raise TypeError("the accelerated ORCA path supports FixedWaypointTracker")
+        if self._tracker.state is None:
+            self._tracker.resample_all({i: poses[i] for i in range(self._n)})
+        self._robot_visible = robot_visible
+        self._sim = BatchedOrca(dt, 1, self._n, params, device=device)
+        self._sim.set_agents(poses[None, :, :2], vels[None, :, :2], max_speeds[None], preferred_speeds[None])
+        ids, table = self._tracker.table()
+        idx = np.array([self._tracker.state.current_indices[i] for i in range(self._n)], dtype=np.int32)[None]
+        self._sim.set_waypoints_fixed(table[None], start_index=idx, reach_distance=self._tracker.reach_distance, loop=self._tracker.loop)
+        self._state = ORCAState({i: (poses[i].copy(), vels[i].copy()) for i in range(self._n)}, self._tracker.state)
+
+    @property
+    def state(self) -> ORCAState:
+        return self._state
+
+    def step(self, dt: float = None, robot_pose: Optional[np.ndarray] = None, robot_velocity: Optional[np.ndarray] = None):
+        self._sim.step(1)
+        poses, vels = self._sim.get_agents()
+        if self._tracker.state is not None:
+            self._tracker.update_waypoints({i: poses[0, i] for i in range(self._n)})   # host mirror of the device hand-off
+        self._state = ORCAState({i: (poses[0, i].copy(), vels[0, i].copy()) for i in range(self._n)}, self._tracker.state)
+
+    def reset_to_state(self, state: ORCAState):
+        self._state = state                       # like the reference, the agents themselves are not reset (:114-116)
+        self._tracker.reset_to_state(state.waypoints)

@@ -1,0 +1,178 @@
+"""Drop-in single-world classes (pyminisim_b200.core / .pedestrians / .sensors) against the golden
+fixtures of the live reference: the tests read like the reference's examples."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ped_arrays(state):
+    n = len(state.poses)
+    return np.stack([state.poses[i] for i in range(n)]), np.stack([state.velocities[i] for i in range(n)])
+
+
+def test_kat2_through_simulation(golden):
+    from pyminisim_b200.core import Simulation
+    from pyminisim_b200.pedestrians import FixedWaypointTracker, HeadedSocialForceModelPolicy
+    from pyminisim_b200.robot import UnicycleRobotModel
+    from pyminisim_b200.sensors import PedestrianDetector, PedestrianDetectorConfig
+    from pyminisim_b200.world_map import EmptyWorld
+    g = golden("kat2")
+    poses, table = g["init_poses"], g["table"]
+    tracker = FixedWaypointTracker(initial_positions=table[:, 0].copy(), waypoints=table[:, 1:].copy(), loop=True)
+    model = HeadedSocialForceModelPolicy(waypoint_tracker=tracker, n_pedestrians=3, initial_poses=poses.copy())
+    sim = Simulation(world_map=EmptyWorld(), robot_model=UnicycleRobotModel(np.array([0., 0., 0.]), np.array([0.5, 0.2])),
+                     pedestrians_model=model, sensors=[PedestrianDetector(PedestrianDetectorConfig(5.0, np.deg2rad(120.), "polar"))],
+                     sim_dt=0.01, rt_factor=None)
+    k = 0
+    for step in range(1, 301):
+        st = sim.step()
+        assert st.world.robot_to_pedestrians_collisions == []
+        if step == g["horizons"][k]:
+            p, v = _ped_arrays(st.world.pedestrians)
+            assert rel_err(p, g["poses"][k]) < 1e-10
+            assert np.allclose(st.world.robot.pose, g["robot_pose"][k], atol=1e-13)
+            det = st.sensors["pedestrian_detector"].reading.pedestrians
+            ref_ids = [i for i in range(3) if (int(g["det_mask"][k][0]) >> i) & 1]
+            assert list(det.keys()) == ref_ids
+            for i in ref_ids:
+                assert np.allclose(det[i], g["det_vals"][k][i], atol=1e-9)
+            k += 1
+    # SURVEY.md Appendix C literal
+    assert st.sensors["pedestrian_detector"].reading.pedestrians == {}
+    # state value semantics: getters return copies
+    s = sim.current_state.world.pedestrians
+    s.poses[0][0] = 99.0
+    assert s.poses[0][0] != 99.0
+    # reset_to_state round trip
+    snap = sim.current_state.world
+    a = sim.step().world.pedestrians.poses[0].copy()
+    sim.reset_to_state(snap)
+    b = sim.step().world.pedestrians.poses[0]
+    assert np.allclose(a, b, atol=1e-12)
+
+
+def test_kat3_random_tracker_seed_exact(golden):
+    """examples/basic.py set-up with Simulation.seed(42): the device pops the waypoint queue, the host replays
+    the event log to draw the new tails from the global RNG in the reference's order."""
+    from pyminisim_b200.core import Simulation
+    from pyminisim_b200.pedestrians import HeadedSocialForceModelPolicy, RandomWaypointTracker
+    from pyminisim_b200.robot import UnicycleRobotModel
+    from pyminisim_b200.sensors import PedestrianDetector
+    from pyminisim_b200.world_map import EmptyWorld
+    g = golden("random_tracker")
+    Simulation.seed(42)
+    robot = UnicycleRobotModel(initial_pose=np.array([0., 0., 0.0]), initial_control=np.array([0.0, np.deg2rad(25.0)]))
+    tracker = RandomWaypointTracker(world_size=(7.0, 7.0))
+    model = HeadedSocialForceModelPolicy(n_pedestrians=2, waypoint_tracker=tracker,
+                                         pedestrian_linear_velocity_magnitude=np.array([1.5, 2.5]),
+                                         initial_poses=g["init_poses"].copy())
+    sim = Simulation(world_map=EmptyWorld(), robot_model=robot, pedestrians_model=model, sensors=[PedestrianDetector()],
+                     rt_factor=None)
+    k = 0
+    for step in range(1, int(g["horizons"][-1]) + 1):
+        st = sim.step()
+        if step == g["horizons"][k]:
+            p, v = _ped_arrays(st.world.pedestrians)
+            cur = np.stack([tracker.state.current_waypoints[i] for i in range(2)])
+            assert np.array_equal(cur, g["cur"][k]), step          # waypoints are bit-exact (host RNG replay)
+            assert rel_err(p, g["poses"][k]) < 1e-7, (step, rel_err(p, g["poses"][k]))
+            k += 1
+    assert k == len(g["horizons"])
+
+
+@pytest.mark.parametrize("world", ["circles", "aabb", "empty"])
+def test_lidar_and_omni_sensors_match_reference(golden, world):
+    from pyminisim_b200.core import WorldState
+    from pyminisim_b200.robot import UnicycleRobotModel
+    from pyminisim_b200.sensors import LidarSensor, LidarSensorConfig, LidarSensorNoise, OmniObstacleDetector
+    from pyminisim_b200.world_map import AABBObject, AABBWorld, CirclesWorld, EmptyWorld
+    g = golden("sensors")
+    wm = {"circles": lambda: CirclesWorld(g["circles"]), "aabb": lambda: AABBWorld([AABBObject(box=tuple(b)) for b in g["boxes"]]),
+          "empty": EmptyWorld}[world]()
+    for cfgname, cfg in (("default", LidarSensorConfig()), ("coarse", LidarSensorConfig(n_beams=37, max_dist=5.0, resolution=0.03))):
+        lidar = LidarSensor(cfg)
+        assert np.isclose(lidar.period, 0.1) and lidar.sensor_name == "lidar"
+        for w, r in enumerate(g["robots"]):
+            ws = WorldState(wm.current_state, UnicycleRobotModel(r.copy()).state, None, None, False)
+            pts = lidar.get_reading(ws, wm).points.reshape(-1, 2)
+            n = int(g[f"lidar_{world}_{cfgname}_count"][w])
+            assert len(pts) == n                                               # same beams hit (integer output)
+            assert np.array_equal(pts, g[f"lidar_{world}_{cfgname}_points"][w][:n])   # same sample points, bit for bit
+    omni = OmniObstacleDetector()
+    for w, r in enumerate(g["robots"]):
+        ws = WorldState(wm.current_state, UnicycleRobotModel(r.copy()).state, None, None, False)
+        d = omni.get_reading(ws, wm).min_obstacle_dist
+        assert np.isclose(d, g[f"omni_{world}"][w], rtol=1e-13) or (np.isinf(d) and np.isinf(g[f"omni_{world}"][w]))
+    noisy = LidarSensor(LidarSensorConfig(), LidarSensorNoise(drop_prob=0.5))
+    ws = WorldState(wm.current_state, UnicycleRobotModel(g["robots"][0].copy()).state, None, None, False)
+    assert noisy.get_reading(ws, wm).points.ndim in (1, 2)
+
+
+def test_batched_lidar_per_world_maps_vs_oracle():
+    from oracle import oracle as orc
+    from pyminisim_b200.batched import BatchedSimulation
+    rng = np.random.default_rng(11)
+    W, C = 64, 6
+    circles = np.concatenate([rng.uniform(-6, 6, (W, C, 2)), rng.uniform(0.2, 1.2, (W, C, 1))], axis=2)
+    robots = np.concatenate([rng.uniform(-3, 3, (W, 2)), rng.uniform(-3, 3, (W, 1))], axis=1)
+    boxes = np.concatenate([rng.uniform(-6, 6, (W, C, 2)), rng.uniform(0.3, 2.0, (W, C, 2))], axis=2)
+    for kind, data in ((1, circles), (2, boxes)):
+        sim = BatchedSimulation(W, 1, precision="fp64")
+        sim.set_state(np.zeros((W, 1, 3)))
+        sim.set_robot(1, robots, velocity=np.zeros((W, 3)))
+        sim.set_map(kind, data)
+        o = orc.OracleBatch(np.zeros((W, 1, 3)))
+        o.set_robot(orc.ROBOT_EXTERNAL, robots)
+        o.set_map(kind, data)
+        for cfg in ((100, 8.0, 0.01), (64, 6.0, 0.05)):
+            hit, pts = sim.lidar_scan(*cfg)
+            ohit, opts = o.lidar(*cfg)
+            assert (ohit >= 0).any() and np.array_equal(hit, ohit)             # hit indices: bit-exact
+            assert np.array_equal(pts, opts)
+        assert np.allclose(sim.omni_scan(), o.omni(), rtol=1e-14)
+
+
+def test_detector_noise_and_hsfm_noise_paths_run():
+    from pyminisim_b200.core import Simulation
+    from pyminisim_b200.pedestrians import FixedWaypointTracker, HeadedSocialForceModelPolicy
+    from pyminisim_b200.robot import BicycleRobotModel
+    from pyminisim_b200.sensors import PedestrianDetector, PedestrianDetectorConfig, PedestrianDetectorNoise
+    from pyminisim_b200.world_map import CirclesWorld
+    init = np.array([[1.0, 0.2, 0.0], [1.5, -0.4, 1.0], [-2.0, 1.0, 2.0], [0.5, 1.5, -1.0]])
+    wps = init[:, None, :2] + np.array([[[3.0, 0.0], [0.0, 3.0]]])
+    tracker = FixedWaypointTracker(init[:, :2].copy(), wps, loop=True)
+    model = HeadedSocialForceModelPolicy(tracker, 4, initial_poses=init.copy(), noise_std=0.05, precision="fp32")
+    det = PedestrianDetector(PedestrianDetectorConfig(6.0, np.deg2rad(300.), "absolute"),
+                             PedestrianDetectorNoise(0.0, 0.05, 0.0, 0.01, 0.2))
+    Simulation.seed(1)
+    sim = Simulation(CirclesWorld(np.array([[8.0, 8.0, 1.0]])), BicycleRobotModel(0.324, np.array([0., 0., 0.]), np.array([0.5, 0.1])),
+                     model, [det])
+    seen = 0
+    for _ in range(50):
+        st = sim.step()
+        seen += len(st.sensors["pedestrian_detector"].reading.pedestrians)
+    assert seen > 0
+    p, _ = _ped_arrays(st.world.pedestrians)
+    assert np.isfinite(p).all()
+
+
+def test_orca_dropin_model():
+    from oracle import oracle as orc
+    from pyminisim_b200.pedestrians import FixedWaypointTracker, ORCAParams, ORCAPedestriansModel
+    init = np.array([(4, 0, 0), (0, -4, 0), (0, 4, 0), (2.82, 2.82, 0), (-2.82, -2.82, 0), (2.82, -2.82, 0), (-2.82, 2.82, 0)], dtype=float)
+    goals = np.array([[[-4, 0]], [[0, 4]], [[0, -4]], [[-2.82, -2.82]], [[2.82, 2.82]], [[-2.82, 2.82]], [[2.82, -2.82]]], dtype=float)
+    ms = np.linspace(1.0, 1.8, 7)
+    tracker = FixedWaypointTracker(initial_positions=init[:, :2].copy(), waypoints=goals, loop=True)
+    model = ORCAPedestriansModel(0.01, tracker, 7, initial_poses=init.copy(), params=ORCAParams(default_max_speed=2.), max_speeds=ms)
+    table = np.concatenate([init[:, None, :2], goals], axis=1)[None]
+    o = orc.OracleOrca(0.01, init[None], table, loop=True, max_speed=ms[None], default_max_speed=2.0)
+    for _ in range(300):
+        model.step()
+    o.rollout(300)
+    p, v = _ped_arrays(model.state)
+    assert np.array_equal(p[:, :2].astype(np.float32), o.pos[0])
+    assert np.allclose(p[:, 2], o.heading[0], atol=1e-12)
+    assert model.state.waypoints.current_indices == {i: int(o.wp_index[0, i]) for i in range(7)}
