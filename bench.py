@@ -133,11 +133,12 @@ def cpu_reference_run(args, n_steps_timed: int, warmup: int):
 
 
 def config_dict(args, world_size):
-    return {"workload": f"C4: {args.worlds} worlds x {args.peds} pedestrians per GPU, HSFM + unicycle robot + "
+    per = "per GPU" if args.scaling == "weak" else f"in total over {world_size} GPU(s)"
+    return {"workload": f"C4: {args.worlds} worlds x {args.peds} pedestrians {per}, HSFM + unicycle robot + "
                         f"pedestrian detector (5 m, 120 deg) + collision list, jittered grid with local looped goals "
                         f"(scenarios.make_bench_crowd), {args.sim_steps} fused sim-steps "
                         f"of dt=0.01 per bench step",
-            "worlds_per_gpu": args.worlds, "peds_per_world": args.peds, "sim_steps_per_step": args.sim_steps,
+            "worlds": args.worlds, "worlds_are": "per GPU" if args.scaling == "weak" else "total", "peds_per_world": args.peds, "sim_steps_per_step": args.sim_steps,
             "dt": 0.01, "precision": args.precision, "parallelism": f"worlds sharded over {world_size} GPU(s), "
             "no collective on the step path", "l2": "256 MiB L2 flush between timed steps (state is 16 MB and "
             "lives on-chip during a step)"}
@@ -179,10 +180,16 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world_size > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    worlds = args.worlds if args.scaling == "weak" else max(1, args.worlds // world_size)
-    sc = make_bench_crowd(worlds, args.peds, first_world=rank * worlds)
+    from pyminisim_b200.distributed import gather_episode_stats, local_episode_stats, max_over_ranks, shard_worlds
+    if args.scaling == "weak":          # fixed work per GPU: rank r owns worlds [r*W, (r+1)*W)
+        first_world, worlds = rank * args.worlds, args.worlds
+    else:                               # fixed total work: the W worlds are split over the ranks
+        first_world, worlds = shard_worlds(args.worlds, rank, world_size)
+    sc = make_bench_crowd(worlds, args.peds, first_world=first_world)
     W, N, K = worlds, args.peds, args.sim_steps
 
     sim = BatchedSimulation(W, N, precision=args.precision, device=local_rank)
@@ -236,12 +243,10 @@ def main():
     launches = sim.launch_info()["kernel_launches"] - launches_before
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    updates_per_rank = float(W) * N * K * args.steps
-    value = updates_per_rank * world_size / (ms_max * 1e-3)
+    ms_max = max_over_ranks(ms, device="cuda")
+    total_worlds = args.worlds * world_size if args.scaling == "weak" else args.worlds
+    updates_total = float(total_worlds) * N * K * args.steps
+    value = updates_total / (ms_max * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ----
     def e2e_step():
@@ -261,21 +266,16 @@ def main():
         mask, vals, coll, stats = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = updates_per_rank * world_size / float(te.item())
+    e2e_value = updates_total / max_over_ranks(e2e_s, device="cuda")
     h2d = h_poses.nbytes + h_vels.nbytes
     d2h = o_poses.nbytes + o_vels.nbytes + mask.nbytes + vals.nbytes + coll.nbytes + sum(s.nbytes for s in stats)
 
     # ---- episode statistics: the only collective (NCCL all-reduce of a few numbers) ----
     det, col, nf = stats
-    st = torch.tensor([float(det.sum()), float(col.sum()), float((nf != 0).sum()),
-                       float(np.linalg.norm(o_vels[..., :2], axis=-1).mean())], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        dist.all_reduce(st, op=dist.ReduceOp.SUM)
-    episode = {"detections": int(st[0].item()), "robot_ped_collisions": int(st[1].item()),
-               "nonfinite_worlds": int(st[2].item()), "mean_speed": float(st[3].item()) / world_size}
+    g = gather_episode_stats(local_episode_stats(det, col, nf, o_vels), device="cuda")
+    episode = {"detections": int(g["detections"]), "robot_ped_collisions": int(g["robot_ped_collisions"]),
+               "nonfinite_worlds": int(g["nonfinite_worlds"]), "worlds": int(g["worlds"]),
+               "mean_speed": g["speed_sum"] / max(g["pedestrians"], 1.0)}
 
     extra = {}
     if args.extra and rank == 0:
