@@ -227,6 +227,81 @@ __device__ __forceinline__ SenseOut sense_ped(const HsfmArgs &a, const RobotSlot
     return o;
 }
 
+// Owner-side view of one world's shared-memory state (scalar SoA arrays, see SmallSmem).
+template <typename ST> struct OwnerView {
+    ST *x, *y, *vx, *vy, *th, *om, *wx, *wy, *vm, *c, *s;
+    int *widx;
+    __device__ __forceinline__ explicit OwnerView(unsigned char *base, int Np, size_t off_widx)
+    {
+        x = reinterpret_cast<ST *>(base); y = x + Np; vx = x + 2 * Np; vy = x + 3 * Np; th = x + 4 * Np; om = x + 5 * Np;
+        wx = x + 6 * Np; wy = x + 7 * Np; vm = x + 8 * Np; c = x + 9 * Np; s = x + 10 * Np;
+        widx = reinterpret_cast<int *>(base + off_widx);
+    }
+};
+
+// One owner step for pedestrian i of world w: O(1) dynamics + explicit Euler (_hsfm.py:86-110,290-294), waypoint
+// tracker on the new pose (:301-304), state write-back to shared memory, collision list + detector predicate.
+template <typename ST, typename Publish>
+__device__ __forceinline__ SenseOut owner_update(const HsfmArgs &a, const OwnerView<ST> &ow, int i, size_t g, int w, int t,
+                                                 ST fx, ST fy, const RobotSlot &rb, bool has_robot, bool last,
+                                                 int &first_bad, Publish &&publish)
+{
+    using ST2 = typename Vec2<ST>::type;
+    const PedConsts<ST> &kc = kc_of(a, ST{});
+    ST *o_x = ow.x, *o_y = ow.y, *o_vx = ow.vx, *o_vy = ow.vy, *o_th = ow.th, *o_om = ow.om;
+    ST *o_wx = ow.wx, *o_wy = ow.wy, *o_vm = ow.vm, *o_c = ow.c, *o_s = ow.s;
+    int *o_widx = ow.widx;
+    SenseOut so{false, false, 0.0, 0.0};
+    ST x = o_x[i], y = o_y[i], vx = o_vx[i], vy = o_vy[i], th = o_th[i], om = o_om[i];
+    ST wx = o_wx[i], wy = o_wy[i], c = o_c[i], sn = o_s[i];
+    const ST x0 = x, y0 = y, th0 = th;
+    ST nzx = 0, nzy = 0;
+    if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
+    ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, nzx, nzy);
+    // ---- waypoint tracker on the NEW pose (_hsfm.py:301) ----
+    const ST ex = wx - x, ey = wy - y;
+    bool reached;
+    if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
+    else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
+    if (reached) {
+        if (a.tracker_kind == TRACKER_FIXED) {       // _fixed_waypoint_tracker.py:68-87
+            int ni = o_widx[i] + 1;
+            bool steady = false;
+            if (ni >= a.n_table) {
+                if (a.loop) ni = 0; else { ni = a.n_table - 1; steady = true; }
+            }
+            o_widx[i] = ni;
+            const ST2 nw = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
+            wx = nw.x; wy = nw.y;
+            if (steady) {                            // _hsfm.py:302-304
+                x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0;
+                m_sincos(th, &sn, &c);
+            }
+        } else {                                     // _random_waypoint_tracker.py:66-91
+            const int cnt = a.q_count[g];
+            const int slot = atomicAdd(a.ev_count, 1);
+            if (cnt > 0) {
+                const int head = a.q_head[g];
+                const ST2 nw = reinterpret_cast<const ST2 *>(a.queue)[g * a.q_cap + head];
+                wx = nw.x; wy = nw.y;
+                a.q_head[g] = (head + 1) % a.q_cap;
+                a.q_count[g] = cnt - 1;
+                if (slot < a.ev_cap) { a.events[3 * slot] = t; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i; }
+            } else if (slot < a.ev_cap) {            // starved queue: negative step marks it
+                a.events[3 * slot] = -1 - t; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i;
+            }
+        }
+        o_wx[i] = wx; o_wy[i] = wy;
+    }
+    o_x[i] = x; o_y[i] = y; o_vx[i] = vx; o_vy[i] = vy; o_th[i] = th; o_om[i] = om; o_c[i] = c; o_s[i] = sn;
+    publish(x, y, vx, vy);
+    if (!first_bad && !m_finite(x + y + vx + vy + th + om)) first_bad = (int)(a.steps_done + t + 1);
+    // ---- collision list + detector on the new state ----
+    if (has_robot) so = sense_ped<ST>(a, rb, x, y, last);
+    if (last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
+    return so;
+}
+
 // ---- the fused kernel -------------------------------------------------------------------------
 // CTA-wide barrier 0.  The robot warp and the pedestrian warps run different loops and meet at the
 // same hardware barrier from different instructions (warp-specialised producer / consumer).
@@ -292,10 +367,10 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
 
     // carve the shared memory of local world wl
     unsigned char *base = smem_raw + (size_t)(wl < a.wpc ? wl : 0) * L::bytes(Np, S);
-    ST *o_x = reinterpret_cast<ST *>(base);
-    ST *o_y = o_x + Np, *o_vx = o_x + 2 * Np, *o_vy = o_x + 3 * Np, *o_th = o_x + 4 * Np, *o_om = o_x + 5 * Np;
-    ST *o_wx = o_x + 6 * Np, *o_wy = o_x + 7 * Np, *o_vm = o_x + 8 * Np, *o_c = o_x + 9 * Np, *o_s = o_x + 10 * Np;
-    int *o_widx = reinterpret_cast<int *>(base + L::off_widx(Np));
+    const OwnerView<ST> ow(base, Np, L::off_widx(Np));
+    ST *o_x = ow.x, *o_y = ow.y, *o_vx = ow.vx, *o_vy = ow.vy, *o_th = ow.th, *o_om = ow.om;
+    ST *o_wx = ow.wx, *o_wy = ow.wy, *o_vm = ow.vm, *o_c = ow.c, *o_s = ow.s;
+    int *o_widx = ow.widx;
     PT *xs = reinterpret_cast<PT *>(base + L::off_pair(Np));
     PT *ys = xs + Np, *vxs = xs + 2 * Np, *vys = xs + 3 * Np;
     float *xlo = reinterpret_cast<float *>(base + L::off_lo(Np));
@@ -474,53 +549,7 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
 #pragma unroll
                     for (int q = 0; q < S; ++q) { fx += fxp[q * Np + i]; fy += fyp[q * Np + i]; }
                 }
-                ST x = o_x[i], y = o_y[i], vx = o_vx[i], vy = o_vy[i], th = o_th[i], om = o_om[i];
-                ST wx = o_wx[i], wy = o_wy[i], c = o_c[i], sn = o_s[i];
-                const ST x0 = x, y0 = y, th0 = th;
-                ST nzx = 0, nzy = 0;
-                if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
-                ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, nzx, nzy);
-                // ---- waypoint tracker on the NEW pose (_hsfm.py:301) ----
-                const ST ex = wx - x, ey = wy - y;
-                bool reached;
-                if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
-                else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
-                if (reached) {
-                    if (a.tracker_kind == TRACKER_FIXED) {       // _fixed_waypoint_tracker.py:68-87
-                        int ni = o_widx[i] + 1;
-                        bool steady = false;
-                        if (ni >= a.n_table) {
-                            if (a.loop) ni = 0; else { ni = a.n_table - 1; steady = true; }
-                        }
-                        o_widx[i] = ni;
-                        const ST2 nw = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
-                        wx = nw.x; wy = nw.y;
-                        if (steady) {                            // _hsfm.py:302-304
-                            x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0;
-                            m_sincos(th, &sn, &c);
-                        }
-                    } else {                                     // _random_waypoint_tracker.py:66-91
-                        const int cnt = a.q_count[g];
-                        const int slot = atomicAdd(a.ev_count, 1);
-                        if (cnt > 0) {
-                            const int head = a.q_head[g];
-                            const ST2 nw = reinterpret_cast<const ST2 *>(a.queue)[g * a.q_cap + head];
-                            wx = nw.x; wy = nw.y;
-                            a.q_head[g] = (head + 1) % a.q_cap;
-                            a.q_count[g] = cnt - 1;
-                            if (slot < a.ev_cap) { a.events[3 * slot] = t; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i; }
-                        } else if (slot < a.ev_cap) {            // starved queue: negative step marks it
-                            a.events[3 * slot] = -1 - t; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i;
-                        }
-                    }
-                    o_wx[i] = wx; o_wy[i] = wy;
-                }
-                o_x[i] = x; o_y[i] = y; o_vx[i] = vx; o_vy[i] = vy; o_th[i] = th; o_om[i] = om; o_c[i] = c; o_s[i] = sn;
-                publish(x, y, vx, vy);
-                if (!first_bad && !m_finite(x + y + vx + vy + th + om)) first_bad = (int)(a.steps_done + t + 1);
-                // ---- collision list + detector on the new state ----
-                if (has_robot) so = sense_ped<ST>(a, rb, x, y, last);
-                if (last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
+                so = owner_update<ST>(a, ow, i, g, w, t, (ST)fx, (ST)fy, rb, has_robot, last, first_bad, publish);
             }
             if (has_robot) {   // owner warps are whole warps: ballots are safe
                 const unsigned dm = __ballot_sync(0xffffffffu, so.det);
