@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpms_b200.so")
 SOURCES = ["pms_api.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
-HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
+HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_warp.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
 
 
 def nvcc_path() -> str:

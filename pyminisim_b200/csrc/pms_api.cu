@@ -5,11 +5,13 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "hsfm_small.cuh"
+#include "hsfm_warp.cuh"
 #include "hsfm_large.cuh"
 #include "sensors.cuh"
 #include "orca.cuh"
@@ -134,7 +136,7 @@ struct pms_sim {
     long long snap_steps = 0;
     bool has_snapshot = false;
     // tuning / introspection
-    int tune_S = 0, tune_wpc = 0, tune_chunks = 0, tune_cluster = 0;
+    int tune_S = 0, tune_wpc = 0, tune_chunks = 0, tune_cluster = 0, tune_minb = 0;
     bool force_large = false;
     int sm_count = 148;
     int sched_cap = 0;
@@ -231,7 +233,7 @@ template <int S> int launch_small_s(pms_sim *h, int wpc, bool big)
 int launch_small(pms_sim *h)
 {
     const int Np = h->Np;
-    int S = h->tune_S;
+    int S = h->tune_S < 0 ? -h->tune_S - 1 : h->tune_S;   // j_split = -1: automatic, -1-S: forced S
     if (S <= 0) {
         // enough threads to fill 148 SMs; every slice keeps >= 8 pairs for ILP
         const long long target = 148LL * 1536;
@@ -254,6 +256,78 @@ int launch_small(pms_sim *h)
     case 4: return launch_small_s<4>(h, wpc, big);
     default: return launch_small_s<8>(h, wpc, big);
     }
+}
+
+// ---- launch of the warp-per-world symmetric-pair kernel (hsfm_warp.cuh): fp32 pair modes, N <= 128 ----
+template <typename ST, bool SPLIT, int T, int MINB>
+int launch_warp_t(pms_sim *h, int wpc)
+{
+    const size_t smem = WarpSmem<ST, SPLIT>::bytes(32 * T) * wpc;
+    const int threads = (wpc + 1) * 32;
+    const int groups = (h->W + wpc - 1) / wpc;
+    int blocks = groups;
+    h->a.wpc = wpc;
+    auto kern = hsfm_warp_kernel<ST, SPLIT, T, MINB>;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    const int slots = occ * h->sm_count;
+    h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
+    int want = h->tune_chunks;
+    if (want == 0 && groups > slots && h->a.n_steps >= 64) want = h->a.n_steps / 32 < 8 ? h->a.n_steps / 32 : 8;
+    if (want > 1 && slots > 0) {
+        h->a.chunk_steps = (h->a.n_steps + want - 1) / want;
+        h->a.n_chunks = (h->a.n_steps + h->a.chunk_steps - 1) / h->a.chunk_steps;
+    }
+    if (h->a.n_chunks > 1) {
+        if (groups > h->sched_cap) {
+            if (h->a.group_done) cudaFree(h->a.group_done);
+            h->a.group_done = nullptr; h->sched_cap = 0;
+            CK(cudaMalloc((void **)&h->a.group_done, sizeof(int) * (size_t)groups));
+            h->sched_cap = groups;
+        }
+        CK(cudaMemsetAsync(h->a.group_done, 0, sizeof(int) * (size_t)groups, h->stream));
+        CK(cudaMemsetAsync(h->a.work_counter, 0, sizeof(int), h->stream));
+        const long long total = (long long)groups * h->a.n_chunks;
+        blocks = (int)(total < slots ? total : slots);
+    }
+    kern<<<blocks, threads, smem, h->stream>>>(h->a);
+    CK(cudaGetLastError());
+    h->info.kernel = 3;
+    h->info.threads_per_block = threads;
+    h->info.blocks = blocks;
+    h->info.worlds_per_block = wpc;
+    h->info.j_split = 0;
+    h->info.smem_bytes = (int)smem;
+    h->info.n_chunks = h->a.n_chunks;
+    h->info.blocks_per_sm = occ;
+    h->info.kernel_launches++;
+    return 0;
+}
+
+template <int T, int MINB> int launch_warp_p(pms_sim *h, int wpc)
+{
+    if (h->precision == PMS_FP32) return launch_warp_t<float, false, T, MINB>(h, wpc);
+    return launch_warp_t<double, true, T, MINB>(h, wpc);
+}
+
+template <int MINB> int launch_warp_m(pms_sim *h, int wpc)
+{
+    switch (h->Np / 32) {
+    case 1: return launch_warp_p<1, MINB>(h, wpc);
+    case 2: return launch_warp_p<2, MINB>(h, wpc);
+    case 3: return launch_warp_p<3, MINB>(h, wpc);
+    default: return launch_warp_p<4, MINB>(h, wpc);
+    }
+}
+
+int launch_warp(pms_sim *h)
+{
+    int wpc = h->tune_wpc > 0 ? h->tune_wpc : WARP_MAX_WPC;
+    if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
+    if (wpc > h->W) wpc = h->W;
+    if (const char *e = getenv("PMS_WARP_MINB")) h->tune_minb = atoi(e);   // experiment knob
+    return h->tune_minb == 2 ? launch_warp_m<2>(h, wpc) : launch_warp_m<3>(h, wpc);
 }
 
 // large crowds: one launch per step, cluster-multicast j-tiles (hsfm_large.cuh)
@@ -695,7 +769,11 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     fill_consts(h->a);
     int rc;
     if (h->a.robot_model == ROBOT_NONE && (rc = clear_sensor_outputs(h))) return rc;
-    if (h->Np + 32 <= 1024 && !h->force_large) rc = launch_small(h);
+    // j_split < 0 selects the directed-pair kernel for small worlds too (tests, comparisons)
+    const bool warp_ok = h->precision != PMS_FP64 && h->Np <= 32 * WARP_MAX_TILES && h->tune_S >= 0;
+    if (h->force_large) rc = launch_large(h);
+    else if (warp_ok) rc = launch_warp(h);
+    else if (h->Np + 32 <= 1024) rc = launch_small(h);
     else rc = launch_large(h);
     if (rc) return rc;
     h->a.steps_done += n_steps;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <math.h>
 
 #define PMS_PI 3.14159265358979323846
 #define PMS_TWO_PI 6.28318530717958647692
@@ -72,6 +73,8 @@ struct HsfmArgs {
     PedConsts<float> kc_f;
     PedConsts<double> kc_d;
     double sense_lim2;               // squared cheap-reject radius of the sensor pass
+    // hsfm_warp.cuh: exponent offset r_ij*log2(e)/B rounded to fp32, and A rescaled by the rounding residue
+    float warp_rc, warp_A;
 };
 
 template <typename T> __host__ __device__ inline void fill_pair(PairK<T> &k, const HsfmArgs &a, double radius_j)
@@ -95,6 +98,9 @@ inline void fill_consts(HsfmArgs &a)
     const double coll_r = a.robot_radius + PMS_PED_RADIUS_CONST;
     const double lim = (a.det_enabled ? (a.det_max_dist > coll_r ? a.det_max_dist : coll_r) : coll_r) * 1.001 + 1e-3;
     a.sense_lim2 = lim * lim;
+    const double rc = (a.ped_radius + a.ped_radius) * (1.4426950408889634 / a.B);
+    a.warp_rc = (float)rc;
+    a.warp_A = (float)(a.A * exp2(rc - (double)a.warp_rc));
 }
 __device__ __forceinline__ const PairK<float> &kpp_of(const HsfmArgs &a, float) { return a.kpp_f; }
 __device__ __forceinline__ const PairK<double> &kpp_of(const HsfmArgs &a, double) { return a.kpp_d; }
