@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpms_b200.so")
-SOURCES = ["pms_api.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
-HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_warp.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
+SOURCES = ["pms_api.cu", "hsfm_warp.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
+HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_warp.cuh", "hsfm_warp_api.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
 
 
 def nvcc_path() -> str:
@@ -35,12 +35,15 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
              [f"-D{d}" for d in defines]
     if verbose:
         common.insert(0, "-Xptxas=-v")
-    objs = []
-    for src in SOURCES:
+    objs, procs = [], []
+    for src in SOURCES:   # one nvcc per translation unit, in parallel
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + (".o" if out == LIB else ".exp.o"))
         extra = ["-fmad=false"] if src == "orca.cu" else []
-        subprocess.run([nvcc] + common + extra + ["-c", os.path.join(CSRC, src), "-o", obj], check=True)
+        procs.append((src, subprocess.Popen([nvcc] + common + extra + ["-c", os.path.join(CSRC, src), "-o", obj])))
         objs.append(obj)
+    for src, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, f"nvcc {src}")
     subprocess.run([nvcc, "-shared", "-o", out] + objs, check=True)
     return out
     return LIB

@@ -27,6 +27,7 @@ struct RobotSlot {
 
 struct RobotRegs {
     double x, y, th, c0, c1, rx, ry, rth, vx, vy, vw;
+    double cs, sn;          // cos / sin of th (kept current by robot_load / robot_step)
     int world_collision;
 };
 
@@ -66,6 +67,7 @@ __device__ __forceinline__ void robot_load(const HsfmArgs &a, int w, RobotRegs &
     r.rx = a.robot_rear[3 * w]; r.ry = a.robot_rear[3 * w + 1]; r.rth = a.robot_rear[3 * w + 2];
     r.vx = a.robot_vel[3 * w]; r.vy = a.robot_vel[3 * w + 1]; r.vw = a.robot_vel[3 * w + 2];
     r.world_collision = a.robot_world_collision[w];
+    sincos(r.th, &r.sn, &r.cs);
 }
 
 __device__ __forceinline__ void robot_store(const HsfmArgs &a, int w, const RobotRegs &r)
@@ -78,7 +80,7 @@ __device__ __forceinline__ void robot_store(const HsfmArgs &a, int w, const Robo
 }
 
 // One robot step `s` of world w (robot/_unicycle.py:53-69,27-33; robot/_bicycle.py:71-95,30-32).
-__device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, RobotRegs &r)
+static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, RobotRegs &r)
 {
     if (a.robot_model != ROBOT_UNICYCLE && a.robot_model != ROBOT_BICYCLE) return;
     double u0 = r.c0, u1 = r.c1;
@@ -102,6 +104,7 @@ __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, RobotRe
             r.x = nx; r.y = ny; r.th = nth; r.c0 = u0; r.c1 = u1;
         }
         sincos(r.th, &sn, &cs_);
+        r.cs = cs_; r.sn = sn;
         r.vx = r.c0 * cs_; r.vy = r.c0 * sn; r.vw = r.c1;
     } else {
         double sn, cs_;
@@ -117,7 +120,7 @@ __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, RobotRe
             r.world_collision = 1;
         } else {
             r.world_collision = 0;
-            r.x = xc; r.y = yc; r.th = nth;
+            r.x = xc; r.y = yc; r.th = nth; r.cs = cs_; r.sn = sn;
             r.rx = xr; r.ry = yr; r.rth = nth;
             r.c0 = u0; r.c1 = u1;
         }
@@ -192,7 +195,7 @@ struct SenseOut {
 };
 
 // exact fp64 evaluation for a pedestrian that survived the cheap reject (rare -> out of line)
-__device__ __noinline__ void sense_ped_exact(const HsfmArgs &a, const RobotSlot &rb, double px, double py,
+static __device__ __noinline__ void sense_ped_exact(const HsfmArgs &a, const RobotSlot &rb, double px, double py,
                                              bool want_values, SenseOut &o)
 {
     const double coll_r = a.robot_radius + PMS_PED_RADIUS_CONST;

@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "hsfm_small.cuh"
-#include "hsfm_warp.cuh"
+#include "hsfm_warp_api.cuh"
 #include "hsfm_large.cuh"
 #include "sensors.cuh"
 #include "orca.cuh"
@@ -258,19 +258,21 @@ int launch_small(pms_sim *h)
     }
 }
 
-// ---- launch of the warp-per-world symmetric-pair kernel (hsfm_warp.cuh): fp32 pair modes, N <= 128 ----
-template <typename ST, bool SPLIT, int T, int MINB>
-int launch_warp_t(pms_sim *h, int wpc)
+// ---- launch of the warp-per-world symmetric-pair kernel (hsfm_warp.cu): fp32 pair modes, N <= 128 ----
+int launch_warp(pms_sim *h)
 {
-    const size_t smem = WarpSmem<ST, SPLIT>::bytes(32 * T) * wpc;
+    int wpc = h->tune_wpc > 0 ? h->tune_wpc : WARP_MAX_WPC;
+    if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
+    if (wpc > h->W) wpc = h->W;
+    if (const char *e = getenv("PMS_WARP_MINB")) h->tune_minb = atoi(e);   // experiment knob
+    const int T = h->Np / 32, minb = h->tune_minb == 2 ? 2 : 3;
+    const bool split = h->precision == PMS_MIXED;
     const int threads = (wpc + 1) * 32;
     const int groups = (h->W + wpc - 1) / wpc;
-    int blocks = groups;
+    int blocks = groups, occ = 0;
+    size_t smem = 0;
     h->a.wpc = wpc;
-    auto kern = hsfm_warp_kernel<ST, SPLIT, T, MINB>;
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    CK(warp_kernel_prepare(split, T, minb, wpc, &occ, &smem));
     const int slots = occ * h->sm_count;
     h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
     int want = h->tune_chunks;
@@ -291,8 +293,7 @@ int launch_warp_t(pms_sim *h, int wpc)
         const long long total = (long long)groups * h->a.n_chunks;
         blocks = (int)(total < slots ? total : slots);
     }
-    kern<<<blocks, threads, smem, h->stream>>>(h->a);
-    CK(cudaGetLastError());
+    CK(warp_kernel_launch(split, T, minb, h->a, blocks, threads, smem, h->stream));
     h->info.kernel = 3;
     h->info.threads_per_block = threads;
     h->info.blocks = blocks;
@@ -303,31 +304,6 @@ int launch_warp_t(pms_sim *h, int wpc)
     h->info.blocks_per_sm = occ;
     h->info.kernel_launches++;
     return 0;
-}
-
-template <int T, int MINB> int launch_warp_p(pms_sim *h, int wpc)
-{
-    if (h->precision == PMS_FP32) return launch_warp_t<float, false, T, MINB>(h, wpc);
-    return launch_warp_t<double, true, T, MINB>(h, wpc);
-}
-
-template <int MINB> int launch_warp_m(pms_sim *h, int wpc)
-{
-    switch (h->Np / 32) {
-    case 1: return launch_warp_p<1, MINB>(h, wpc);
-    case 2: return launch_warp_p<2, MINB>(h, wpc);
-    case 3: return launch_warp_p<3, MINB>(h, wpc);
-    default: return launch_warp_p<4, MINB>(h, wpc);
-    }
-}
-
-int launch_warp(pms_sim *h)
-{
-    int wpc = h->tune_wpc > 0 ? h->tune_wpc : WARP_MAX_WPC;
-    if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
-    if (wpc > h->W) wpc = h->W;
-    if (const char *e = getenv("PMS_WARP_MINB")) h->tune_minb = atoi(e);   // experiment knob
-    return h->tune_minb == 2 ? launch_warp_m<2>(h, wpc) : launch_warp_m<3>(h, wpc);
 }
 
 // large crowds: one launch per step, cluster-multicast j-tiles (hsfm_large.cuh)

@@ -75,6 +75,9 @@ struct HsfmArgs {
     double sense_lim2;               // squared cheap-reject radius of the sensor pass
     // hsfm_warp.cuh: exponent offset r_ij*log2(e)/B rounded to fp32, and A rescaled by the rounding residue
     float warp_rc, warp_A;
+    // fp32 pre-filter of the collision list / detector: squared radii 1e-5 inside and outside the exact thresholds and
+    // cos(fov/2); only pedestrians between the two (or detected on the last step) reach the fp64 predicate
+    float sn_coll_lo2, sn_coll_hi2, sn_det_lo2, sn_det_hi2, sn_any_hi2, sn_chf;
 };
 
 template <typename T> __host__ __device__ inline void fill_pair(PairK<T> &k, const HsfmArgs &a, double radius_j)
@@ -98,6 +101,15 @@ inline void fill_consts(HsfmArgs &a)
     const double coll_r = a.robot_radius + PMS_PED_RADIUS_CONST;
     const double lim = (a.det_enabled ? (a.det_max_dist > coll_r ? a.det_max_dist : coll_r) : coll_r) * 1.001 + 1e-3;
     a.sense_lim2 = lim * lim;
+    {
+        const double eps = 1e-5, lo = (1.0 - eps) * (1.0 - eps), hi = (1.0 + eps) * (1.0 + eps);
+        a.sn_coll_lo2 = (float)(coll_r * coll_r * lo); a.sn_coll_hi2 = (float)(coll_r * coll_r * hi);
+        const double md = a.det_enabled && a.det_max_dist > 0.0 ? a.det_max_dist : 0.0;
+        a.sn_det_lo2 = (float)(md * md * lo); a.sn_det_hi2 = a.det_enabled ? (float)(md * md * hi) : -1.0f;
+        a.sn_any_hi2 = a.sn_coll_hi2 > a.sn_det_hi2 ? a.sn_coll_hi2 : a.sn_det_hi2;
+        // |diff| <= fov/2  <=>  cos(diff) >= cos(fov/2) for 0 <= fov/2 < pi; always true beyond, never for fov < 0
+        a.sn_chf = a.det_half_fov < 0.0 ? 2.0f : (a.det_half_fov >= PMS_PI ? -2.0f : (float)cos(a.det_half_fov));
+    }
     const double rc = (a.ped_radius + a.ped_radius) * (1.4426950408889634 / a.B);
     a.warp_rc = (float)rc;
     a.warp_A = (float)(a.A * exp2(rc - (double)a.warp_rc));
