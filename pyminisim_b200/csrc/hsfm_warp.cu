@@ -6,12 +6,12 @@ namespace {
 
 template <typename F> cudaError_t dispatch(bool split, int T, int minb, F &&f)
 {
+#define PMS_WARP_INST(TT, MB)                                                                               \
+    (split ? f(hsfm_warp_kernel<double, true, TT, MB>, WarpSmem<double, true>::bytes(32 * TT))              \
+           : f(hsfm_warp_kernel<float, false, TT, MB>, WarpSmem<float, false>::bytes(32 * TT)))
 #define PMS_WARP_CASE(TT)                                                                                   \
     case TT:                                                                                                \
-        if (split) return minb == 2 ? f(hsfm_warp_kernel<double, true, TT, 2>, WarpSmem<double, true>::bytes(32 * TT))   \
-                                    : f(hsfm_warp_kernel<double, true, TT, 3>, WarpSmem<double, true>::bytes(32 * TT));  \
-        return minb == 2 ? f(hsfm_warp_kernel<float, false, TT, 2>, WarpSmem<float, false>::bytes(32 * TT))              \
-                         : f(hsfm_warp_kernel<float, false, TT, 3>, WarpSmem<float, false>::bytes(32 * TT));
+        return minb == 3 ? PMS_WARP_INST(TT, 3) : (minb == 4 ? PMS_WARP_INST(TT, 4) : PMS_WARP_INST(TT, 2));
     switch (T) {
         PMS_WARP_CASE(1)
         PMS_WARP_CASE(2)
@@ -20,6 +20,7 @@ template <typename F> cudaError_t dispatch(bool split, int T, int minb, F &&f)
     default: return cudaErrorInvalidValue;
     }
 #undef PMS_WARP_CASE
+#undef PMS_WARP_INST
 }
 
 } // namespace
@@ -33,7 +34,7 @@ cudaError_t warp_kernel_prepare(bool split, int T, int minb, int wpc, int *block
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, (wpc + 1) * 32, smem);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, wpc * 32, smem);
     });
 }
 

@@ -5,7 +5,7 @@
 namespace pms {
 
 constexpr int WARP_MAX_TILES = 4;           // N <= 128
-constexpr int WARP_MAX_WPC = 8;             // world warps per CTA (+ 1 robot warp = 288 threads)
+constexpr int WARP_MAX_WPC = 8;             // world warps per CTA (256 threads)
 
 // shared-memory opt-in + occupancy of the instantiation (split = MIXED precision, T = ceil(N/32) tiles,
 // minb = __launch_bounds__ minimum CTAs per SM: 2 or 3) for `wpc` worlds per CTA

@@ -261,13 +261,13 @@ int launch_small(pms_sim *h)
 // ---- launch of the warp-per-world symmetric-pair kernel (hsfm_warp.cu): fp32 pair modes, N <= 128 ----
 int launch_warp(pms_sim *h)
 {
-    int wpc = h->tune_wpc > 0 ? h->tune_wpc : WARP_MAX_WPC;
+    int wpc = h->tune_wpc > 0 ? h->tune_wpc : 4;
     if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
     if (wpc > h->W) wpc = h->W;
     if (const char *e = getenv("PMS_WARP_MINB")) h->tune_minb = atoi(e);   // experiment knob
-    const int T = h->Np / 32, minb = h->tune_minb == 2 ? 2 : 3;
+    const int T = h->Np / 32, minb = (h->tune_minb == 3 || h->tune_minb == 4) ? h->tune_minb : 2;
     const bool split = h->precision == PMS_MIXED;
-    const int threads = (wpc + 1) * 32;
+    const int threads = wpc * 32;
     const int groups = (h->W + wpc - 1) / wpc;
     int blocks = groups, occ = 0;
     size_t smem = 0;
