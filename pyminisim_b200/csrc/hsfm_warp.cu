@@ -4,14 +4,19 @@
 namespace pms {
 namespace {
 
-template <typename F> cudaError_t dispatch(bool split, int T, int minb, F &&f)
+template <typename F> cudaError_t dispatch(bool split, int T, int cfg, F &&f)
 {
-#define PMS_WARP_INST(TT, MB)                                                                               \
-    (split ? f(hsfm_warp_kernel<double, true, TT, MB>, WarpSmem<double, true>::bytes(32 * TT))              \
-           : f(hsfm_warp_kernel<float, false, TT, MB>, WarpSmem<float, false>::bytes(32 * TT)))
+#define PMS_WARP_INST(TT, CF)                                                                               \
+    (split ? f(hsfm_warp_kernel<double, true, TT, CF>, WarpSmem<double, true>::bytes(32 * TT))              \
+           : f(hsfm_warp_kernel<float, false, TT, CF>, WarpSmem<float, false>::bytes(32 * TT)))
 #define PMS_WARP_CASE(TT)                                                                                   \
     case TT:                                                                                                \
-        return minb == 3 ? PMS_WARP_INST(TT, 3) : (minb == 4 ? PMS_WARP_INST(TT, 4) : PMS_WARP_INST(TT, 2));
+        switch (cfg) {                                                                                      \
+        case 1: return PMS_WARP_INST(TT, 1);                                                                \
+        case 2: return PMS_WARP_INST(TT, 2);                                                                \
+        case 3: return PMS_WARP_INST(TT, 3);                                                                \
+        default: return PMS_WARP_INST(TT, 0);                                                               \
+        }
     switch (T) {
         PMS_WARP_CASE(1)
         PMS_WARP_CASE(2)
@@ -25,9 +30,9 @@ template <typename F> cudaError_t dispatch(bool split, int T, int minb, F &&f)
 
 } // namespace
 
-cudaError_t warp_kernel_prepare(bool split, int T, int minb, int wpc, int *blocks_per_sm, size_t *smem_bytes)
+cudaError_t warp_kernel_prepare(bool split, int T, int cfg, int wpc, int *blocks_per_sm, size_t *smem_bytes)
 {
-    return dispatch(split, T, minb, [&](auto kern, size_t per_world) {
+    return dispatch(split, T, cfg, [&](auto kern, size_t per_world) {
         const size_t smem = per_world * wpc;
         *smem_bytes = smem;
         if (smem > 48 * 1024) {
@@ -38,10 +43,10 @@ cudaError_t warp_kernel_prepare(bool split, int T, int minb, int wpc, int *block
     });
 }
 
-cudaError_t warp_kernel_launch(bool split, int T, int minb, const HsfmArgs &a, int blocks, int threads, size_t smem,
+cudaError_t warp_kernel_launch(bool split, int T, int cfg, const HsfmArgs &a, int blocks, int threads, size_t smem,
                                cudaStream_t stream)
 {
-    return dispatch(split, T, minb, [&](auto kern, size_t) {
+    return dispatch(split, T, cfg, [&](auto kern, size_t) {
         kern<<<blocks, threads, smem, stream>>>(a);
         return cudaGetLastError();
     });

@@ -264,8 +264,9 @@ int launch_warp(pms_sim *h)
     int wpc = h->tune_wpc > 0 ? h->tune_wpc : 4;
     if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
     if (wpc > h->W) wpc = h->W;
-    if (const char *e = getenv("PMS_WARP_MINB")) h->tune_minb = atoi(e);   // experiment knob
-    const int T = h->Np / 32, minb = (h->tune_minb == 3 || h->tune_minb == 4) ? h->tune_minb : 2;
+    if (const char *e = getenv("PMS_WARP_CFG")) h->tune_minb = atoi(e);    // experiment knob: register budget
+    const int T = h->Np / 32, minb = h->tune_minb >= 0 && h->tune_minb <= 3 ? h->tune_minb : 0;
+    if ((minb == 1 || minb == 2) && wpc > 4) wpc = 4;
     const bool split = h->precision == PMS_MIXED;
     const int threads = wpc * 32;
     const int groups = (h->W + wpc - 1) / wpc;
