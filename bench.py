@@ -56,6 +56,11 @@ def parse_args():
     return ap.parse_args()
 
 
+KERNEL_NAMES = {0: "hsfm_small_kernel", 1: "hsfm_large_kernel", 3: "hsfm_warp_kernel"}
+# DRAM bytes per launch of the default workload from the committed ncu capture (None: not captured for that kernel)
+TRAFFIC_BYTES_PER_LAUNCH = {}
+
+
 def flops_per_update(n_peds: int) -> float:
     return 30.0 * n_peds + 120.0
 
@@ -321,11 +326,17 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak, "traffic": None,
+                         "frac": achieved_tflops / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(info["kernel"]),
                          "peak_source": "FP32 FMA-chain microbenchmark measured in this run (pms_measure_fp32_tflops); "
                                         "MEASURED_PEAKS.json has no non-tensor FP32 figure",
-                         "kernel": "hsfm_small_kernel", "flops_per_pedestrian_update": flops_per_update(N),
-                         "kernel_ms": kernel_ms},
+                         "kernel": KERNEL_NAMES.get(info["kernel"], str(info["kernel"])),
+                         "flops_per_pedestrian_update": flops_per_update(N), "kernel_ms": kernel_ms,
+                         "note": "achieved = ALGORITHMIC flops (30 per directed pair, SURVEY.md 8d) / measured kernel time. "
+                                 "hsfm_warp_kernel evaluates every UNORDERED pair once (f_ij = -f_ji), i.e. executes about "
+                                 "half of the algorithmic flops, so frac can exceed what the FMA pipe executes; the binding "
+                                 "unit is the XU (MUFU) pipe: one rsqrt + one ex2 per unordered pair (profiles/)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                           "of this command (profiles/r1_warp_kernel_ncu.md); bytes per launch"},
             "cpu_baseline": cpu, "clocks": clocks, "launch": info, "episode_stats": episode,
         }
         line.update(extra)
