@@ -111,8 +111,8 @@ def cpu_reference_run(args, n_steps_timed: int, warmup: int):
     from oracle import oracle as orc
     from pyminisim_b200.scenarios import make_bench_crowd
     cores = os.cpu_count() or 1
-    sample_worlds = min(args.worlds, max(2 * cores, 16))
-    sample_steps = min(args.sim_steps, 100)
+    sample_worlds = min(args.worlds, max(16 * cores, 64))       # ~1 s of CPU work per timed step on all cores
+    sample_steps = min(args.sim_steps, 1000)
     sc = make_bench_crowd(sample_worlds, args.peds)
 
     def fresh():
@@ -163,11 +163,33 @@ def run_reference(args):
             "gpu_launches": 0,
             "note": "reference is Python+numba and cannot travel to the GPU box; this arm is the C port of its "
                     "algorithm (oracle/), pinned to the live reference by tests/golden, on all host cores"}
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout (saved before fd 1 was pointed at stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner on stdout) must not pollute the JSON line: everything written to
+    fd 1 from here on lands on stderr; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -340,7 +362,7 @@ def main():
             "cpu_baseline": cpu, "clocks": clocks, "launch": info, "episode_stats": episode,
         }
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     sim.close()
     if world_size > 1:
         dist.destroy_process_group()
