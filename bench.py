@@ -58,7 +58,7 @@ def parse_args():
 
 KERNEL_NAMES = {0: "hsfm_small_kernel", 1: "hsfm_large_kernel", 3: "hsfm_warp_kernel"}
 # DRAM bytes per launch of the default workload from the committed ncu capture (None: not captured for that kernel)
-TRAFFIC_BYTES_PER_LAUNCH = {}
+TRAFFIC_BYTES_PER_LAUNCH = {3: 17762304}
 
 
 def flops_per_update(n_peds: int) -> float:
@@ -348,7 +348,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(info["kernel"]),
+                         "frac": achieved_tflops / peak,
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(info["kernel"]) if (W, N, K, args.precision) == (4096, 64, 1000, "fp32") else None,
                          "peak_source": "FP32 FMA-chain microbenchmark measured in this run (pms_measure_fp32_tflops); "
                                         "MEASURED_PEAKS.json has no non-tensor FP32 figure",
                          "kernel": KERNEL_NAMES.get(info["kernel"], str(info["kernel"])),

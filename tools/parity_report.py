@@ -33,10 +33,15 @@ def main():
                     done = h
                     p, v = c.get_state()
                     fin = np.isfinite(o.poses).all(axis=(1, 2)) & (np.abs(o.vels[..., :2]).max(axis=(1, 2)) < 10)
+                    # a world on the brink of the explicit-Euler blow-up may blow up on one side only: counted, not averaged
+                    with np.errstate(invalid="ignore"):
+                        cuda_ok = np.isfinite(p).all(axis=(1, 2)) & (np.abs(v[..., :2]).max(axis=(1, 2)) < 10)
+                    diverged = int((fin & ~cuda_ok).sum())
+                    fin &= cuda_ok
                     if not fin.any():
                         continue
                     perw = [rel(p[w], o.poses[w]) for w in np.nonzero(fin)[0]]
-                    out.append(dict(scenario=gen_name, n=n, precision=prec, steps=h, worlds=int(fin.sum()),
+                    out.append(dict(scenario=gen_name, n=n, precision=prec, steps=h, worlds=int(fin.sum()), blown_up_on_gpu_only=diverged,
                                     pos_max=max(perw), pos_median=float(np.median(perw)),
                                     vel_max=rel(v[fin], o.vels[fin])))
                     print(json.dumps(out[-1]))
