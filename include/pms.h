@@ -163,7 +163,7 @@ int pms_orca_get_agents(pms_sim *h, double *poses /*(W,N,3)*/, double *velocitie
 
 /* ---- launch introspection (bench / tests) ---- */
 typedef struct {
-    int kernel;            /* 0 = small-world fused kernel, 1 = large-crowd kernel */
+    int kernel;            /* 0 = directed-pair small-world kernel, 1 = large-crowd kernel, 2 = ORCA, 3 = warp-per-world kernel */
     int threads_per_block, blocks, worlds_per_block, j_split; /* large kernel: j_split = cluster size */
     int smem_bytes;
     int n_chunks;          /* > 1: persistent CTAs pull (chunk, world-group) items dynamically */
@@ -171,8 +171,14 @@ typedef struct {
     int64_t kernel_launches; /* cumulative count of kernels launched by this handle */
 } pms_launch_info;
 int pms_get_launch_info(pms_sim *h, pms_launch_info *out);
-/* tuning overrides; 0 = automatic.  n_chunks = 1 forces the static grid.  cluster_size (1,2,4,8) is the
- * multicast width of the large-crowd kernel; a negative value also forces that kernel for small N. */
+/* tuning overrides; 0 = automatic.
+ *   j_split        : FP32 / MIXED worlds of up to 128 pedestrians run the warp-per-world symmetric-pair kernel; there
+ *                    j_split 1..3 selects a smaller register budget (96 / 80 / 80 registers per thread, more resident warps), and a negative
+ *                    value selects the directed-pair kernel instead (-1: automatic j-slices, -1-S: S slices).  For the
+ *                    directed-pair kernel (FP64, larger worlds) j_split = 1, 2, 4, 8 is the number of j-slices.
+ *   n_chunks       : 1 forces the static grid; negative: the large-crowd kernel visits every j-tile (no exact pruning).
+ *   cluster_size   : (1,2,4,8) multicast width of the large-crowd kernel; a negative value also forces that kernel
+ *                    for small N. */
 int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, int cluster_size);
 
 /* measured FP32 FMA-pipe peak (TFLOP/s, FMA = 2 FLOP) of `device`: the roofline denominator of the

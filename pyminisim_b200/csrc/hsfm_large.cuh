@@ -11,6 +11,13 @@
 //                         memory of all C CTAs, so a tile is read from L2 once per cluster.  Buffer reuse is
 //                         guarded by a split cluster barrier (arrive after compute, wait before refill).
 // The pair math is the same packed-FP32 (FFMA2) code as the small-world kernel.
+//
+// Exact j-tile pruning (fp32 pair arithmetic): A exp((r_ij - d)/B) is computed as ex2.approx.ftz of an exponent that is
+// below -126 for d > r_ij + 126 B / log2(e) (7.6 m with the default parameters), where the instruction returns exactly 0 and
+// the pair contributes exactly nothing.  large_box_kernel keeps one bounding box per j-tile; a cluster skips every j-tile
+// whose box is farther than that from the box of its own pedestrians -- no load, no arithmetic, bit-identical forces.
+// With spatially coherent pedestrian indices (any grid- or scan-line ordered crowd) most of the N^2 work disappears;
+// with random indices nothing is skipped and the cost is one tiny extra launch per step.
 #pragma once
 #include "hsfm_small.cuh"
 
@@ -32,6 +39,8 @@ struct LargeArgs {
     int step;                        // global step index of this launch (events, controls)
     int last;                        // 1 if this is the last step of the pms_hsfm_step call
     const RobotSlot *robot_slot;     // (W) robot state for this step
+    const float4 *boxes;             // (W, tiles_j) bounding box {xmin, xmax, ymin, ymax} of every j-tile of view_src, or NULL
+    float cut2;                      // squared distance beyond which the pair force is exactly 0 (fp32 pair arithmetic)
 };
 
 struct LargeScratch {
@@ -39,6 +48,7 @@ struct LargeScratch {
     void *view[2] = {nullptr, nullptr};
     RobotSlot *robot_slot = nullptr;
     RobotRegs *robot_regs = nullptr;
+    float4 *boxes = nullptr;
     int Npad = 0;
     int parity = 0;                  // which view buffer holds the current state
     bool view_valid = false;
@@ -47,7 +57,7 @@ struct LargeScratch {
 
 inline void large_free(LargeScratch &s)
 {
-    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs};
+    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes};
     for (void *q : p) if (q) cudaFree(q);
     s = LargeScratch{};
 }
@@ -132,6 +142,44 @@ __global__ void large_view_kernel(const __grid_constant__ HsfmArgs a, PT *view, 
     }
 }
 
+// ---- bounding box of every j-tile of the pair view (exact pruning, see the file header) ------------------------
+// One CTA of 128 threads per (world, j-tile).  Padding pedestrians are left out; a tile that holds a non-finite
+// coordinate gets an infinite box (never skipped: its NaN must reach every other pedestrian like in the reference).
+template <typename PT>
+__global__ void __launch_bounds__(128) large_box_kernel(int N, int Npad, int tiles_j, const PT *view, size_t stride, float4 *boxes)
+{
+    const int w = blockIdx.x / tiles_j, jt = blockIdx.x - w * tiles_j;
+    const PT *xs = view + (size_t)w * Npad + (size_t)jt * LARGE_TJ, *ys = xs + stride;
+    float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F;
+    bool bad = false;
+    for (int k = threadIdx.x; k < LARGE_TJ; k += 128) {
+        if (jt * LARGE_TJ + k >= N) break;
+        const float x = (float)xs[k], y = (float)ys[k];
+        bad |= !(fabsf(x) <= 3.0e38f) || !(fabsf(y) <= 3.0e38f);
+        xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    __shared__ float4 part[4];
+    __shared__ int sbad[4];
+    if ((threadIdx.x & 31) == 0) { part[threadIdx.x >> 5] = make_float4(xmin, xmax, ymin, ymax); sbad[threadIdx.x >> 5] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float4 b = part[0];
+        int any_bad = sbad[0];
+        for (int q = 1; q < 4; ++q) {
+            b.x = fminf(b.x, part[q].x); b.y = fmaxf(b.y, part[q].y); b.z = fminf(b.z, part[q].z); b.w = fmaxf(b.w, part[q].w);
+            any_bad |= sbad[q];
+        }
+        if (any_bad) b = make_float4(-CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, CUDART_INF_F);
+        boxes[blockIdx.x] = b;
+    }
+}
+
 // ---- the step kernel --------------------------------------------------------------------------------
 template <typename PT, typename ST, bool SPLIT>
 __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
@@ -142,6 +190,7 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     // [2 stages][NARR arrays][TJ] of PT (lo arrays are float == PT in MIXED), then 2 mbarriers
     PT *tiles = reinterpret_cast<PT *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 2 * NARR * LARGE_TJ * sizeof(PT));
+    int *tile_list = reinterpret_cast<int *>(full + 2);      // [tiles_j] j-tiles this cluster has to visit, then their count
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int w = blockIdx.x / la.tiles_i, it = blockIdx.x - w * la.tiles_i;
@@ -157,14 +206,35 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // j-tiles to visit: every CTA of the cluster derives the same list from the same boxes
+        int K = 0;
+        if (la.boxes != nullptr && sizeof(PT) == 4) {
+            const float4 *bx = la.boxes + (size_t)w * la.tiles_j;
+            const int it0 = it - (int)crank;                                   // first i-tile of the cluster
+            const int jlo = it0 * LARGE_TI / LARGE_TJ;
+            const int jhi = min(la.tiles_j - 1, ((it0 + la.cluster) * LARGE_TI - 1) / LARGE_TJ);
+            float4 c = bx[jlo];
+            for (int q = jlo + 1; q <= jhi; ++q) {
+                const float4 o = bx[q];
+                c.x = fminf(c.x, o.x); c.y = fmaxf(c.y, o.y); c.z = fminf(c.z, o.z); c.w = fmaxf(c.w, o.w);
+            }
+            for (int jt = 0; jt < la.tiles_j; ++jt) {
+                const float4 o = bx[jt];
+                const float gx = fmaxf(0.f, fmaxf(o.x - c.y, c.x - o.y)), gy = fmaxf(0.f, fmaxf(o.z - c.w, c.z - o.w));
+                if (!(gx * gx + gy * gy > la.cut2)) tile_list[K++] = jt;        // NaN / inf boxes are never skipped
+            }
+        } else {
+            for (int jt = 0; jt < la.tiles_j; ++jt) tile_list[K++] = jt;
+        }
+        tile_list[la.tiles_j] = K;
     }
     __syncthreads();
     cluster_arrive();
     cluster_wait();          // every CTA of the cluster has initialised its barriers
 
     constexpr uint32_t kTileBytes = NARR * LARGE_TJ * sizeof(PT);
-    auto issue = [&](int jt) {   // thread 0 only
-        const int b = jt & 1;
+    auto issue = [&](int k, int jt) {   // thread 0 only: tile jt into buffer k & 1
+        const int b = k & 1;
         PT *dst = tiles + (size_t)b * NARR * LARGE_TJ;
         mbar_expect_tx(&full[b], kTileBytes);
         const int C = la.cluster;
@@ -190,13 +260,14 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     PT fx = 0, fy = 0;
     float2 fxa = make_float2(0.f, 0.f), fya = fxa, fxb = fxa, fyb = fxa;
     const int i0 = i & ~31;
-    const int T = la.tiles_j;
-    if (tid == 0) issue(0);
-    for (int jt = 0; jt < T; ++jt) {
-        if (jt >= 1) cluster_wait();                 // everybody is done with the buffer tile jt+1 will overwrite
-        if (jt + 1 < T && tid == 0) issue(jt + 1);
-        mbar_wait(&full[jt & 1], (jt >> 1) & 1);
-        const PT *xs = tiles + (size_t)(jt & 1) * NARR * LARGE_TJ;
+    const int T = tile_list[la.tiles_j];
+    if (tid == 0) issue(0, tile_list[0]);
+    for (int k = 0; k < T; ++k) {
+        const int jt = tile_list[k];
+        if (k >= 1) cluster_wait();                  // everybody is done with the buffer the next tile will overwrite
+        if (k + 1 < T && tid == 0) issue(k + 1, tile_list[k + 1]);
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        const PT *xs = tiles + (size_t)(k & 1) * NARR * LARGE_TJ;
         const PT *ys = xs + LARGE_TJ, *vxs = xs + 2 * LARGE_TJ, *vys = xs + 3 * LARGE_TJ;
         const int jbase = jt * LARGE_TJ;
         if constexpr (sizeof(PT) == 4) {
@@ -244,7 +315,7 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
             for (int jl = 0; jl < jn; ++jl)
                 pair_accum(kpp, mx - xs[jl], my - ys[jl], vxs[jl] - mvx, vys[jl] - mvy, jbase + jl == i, fx, fy);
         }
-        cluster_arrive();                            // done reading buffer jt & 1
+        cluster_arrive();                            // done reading buffer k & 1
     }
     cluster_wait();
     if constexpr (sizeof(PT) == 4) {
@@ -351,8 +422,8 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
 
 // ---- host-side launch of n_steps large-crowd steps ---------------------------------------------------
 template <typename PT, typename ST, bool SPLIT>
-inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, cudaStream_t stream, long long *launches, int *out_blocks,
-                          int *out_smem)
+inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_tiles, cudaStream_t stream, long long *launches,
+                          int *out_blocks, int *out_smem)
 {
     constexpr int NARR = SPLIT ? 6 : 4;
     const int Npad = (a.N + LARGE_TJ - 1) / LARGE_TJ * LARGE_TJ;
@@ -360,7 +431,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, cudaStream_
     const size_t e2 = sizeof(ST) * 2;
     cudaError_t e;
     if (!s.pos2 || s.Npad != Npad) {
-        void *keep[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs};
+        void *keep[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes};
         for (void *q : keep) if (q) cudaFree(q);
         s = LargeScratch{};
         if ((e = cudaMalloc(&s.pos2, n * 16)) != cudaSuccess) return -2;
@@ -371,6 +442,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, cudaStream_
         if ((e = cudaMalloc(&s.view[1], s.view_bytes)) != cudaSuccess) return -2;
         if ((e = cudaMalloc((void **)&s.robot_slot, sizeof(RobotSlot) * a.W)) != cudaSuccess) return -2;
         if ((e = cudaMalloc((void **)&s.robot_regs, sizeof(RobotRegs) * a.W)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc((void **)&s.boxes, sizeof(float4) * (size_t)a.W * (Npad / LARGE_TJ))) != cudaSuccess) return -2;
         s.Npad = Npad;
     }
     // the pair view is rebuilt from the state at the start of every call (the host may have changed it)
@@ -381,7 +453,8 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, cudaStream_
     const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ;
     // grid must be a multiple of the cluster size and a cluster must stay inside one world
     while (cluster > 1 && (tiles_i % cluster != 0 || LARGE_TJ % cluster != 0)) cluster >>= 1;
-    const size_t smem = 2 * NARR * LARGE_TJ * sizeof(PT) + 2 * sizeof(uint64_t);
+    const size_t smem = 2 * NARR * LARGE_TJ * sizeof(PT) + 2 * sizeof(uint64_t) + sizeof(int) * (tiles_j + 1);
+    const bool prune = sizeof(PT) == 4 && prune_tiles;
     auto kern = hsfm_large_kernel<PT, ST, SPLIT>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
 
@@ -398,6 +471,12 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, cudaStream_
         la.view_src = s.view[src]; la.view_dst = s.view[dst];
         la.view_stride = nv; la.Npad = Npad; la.tiles_i = tiles_i; la.tiles_j = tiles_j; la.cluster = cluster;
         la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = s.robot_slot;
+        la.boxes = prune ? s.boxes : nullptr; la.cut2 = a.warp_cut2;
+        if (prune) {
+            if constexpr (sizeof(PT) == 4)
+                large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a.N, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes);
+            ++*launches;
+        }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(a.W * tiles_i)); cfg.blockDim = dim3(LARGE_TI); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
         cudaLaunchAttribute attr[1];

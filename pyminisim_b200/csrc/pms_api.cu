@@ -5,7 +5,6 @@
 
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -136,8 +135,9 @@ struct pms_sim {
     long long snap_steps = 0;
     bool has_snapshot = false;
     // tuning / introspection
-    int tune_S = 0, tune_wpc = 0, tune_chunks = 0, tune_cluster = 0, tune_minb = 0;
+    int tune_S = 0, tune_wpc = 0, tune_chunks = 0, tune_cluster = 0;
     bool force_large = false;
+    bool no_prune = false;   // large-crowd kernel: visit every j-tile (comparison / tests)
     int sm_count = 148;
     int sched_cap = 0;
     pms_launch_info info{};
@@ -264,8 +264,8 @@ int launch_warp(pms_sim *h)
     int wpc = h->tune_wpc > 0 ? h->tune_wpc : 4;
     if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
     if (wpc > h->W) wpc = h->W;
-    if (const char *e = getenv("PMS_WARP_CFG")) h->tune_minb = atoi(e);    // experiment knob: register budget
-    const int T = h->Np / 32, minb = h->tune_minb >= 0 && h->tune_minb <= 3 ? h->tune_minb : 0;
+    // register budget of the instantiation (WarpCfg in hsfm_warp.cuh): j_split 0 = 128 registers, 1 = 96, 2 = 80, 3 = 80 (256 threads)
+    const int T = h->Np / 32, minb = h->tune_S >= 1 && h->tune_S <= 3 ? h->tune_S : 0;
     if ((minb == 1 || minb == 2) && wpc > 4) wpc = 4;
     const bool split = h->precision == PMS_MIXED;
     const int threads = wpc * 32;
@@ -315,9 +315,9 @@ int launch_large(pms_sim *h)
     int blocks = 0, smem = 0, rc;
     long long launches = 0;
     switch (h->precision) {
-    case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, h->stream, &launches, &blocks, &smem); break;
-    case PMS_MIXED: rc = launch_large_t<float, double, true>(h->large, h->a, cluster, h->stream, &launches, &blocks, &smem); break;
-    default: rc = launch_large_t<double, double, false>(h->large, h->a, cluster, h->stream, &launches, &blocks, &smem); break;
+    case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, !h->no_prune, h->stream, &launches, &blocks, &smem); break;
+    case PMS_MIXED: rc = launch_large_t<float, double, true>(h->large, h->a, cluster, !h->no_prune, h->stream, &launches, &blocks, &smem); break;
+    default: rc = launch_large_t<double, double, false>(h->large, h->a, cluster, false, h->stream, &launches, &blocks, &smem); break;
     }
     if (rc) return fail(PMS_ERR_CUDA, std::string("large-crowd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->info.kernel = 1;
@@ -933,7 +933,8 @@ int pms_get_launch_info(pms_sim *h, pms_launch_info *out)
 int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, int cluster_size)
 {
     if (!h) return fail(PMS_ERR_INVALID, "handle is NULL");
-    h->tune_S = j_split; h->tune_wpc = worlds_per_block; h->tune_chunks = n_chunks;
+    h->tune_S = j_split; h->tune_wpc = worlds_per_block; h->tune_chunks = n_chunks < 0 ? 0 : n_chunks;
+    h->no_prune = n_chunks < 0;                       // negative: the large-crowd kernel visits every j-tile
     h->force_large = cluster_size < 0;               // negative: force the large-crowd kernel (tests)
     h->tune_cluster = cluster_size < 0 ? -cluster_size : cluster_size;
     return PMS_OK;

@@ -75,6 +75,7 @@ struct HsfmArgs {
     double sense_lim2;               // squared cheap-reject radius of the sensor pass
     // hsfm_warp.cuh: exponent offset r_ij*log2(e)/B rounded to fp32, and A rescaled by the rounding residue
     float warp_rc, warp_A;
+    float warp_cut2;                 // squared distance beyond which ex2.approx.ftz of the pair exponent is exactly 0
     // fp32 pre-filter of the collision list / detector: squared radii 1e-5 inside and outside the exact thresholds and
     // cos(fov/2); only pedestrians between the two (or detected on the last step) reach the fp64 predicate
     float sn_coll_lo2, sn_coll_hi2, sn_det_lo2, sn_det_hi2, sn_any_hi2, sn_chf;
@@ -113,6 +114,12 @@ inline void fill_consts(HsfmArgs &a)
     const double rc = (a.ped_radius + a.ped_radius) * (1.4426950408889634 / a.B);
     a.warp_rc = (float)rc;
     a.warp_A = (float)(a.A * exp2(rc - (double)a.warp_rc));
+    {   // (r_ij - d) log2(e)/B < -127.5 (ex2.approx.ftz flushes results below 2^-126 to exactly 0), 1e-3 relative margin;
+        // r_ij: the larger of the pedestrian-pedestrian and pedestrian-robot radius sums
+        const double rmax = a.ped_radius + (a.ped_radius > a.hsfm_robot_radius ? a.ped_radius : a.hsfm_robot_radius);
+        const double cut = (rmax + 127.5 * a.B / 1.4426950408889634) * (1.0 + 1e-3);
+        a.warp_cut2 = a.B > 0.0 ? (float)(cut * cut) : 3.0e38f;
+    }
 }
 __device__ __forceinline__ const PairK<float> &kpp_of(const HsfmArgs &a, float) { return a.kpp_f; }
 __device__ __forceinline__ const PairK<double> &kpp_of(const HsfmArgs &a, double) { return a.kpp_d; }

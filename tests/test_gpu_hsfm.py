@@ -363,3 +363,24 @@ def test_large_crowd_vs_oracle(n, steps):
         p, v = c.get_state()
         assert rel_err(p, o.poses) < tol, (precision, rel_err(p, o.poses))
         assert np.abs(v - o.vels).max() < tol * 1e4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "mixed"])
+def test_large_crowd_tile_pruning_is_bit_identical(precision):
+    """Skipping j-tiles whose bounding box is beyond the distance where ex2.approx.ftz underflows to exactly 0 changes
+    nothing: same bits with and without pruning, on a grid-ordered crowd (most tiles skipped) and on a shuffled one."""
+    n = 6000
+    sc = make_crowd(1, n, side=2.0 * np.sqrt(n), local_goals=5.0)
+    perm = np.random.default_rng(2).permutation(n)
+    for shuffled in (False, True):
+        if shuffled:
+            sc.poses, sc.table, sc.vmag, sc.vels = sc.poses[:, perm], sc.table[:, perm], sc.vmag[:, perm], sc.vels[:, perm]
+        outs = []
+        for n_chunks in (0, -1):          # -1: visit every j-tile
+            c = make_cuda(sc, precision)
+            c.set_tuning(0, 0, n_chunks, 0)
+            c.step(0.01, 7)
+            assert c.launch_info()["kernel"] == 1
+            outs.append(c.get_state() + c.get_detector() + (c.get_collisions(),) + c.get_stats())
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b, equal_nan=True)

@@ -20,11 +20,14 @@ from pyminisim_b200.batched import BatchedOrca, BatchedSimulation  # noqa: E402
 from pyminisim_b200.scenarios import make_bench_crowd, make_crowd  # noqa: E402
 
 
-def time_hsfm(name, W, N, steps, precision="fp32", tuning=None, large=False, reps=3):
+def time_hsfm(name, W, N, steps, precision="fp32", tuning=None, large=False, reps=3, shuffle=False):
     if large:
         sc = make_crowd(W, N, side=2.0 * np.sqrt(N), local_goals=5.0)
     else:
         sc = make_bench_crowd(W, N)
+    if shuffle:
+        perm = np.random.default_rng(0).permutation(N)
+        sc.poses, sc.table, sc.vmag, sc.vels = sc.poses[:, perm], sc.table[:, perm], sc.vmag[:, perm], sc.vels[:, perm]
     sim = BatchedSimulation(W, N, precision=precision)
     sim.set_state(sc.poses, sc.vels)
     sim.set_speeds(sc.vmag)
@@ -88,6 +91,9 @@ def main():
         time_hsfm("16384 x 32 warp kernel", 16384, 32, 1000)
     if "c3" in which:
         time_hsfm("C3 large crowd", 1, 65536, 20, large=True)
+        time_hsfm("C3 large crowd, every j-tile visited (no exact pruning)", 1, 65536, 20, large=True, tuning=(0, 0, -1, 0))
+        time_hsfm("C3 large crowd, shuffled pedestrian order", 1, 65536, 20, large=True, shuffle=True)
+        time_hsfm("C3 large crowd, MIXED", 1, 65536, 20, large=True, precision="mixed")
     if "c5" in which:
         time_orca("C5 ORCA", 2048, 64, 200)
 
