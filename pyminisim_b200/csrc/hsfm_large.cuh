@@ -40,6 +40,7 @@ struct LargeArgs {
     int last;                        // 1 if this is the last step of the pms_hsfm_step call
     const RobotSlot *robot_slot;     // (W) robot state for this step
     const float4 *boxes;             // (W, tiles_j) bounding box {xmin, xmax, ymin, ymax} of every j-tile of view_src, or NULL
+    const float4 *chunk_boxes;       // (W, Npad / 32) the same per chunk of 32 pedestrians
     float cut2;                      // squared distance beyond which the pair force is exactly 0 (fp32 pair arithmetic)
 };
 
@@ -48,7 +49,7 @@ struct LargeScratch {
     void *view[2] = {nullptr, nullptr};
     RobotSlot *robot_slot = nullptr;
     RobotRegs *robot_regs = nullptr;
-    float4 *boxes = nullptr;
+    float4 *boxes = nullptr, *chunk_boxes = nullptr;
     int Npad = 0;
     int parity = 0;                  // which view buffer holds the current state
     bool view_valid = false;
@@ -57,7 +58,7 @@ struct LargeScratch {
 
 inline void large_free(LargeScratch &s)
 {
-    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes};
+    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes};
     for (void *q : p) if (q) cudaFree(q);
     s = LargeScratch{};
 }
@@ -143,40 +144,50 @@ __global__ void large_view_kernel(const __grid_constant__ HsfmArgs a, PT *view, 
 }
 
 // ---- bounding box of every j-tile of the pair view (exact pruning, see the file header) ------------------------
-// One CTA of 128 threads per (world, j-tile).  Padding pedestrians are left out; a tile that holds a non-finite
-// coordinate gets an infinite box (never skipped: its NaN must reach every other pedestrian like in the reference).
+// One CTA of 128 threads per (world, j-tile): a box per chunk of 32 pedestrians (the warp-level skip unit of the step
+// kernel) and their union per tile (the cluster-level skip unit).  Padding pedestrians are left out (an all-padding chunk
+// has an empty box, which is far from everything); a chunk that holds a non-finite coordinate gets an infinite box (never
+// skipped: its NaN must reach every other pedestrian like in the reference).
+constexpr int LARGE_CHUNK = 32;       // pedestrians per chunk box (one warp's rows / one warp-level skip unit)
+
 template <typename PT>
-__global__ void __launch_bounds__(128) large_box_kernel(int N, int Npad, int tiles_j, const PT *view, size_t stride, float4 *boxes)
+__global__ void __launch_bounds__(128) large_box_kernel(int N, int Npad, int tiles_j, const PT *view, size_t stride, float4 *boxes,
+                                                        float4 *chunk_boxes)
 {
     const int w = blockIdx.x / tiles_j, jt = blockIdx.x - w * tiles_j;
     const PT *xs = view + (size_t)w * Npad + (size_t)jt * LARGE_TJ, *ys = xs + stride;
-    float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F;
-    bool bad = false;
-    for (int k = threadIdx.x; k < LARGE_TJ; k += 128) {
-        if (jt * LARGE_TJ + k >= N) break;
-        const float x = (float)xs[k], y = (float)ys[k];
-        bad |= !(fabsf(x) <= 3.0e38f) || !(fabsf(y) <= 3.0e38f);
-        xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
-    }
+    const float inf = CUDART_INF_F;
+    float4 tb = make_float4(inf, -inf, inf, -inf);            // this warp's share of the tile box
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    for (int m = 0; m < LARGE_TJ / 128; ++m) {                // warp q owns chunks q, q+4, q+8, ... of the tile
+        const int k = m * 128 + threadIdx.x;
+        float xmin = inf, xmax = -inf, ymin = inf, ymax = -inf;
+        bool bad = false;
+        if (jt * LARGE_TJ + k < N) {
+            const float x = (float)xs[k], y = (float)ys[k];
+            bad = !(fabsf(x) <= 3.0e38f) || !(fabsf(y) <= 3.0e38f);
+            xmin = xmax = x; ymin = ymax = y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        float4 cb = make_float4(xmin, xmax, ymin, ymax);
+        if (__any_sync(0xffffffffu, bad)) cb = make_float4(-inf, inf, -inf, inf);
+        if (lane == 0) chunk_boxes[((size_t)w * Npad + (size_t)jt * LARGE_TJ + k) / LARGE_CHUNK] = cb;
+        tb.x = fminf(tb.x, cb.x); tb.y = fmaxf(tb.y, cb.y); tb.z = fminf(tb.z, cb.z); tb.w = fmaxf(tb.w, cb.w);
     }
-    bad = __any_sync(0xffffffffu, bad);
     __shared__ float4 part[4];
-    __shared__ int sbad[4];
-    if ((threadIdx.x & 31) == 0) { part[threadIdx.x >> 5] = make_float4(xmin, xmax, ymin, ymax); sbad[threadIdx.x >> 5] = bad; }
+    if (lane == 0) part[warp] = tb;
     __syncthreads();
     if (threadIdx.x == 0) {
-        float4 b = part[0];
-        int any_bad = sbad[0];
+        float4 bx = part[0];
         for (int q = 1; q < 4; ++q) {
-            b.x = fminf(b.x, part[q].x); b.y = fmaxf(b.y, part[q].y); b.z = fminf(b.z, part[q].z); b.w = fmaxf(b.w, part[q].w);
-            any_bad |= sbad[q];
+            bx.x = fminf(bx.x, part[q].x); bx.y = fmaxf(bx.y, part[q].y); bx.z = fminf(bx.z, part[q].z); bx.w = fmaxf(bx.w, part[q].w);
         }
-        if (any_bad) b = make_float4(-CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, CUDART_INF_F);
-        boxes[blockIdx.x] = b;
+        boxes[blockIdx.x] = bx;
     }
 }
 
@@ -260,6 +271,9 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     PT fx = 0, fy = 0;
     float2 fxa = make_float2(0.f, 0.f), fya = fxa, fxb = fxa, fyb = fxa;
     const int i0 = i & ~31;
+    const bool prune_chunks = la.boxes != nullptr && sizeof(PT) == 4;
+    float4 wbox = make_float4(0.f, 0.f, 0.f, 0.f);               // box of this warp's 32 pedestrians
+    if (prune_chunks) wbox = __ldg(la.chunk_boxes + ((size_t)w * la.Npad + i0) / LARGE_CHUNK);
     const int T = tile_list[la.tiles_j];
     if (tid == 0) issue(0, tile_list[0]);
     for (int k = 0; k < T; ++k) {
@@ -305,11 +319,23 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
                     pair_contact(kpp, dxb.y, dyb.y, VX.w - mvx, VY.w - mvy, invb.y, sb.y, fx, fy);
                 }
             };
-            // groups that may contain j == i: [i0, i0+32) if it falls inside this tile
-            const int m_lo = min(LARGE_TJ, max(0, i0 - jbase)), m_hi = min(LARGE_TJ, max(0, i0 + 32 - jbase));
-            for (int jl = 0; jl < m_lo; jl += 4) group(jl, std::false_type{});
-            for (int jl = m_lo; jl < m_hi; jl += 4) group(jl, std::true_type{});
-            for (int jl = m_hi; jl < LARGE_TJ; jl += 4) group(jl, std::false_type{});
+            // chunk by chunk (32 consecutive j): skipped when its box is out of reach of this warp's box (warp-uniform, exact);
+            // the chunk [i0, i0+32) holds j == i
+            const float4 *cb = la.chunk_boxes + ((size_t)w * la.Npad + jbase) / LARGE_CHUNK;
+            for (int jc = 0; jc < LARGE_TJ; jc += LARGE_CHUNK) {
+                if (prune_chunks) {
+                    const float4 o = __ldg(cb + jc / LARGE_CHUNK);
+                    const float gx = fmaxf(0.f, fmaxf(o.x - wbox.y, wbox.x - o.y)), gy = fmaxf(0.f, fmaxf(o.z - wbox.w, wbox.z - o.w));
+                    if (gx * gx + gy * gy > la.cut2) continue;
+                }
+                if (jbase + jc == i0) {
+#pragma unroll
+                    for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(jc + jl, std::true_type{});
+                } else {
+#pragma unroll
+                    for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(jc + jl, std::false_type{});
+                }
+            }
         } else {
             const int jn = min(LARGE_TJ, N - jbase);
             for (int jl = 0; jl < jn; ++jl)
@@ -431,7 +457,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
     const size_t e2 = sizeof(ST) * 2;
     cudaError_t e;
     if (!s.pos2 || s.Npad != Npad) {
-        void *keep[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes};
+        void *keep[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes};
         for (void *q : keep) if (q) cudaFree(q);
         s = LargeScratch{};
         if ((e = cudaMalloc(&s.pos2, n * 16)) != cudaSuccess) return -2;
@@ -443,6 +469,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         if ((e = cudaMalloc((void **)&s.robot_slot, sizeof(RobotSlot) * a.W)) != cudaSuccess) return -2;
         if ((e = cudaMalloc((void **)&s.robot_regs, sizeof(RobotRegs) * a.W)) != cudaSuccess) return -2;
         if ((e = cudaMalloc((void **)&s.boxes, sizeof(float4) * (size_t)a.W * (Npad / LARGE_TJ))) != cudaSuccess) return -2;
+        if ((e = cudaMalloc((void **)&s.chunk_boxes, sizeof(float4) * (size_t)a.W * (Npad / LARGE_CHUNK))) != cudaSuccess) return -2;
         s.Npad = Npad;
     }
     // the pair view is rebuilt from the state at the start of every call (the host may have changed it)
@@ -471,10 +498,10 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         la.view_src = s.view[src]; la.view_dst = s.view[dst];
         la.view_stride = nv; la.Npad = Npad; la.tiles_i = tiles_i; la.tiles_j = tiles_j; la.cluster = cluster;
         la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = s.robot_slot;
-        la.boxes = prune ? s.boxes : nullptr; la.cut2 = a.warp_cut2;
+        la.boxes = prune ? s.boxes : nullptr; la.chunk_boxes = s.chunk_boxes; la.cut2 = a.warp_cut2;
         if (prune) {
             if constexpr (sizeof(PT) == 4)
-                large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a.N, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes);
+                large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a.N, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes, s.chunk_boxes);
             ++*launches;
         }
         cudaLaunchConfig_t cfg{};
