@@ -217,27 +217,36 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // j-tiles to visit: every CTA of the cluster derives the same list from the same boxes
-        int K = 0;
-        if (la.boxes != nullptr && sizeof(PT) == 4) {
-            const float4 *bx = la.boxes + (size_t)w * la.tiles_j;
+    }
+    if (tid < 32) {
+        // j-tiles to visit (warp 0, 32 tiles per pass): every CTA of the cluster derives the same list from the same boxes
+        const bool prune = la.boxes != nullptr && sizeof(PT) == 4;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *bx = prune ? la.boxes + (size_t)w * la.tiles_j : nullptr;
+        if (prune) {
             const int it0 = it - (int)crank;                                   // first i-tile of the cluster
             const int jlo = it0 * LARGE_TI / LARGE_TJ;
             const int jhi = min(la.tiles_j - 1, ((it0 + la.cluster) * LARGE_TI - 1) / LARGE_TJ);
-            float4 c = bx[jlo];
+            c = bx[jlo];
             for (int q = jlo + 1; q <= jhi; ++q) {
                 const float4 o = bx[q];
                 c.x = fminf(c.x, o.x); c.y = fmaxf(c.y, o.y); c.z = fminf(c.z, o.z); c.w = fmaxf(c.w, o.w);
             }
-            for (int jt = 0; jt < la.tiles_j; ++jt) {
+        }
+        int K = 0;
+        for (int base = 0; base < la.tiles_j; base += 32) {
+            const int jt = base + lane;
+            bool keep = jt < la.tiles_j;
+            if (keep && prune) {
                 const float4 o = bx[jt];
                 const float gx = fmaxf(0.f, fmaxf(o.x - c.y, c.x - o.y)), gy = fmaxf(0.f, fmaxf(o.z - c.w, c.z - o.w));
-                if (!(gx * gx + gy * gy > la.cut2)) tile_list[K++] = jt;        // NaN / inf boxes are never skipped
+                keep = !(gx * gx + gy * gy > la.cut2);                          // NaN / infinite boxes are never skipped
             }
-        } else {
-            for (int jt = 0; jt < la.tiles_j; ++jt) tile_list[K++] = jt;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) tile_list[K + __popc(m & ((1u << lane) - 1u))] = jt;
+            K += __popc(m);
         }
-        tile_list[la.tiles_j] = K;
+        if (lane == 0) tile_list[la.tiles_j] = K;
     }
     __syncthreads();
     cluster_arrive();
@@ -321,13 +330,19 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
             };
             // chunk by chunk (32 consecutive j): skipped when its box is out of reach of this warp's box (warp-uniform, exact);
             // the chunk [i0, i0+32) holds j == i
-            const float4 *cb = la.chunk_boxes + ((size_t)w * la.Npad + jbase) / LARGE_CHUNK;
-            for (int jc = 0; jc < LARGE_TJ; jc += LARGE_CHUNK) {
-                if (prune_chunks) {
-                    const float4 o = __ldg(cb + jc / LARGE_CHUNK);
+            unsigned near = (1u << (LARGE_TJ / LARGE_CHUNK)) - 1u;           // bit c: chunk c of this tile has to be visited
+            if (prune_chunks) {                                                 // lane c tests chunk c
+                bool keep = false;
+                if (lane < LARGE_TJ / LARGE_CHUNK) {
+                    const float4 o = __ldg(la.chunk_boxes + ((size_t)w * la.Npad + jbase) / LARGE_CHUNK + lane);
                     const float gx = fmaxf(0.f, fmaxf(o.x - wbox.y, wbox.x - o.y)), gy = fmaxf(0.f, fmaxf(o.z - wbox.w, wbox.z - o.w));
-                    if (gx * gx + gy * gy > la.cut2) continue;
+                    keep = !(gx * gx + gy * gy > la.cut2);
                 }
+                near = __ballot_sync(0xffffffffu, keep);
+            }
+            while (near) {
+                const int jc = (__ffs(near) - 1) * LARGE_CHUNK;
+                near &= near - 1;
                 if (jbase + jc == i0) {
 #pragma unroll
                     for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(jc + jl, std::true_type{});
