@@ -127,8 +127,10 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
     const int wl = threadIdx.x / Np, i = threadIdx.x - wl * Np;
     const int w = blockIdx.x * a.wpc + wl;
     const bool valid = w < a.W && i < N;
-    float2 *spos = reinterpret_cast<float2 *>(smem_raw) + (size_t)wl * 2 * Np;
-    float2 *svel = spos + Np;
+    // per world: positions as two arrays sx | sy (four candidates per LDS.128, packed-FP32 differences), velocities float2
+    float *sx = reinterpret_cast<float *>(smem_raw) + (size_t)wl * 4 * Np;
+    float *sy = sx + Np;
+    float2 *svel = reinterpret_cast<float2 *>(sx + 2 * Np);
     const size_t g = (size_t)(valid ? w : 0) * N + (valid ? i : 0);
 
     V2 p = mk(0.f, 0.f), v = p, pref = p;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
     const float R = a.radius + a.radius, R2 = R * R;
 
     for (int step = 0; step < a.n_steps; ++step) {
-        if (i < Np) { spos[i] = make_float2(p.x, p.y); svel[i] = make_float2(v.x, v.y); }
+        if (i < Np) { sx[i] = p.x; sy[i] = p.y; svel[i] = make_float2(v.x, v.y); }
         __syncthreads();
         V2 newv = v;
         if (valid) {
@@ -156,23 +158,37 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
             cnt = 0;
             float range2 = a.neighbor_dist * a.neighbor_dist;
             if (kmax > 0) {
-                for (int o = 0; o < N; ++o) {
-                    if (o == i) continue;
-                    const float2 q = spos[o];
-                    const float d2 = norm2(p - mk(q.x, q.y));
-                    if (!(d2 < range2)) continue;
+                // candidates in index order, four per trip (two LDS.128); the insertion logic of the library runs only for
+                // the rare candidate inside the current range
+                auto consider = [&](int o, float d2) {
+                    if (o == i || o >= N || !(d2 < range2)) return;
                     if (cnt < kmax) ++cnt;
                     int k = cnt - 1;
                     while (k != 0 && d2 < nd[k - 1]) { nd[k] = nd[k - 1]; ni[k] = ni[k - 1]; --k; }
                     nd[k] = d2; ni[k] = o;
                     if (cnt == kmax) range2 = nd[cnt - 1];
+                };
+                const float2 px2 = make_float2(p.x, p.x), py2 = make_float2(p.y, p.y);
+                for (int o = 0; o < N; o += 4) {
+                    // |p - q|^2 = dx*dx + dy*dy with every operation rounded separately.  The final adds stay scalar: ptxas
+                    // contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, which would break the bit-exact
+                    // match with the library's arithmetic.
+                    const float4 X = *reinterpret_cast<const float4 *>(sx + o), Y = *reinterpret_cast<const float4 *>(sy + o);
+                    const float2 dxa = __fadd2_rn(px2, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(px2, make_float2(-X.z, -X.w));
+                    const float2 dya = __fadd2_rn(py2, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(py2, make_float2(-Y.z, -Y.w));
+                    const float2 xa = __fmul2_rn(dxa, dxa), ya = __fmul2_rn(dya, dya), xb = __fmul2_rn(dxb, dxb), yb = __fmul2_rn(dyb, dyb);
+                    const float2 da = make_float2(__fadd_rn(xa.x, ya.x), __fadd_rn(xa.y, ya.y));
+                    const float2 db = make_float2(__fadd_rn(xb.x, yb.x), __fadd_rn(xb.y, yb.y));
+                    if (fminf(fminf(da.x, da.y), fminf(db.x, db.y)) < range2) {
+                        consider(o, da.x); consider(o + 1, da.y); consider(o + 2, db.x); consider(o + 3, db.y);
+                    }
                 }
             }
             // ---- one ORCA half-plane per neighbour ----
             HalfPlane hp[ORCA_MAX_NEIGHBORS];
             for (int k = 0; k < cnt; ++k) {
-                const float2 qp = spos[ni[k]], qv = svel[ni[k]];
-                const V2 rp = mk(qp.x, qp.y) - p;
+                const float2 qv = svel[ni[k]];
+                const V2 rp = mk(sx[ni[k]], sy[ni[k]]) - p;
                 const V2 rv = v - mk(qv.x, qv.y);
                 const float d2 = norm2(rp);
                 V2 u;
@@ -211,25 +227,25 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
         if (valid) {
             v = newv;
             p = mk(p.x + v.x * a.time_step, p.y + v.y * a.time_step);
-            head = atan2((double)v.y, (double)v.x);                                    // _orca.py:103-104
+            // the heading atan2(v) (_orca.py:103-104) is an output only: evaluated once after the last step
             // FixedWaypointTracker.update_waypoints on the new position (:106-107), steady flag ignored
-            if (a.n_table > 0) {
-                const double dx = wp.x - (double)p.x, dy = wp.y - (double)p.y;
-                if (sqrt(dx * dx + dy * dy) <= a.reach) {
-                    int nx = widx + 1;
-                    if (nx >= a.n_table) nx = a.loop ? 0 : a.n_table - 1;
-                    widx = nx;
-                    wp = a.table[g * a.n_table + nx];
-                }
+            double dx = wp.x - (double)p.x, dy = wp.y - (double)p.y;
+            double nr = sqrt(dx * dx + dy * dy);
+            if (a.n_table > 0 && nr <= a.reach) {
+                int nx = widx + 1;
+                if (nx >= a.n_table) nx = a.loop ? 0 : a.n_table - 1;
+                widx = nx;
+                wp = a.table[g * a.n_table + nx];
+                dx = wp.x - (double)p.x; dy = wp.y - (double)p.y;
+                nr = sqrt(dx * dx + dy * dy);
             }
             // _update_preferred_velocities (:118-127)
-            const double dx = wp.x - (double)p.x, dy = wp.y - (double)p.y;
-            const double nr = sqrt(dx * dx + dy * dy);
             if (nr <= a.goal_threshold) pref = mk(0.f, 0.f);
             else pref = mk((float)(dx / nr * pspeed), (float)(dy / nr * pspeed));
         }
     }
     if (valid) {
+        if (a.n_steps > 0) head = atan2((double)v.y, (double)v.x);
         a.pos[g] = make_float2(p.x, p.y); a.vel[g] = make_float2(v.x, v.y); a.pref[g] = make_float2(pref.x, pref.y);
         a.cur_wp[g] = wp; a.wp_index[g] = widx; a.heading[g] = head; a.n_constraints[g] = cnt;
     }
