@@ -79,6 +79,11 @@ int pms_n_peds(const pms_sim *h);
 int pms_set_ped_state(pms_sim *h, const double *poses /*(W,N,3)*/, const double *vels /*(W,N,3)*/);
 int pms_get_ped_state(pms_sim *h, double *poses /*(W,N,3)*/, double *vels /*(W,N,3)*/);
 int pms_set_ped_speeds(pms_sim *h, const double *vmag /*(W,N)*/); /* pedestrian_linear_velocity_magnitude */
+/* Asynchronous I/O mode (pipelining several handles): pms_set_ped_state, pms_get_ped_state, pms_get_detector,
+ * pms_get_collisions and pms_get_stats enqueue their copies on the handle's stream and return; the host buffers must be
+ * page-locked (pms_host_alloc) and stay valid until pms_sync.  pms_get_stats then leaves INT32_MAX ("never") in
+ * first_nonfinite_step instead of 0. */
+int pms_set_async_io(pms_sim *h, int enabled);
 /* device-side snapshot of the complete simulation state (checkpoint / resume) */
 int pms_snapshot_save(pms_sim *h);
 int pms_snapshot_restore(pms_sim *h);

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "pms_set_ped_state": (C.c_int, [_h, _dp, _dp]),
     "pms_get_ped_state": (C.c_int, [_h, _dp, _dp]),
     "pms_set_ped_speeds": (C.c_int, [_h, _dp]),
+    "pms_set_async_io": (C.c_int, [_h, C.c_int]),
     "pms_snapshot_save": (C.c_int, [_h]),
     "pms_snapshot_restore": (C.c_int, [_h]),
     "pms_set_waypoints_fixed": (C.c_int, [_h, _dp, C.c_int, _ip, C.c_double, C.c_int]),

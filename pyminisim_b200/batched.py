@@ -77,6 +77,12 @@ class BatchedSimulation:
     def set_speeds(self, vmag):
         check(self._lib.pms_set_ped_speeds(self._h, dptr(f64(vmag, (self.W, self.N)))))
 
+    def set_async_io(self, enabled: bool = True):
+        """Transfers (set_state / get_state / get_detector / get_collisions / get_stats) stop synchronising: they are
+        enqueued on the handle's stream and complete at ``sync()``.  Host arrays must be page-locked (``_capi.pinned_array``)
+        and must not be touched before ``sync()``.  Lets several handles overlap copies with each other's kernels."""
+        check(self._lib.pms_set_async_io(self._h, int(bool(enabled))))
+
     def snapshot_save(self):
         check(self._lib.pms_snapshot_save(self._h))
 
@@ -175,21 +181,20 @@ class BatchedSimulation:
     def sense(self):
         check(self._lib.pms_sense(self._h))
 
-    def get_detector(self) -> Tuple[np.ndarray, np.ndarray]:
-        mask = np.empty((self.W, self.words), dtype=np.uint32)
-        vals = np.empty((self.W, self.N, 2))
+    def get_detector(self, out_mask=None, out_vals=None) -> Tuple[np.ndarray, np.ndarray]:
+        mask = np.empty((self.W, self.words), dtype=np.uint32) if out_mask is None else out_mask
+        vals = np.empty((self.W, self.N, 2)) if out_vals is None else out_vals
         check(self._lib.pms_get_detector(self._h, uptr(mask), dptr(vals)))
         return mask, vals
 
-    def get_collisions(self) -> np.ndarray:
-        mask = np.empty((self.W, self.words), dtype=np.uint32)
+    def get_collisions(self, out_mask=None) -> np.ndarray:
+        mask = np.empty((self.W, self.words), dtype=np.uint32) if out_mask is None else out_mask
         check(self._lib.pms_get_collisions(self._h, uptr(mask)))
         return mask
 
-    def get_stats(self):
-        det = np.empty(self.W, dtype=np.int64)
-        col = np.empty(self.W, dtype=np.int64)
-        nf = np.empty(self.W, dtype=np.int32)
+    def get_stats(self, out=None):
+        det, col, nf = out if out is not None else (np.empty(self.W, dtype=np.int64), np.empty(self.W, dtype=np.int64),
+                                                    np.empty(self.W, dtype=np.int32))
         check(self._lib.pms_get_stats(self._h, lptr(det), lptr(col), iptr(nf)))
         return det, col, nf
 

@@ -138,6 +138,7 @@ struct pms_sim {
     int tune_S = 0, tune_wpc = 0, tune_chunks = 0, tune_cluster = 0;
     bool force_large = false;
     bool no_prune = false;   // large-crowd kernel: visit every j-tile (comparison / tests)
+    bool async_io = false;   // state / reading transfers do not synchronise (pms_set_async_io)
     int sm_count = 148;
     int sched_cap = 0;
     pms_launch_info info{};
@@ -472,6 +473,19 @@ int pms_n_peds(const pms_sim *h) { return h ? h->N : 0; }
     if ((h)->kind != 0) return fail(PMS_ERR_STATE, "not an HSFM handle"); \
     Guard gd__((h)->device)
 
+// end of a transfer call: blocking unless the handle is in asynchronous-I/O mode
+#define IO_DONE(h)                                                   \
+    do {                                                             \
+        if (!(h)->async_io) CK(cudaStreamSynchronize((h)->stream));  \
+    } while (0)
+
+int pms_set_async_io(pms_sim *h, int enabled)
+{
+    if (!h) return fail(PMS_ERR_INVALID, "handle is NULL");
+    h->async_io = enabled != 0;
+    return PMS_OK;
+}
+
 int pms_set_ped_state(pms_sim *h, const double *poses, const double *vels)
 {
     HCHECK(h);
@@ -484,7 +498,7 @@ int pms_set_ped_state(pms_sim *h, const double *poses, const double *vels)
     if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
     else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(h->stream));
+    IO_DONE(h);
     return PMS_OK;
 }
 
@@ -498,7 +512,7 @@ int pms_get_ped_state(pms_sim *h, double *poses, double *vels)
     CK(cudaGetLastError());
     if (poses) CK(cudaMemcpyAsync(poses, h->stage, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (vels) CK(cudaMemcpyAsync(vels, h->stage + n * 3, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    IO_DONE(h);
     return PMS_OK;
 }
 
@@ -796,7 +810,7 @@ int pms_get_detector(pms_sim *h, uint32_t *mask, double *values)
     const size_t n = (size_t)h->W * h->N;
     if (mask) CK(cudaMemcpyAsync(mask, h->a.det_mask, sizeof(uint32_t) * h->W * h->words, cudaMemcpyDeviceToHost, h->stream));
     if (values) CK(cudaMemcpyAsync(values, h->a.det_vals, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    IO_DONE(h);
     return PMS_OK;
 }
 
@@ -804,7 +818,7 @@ int pms_get_collisions(pms_sim *h, uint32_t *mask)
 {
     HCHECK(h);
     if (mask) CK(cudaMemcpyAsync(mask, h->a.coll_mask, sizeof(uint32_t) * h->W * h->words, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    IO_DONE(h);
     return PMS_OK;
 }
 
@@ -815,6 +829,7 @@ int pms_get_stats(pms_sim *h, int64_t *detections, int64_t *collisions, int32_t 
     if (detections) CK(cudaMemcpyAsync(detections, h->a.det_count, sizeof(int64_t) * W, cudaMemcpyDeviceToHost, h->stream));
     if (collisions) CK(cudaMemcpyAsync(collisions, h->a.coll_count, sizeof(int64_t) * W, cudaMemcpyDeviceToHost, h->stream));
     if (first_nonfinite_step) CK(cudaMemcpyAsync(first_nonfinite_step, h->a.nonfinite, sizeof(int) * W, cudaMemcpyDeviceToHost, h->stream));
+    if (h->async_io) return PMS_OK;       // the caller maps the "never" sentinel INT32_MAX to 0 after pms_sync
     CK(cudaStreamSynchronize(h->stream));
     if (first_nonfinite_step)
         for (int w = 0; w < W; ++w) if (first_nonfinite_step[w] == 0x7fffffff) first_nonfinite_step[w] = 0;

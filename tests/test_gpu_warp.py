@@ -234,3 +234,43 @@ def test_warp_kernel_tracker_variants(precision):
     exp = 0.01 * np.stack([np.cos(th) * noise[..., 0] - np.sin(th) * noise[..., 1],
                            np.sin(th) * noise[..., 0] + np.cos(th) * noise[..., 1]], axis=-1)
     assert np.abs(dv - exp).max() < 2e-6
+
+
+def test_async_io_pipeline_equals_blocking_calls():
+    """Two handles in asynchronous-I/O mode (copies enqueued, results valid after sync) give the bits of the blocking API."""
+    from pyminisim_b200 import _capi as capi
+    sc = make_bench_crowd(64, 64)
+    ref = make_cuda(sc, "fp32")
+    ref.step(0.01, 90)
+    p_ref, v_ref = ref.get_state()
+    m_ref, d_ref = ref.get_detector()
+    det_ref, col_ref, nf_ref = ref.get_stats()
+    W, N = 64, 64
+    h_p = capi.pinned_array((W, N, 3)); h_p[:] = sc.poses
+    h_v = capi.pinned_array((W, N, 3)); h_v[:] = sc.vels
+    sims, bufs = [], []
+    for _ in range(2):
+        s = make_cuda(sc, "fp32")
+        s.snapshot_save()
+        s.set_async_io(True)
+        sims.append(s)
+        bufs.append(dict(p=capi.pinned_array((W, N, 3)), v=capi.pinned_array((W, N, 3)),
+                         m=capi.pinned_array((W, 2), np.uint32), d=capi.pinned_array((W, N, 2)),
+                         det=capi.pinned_array((W,), np.int64), col=capi.pinned_array((W,), np.int64),
+                         nf=capi.pinned_array((W,), np.int32)))
+    for k in range(4):                       # submit k, then collect k - 1
+        s, b = sims[k & 1], bufs[k & 1]
+        s.snapshot_restore()
+        s.set_state(h_p, h_v)
+        s.step_async(0.01, 90)
+        s.get_state(b["p"], b["v"])
+        s.get_detector(b["m"], b["d"])
+        s.get_stats((b["det"], b["col"], b["nf"]))
+        if k:
+            sims[(k - 1) & 1].sync()
+            o = bufs[(k - 1) & 1]
+            assert np.array_equal(o["p"], p_ref) and np.array_equal(o["v"], v_ref)
+            assert np.array_equal(o["m"], m_ref) and np.array_equal(o["d"], d_ref)
+            assert np.array_equal(o["det"], det_ref) and np.array_equal(o["col"], col_ref)
+            assert (o["nf"] == np.iinfo(np.int32).max).all() and (nf_ref == 0).all()   # async: the raw "never" sentinel
+    sims[1].sync()
