@@ -181,7 +181,8 @@ int pms_get_launch_info(pms_sim *h, pms_launch_info *out);
  *                    j_split 1..3 selects a smaller register budget (96 / 80 / 80 registers per thread, more resident warps), and a negative
  *                    value selects the directed-pair kernel instead (-1: automatic j-slices, -1-S: S slices).  For the
  *                    directed-pair kernel (FP64, larger worlds) j_split = 1, 2, 4, 8 is the number of j-slices.
- *   n_chunks       : 1 forces the static grid; negative: the large-crowd kernel visits every j-tile (no exact pruning).
+ *   n_chunks       : 1 forces the static grid; for the large-crowd kernel -2 keeps the caller's pedestrian order (no
+ *                    sorted working copy) and -1 also visits every j-tile (no exact pruning).
  *   cluster_size   : (1,2,4,8) multicast width of the large-crowd kernel; a negative value also forces that kernel
  *                    for small N. */
 int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, int cluster_size);

@@ -16,9 +16,13 @@
 // below -126 for d > r_ij + 126 B / log2(e) (7.6 m with the default parameters), where the instruction returns exactly 0 and
 // the pair contributes exactly nothing.  large_box_kernel keeps one bounding box per j-tile; a cluster skips every j-tile
 // whose box is farther than that from the box of its own pedestrians -- no load, no arithmetic, bit-identical forces.
-// With spatially coherent pedestrian indices (any grid- or scan-line ordered crowd) most of the N^2 work disappears;
-// with random indices nothing is skipped and the cost is one tiny extra launch per step.
+// The pruning needs spatially coherent indices, so the kernel works on a spatially sorted copy of the state: every
+// LARGE_RESORT steps the pedestrians are sorted by (strip of one cut-off width, y) with a cub radix sort and
+// position / velocity / heading are gathered into sorted buffers; per-pedestrian data that the host owns (waypoints,
+// speeds, tracker tables and queues, detector outputs, event ids) stay in the caller's order and are reached through
+// the permutation.  At the end of the call the state is scattered back.  Any input order gets the pruning.
 #pragma once
+#include <cub/device/device_radix_sort.cuh>
 #include "hsfm_small.cuh"
 
 namespace pms {
@@ -42,6 +46,7 @@ struct LargeArgs {
     const float4 *boxes;             // (W, tiles_j) bounding box {xmin, xmax, ymin, ymax} of every j-tile of view_src, or NULL
     const float4 *chunk_boxes;       // (W, Npad / 32) the same per chunk of 32 pedestrians
     float cut2;                      // squared distance beyond which the pair force is exactly 0 (fp32 pair arithmetic)
+    const int *perm;                 // (W*N) sorted slot -> caller's global pedestrian index, or NULL (identity)
 };
 
 struct LargeScratch {
@@ -50,6 +55,12 @@ struct LargeScratch {
     RobotSlot *robot_slot = nullptr;
     RobotRegs *robot_regs = nullptr;
     float4 *boxes = nullptr, *chunk_boxes = nullptr;
+    // spatially sorted working copy: sorted state (ping), keys / permutation double buffers, cub scratch
+    void *pos3 = nullptr, *vel3 = nullptr, *th3 = nullptr;
+    unsigned long long *keys[2] = {nullptr, nullptr};
+    int *perm[2] = {nullptr, nullptr};
+    void *sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     int Npad = 0;
     int parity = 0;                  // which view buffer holds the current state
     bool view_valid = false;
@@ -58,7 +69,8 @@ struct LargeScratch {
 
 inline void large_free(LargeScratch &s)
 {
-    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes};
+    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes,
+                 s.pos3, s.vel3, s.th3, s.keys[0], s.keys[1], s.perm[0], s.perm[1], s.sort_tmp};
     for (void *q : p) if (q) cudaFree(q);
     s = LargeScratch{};
 }
@@ -148,6 +160,44 @@ __global__ void large_view_kernel(const __grid_constant__ HsfmArgs a, PT *view, 
 // kernel) and their union per tile (the cluster-level skip unit).  Padding pedestrians are left out (an all-padding chunk
 // has an empty box, which is far from everything); a chunk that holds a non-finite coordinate gets an infinite box (never
 // skipped: its NaN must reach every other pedestrian like in the reference).
+constexpr int LARGE_RESORT = 128;     // steps between two spatial sorts
+
+// Sort key = world : strip : y.  Strips are columns as wide as the cut-off distance; inside a strip the pedestrians are
+// ordered by y, upwards in even strips and downwards in odd ones (a snake through the world).  32 consecutive pedestrians (a chunk) then fill a compact box of one strip width, 512 (a tile) a piece of
+// one or two strips -- without the jumps a Z-order curve makes at its quadrant boundaries.  value = the global index.
+template <typename ST>
+__global__ void large_sortkey_kernel(const __grid_constant__ HsfmArgs a, float inv_strip, unsigned long long *keys, int *vals)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= (size_t)a.W * a.N) return;
+    ST x, y, vx, vy;
+    load_pv(a, g, x, y, vx, vy);
+    const float sx = fminf(fmaxf(floorf((float)x * inv_strip) + 32768.f, 0.f), 65535.f);   // NaN -> strip 0
+    unsigned yb = __float_as_uint((float)y);
+    yb = (yb & 0x80000000u) ? ~yb : (yb | 0x80000000u);                                     // order-preserving float bits
+    if ((unsigned)sx & 1u) yb = ~yb;               // boustrophedon: odd strips run downwards, so a chunk or tile that
+                                                   // straddles two strips stays compact (it turns the corner)
+    keys[g] = ((unsigned long long)(g / a.N) << 48) | ((unsigned long long)(unsigned)sx << 32) | yb;
+    vals[g] = (int)g;
+}
+// sorted <- caller order (gather) or caller order <- sorted (scatter) of position / velocity / heading
+template <typename ST, bool GATHER>
+__global__ void large_permute_kernel(size_t n, const int *perm, const void *pos_in, const void *vel_in, const void *th_in,
+                                     void *pos_out, void *vel_out, void *th_out)
+{
+    using ST2 = typename Vec2<ST>::type;
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t src = GATHER ? (size_t)perm[k] : k, dst = GATHER ? k : (size_t)perm[k];
+    if constexpr (sizeof(ST) == 4) {
+        reinterpret_cast<float4 *>(pos_out)[dst] = reinterpret_cast<const float4 *>(pos_in)[src];
+    } else {
+        reinterpret_cast<double2 *>(pos_out)[dst] = reinterpret_cast<const double2 *>(pos_in)[src];
+        reinterpret_cast<double2 *>(vel_out)[dst] = reinterpret_cast<const double2 *>(vel_in)[src];
+    }
+    reinterpret_cast<ST2 *>(th_out)[dst] = reinterpret_cast<const ST2 *>(th_in)[src];
+}
+
 constexpr int LARGE_CHUNK = 32;       // pedestrians per chunk box (one warp's rows / one warp-level skip unit)
 
 template <typename PT>
@@ -208,7 +258,9 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     const int i = it * LARGE_TI + tid;
     const int N = a.N;
     const bool valid = i < N;
-    const size_t g = (size_t)w * N + (valid ? i : 0);
+    const size_t gs = (size_t)w * N + (valid ? i : 0);                 // slot in the (spatially sorted) working state
+    const size_t g = la.perm ? (size_t)la.perm[gs] : gs;               // the caller's index of this pedestrian
+    const int ie = (int)(g - (size_t)w * N);
     const uint32_t crank = la.cluster > 1 ? cluster_ctarank() : 0;
     const PT *vsrc = reinterpret_cast<const PT *>(la.view_src) + (size_t)w * la.Npad;
     const size_t vs = la.view_stride;
@@ -383,14 +435,14 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         const PedConsts<ST> &kc = kc_of(a, ST{});
         ST x, y, vx, vy;
         if constexpr (sizeof(ST) == 4) {
-            const float4 p = __ldcg(reinterpret_cast<const float4 *>(la.pos_src) + g);
+            const float4 p = __ldcg(reinterpret_cast<const float4 *>(la.pos_src) + gs);
             x = p.x; y = p.y; vx = p.z; vy = p.w;
         } else {
-            const double2 p = __ldcg(reinterpret_cast<const double2 *>(la.pos_src) + g);
-            const double2 v = __ldcg(reinterpret_cast<const double2 *>(la.vel_src) + g);
+            const double2 p = __ldcg(reinterpret_cast<const double2 *>(la.pos_src) + gs);
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(la.vel_src) + gs);
             x = p.x; y = p.y; vx = v.x; vy = v.y;
         }
-        const ST2 tw = __ldcg(reinterpret_cast<const ST2 *>(la.th_src) + g);
+        const ST2 tw = __ldcg(reinterpret_cast<const ST2 *>(la.th_src) + gs);
         ST th = tw.x, om = tw.y, c, sn;
         m_sincos(th, &sn, &c);
         ST2 wp = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
@@ -419,22 +471,22 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
                     wp = reinterpret_cast<const ST2 *>(a.queue)[g * a.q_cap + head];
                     a.q_head[g] = (head + 1) % a.q_cap;
                     a.q_count[g] = cnt - 1;
-                    if (slot < a.ev_cap) { a.events[3 * slot] = la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i; }
+                    if (slot < a.ev_cap) { a.events[3 * slot] = la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = ie; }
                 } else if (slot < a.ev_cap) {
-                    a.events[3 * slot] = -1 - la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = i;
+                    a.events[3 * slot] = -1 - la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = ie;
                 }
             }
             reinterpret_cast<ST2 *>(a.wp)[g] = wp;
         }
         // new state -> destination buffers + destination pair view
         if constexpr (sizeof(ST) == 4) {
-            reinterpret_cast<float4 *>(la.pos_dst)[g] = make_float4(x, y, vx, vy);
+            reinterpret_cast<float4 *>(la.pos_dst)[gs] = make_float4(x, y, vx, vy);
         } else {
-            reinterpret_cast<double2 *>(la.pos_dst)[g] = make_double2(x, y);
-            reinterpret_cast<double2 *>(la.vel_dst)[g] = make_double2(vx, vy);
+            reinterpret_cast<double2 *>(la.pos_dst)[gs] = make_double2(x, y);
+            reinterpret_cast<double2 *>(la.vel_dst)[gs] = make_double2(vx, vy);
         }
         ST2 t2; t2.x = th; t2.y = om;
-        reinterpret_cast<ST2 *>(la.th_dst)[g] = t2;
+        reinterpret_cast<ST2 *>(la.th_dst)[gs] = t2;
         if constexpr (SPLIT) {
             const float xh = (float)x, yh = (float)y;
             vdst[i] = xh; vdst[vs + i] = yh; vdst[2 * vs + i] = (float)vx; vdst[3 * vs + i] = (float)vy;
@@ -453,28 +505,33 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
             if (dm) atomicAdd(&a.det_count[w], (unsigned long long)__popc(dm));
             if (cm) atomicAdd(&a.coll_count[w], (unsigned long long)__popc(cm));
             const int words = (N + 31) >> 5;
-            if (la.last && (i >> 5) < words) {
+            if (la.last && !la.perm && (i >> 5) < words) {
                 a.det_mask[(size_t)w * words + (i >> 5)] = dm;
                 a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
             }
+        }
+        if (la.last && la.perm) {          // sorted slots: set the caller's bit (the masks were cleared before the call)
+            const int words = (N + 31) >> 5;
+            if (so.det) atomicOr(&a.det_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
+            if (so.coll) atomicOr(&a.coll_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
         }
     }
 }
 
 // ---- host-side launch of n_steps large-crowd steps ---------------------------------------------------
 template <typename PT, typename ST, bool SPLIT>
-inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_tiles, cudaStream_t stream, long long *launches,
-                          int *out_blocks, int *out_smem)
+inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_tiles, bool reorder, cudaStream_t stream,
+                          long long *launches, int *out_blocks, int *out_smem)
 {
     constexpr int NARR = SPLIT ? 6 : 4;
     const int Npad = (a.N + LARGE_TJ - 1) / LARGE_TJ * LARGE_TJ;
     const size_t n = (size_t)a.W * a.N, nv = (size_t)a.W * Npad;
     const size_t e2 = sizeof(ST) * 2;
+    const bool prune = sizeof(PT) == 4 && prune_tiles;
+    reorder = reorder && prune;
     cudaError_t e;
     if (!s.pos2 || s.Npad != Npad) {
-        void *keep[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes};
-        for (void *q : keep) if (q) cudaFree(q);
-        s = LargeScratch{};
+        large_free(s);
         if ((e = cudaMalloc(&s.pos2, n * 16)) != cudaSuccess) return -2;
         if ((e = cudaMalloc(&s.vel2, n * 16)) != cudaSuccess) return -2;
         if ((e = cudaMalloc(&s.th2, n * e2)) != cudaSuccess) return -2;
@@ -487,49 +544,85 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         if ((e = cudaMalloc((void **)&s.chunk_boxes, sizeof(float4) * (size_t)a.W * (Npad / LARGE_CHUNK))) != cudaSuccess) return -2;
         s.Npad = Npad;
     }
-    // the pair view is rebuilt from the state at the start of every call (the host may have changed it)
-    large_view_kernel<PT, ST, SPLIT><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(a, reinterpret_cast<PT *>(s.view[0]), nv, Npad);
-    large_view_kernel<PT, ST, SPLIT><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(a, reinterpret_cast<PT *>(s.view[1]), nv, Npad);
-    *launches += 2;
+    int end_bit = 48;
+    while ((1ll << (end_bit - 48)) < a.W) ++end_bit;
+    if (reorder && !s.pos3) {
+        if ((e = cudaMalloc(&s.pos3, n * 16)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc(&s.vel3, n * 16)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc(&s.th3, n * e2)) != cudaSuccess) return -2;
+        for (int q = 0; q < 2; ++q) {
+            if ((e = cudaMalloc((void **)&s.keys[q], n * sizeof(unsigned long long))) != cudaSuccess) return -2;
+            if ((e = cudaMalloc((void **)&s.perm[q], n * sizeof(int))) != cudaSuccess) return -2;
+        }
+        cub::DeviceRadixSort::SortPairs(nullptr, s.sort_tmp_bytes, s.keys[0], s.keys[1], s.perm[0], s.perm[1], (int)n, 0, end_bit, stream);
+        if ((e = cudaMalloc(&s.sort_tmp, s.sort_tmp_bytes ? s.sort_tmp_bytes : 1)) != cudaSuccess) return -2;
+    }
 
     const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ;
     // grid must be a multiple of the cluster size and a cluster must stay inside one world
     while (cluster > 1 && (tiles_i % cluster != 0 || LARGE_TJ % cluster != 0)) cluster >>= 1;
     const size_t smem = 2 * NARR * LARGE_TJ * sizeof(PT) + 2 * sizeof(uint64_t) + sizeof(int) * (tiles_j + 1);
-    const bool prune = sizeof(PT) == 4 && prune_tiles;
     auto kern = hsfm_large_kernel<PT, ST, SPLIT>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+    const unsigned gn = (unsigned)((n + 255) / 256), gv = (unsigned)((nv + 255) / 256);
+    const float inv_strip = 1.0f / sqrtf(a.warp_cut2);            // strips one cut-off distance wide
 
+    // working state: the caller's arrays, or the spatially sorted copy (home[0] is then s.pos3 ...)
     void *pos[2] = {a.pos, s.pos2}, *vel[2] = {a.vel, s.vel2}, *th[2] = {a.th, s.th2};
-    for (int t = 0; t < a.n_steps; ++t) {
-        const int src = t & 1, dst = src ^ 1;
-        if (a.robot_model != ROBOT_NONE) {
-            robot_step_kernel<<<(a.W + 127) / 128, 128, 0, stream>>>(a, s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
+    if (reorder) { pos[0] = s.pos3; vel[0] = s.vel3; th[0] = s.th3; }
+    int cur = 0;                                                   // buffer that holds the current state
+    for (int t0 = 0; t0 < a.n_steps; t0 += LARGE_RESORT) {
+        const int t1 = t0 + LARGE_RESORT < a.n_steps ? t0 + LARGE_RESORT : a.n_steps;
+        if (reorder) {
+            // sort by (world, strip, y) of the CURRENT positions (in the caller's arrays), gather the state
+            large_sortkey_kernel<ST><<<gn, 256, 0, stream>>>(a, inv_strip, s.keys[0], s.perm[0]);
+            cub::DeviceRadixSort::SortPairs(s.sort_tmp, s.sort_tmp_bytes, s.keys[0], s.keys[1], s.perm[0], s.perm[1], (int)n, 0, end_bit, stream);
+            large_permute_kernel<ST, true><<<gn, 256, 0, stream>>>(n, s.perm[1], a.pos, a.vel, a.th, pos[0], vel[0], th[0]);
+            *launches += 3;
+            cur = 0;
+        }
+        // the pair view is rebuilt from the working state (the host may have changed it between calls)
+        HsfmArgs av = a;
+        av.pos = pos[cur]; av.vel = vel[cur]; av.th = th[cur];
+        large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur]), nv, Npad);
+        if (t0 == 0) large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur ^ 1]), nv, Npad);
+        *launches += 2;
+        for (int t = t0; t < t1; ++t) {
+            const int src = cur, dst = cur ^ 1;
+            if (a.robot_model != ROBOT_NONE) {
+                robot_step_kernel<<<(a.W + 127) / 128, 128, 0, stream>>>(a, s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
+                ++*launches;
+            }
+            LargeArgs la{};
+            la.pos_src = pos[src]; la.vel_src = vel[src]; la.th_src = th[src];
+            la.pos_dst = pos[dst]; la.vel_dst = vel[dst]; la.th_dst = th[dst];
+            la.view_src = s.view[src]; la.view_dst = s.view[dst];
+            la.view_stride = nv; la.Npad = Npad; la.tiles_i = tiles_i; la.tiles_j = tiles_j; la.cluster = cluster;
+            la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = s.robot_slot;
+            la.boxes = prune ? s.boxes : nullptr; la.chunk_boxes = s.chunk_boxes; la.cut2 = a.warp_cut2;
+            la.perm = reorder ? s.perm[1] : nullptr;
+            if (prune) {
+                if constexpr (sizeof(PT) == 4)
+                    large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a.N, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes, s.chunk_boxes);
+                ++*launches;
+            }
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(a.W * tiles_i)); cfg.blockDim = dim3(LARGE_TI); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if ((e = cudaLaunchKernelEx(&cfg, kern, a, la)) != cudaSuccess) return -2;
+            ++*launches;
+            cur = dst;
+        }
+        if (reorder) {             // back to the caller's order (the next sort reads the caller's arrays)
+            large_permute_kernel<ST, false><<<gn, 256, 0, stream>>>(n, s.perm[1], pos[cur], vel[cur], th[cur], a.pos, a.vel, a.th);
             ++*launches;
         }
-        LargeArgs la{};
-        la.pos_src = pos[src]; la.vel_src = vel[src]; la.th_src = th[src];
-        la.pos_dst = pos[dst]; la.vel_dst = vel[dst]; la.th_dst = th[dst];
-        la.view_src = s.view[src]; la.view_dst = s.view[dst];
-        la.view_stride = nv; la.Npad = Npad; la.tiles_i = tiles_i; la.tiles_j = tiles_j; la.cluster = cluster;
-        la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = s.robot_slot;
-        la.boxes = prune ? s.boxes : nullptr; la.chunk_boxes = s.chunk_boxes; la.cut2 = a.warp_cut2;
-        if (prune) {
-            if constexpr (sizeof(PT) == 4)
-                large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a.N, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes, s.chunk_boxes);
-            ++*launches;
-        }
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(a.W * tiles_i)); cfg.blockDim = dim3(LARGE_TI); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if ((e = cudaLaunchKernelEx(&cfg, kern, a, la)) != cudaSuccess) return -2;
-        ++*launches;
     }
-    // an odd number of steps leaves the newest state in the scratch buffers: copy it home
-    if (a.n_steps & 1) {
+    // without re-ordering an odd number of steps leaves the newest state in the scratch buffers: copy it home
+    if (!reorder && cur == 1) {
         cudaMemcpyAsync(a.pos, s.pos2, n * 16, cudaMemcpyDeviceToDevice, stream);
         if (sizeof(ST) == 8) cudaMemcpyAsync(a.vel, s.vel2, n * 16, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(a.th, s.th2, n * e2, cudaMemcpyDeviceToDevice, stream);

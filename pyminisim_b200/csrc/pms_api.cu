@@ -138,6 +138,7 @@ struct pms_sim {
     int tune_S = 0, tune_wpc = 0, tune_chunks = 0, tune_cluster = 0;
     bool force_large = false;
     bool no_prune = false;   // large-crowd kernel: visit every j-tile (comparison / tests)
+    bool no_reorder = false; // large-crowd kernel: keep the caller's pedestrian order (no sorted working copy)
     bool async_io = false;   // state / reading transfers do not synchronise (pms_set_async_io)
     int sm_count = 148;
     int sched_cap = 0;
@@ -316,9 +317,9 @@ int launch_large(pms_sim *h)
     int blocks = 0, smem = 0, rc;
     long long launches = 0;
     switch (h->precision) {
-    case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, !h->no_prune, h->stream, &launches, &blocks, &smem); break;
-    case PMS_MIXED: rc = launch_large_t<float, double, true>(h->large, h->a, cluster, !h->no_prune, h->stream, &launches, &blocks, &smem); break;
-    default: rc = launch_large_t<double, double, false>(h->large, h->a, cluster, false, h->stream, &launches, &blocks, &smem); break;
+    case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, !h->no_prune, !h->no_reorder, h->stream, &launches, &blocks, &smem); break;
+    case PMS_MIXED: rc = launch_large_t<float, double, true>(h->large, h->a, cluster, !h->no_prune, !h->no_reorder, h->stream, &launches, &blocks, &smem); break;
+    default: rc = launch_large_t<double, double, false>(h->large, h->a, cluster, false, false, h->stream, &launches, &blocks, &smem); break;
     }
     if (rc) return fail(PMS_ERR_CUDA, std::string("large-crowd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->info.kernel = 1;
@@ -759,13 +760,14 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     h->a.dt = dt; h->a.n_steps = n_steps;
     fill_consts(h->a);
     int rc;
-    if (h->a.robot_model == ROBOT_NONE && (rc = clear_sensor_outputs(h))) return rc;
     // j_split < 0 selects the directed-pair kernel for small worlds too (tests, comparisons)
     const bool warp_ok = h->precision != PMS_FP64 && h->Np <= 32 * WARP_MAX_TILES && h->tune_S >= 0;
-    if (h->force_large) rc = launch_large(h);
+    const bool large_path = h->force_large || (!warp_ok && h->Np + 32 > 1024);
+    // the large-crowd kernel sets mask bits with atomicOr when it works on the sorted copy: start from zero
+    if ((h->a.robot_model == ROBOT_NONE || large_path) && (rc = clear_sensor_outputs(h))) return rc;
+    if (large_path) rc = launch_large(h);
     else if (warp_ok) rc = launch_warp(h);
-    else if (h->Np + 32 <= 1024) rc = launch_small(h);
-    else rc = launch_large(h);
+    else rc = launch_small(h);
     if (rc) return rc;
     h->a.steps_done += n_steps;
     return PMS_OK;
@@ -949,7 +951,8 @@ int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, 
 {
     if (!h) return fail(PMS_ERR_INVALID, "handle is NULL");
     h->tune_S = j_split; h->tune_wpc = worlds_per_block; h->tune_chunks = n_chunks < 0 ? 0 : n_chunks;
-    h->no_prune = n_chunks < 0;                       // negative: the large-crowd kernel visits every j-tile
+    h->no_prune = n_chunks == -1;                     // -1: the large-crowd kernel visits every j-tile
+    h->no_reorder = n_chunks < 0;                     // -1, -2: no sorted working copy
     h->force_large = cluster_size < 0;               // negative: force the large-crowd kernel (tests)
     h->tune_cluster = cluster_size < 0 ? -cluster_size : cluster_size;
     return PMS_OK;

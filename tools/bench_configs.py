@@ -91,8 +91,11 @@ def main():
         time_hsfm("16384 x 32 warp kernel", 16384, 32, 1000)
     if "c3" in which:
         time_hsfm("C3 large crowd", 1, 65536, 20, large=True)
+        time_hsfm("C3 large crowd, 200 steps per call", 1, 65536, 200, large=True)
+        time_hsfm("C3 large crowd, caller's order kept (no sorted working copy)", 1, 65536, 20, large=True, tuning=(0, 0, -2, 0))
         time_hsfm("C3 large crowd, every j-tile visited (no exact pruning)", 1, 65536, 20, large=True, tuning=(0, 0, -1, 0))
         time_hsfm("C3 large crowd, shuffled pedestrian order", 1, 65536, 20, large=True, shuffle=True)
+        time_hsfm("C3 large crowd, shuffled pedestrian order, caller's order kept", 1, 65536, 20, large=True, shuffle=True, tuning=(0, 0, -2, 0))
         time_hsfm("C3 large crowd, MIXED", 1, 65536, 20, large=True, precision="mixed")
     if "c5" in which:
         time_orca("C5 ORCA", 2048, 64, 200)
