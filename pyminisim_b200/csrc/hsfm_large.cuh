@@ -6,7 +6,7 @@
 //   hsfm_large_kernel   : grid = worlds x i-tiles.  A CTA owns TI pedestrians (one per thread) and streams
 //                         the whole world's "pair view" (structure-of-arrays x, y, vx, vy [, xlo, ylo])
 //                         through shared memory in j-tiles of TJ with cp.async.bulk (TMA 1-D bulk copy)
-//                         completing on an mbarrier, double-buffered.  CTAs are launched in clusters; each
+//                         completing on an mbarrier, LARGE_STAGES buffers deep.  CTAs are launched in clusters; each
 //                         CTA of a cluster fetches 1/C of every j-tile and MULTICASTS it into the shared
 //                         memory of all C CTAs, so a tile is read from L2 once per cluster.  Buffer reuse is
 //                         guarded by a split cluster barrier (arrive after compute, wait before refill).
@@ -29,6 +29,7 @@ namespace pms {
 
 constexpr int LARGE_TI = 128;        // pedestrians (threads) per CTA
 constexpr int LARGE_TJ = 512;        // pedestrians per streamed j-tile
+constexpr int LARGE_STAGES = 4;      // j-tile buffers in shared memory (TMA runs LARGE_STAGES - 1 tiles ahead)
 
 struct LargeArgs {
     // ping-pong state (element g = w*N + i); src is read, dst is written
@@ -248,10 +249,10 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     using ST2 = typename Vec2<ST>::type;
     constexpr int NARR = SPLIT ? 6 : 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [2 stages][NARR arrays][TJ] of PT (lo arrays are float == PT in MIXED), then 2 mbarriers
+    // [LARGE_STAGES][NARR arrays][TJ] of PT (lo arrays are float == PT in MIXED), then 2 mbarriers
     PT *tiles = reinterpret_cast<PT *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 2 * NARR * LARGE_TJ * sizeof(PT));
-    int *tile_list = reinterpret_cast<int *>(full + 2);      // [tiles_j] j-tiles this cluster has to visit, then their count
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + LARGE_STAGES * NARR * LARGE_TJ * sizeof(PT));
+    int *tile_list = reinterpret_cast<int *>(full + LARGE_STAGES);      // [tiles_j] j-tiles this cluster has to visit, then their count
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int w = blockIdx.x / la.tiles_i, it = blockIdx.x - w * la.tiles_i;
@@ -266,8 +267,7 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     const size_t vs = la.view_stride;
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        for (int q = 0; q < LARGE_STAGES; ++q) mbar_init(&full[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) {
@@ -305,8 +305,8 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     cluster_wait();          // every CTA of the cluster has initialised its barriers
 
     constexpr uint32_t kTileBytes = NARR * LARGE_TJ * sizeof(PT);
-    auto issue = [&](int k, int jt) {   // thread 0 only: tile jt into buffer k & 1
-        const int b = k & 1;
+    auto issue = [&](int k, int jt) {   // thread 0 only: tile jt into buffer k % LARGE_STAGES
+        const int b = k % LARGE_STAGES;
         PT *dst = tiles + (size_t)b * NARR * LARGE_TJ;
         mbar_expect_tx(&full[b], kTileBytes);
         const int C = la.cluster;
@@ -336,13 +336,14 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     float4 wbox = make_float4(0.f, 0.f, 0.f, 0.f);               // box of this warp's 32 pedestrians
     if (prune_chunks) wbox = __ldg(la.chunk_boxes + ((size_t)w * la.Npad + i0) / LARGE_CHUNK);
     const int T = tile_list[la.tiles_j];
-    if (tid == 0) issue(0, tile_list[0]);
+    if (tid == 0)
+        for (int q = 0; q < LARGE_STAGES - 1 && q < T; ++q) issue(q, tile_list[q]);
     for (int k = 0; k < T; ++k) {
         const int jt = tile_list[k];
-        if (k >= 1) cluster_wait();                  // everybody is done with the buffer the next tile will overwrite
-        if (k + 1 < T && tid == 0) issue(k + 1, tile_list[k + 1]);
-        mbar_wait(&full[k & 1], (k >> 1) & 1);
-        const PT *xs = tiles + (size_t)(k & 1) * NARR * LARGE_TJ;
+        if (k >= 1) cluster_wait();                  // everybody is done with tile k - 1: its buffer may be refilled
+        if (k + LARGE_STAGES - 1 < T && tid == 0) issue(k + LARGE_STAGES - 1, tile_list[k + LARGE_STAGES - 1]);
+        mbar_wait(&full[k % LARGE_STAGES], (k / LARGE_STAGES) & 1);
+        const PT *xs = tiles + (size_t)(k % LARGE_STAGES) * NARR * LARGE_TJ;
         const PT *ys = xs + LARGE_TJ, *vxs = xs + 2 * LARGE_TJ, *vys = xs + 3 * LARGE_TJ;
         const int jbase = jt * LARGE_TJ;
         if constexpr (sizeof(PT) == 4) {
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
             for (int jl = 0; jl < jn; ++jl)
                 pair_accum(kpp, mx - xs[jl], my - ys[jl], vxs[jl] - mvx, vys[jl] - mvy, jbase + jl == i, fx, fy);
         }
-        cluster_arrive();                            // done reading buffer k & 1
+        cluster_arrive();                            // done reading the buffer of tile k
     }
     cluster_wait();
     if constexpr (sizeof(PT) == 4) {
@@ -561,7 +562,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
     const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ;
     // grid must be a multiple of the cluster size and a cluster must stay inside one world
     while (cluster > 1 && (tiles_i % cluster != 0 || LARGE_TJ % cluster != 0)) cluster >>= 1;
-    const size_t smem = 2 * NARR * LARGE_TJ * sizeof(PT) + 2 * sizeof(uint64_t) + sizeof(int) * (tiles_j + 1);
+    const size_t smem = LARGE_STAGES * NARR * LARGE_TJ * sizeof(PT) + LARGE_STAGES * sizeof(uint64_t) + sizeof(int) * (tiles_j + 1);
     auto kern = hsfm_large_kernel<PT, ST, SPLIT>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
     const unsigned gn = (unsigned)((n + 255) / 256), gv = (unsigned)((nv + 255) / 256);
