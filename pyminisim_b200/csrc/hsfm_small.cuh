@@ -325,17 +325,13 @@ __device__ __forceinline__ void pair_far2(const PairK<float> &k, float2 dx, floa
     const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
     inv.x = fast_rsqrt(d2.x); inv.y = fast_rsqrt(d2.y);
     float2 d = __fmul2_rn(d2, inv);
-#ifdef PMS_REFINE_SQRT   // off: measured to make no difference to parity (profiles/parity_r1.md), costs 9 %
+#ifdef PMS_REFINE_SQRT   // off: measured to make no difference to parity (profiles/r1_history.md), costs 9 %
     const float2 err = __ffma2_rn(make_float2(-d.x, -d.y), d, d2);
     d = __ffma2_rn(err, __fmul2_rn(inv, make_float2(0.5f, 0.5f)), d);
 #endif
     sg = __fadd2_rn(make_float2(k.rij, k.rij), make_float2(-d.x, -d.y));
     const float2 arg = __fmul2_rn(sg, make_float2(k.cexp, k.cexp));
-#ifdef PMS_EXP_NOEX2
-    float2 e = __ffma2_rn(arg, make_float2(1e-9f, 1e-9f), make_float2(1e-9f, 1e-9f));   // experiment only: no MUFU.EX2
-#else
     float2 e; e.x = fast_ex2(arg.x); e.y = fast_ex2(arg.y);
-#endif
     const float2 a = __fmul2_rn(e, __fmul2_rn(inv, make_float2(k.A, k.A)));
     fx = __ffma2_rn(a, dx, fx);
     fy = __ffma2_rn(a, dy, fy);
