@@ -105,6 +105,16 @@ template <int OP> __global__ void k(float *out, int iters)
                 p2 = __ffma2_rn(p2, c, d); p3 = __ffma2_rn(p3, c, d); p2 = __ffma2_rn(p2, c, d); p3 = __ffma2_rn(p3, c, d);
                 p2 = __ffma2_rn(p2, c, d); p3 = __ffma2_rn(p3, c, d); p2 = __ffma2_rn(p2, c, d); p3 = __ffma2_rn(p3, c, d);
                 a4 = p2.x; a5 = p2.y; a6 = p3.x; a7 = p3.y;
+            } else if (OP == 14) {   // FFMA2 with three distinct packed register operands (6 registers read per instruction)
+                float2 p0 = make_float2(a0, a1), p1 = make_float2(a2, a3), p2 = make_float2(a4, a5), p3 = make_float2(a6, a7);
+                p0 = __ffma2_rn(p1, p2, p0); p1 = __ffma2_rn(p2, p3, p1); p2 = __ffma2_rn(p3, p0, p2); p3 = __ffma2_rn(p0, p1, p3);
+                p0 = __ffma2_rn(p1, p2, p0); p1 = __ffma2_rn(p2, p3, p1); p2 = __ffma2_rn(p3, p0, p2); p3 = __ffma2_rn(p0, p1, p3);
+                a0 = p0.x; a1 = p0.y; a2 = p1.x; a3 = p1.y; a4 = p2.x; a5 = p2.y; a6 = p3.x; a7 = p3.y;
+            } else if (OP == 15) {   // FMUL2 with two distinct packed register operands
+                float2 p0 = make_float2(a0, a1), p1 = make_float2(a2, a3), p2 = make_float2(a4, a5), p3 = make_float2(a6, a7);
+                p0 = __fmul2_rn(p1, p2); p1 = __fmul2_rn(p2, p3); p2 = __fmul2_rn(p3, p0); p3 = __fmul2_rn(p0, p1);
+                p0 = __fmul2_rn(p1, p2); p1 = __fmul2_rn(p2, p3); p2 = __fmul2_rn(p3, p0); p3 = __fmul2_rn(p0, p1);
+                a0 = p0.x; a1 = p0.y; a2 = p1.x; a3 = p1.y; a4 = p2.x; a5 = p2.y; a6 = p3.x; a7 = p3.y;
             } else if (OP == 8) {   // mix: the far-field chain (2 pairs): 11 packed + 4 MUFU
                 float2 dx = make_float2(a0, a1), dy = make_float2(a2, a3), fx = make_float2(a4, a5), fy = make_float2(a6, a7);
                 const float2 nc = make_float2(-18.f, -18.f), rc = make_float2(10.8f, 10.8f);
@@ -149,6 +159,7 @@ int main()
         run<6>("SHFL.IDX", 8, t, 2); run<11>("LDS.64 x8 (+4 FADD)", 8, t, 2); run<8>("far chain (15 inst/2 pairs)", 15, t, 2);
         run<9>("4 MUFU + 4 SHFL (per 8)", 8, t, 2); run<10>("4 MUFU + 4 LDS.64 (per 8)", 8, t, 2); run<12>("4 SHFL + 4 LDS.64 (per 8)", 8, t, 2);
         run<13>("4 MUFU + 8 FFMA2 (per 12)", 12, t, 2);
+        run<14>("FFMA2, 3 packed register operands", 8, t, 2); run<15>("FMUL2, 2 packed register operands", 8, t, 2);
     }
     return 0;
 }
