@@ -118,9 +118,8 @@ __device__ __forceinline__ uint32_t cluster_ctarank()
 }
 
 // ---- robot: one thread per world ---------------------------------------------------------------------
-__global__ void robot_step_kernel(const __grid_constant__ HsfmArgs a, RobotRegs *regs, RobotSlot *slot, int step, int first, int last)
+__device__ __forceinline__ void large_robot_step(const HsfmArgs &a, int w, RobotRegs *regs, RobotSlot *slot, int step, int first, int last)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= a.W || a.robot_model == ROBOT_NONE) return;
     RobotRegs r;
     if (first) robot_load(a, w, r); else r = regs[w];
@@ -128,6 +127,10 @@ __global__ void robot_step_kernel(const __grid_constant__ HsfmArgs a, RobotRegs 
     regs[w] = r;
     slot[w] = RobotSlot{r.x, r.y, r.th, r.vx, r.vy};
     if (last) robot_store(a, w, r);
+}
+__global__ void robot_step_kernel(const __grid_constant__ HsfmArgs a, RobotRegs *regs, RobotSlot *slot, int step, int first, int last)
+{
+    large_robot_step(a, blockIdx.x * blockDim.x + threadIdx.x, regs, slot, step, first, last);
 }
 
 // ---- pair view initialisation from the state (first step of a call) --------------------------------------
@@ -202,9 +205,14 @@ __global__ void large_permute_kernel(size_t n, const int *perm, const void *pos_
 constexpr int LARGE_CHUNK = 32;       // pedestrians per chunk box (one warp's rows / one warp-level skip unit)
 
 template <typename PT>
-__global__ void __launch_bounds__(128) large_box_kernel(int N, int Npad, int tiles_j, const PT *view, size_t stride, float4 *boxes,
-                                                        float4 *chunk_boxes)
+__global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ HsfmArgs a, int Npad, int tiles_j, const PT *view,
+                                                        size_t stride, float4 *boxes, float4 *chunk_boxes, RobotRegs *regs,
+                                                        RobotSlot *slot, int step, int first, int last)
 {
+    // the robots ride along in the first CTA (one launch less per step)
+    if (blockIdx.x == 0)
+        for (int rw = threadIdx.x; rw < a.W; rw += 128) large_robot_step(a, rw, regs, slot, step, first, last);
+    const int N = a.N;
     const int w = blockIdx.x / tiles_j, jt = blockIdx.x - w * tiles_j;
     const PT *xs = view + (size_t)w * Npad + (size_t)jt * LARGE_TJ, *ys = xs + stride;
     const float inf = CUDART_INF_F;
@@ -590,7 +598,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         *launches += 2;
         for (int t = t0; t < t1; ++t) {
             const int src = cur, dst = cur ^ 1;
-            if (a.robot_model != ROBOT_NONE) {
+            if (a.robot_model != ROBOT_NONE && !prune) {      // with pruning the robots ride along in the box kernel
                 robot_step_kernel<<<(a.W + 127) / 128, 128, 0, stream>>>(a, s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
                 ++*launches;
             }
@@ -604,7 +612,8 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             la.perm = reorder ? s.perm[1] : nullptr;
             if (prune) {
                 if constexpr (sizeof(PT) == 4)
-                    large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a.N, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes, s.chunk_boxes);
+                    large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes, s.chunk_boxes,
+                                                                                     s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
                 ++*launches;
             }
             cudaLaunchConfig_t cfg{};
