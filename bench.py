@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU (weak scaling)")
     ap.add_argument("--peds", type=int, default=64)
     ap.add_argument("--sim-steps", type=int, default=1000, help="fused simulation steps per bench step")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "mixed", "fp64"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_plain", "mixed", "fp64"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--j-split", type=int, default=0)
     ap.add_argument("--wpc", type=int, default=0)
@@ -58,7 +58,7 @@ def parse_args():
 
 KERNEL_NAMES = {0: "hsfm_small_kernel", 1: "hsfm_large_kernel", 3: "hsfm_warp_kernel"}
 # DRAM bytes per launch of the default workload from the committed ncu capture (None: not captured for that kernel)
-TRAFFIC_BYTES_PER_LAUNCH = {3: 17762304}
+TRAFFIC_BYTES_PER_LAUNCH = {(3, "fp32"): 24788992, (3, "fp32_plain"): 17762304}
 
 
 def flops_per_update(n_peds: int) -> float:
@@ -358,7 +358,7 @@ def main():
 
     extra = {}
     if args.extra and rank == 0:
-        for prec in ("mixed", "fp64"):
+        for prec in ("fp32_plain", "mixed", "fp64"):
             s2 = BatchedSimulation(W, N, precision=prec, device=local_rank)
             s2.set_state(sc.poses, sc.vels); s2.set_speeds(sc.vmag); s2.set_waypoints_fixed(sc.table, loop=True)
             s2.set_robot(capi.ROBOT_UNICYCLE, sc.robot_pose, control=sc.robot_control)
@@ -395,7 +395,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": {"fp32": "f32", "mixed": "f32/f64", "fp64": "f64"}[args.precision],
+            "scaling": args.scaling, "vs_baseline": None, "dtype": {"fp32": "f32", "fp32_plain": "f32", "mixed": "f32/f64", "fp64": "f64"}[args.precision],
             "data": "synthetic", "config": config_dict(args, world_size),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "how": "two handles alternate in asynchronous-I/O mode: the copies of one step overlap the kernel of the "
@@ -404,7 +404,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(info["kernel"]) if (W, N, K, args.precision) == (4096, 64, 1000, "fp32") else None,
+                         "traffic": TRAFFIC_BYTES_PER_LAUNCH.get((info["kernel"], args.precision)) if (W, N, K) == (4096, 64, 1000) else None,
                          "peak_source": "FP32 FMA-chain microbenchmark measured in this run (pms_measure_fp32_tflops); "
                                         "MEASURED_PEAKS.json has no non-tensor FP32 figure",
                          "kernel": KERNEL_NAMES.get(info["kernel"], str(info["kernel"])),
@@ -414,7 +414,7 @@ def main():
                                  "half of the algorithmic flops, so frac can exceed what the FMA pipe executes; the binding "
                                  "unit is the XU (MUFU) pipe: one rsqrt + one ex2 per unordered pair (profiles/)",
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                           "of this command (profiles/r1_warp_kernel_ncu.md); bytes per launch"},
+                                           "of this command (profiles/r1_warp_kernel_comp_ncu.md, fp32_plain: r1_warp_kernel_ncu.md); bytes per launch"},
             "cpu_baseline": cpu, "clocks": clocks, "launch": info, "episode_stats": episode,
         }
         line.update(extra)

@@ -34,12 +34,17 @@ typedef enum {
 } pms_status;
 
 /* Arithmetic mode of the HSFM kernels.
- *   PMS_FP32  : state, pair forces and per-pedestrian math in fp32 (north-star production mode).
+ *   PMS_FP32  : pair forces and per-pedestrian math in fp32 (north-star production mode).  Worlds of up to 128
+ *               pedestrians carry the state as unevaluated fp32 sums hi + lo with compensated Euler updates, so a
+ *               step no longer rounds the full magnitude of the state to fp32 (the error that dominates plain fp32
+ *               and that the crowd dynamics amplify ~1e6 x over 1000 steps); pair forces see the high parts.
+ *   PMS_FP32_PLAIN : as PMS_FP32 with a plain fp32 state, one rounding per variable per step (what every kernel
+ *               does for larger worlds).
  *   PMS_MIXED : fp64 state and per-pedestrian math; pair forces in fp32 from hi/lo-split
  *               positions (differences exact to fp64).
  *   PMS_FP64  : everything fp64 -- verification mode, algorithmically identical to the reference.
  * Robot pose, detector and collision predicates are evaluated in fp64 in every mode. */
-typedef enum { PMS_FP32 = 0, PMS_MIXED = 1, PMS_FP64 = 2 } pms_precision;
+typedef enum { PMS_FP32 = 0, PMS_MIXED = 1, PMS_FP64 = 2, PMS_FP32_PLAIN = 3 } pms_precision;
 
 typedef enum { PMS_ROBOT_NONE = 0, PMS_ROBOT_EXTERNAL = 1, PMS_ROBOT_UNICYCLE = 2, PMS_ROBOT_BICYCLE = 3 } pms_robot_model;
 typedef enum { PMS_MAP_EMPTY = 0, PMS_MAP_CIRCLES = 1, PMS_MAP_AABB = 2 } pms_map_kind;

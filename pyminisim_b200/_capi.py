@@ -10,11 +10,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PMS_LIB", os.path.join(HERE, "libpms_b200.so"))  # PMS_LIB: experiment builds only
 
-PMS_FP32, PMS_MIXED, PMS_FP64 = 0, 1, 2
+PMS_FP32, PMS_MIXED, PMS_FP64, PMS_FP32_PLAIN = 0, 1, 2, 3
 ROBOT_NONE, ROBOT_EXTERNAL, ROBOT_UNICYCLE, ROBOT_BICYCLE = 0, 1, 2, 3
 MAP_EMPTY, MAP_CIRCLES, MAP_AABB = 0, 1, 2
 DET_POLAR, DET_RELATIVE_ROTATED, DET_RELATIVE, DET_ABSOLUTE = 0, 1, 2, 3
-PRECISIONS = {"fp32": PMS_FP32, "mixed": PMS_MIXED, "fp64": PMS_FP64}
+PRECISIONS = {"fp32": PMS_FP32, "mixed": PMS_MIXED, "fp64": PMS_FP64, "fp32_plain": PMS_FP32_PLAIN}
 
 
 class PmsError(RuntimeError):

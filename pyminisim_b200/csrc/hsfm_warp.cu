@@ -4,11 +4,13 @@
 namespace pms {
 namespace {
 
-template <typename F> cudaError_t dispatch(bool split, int T, int cfg, F &&f)
+// comp: FP32 mode with the state carried as compensated hi + lo sums (PMS_FP32); plain fp32 state is PMS_FP32_PLAIN
+template <typename F> cudaError_t dispatch(bool split, bool comp, int T, int cfg, F &&f)
 {
 #define PMS_WARP_INST(TT, CF)                                                                               \
     (split ? f(hsfm_warp_kernel<double, true, TT, CF>, WarpSmem<double, true>::bytes(32 * TT))              \
-           : f(hsfm_warp_kernel<float, false, TT, CF>, WarpSmem<float, false>::bytes(32 * TT)))
+     : comp ? f(hsfm_warp_kernel<float, false, TT, CF, true>, WarpSmem<float, false, true>::bytes(32 * TT)) \
+            : f(hsfm_warp_kernel<float, false, TT, CF>, WarpSmem<float, false>::bytes(32 * TT)))
 #define PMS_WARP_CASE(TT)                                                                                   \
     case TT:                                                                                                \
         switch (cfg) {                                                                                      \
@@ -30,9 +32,9 @@ template <typename F> cudaError_t dispatch(bool split, int T, int cfg, F &&f)
 
 } // namespace
 
-cudaError_t warp_kernel_prepare(bool split, int T, int cfg, int wpc, int *blocks_per_sm, size_t *smem_bytes)
+cudaError_t warp_kernel_prepare(bool split, bool comp, int T, int cfg, int wpc, int *blocks_per_sm, size_t *smem_bytes)
 {
-    return dispatch(split, T, cfg, [&](auto kern, size_t per_world) {
+    return dispatch(split, comp, T, cfg, [&](auto kern, size_t per_world) {
         const size_t smem = per_world * wpc;
         *smem_bytes = smem;
         if (smem > 48 * 1024) {
@@ -43,10 +45,10 @@ cudaError_t warp_kernel_prepare(bool split, int T, int cfg, int wpc, int *blocks
     });
 }
 
-cudaError_t warp_kernel_launch(bool split, int T, int cfg, const HsfmArgs &a, int blocks, int threads, size_t smem,
+cudaError_t warp_kernel_launch(bool split, bool comp, int T, int cfg, const HsfmArgs &a, int blocks, int threads, size_t smem,
                                cudaStream_t stream)
 {
-    return dispatch(split, T, cfg, [&](auto kern, size_t) {
+    return dispatch(split, comp, T, cfg, [&](auto kern, size_t) {
         kern<<<blocks, threads, smem, stream>>>(a);
         return cudaGetLastError();
     });

@@ -44,7 +44,7 @@ template <typename T> cudaError_t dalloc(T **p, size_t n)
 
 // ---- marshalling kernels: host layout (W,N,3) fp64 <-> native SoA --------------------------------
 template <typename ST>
-__global__ void pack_state_kernel(size_t n, const double *poses, const double *vels, HsfmArgs a)
+__global__ void pack_state_kernel(size_t n, const double *poses, const double *vels, HsfmArgs a, bool keep_lo)
 {
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= n) return;
@@ -52,6 +52,11 @@ __global__ void pack_state_kernel(size_t n, const double *poses, const double *v
     store_pv(a, g, (ST)poses[3 * g], (ST)poses[3 * g + 1], (ST)vels[3 * g], (ST)vels[3 * g + 1]);
     ST2 t; t.x = (ST)poses[3 * g + 2]; t.y = (ST)vels[3 * g + 2];
     reinterpret_cast<ST2 *>(a.th)[g] = t;
+    if constexpr (sizeof(ST) == 4) {       // low parts: zero for a plain fp32 state (keep_lo false), else the fp32 rounding residue
+        auto lo = [&](double v) { return keep_lo ? (float)(v - (double)(float)v) : 0.0f; };
+        reinterpret_cast<float4 *>(a.pos_lo)[g] = make_float4(lo(poses[3 * g]), lo(poses[3 * g + 1]), lo(vels[3 * g]), lo(vels[3 * g + 1]));
+        reinterpret_cast<float2 *>(a.th_lo)[g] = make_float2(lo(poses[3 * g + 2]), lo(vels[3 * g + 2]));
+    }
 }
 template <typename ST>
 __global__ void unpack_state_kernel(size_t n, double *poses, double *vels, HsfmArgs a)
@@ -64,6 +69,12 @@ __global__ void unpack_state_kernel(size_t n, double *poses, double *vels, HsfmA
     const ST2 t = reinterpret_cast<const ST2 *>(a.th)[g];
     poses[3 * g] = (double)x; poses[3 * g + 1] = (double)y; poses[3 * g + 2] = (double)t.x;
     vels[3 * g] = (double)vx; vels[3 * g + 1] = (double)vy; vels[3 * g + 2] = (double)t.y;
+    if constexpr (sizeof(ST) == 4) {       // hi + lo (the low parts are zero unless the compensated kernel ran)
+        const float4 pl = reinterpret_cast<const float4 *>(a.pos_lo)[g];
+        const float2 tl = reinterpret_cast<const float2 *>(a.th_lo)[g];
+        poses[3 * g] += (double)pl.x; poses[3 * g + 1] += (double)pl.y; poses[3 * g + 2] += (double)tl.x;
+        vels[3 * g] += (double)pl.z; vels[3 * g + 1] += (double)pl.w; vels[3 * g + 2] += (double)tl.y;
+    }
 }
 template <typename ST>
 __global__ void convert_array_kernel(size_t n, const double *src, ST *dst)
@@ -117,6 +128,7 @@ struct pms_sim {
     int device = 0;
     int W = 0, N = 0, Np = 0, words = 0;
     int precision = PMS_FP32;
+    bool compensated = false;   // PMS_FP32 (not PMS_FP32_PLAIN): hi + lo state in the warp-per-world kernel
     size_t esz = 4;        // bytes of one state scalar
     cudaStream_t stream = nullptr;
     HsfmArgs a{};          // device pointers + configuration (the kernel argument block)
@@ -270,12 +282,13 @@ int launch_warp(pms_sim *h)
     const int T = h->Np / 32, minb = h->tune_S >= 1 && h->tune_S <= 3 ? h->tune_S : 0;
     if ((minb == 1 || minb == 2) && wpc > 4) wpc = 4;
     const bool split = h->precision == PMS_MIXED;
+    const bool comp = h->precision == PMS_FP32 && h->compensated;
     const int threads = wpc * 32;
     const int groups = (h->W + wpc - 1) / wpc;
     int blocks = groups, occ = 0;
     size_t smem = 0;
     h->a.wpc = wpc;
-    CK(warp_kernel_prepare(split, T, minb, wpc, &occ, &smem));
+    CK(warp_kernel_prepare(split, comp, T, minb, wpc, &occ, &smem));
     const int slots = occ * h->sm_count;
     h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
     int want = h->tune_chunks;
@@ -296,7 +309,12 @@ int launch_warp(pms_sim *h)
         const long long total = (long long)groups * h->a.n_chunks;
         blocks = (int)(total < slots ? total : slots);
     }
-    CK(warp_kernel_launch(split, T, minb, h->a, blocks, threads, smem, h->stream));
+    CK(warp_kernel_launch(split, comp, T, minb, h->a, blocks, threads, smem, h->stream));
+    if (h->precision == PMS_FP32 && !comp) {        // plain fp32 state: the low parts a set_state left are gone
+        const size_t n = (size_t)h->W * h->N;
+        CK(cudaMemsetAsync(h->a.pos_lo, 0, n * 16, h->stream));
+        CK(cudaMemsetAsync(h->a.th_lo, 0, n * 8, h->stream));
+    }
     h->info.kernel = 3;
     h->info.threads_per_block = threads;
     h->info.blocks = blocks;
@@ -368,7 +386,9 @@ int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hs
     if (!out) return fail(PMS_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (n_worlds < 1 || n_peds < 1) return fail(PMS_ERR_INVALID, "n_worlds and n_peds must be >= 1");
-    if (precision < PMS_FP32 || precision > PMS_FP64) return fail(PMS_ERR_INVALID, "unknown precision");
+    if (precision < PMS_FP32 || precision > PMS_FP32_PLAIN) return fail(PMS_ERR_INVALID, "unknown precision");
+    const bool compensated = precision == PMS_FP32;
+    if (precision == PMS_FP32_PLAIN) precision = PMS_FP32;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -382,6 +402,7 @@ int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hs
     h->device = device;
     h->W = n_worlds; h->N = n_peds; h->Np = (n_peds + 31) & ~31; h->words = (n_peds + 31) / 32;
     h->precision = precision;
+    h->compensated = compensated;
     h->esz = precision == PMS_FP32 ? 4 : 8;
     const size_t n = (size_t)n_worlds * n_peds;
     HsfmArgs &a = h->a;
@@ -406,6 +427,10 @@ int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hs
     CKC(dalloc(&raw, n * (precision == PMS_FP32 ? 16 : 16))); a.pos = raw;
     CKC(dalloc(&raw, n * 16)); a.vel = raw;
     CKC(dalloc(&raw, n * e2)); a.th = raw;
+    if (precision == PMS_FP32) {
+        CKC(dalloc(&raw, n * 16)); a.pos_lo = raw;
+        CKC(dalloc(&raw, n * 8)); a.th_lo = raw;
+    }
     CKC(dalloc(&raw, n * e2)); a.wp = raw;
     CKC(dalloc(&raw, n * h->esz)); a.vmag = raw;
     CKC(dalloc(&a.wp_index, n));
@@ -453,7 +478,7 @@ int pms_destroy(pms_sim *h)
     Guard gd(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     HsfmArgs &a = h->a;
-    void *ptrs[] = {a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
+    void *ptrs[] = {a.pos_lo, a.th_lo, a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
                     a.events, a.ev_count, a.robot_pose, a.robot_vel, a.robot_ctrl, a.robot_rear,
                     a.robot_world_collision, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
                     a.nonfinite, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done, h->noise_dev};
@@ -496,8 +521,8 @@ int pms_set_ped_state(pms_sim *h, const double *poses, const double *vels)
     CK(cudaMemcpyAsync(h->stage, poses, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (vels) CK(cudaMemcpyAsync(h->stage + n * 3, vels, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     else CK(cudaMemsetAsync(h->stage + n * 3, 0, n * 3 * sizeof(double), h->stream));
-    if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
-    else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
+    if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a, h->compensated);
+    else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a, false);
     CK(cudaGetLastError());
     IO_DONE(h);
     return PMS_OK;
@@ -769,6 +794,11 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     else if (warp_ok) rc = launch_warp(h);
     else rc = launch_small(h);
     if (rc) return rc;
+    if (h->precision == PMS_FP32 && (large_path || !warp_ok)) {   // these kernels carry a plain fp32 state
+        const size_t n = (size_t)h->W * h->N;
+        CK(cudaMemsetAsync(h->a.pos_lo, 0, n * 16, h->stream));
+        CK(cudaMemsetAsync(h->a.th_lo, 0, n * 8, h->stream));
+    }
     h->a.steps_done += n_steps;
     return PMS_OK;
 }
@@ -859,6 +889,7 @@ static void snapshot_regions(pms_sim *h, std::vector<std::pair<void *, size_t>> 
          {a.robot_pose, W * 24}, {a.robot_vel, W * 24}, {a.robot_ctrl, W * 16}, {a.robot_rear, W * 24},
          {a.robot_world_collision, W * 4}, {a.det_count, W * 8}, {a.coll_count, W * 8}, {a.nonfinite, W * 4}};
     if (a.queue) r.push_back({(void *)a.queue, n * a.q_cap * 2 * h->esz});
+    if (a.pos_lo) { r.push_back({a.pos_lo, n * 16}); r.push_back({a.th_lo, n * 8}); }
 }
 
 int pms_snapshot_save(pms_sim *h)

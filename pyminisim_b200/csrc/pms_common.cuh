@@ -35,6 +35,10 @@ struct HsfmArgs {
     void *pos;                  // FP32: float4 {x,y,vx,vy}   | fp64 state: double2 {x,y}
     void *vel;                  // FP32: unused               | fp64 state: double2 {vx,vy}
     void *th;                   // {theta, omega}  float2 | double2
+    // FP32 mode only: low parts of the state carried as unevaluated sums hi + lo (compensated Euler updates in
+    // hsfm_warp.cuh; the other kernels write high parts only and the API zeroes these after their launches)
+    void *pos_lo;               // float4 {x,y,vx,vy} low parts
+    void *th_lo;                // float2 {theta, omega} low parts
     void *wp;                   // current waypoint float2 | double2
     void *vmag;                 // float | double
     int *wp_index;

@@ -18,7 +18,12 @@ __global__ void sense_kernel(const __grid_constant__ HsfmArgs a)
     if (i < N) {
         ST x, y, vx, vy;
         load_pv(a, g, x, y, vx, vy);
-        so = sense_ped<ST>(a, rb, x, y, true);
+        if constexpr (sizeof(ST) == 4) {          // FP32 state = hi + lo (lo is zero unless the compensated kernel ran)
+            const float4 l = reinterpret_cast<const float4 *>(a.pos_lo)[g];
+            so = sense_ped<double>(a, rb, (double)x + (double)l.x, (double)y + (double)l.y, true);
+        } else {
+            so = sense_ped<ST>(a, rb, x, y, true);
+        }
         if (a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
     }
     const unsigned dm = __ballot_sync(0xffffffffu, so.det);

@@ -58,3 +58,39 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 for needle in ("import oracle", "from oracle", "pms_oracle", "liboracle", "orc_"):
                     assert needle not in src, f"{f} references the oracle ({needle})"
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """include/pms.h is the boundary a maintainer binds from C / cgo / JNI: it must compile as C99 without CUDA or C++
+    headers, and a C caller must link against libpms_b200.so.  The program only queries defaults and the error path of
+    pms_create (no device here), i.e. no compute without a GPU."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    from pyminisim_b200 import build
+    build.build()
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "pms.h"
+int main(void) {
+    pms_hsfm_params p;
+    pms_default_hsfm_params(&p);
+    if (p.A != 2000.0 || p.B != 0.08) return 2;
+    pms_sim *h = 0;
+    int rc = pms_create(0, 4, 8, PMS_FP32, &p, &h);
+    if (rc == PMS_OK) { printf("created\n"); return pms_destroy(h); }   /* GPU box */
+    if (rc != PMS_ERR_CUDA || h != 0) return 3;                          /* CPU box: loud failure, no fallback */
+    printf("%s\n", pms_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libpms_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "created" in out.stdout or "CUDA" in out.stdout or "fallback" in out.stdout

@@ -79,10 +79,12 @@ def main():
     which = set(sys.argv[1:]) or {"c2", "c3", "c4", "c5"}
     if "c2" in which:
         time_hsfm("C2 warp kernel", 1024, 32, 1000)
+        time_hsfm("C2 warp kernel, plain fp32 state", 1024, 32, 1000, precision="fp32_plain")
         time_hsfm("C2 directed-pair kernel", 1024, 32, 1000, tuning=(-1, 0, 0, 0))
         time_hsfm("C2 mixed", 1024, 32, 1000, precision="mixed")
     if "c4" in which:
         time_hsfm("C4 warp kernel", 4096, 64, 1000)
+        time_hsfm("C4 warp kernel, plain fp32 state", 4096, 64, 1000, precision="fp32_plain")
         time_hsfm("C4 directed-pair kernel", 4096, 64, 1000, tuning=(-1, 0, 0, 0))
         time_hsfm("C4 mixed", 4096, 64, 1000, precision="mixed")
         time_hsfm("C4 fp64", 4096, 64, 200, precision="fp64")

@@ -23,7 +23,7 @@ def main():
     for gen_name, gen in (("local-goals", make_bench_crowd), ("mirrored-goals", make_crowd)):
         for n, W in ((8, 16), (32, 16), (64, 16)):
             sc = gen(W, n)
-            for prec in ("fp32", "mixed", "fp64"):
+            for prec in ("fp32", "fp32_plain", "mixed", "fp64"):
                 o = make_oracle(sc)
                 c = make_cuda(sc, prec)
                 done = 0
