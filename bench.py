@@ -77,7 +77,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -269,7 +269,6 @@ def main():
     ms = timed_device_steps(args.steps, K)
     launches = sim.launch_info()["kernel_launches"] - launches_before
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     ms_max = max_over_ranks(ms, device="cuda")
     total_worlds = args.worlds * world_size if args.scaling == "weak" else args.worlds
     updates_total = float(total_worlds) * N * K * args.steps
@@ -341,6 +340,7 @@ def main():
     pipelined(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the device-resident and both end-to-end timed regions
     e2e_value = updates_total / max_over_ranks(e2e_s, device="cuda")
     last_buf = pipe[(args.steps - 1) & 1][1]
     e2e_matches = bool(np.array_equal(last_buf["poses"], o_poses) and np.array_equal(last_buf["mask"], mask)

@@ -127,10 +127,35 @@ int pms_set_map(pms_sim *h, int kind, const double *data /*circles (C,3) | aabb 
  * acceleration dv_b in every step of the following pms_hsfm_step calls; the caller draws it (the
  * reference uses the global numpy RNG).  NULL switches it off. */
 int pms_set_accel_noise(pms_sim *h, const double *noise /*(W,N,2) or NULL*/);
+/* The same noise drawn on the device: N(0, noise_std) per pedestrian and component, afresh in EVERY step of a fused
+ * multi-step launch like np.random.normal in _hsfm.py:289 (the array above is constant over a launch).  Counter-based
+ * Philox4x32-10 keyed by (seed, world*N + pedestrian, absolute step): the stream does not depend on the launch
+ * configuration, the kernel chosen or the split of an episode into calls.  Statistical parity with the reference (its
+ * values come from the global numpy Mersenne twister), not bit parity.  noise_std = 0 switches it off. */
+int pms_set_accel_noise_std(pms_sim *h, double noise_std, uint64_t seed);
+/* The generator itself, on the host, so that a caller can reproduce a device stream: Philox4x32-10 (Salmon et al. 2011;
+ * Random123 known-answer vectors in tests/test_cabi_symbols.py).  The device draws block
+ *   ctr = {id lo, id hi, step lo, step hi ^ (stream << 28)}, key = {seed lo, seed hi},
+ * id = world * n_peds + pedestrian, stream 0 = acceleration noise (words 0, 1 -> Box-Muller pair), 1 = detector noise
+ * (word 0 -> misdetection uniform, words 1, 2 -> Box-Muller pair for distance / angle); uniform = (word + 0.5) / 2^32. */
+void pms_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* LidarSensorNoise (sensors/_lidar.py:52-87) applied by pms_lidar_scan: hit points dropped with probability drop_prob
+ * (hit index -1), N(point_mean, point_cov) added to the survivors; point_mean (2) / point_cov (2,2) NULL = the reference's
+ * defaults (0, diag(0.001)).  Stream 2, id = world * n_beams + beam.  OmniObstacleDetectorNoise
+ * (sensors/_omni_obstacle_detector.py:25-37,64-69) applied by pms_omni_scan: inf with probability misdetection_prob,
+ * else distance + N(mu, sigma).  Stream 3, id = world.  Statistical parity. */
+int pms_set_lidar_noise(pms_sim *h, int enabled, double drop_prob, const double *point_mean, const double *point_cov, uint64_t seed);
+int pms_set_omni_noise(pms_sim *h, int enabled, double misdetection_prob, double distance_mu, double distance_sigma, uint64_t seed);
 
 /* ---- sensors ---- */
 /* PedestrianDetector (sensors/_pedestrian_detector.py:78-134); fov in radians. */
 int pms_detector_config(pms_sim *h, int enabled, double max_dist, double fov, int return_type);
+/* PedestrianDetectorNoise (sensors/_pedestrian_detector.py:60-72,104-112) on the device: pms_get_detector drops every
+ * detected pedestrian with probability misdetection_prob, adds N(distance_mu, distance_sigma) / N(angle_mu, angle_sigma)
+ * to the survivors in the polar frame and converts to the configured return type (:114-134).  Philox stream keyed by
+ * (seed, pedestrian, absolute step): repeated reads of one step return the same noisy reading.  Statistical parity. */
+int pms_set_detector_noise(pms_sim *h, int enabled, double misdetection_prob, double distance_mu, double distance_sigma,
+                           double angle_mu, double angle_sigma, uint64_t seed);
 
 /* ---- the hot path ---- */
 /* n_steps fused iterations of Simulation._make_steps + _get_world_state + detector

@@ -71,7 +71,12 @@ PROTOTYPES = {
     "pms_get_robot": (C.c_int, [_h, _dp, _dp, _ip]),
     "pms_set_map": (C.c_int, [_h, C.c_int, _dp, C.c_int, C.c_int]),
     "pms_set_accel_noise": (C.c_int, [_h, _dp]),
+    "pms_set_accel_noise_std": (C.c_int, [_h, C.c_double, C.c_uint64]),
+    "pms_set_lidar_noise": (C.c_int, [_h, C.c_int, C.c_double, _dp, _dp, C.c_uint64]),
+    "pms_set_omni_noise": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint64]),
+    "pms_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "pms_detector_config": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, C.c_int]),
+    "pms_set_detector_noise": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint64]),
     "pms_hsfm_step": (C.c_int, [_h, C.c_double, C.c_int]),
     "pms_hsfm_step_async": (C.c_int, [_h, C.c_double, C.c_int]),
     "pms_sync": (C.c_int, [_h]),

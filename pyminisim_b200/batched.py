@@ -160,6 +160,31 @@ class BatchedSimulation:
     def set_accel_noise(self, noise):
         check(self._lib.pms_set_accel_noise(self._h, None if noise is None else dptr(f64(noise, (self.W, self.N, 2)))))
 
+    def set_accel_noise_std(self, noise_std: float, seed: int = 0):
+        """``noise_std`` of HeadedSocialForceModelPolicy (_hsfm.py:208,288-289) drawn on the device, afresh in every step of
+        a fused launch (Philox, keyed by seed / pedestrian / absolute step).  Statistical parity with the reference."""
+        check(self._lib.pms_set_accel_noise_std(self._h, float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def set_detector_noise(self, misdetection_prob: float = 0.0, distance_mu: float = 0.0, distance_sigma: float = 0.0,
+                           angle_mu: float = 0.0, angle_sigma: float = 0.0, seed: int = 0, enabled: bool = True):
+        """PedestrianDetectorNoise (sensors/_pedestrian_detector.py:60-72,104-112) applied on the device by ``get_detector``."""
+        check(self._lib.pms_set_detector_noise(self._h, int(bool(enabled)), float(misdetection_prob), float(distance_mu),
+                                               float(distance_sigma), float(angle_mu), float(angle_sigma),
+                                               int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def set_lidar_noise(self, point_mean=None, point_cov=None, drop_prob: float = 0.0, seed: int = 0, enabled: bool = True):
+        """LidarSensorNoise (sensors/_lidar.py:52-87) applied on the device by ``lidar_scan``."""
+        mean = None if point_mean is None else f64(point_mean, (2,))
+        cov = None if point_cov is None else f64(point_cov, (2, 2))
+        check(self._lib.pms_set_lidar_noise(self._h, int(bool(enabled)), float(drop_prob), dptr(mean), dptr(cov),
+                                            int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def set_omni_noise(self, misdetection_prob: float = 0.0, distance_mu: float = 0.0, distance_sigma: float = 0.0,
+                       seed: int = 0, enabled: bool = True):
+        """OmniObstacleDetectorNoise (sensors/_omni_obstacle_detector.py:25-37,64-69) applied on the device by ``omni_scan``."""
+        check(self._lib.pms_set_omni_noise(self._h, int(bool(enabled)), float(misdetection_prob), float(distance_mu),
+                                           float(distance_sigma), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
     def set_detector(self, max_dist: float = 3.0, fov: float = np.deg2rad(30.0), return_type: int = capi.DET_POLAR,
                      enabled: bool = True):
         check(self._lib.pms_detector_config(self._h, int(bool(enabled)), float(max_dist), float(fov), int(return_type)))

@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     for src, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, f"nvcc {src}")
-    subprocess.run([nvcc, "-shared", "-o", out] + objs, check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, check=True)
     return out
     return LIB
 

@@ -459,6 +459,7 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         const ST x0 = x, y0 = y, th0 = th;
         ST nzx = 0, nzy = 0;
         if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
+        else if (a.accel_noise_std > 0.0) { const double2 z = accel_noise_draw(a, g, a.steps_done + la.step); nzx = (ST)z.x; nzy = (ST)z.y; }
         ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
         const ST ex = wp.x - x, ey = wp.y - y;
         bool reached;

@@ -260,6 +260,7 @@ __device__ __forceinline__ SenseOut owner_update(const HsfmArgs &a, const OwnerV
     const ST x0 = x, y0 = y, th0 = th;
     ST nzx = 0, nzy = 0;
     if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
+    else if (a.accel_noise_std > 0.0) { const double2 z = accel_noise_draw(a, g, a.steps_done + t); nzx = (ST)z.x; nzy = (ST)z.y; }
     ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, nzx, nzy);
     // ---- waypoint tracker on the NEW pose (_hsfm.py:301) ----
     const ST ex = wx - x, ey = wy - y;

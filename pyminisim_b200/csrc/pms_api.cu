@@ -129,6 +129,11 @@ struct pms_sim {
     int W = 0, N = 0, Np = 0, words = 0;
     int precision = PMS_FP32;
     bool compensated = false;   // PMS_FP32 (not PMS_FP32_PLAIN): hi + lo state in the warp-per-world kernel
+    DetNoise det_noise{};       // device-side detector noise; det_noise.return_type = the caller's return type
+    LidarNoise lidar_noise{};
+    OmniNoise omni_noise{};
+    uint32_t *noisy_mask = nullptr;
+    double2 *noisy_vals = nullptr;
     size_t esz = 4;        // bytes of one state scalar
     cudaStream_t stream = nullptr;
     HsfmArgs a{};          // device pointers + configuration (the kernel argument block)
@@ -481,7 +486,7 @@ int pms_destroy(pms_sim *h)
     void *ptrs[] = {a.pos_lo, a.th_lo, a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
                     a.events, a.ev_count, a.robot_pose, a.robot_vel, a.robot_ctrl, a.robot_rear,
                     a.robot_world_collision, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
-                    a.nonfinite, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done, h->noise_dev};
+                    a.nonfinite, h->noisy_mask, h->noisy_vals, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done, h->noise_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->snap_dst) if (p) cudaFree(p);
     large_free(h->large);
@@ -760,6 +765,7 @@ int pms_set_accel_noise(pms_sim *h, const double *noise)
     HCHECK(h);
     const size_t n = (size_t)h->W * h->N * 2;
     if (!noise) { h->a.accel_noise = nullptr; return PMS_OK; }
+    h->a.accel_noise_std = 0.0;            // an explicit noise array replaces the device generator
     if (!h->noise_dev) CK(cudaMalloc((void **)&h->noise_dev, n * sizeof(double)));
     CK(cudaMemcpyAsync(h->noise_dev, noise, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -767,12 +773,73 @@ int pms_set_accel_noise(pms_sim *h, const double *noise)
     return PMS_OK;
 }
 
+int pms_set_accel_noise_std(pms_sim *h, double noise_std, uint64_t seed)
+{
+    HCHECK(h);
+    if (!(noise_std >= 0.0)) return fail(PMS_ERR_INVALID, "noise_std must be >= 0");
+    h->a.accel_noise_std = noise_std; h->a.noise_seed = seed;
+    if (noise_std > 0.0) h->a.accel_noise = nullptr;
+    return PMS_OK;
+}
+
+int pms_set_lidar_noise(pms_sim *h, int enabled, double drop_prob, const double *point_mean, const double *point_cov, uint64_t seed)
+{
+    HCHECK(h);
+    if (!enabled) { h->lidar_noise.enabled = 0; return PMS_OK; }
+    if (!(drop_prob >= 0.0 && drop_prob <= 1.0)) return fail(PMS_ERR_INVALID, "need 0 <= drop_prob <= 1");          // _lidar.py:62
+    const double mx = point_mean ? point_mean[0] : 0.0, my = point_mean ? point_mean[1] : 0.0;
+    const double c00 = point_cov ? point_cov[0] : 0.001, c01 = point_cov ? point_cov[1] : 0.0,
+                 c10 = point_cov ? point_cov[2] : 0.0, c11 = point_cov ? point_cov[3] : 0.001;              // :57
+    if (!(c00 >= 0.0 && c01 >= 0.0 && c10 >= 0.0 && c11 >= 0.0)) return fail(PMS_ERR_INVALID, "point_cov must be >= 0"); // :61
+    if (c01 != c10) return fail(PMS_ERR_INVALID, "point_cov must be symmetric");
+    const double l00 = std::sqrt(c00), l10 = l00 > 0.0 ? c10 / l00 : 0.0, rest = c11 - l10 * l10;
+    if (rest < -1e-12 * (c11 > 1.0 ? c11 : 1.0)) return fail(PMS_ERR_INVALID, "point_cov must be positive semi-definite");
+    h->lidar_noise = LidarNoise{drop_prob, mx, my, l00, l10, rest > 0.0 ? std::sqrt(rest) : 0.0, seed, 1};
+    return PMS_OK;
+}
+
+int pms_set_omni_noise(pms_sim *h, int enabled, double misdetection_prob, double distance_mu, double distance_sigma, uint64_t seed)
+{
+    HCHECK(h);
+    if (!enabled) { h->omni_noise.enabled = 0; return PMS_OK; }
+    if (!(misdetection_prob <= 1.0)) return fail(PMS_ERR_INVALID, "misdetection_prob must be <= 1");   // _omni_obstacle_detector.py:49
+    if (!(distance_sigma >= 0.0)) return fail(PMS_ERR_INVALID, "sigma must be >= 0");
+    h->omni_noise = OmniNoise{misdetection_prob, distance_mu, distance_sigma, seed, 1};
+    return PMS_OK;
+}
+
+void pms_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    const uint4 r = philox4x32_10(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
 int pms_detector_config(pms_sim *h, int enabled, double max_dist, double fov, int return_type)
 {
     HCHECK(h);
     if (return_type < PMS_DET_POLAR || return_type > PMS_DET_ABSOLUTE)
         return fail(PMS_ERR_INVALID, "unknown detector return type");   // _pedestrian_detector.py:29-32
-    h->a.det_enabled = enabled ? 1 : 0; h->a.det_max_dist = max_dist; h->a.det_half_fov = fov / 2.0; h->a.det_type = return_type;
+    h->a.det_enabled = enabled ? 1 : 0; h->a.det_max_dist = max_dist; h->a.det_half_fov = fov / 2.0;
+    h->det_noise.return_type = return_type;
+    h->a.det_type = h->det_noise.enabled ? (int)DET_POLAR : return_type;    // noise is added in the polar frame
+    return PMS_OK;
+}
+
+int pms_set_detector_noise(pms_sim *h, int enabled, double misdetection_prob, double distance_mu, double distance_sigma,
+                           double angle_mu, double angle_sigma, uint64_t seed)
+{
+    HCHECK(h);
+    if (enabled) {
+        if (!(misdetection_prob <= 1.0)) return fail(PMS_ERR_INVALID, "misdetection_prob must be <= 1");   // _pedestrian_detector.py:69
+        if (!(distance_sigma >= 0.0) || !(angle_sigma >= 0.0)) return fail(PMS_ERR_INVALID, "sigma must be >= 0");
+        if (!h->noisy_mask) {
+            CK(cudaMalloc((void **)&h->noisy_mask, sizeof(uint32_t) * (size_t)h->W * h->words));
+            CK(cudaMalloc((void **)&h->noisy_vals, sizeof(double2) * (size_t)h->W * h->N));
+        }
+    }
+    const int user_type = h->det_noise.enabled ? h->det_noise.return_type : h->a.det_type;
+    h->det_noise = DetNoise{misdetection_prob, distance_mu, distance_sigma, angle_mu, angle_sigma, seed, enabled ? 1 : 0, user_type};
+    h->a.det_type = enabled ? (int)DET_POLAR : user_type;
     return PMS_OK;
 }
 
@@ -827,8 +894,10 @@ int pms_sense(pms_sim *h)
     if (rc) return rc;
     fill_consts(h->a);
     if (h->a.robot_model != ROBOT_NONE) {
-        if (h->precision == PMS_FP32) sense_kernel<float><<<h->W, h->Np, 0, h->stream>>>(h->a);
-        else sense_kernel<double><<<h->W, h->Np, 0, h->stream>>>(h->a);
+        const dim3 grid(h->W, (h->Np + 255) / 256);
+        const int threads = h->Np < 256 ? h->Np : 256;
+        if (h->precision == PMS_FP32) sense_kernel<float><<<grid, threads, 0, h->stream>>>(h->a);
+        else sense_kernel<double><<<grid, threads, 0, h->stream>>>(h->a);
         CK(cudaGetLastError());
         h->info.kernel_launches++;
     }
@@ -840,8 +909,16 @@ int pms_get_detector(pms_sim *h, uint32_t *mask, double *values)
 {
     HCHECK(h);
     const size_t n = (size_t)h->W * h->N;
-    if (mask) CK(cudaMemcpyAsync(mask, h->a.det_mask, sizeof(uint32_t) * h->W * h->words, cudaMemcpyDeviceToHost, h->stream));
-    if (values) CK(cudaMemcpyAsync(values, h->a.det_vals, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    const uint32_t *src_mask = h->a.det_mask;
+    const double2 *src_vals = h->a.det_vals;
+    if (h->det_noise.enabled && h->a.det_enabled) {     // the stored reading stays exact; the noisy view is made per call
+        detector_noise_kernel<<<dim3(h->W, (h->Np + 255) / 256), h->Np < 256 ? h->Np : 256, 0, h->stream>>>(h->W, h->N, h->words, h->a.det_mask, h->a.det_vals, h->noisy_mask,
+                                                             h->noisy_vals, h->a.robot_pose, h->det_noise, h->a.steps_done);
+        CK(cudaGetLastError());
+        src_mask = h->noisy_mask; src_vals = h->noisy_vals;
+    }
+    if (mask) CK(cudaMemcpyAsync(mask, src_mask, sizeof(uint32_t) * h->W * h->words, cudaMemcpyDeviceToHost, h->stream));
+    if (values) CK(cudaMemcpyAsync(values, src_vals, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
     IO_DONE(h);
     return PMS_OK;
 }
@@ -951,6 +1028,10 @@ int pms_lidar_scan(pms_sim *h, int n_beams, double max_dist, double resolution, 
     lidar_kernel<<<nblk(nb, 128), 128, 0, h->stream>>>(la);
     CK(cudaGetLastError());
     h->info.kernel_launches++;
+    if (h->lidar_noise.enabled) {
+        lidar_noise_kernel<<<nblk(nb, 128), 128, 0, h->stream>>>(nb, d_hit, d_pts, h->lidar_noise, h->a.steps_done);
+        CK(cudaGetLastError());
+    }
     if (hit_index) CK(cudaMemcpyAsync(hit_index, d_hit, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (points) CK(cudaMemcpyAsync(points, d_pts, nb * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -966,6 +1047,10 @@ int pms_omni_scan(pms_sim *h, double *min_dist)
                                                         h->a.map_stride, h->a.map_data, h->stage);
     CK(cudaGetLastError());
     h->info.kernel_launches++;
+    if (h->omni_noise.enabled) {
+        omni_noise_kernel<<<nblk(h->W, 128), 128, 0, h->stream>>>(h->W, h->stage, h->omni_noise, h->a.steps_done);
+        CK(cudaGetLastError());
+    }
     if (min_dist) CK(cudaMemcpyAsync(min_dist, h->stage, sizeof(double) * h->W, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PMS_OK;

@@ -68,6 +68,10 @@ struct HsfmArgs {
     unsigned long long *det_count, *coll_count;
     int *nonfinite;
     const double *accel_noise;  // (W,N,2) added to the body-frame acceleration dv_b, or NULL (_hsfm.py:288-289)
+    // device-side noise (counter-based Philox4x32-10, keyed by seed / pedestrian / absolute step: independent of the launch
+    // configuration): N(0, accel_noise_std) drawn afresh every step like np.random.normal in _hsfm.py:289 (statistical parity)
+    double accel_noise_std;
+    unsigned long long noise_seed;
     // model constants (fp64 masters; kernels down-convert once)
     double dt;
     double tau, A, B, k1, k2, ko, kd, k_lambda, alpha, mass, ped_radius, hsfm_robot_radius;
@@ -154,6 +158,44 @@ __device__ __forceinline__ float m_max(float a, float b) { return fmaxf(a, b); }
 __device__ __forceinline__ double m_max(double a, double b) { return fmax(a, b); }
 __device__ __forceinline__ bool m_finite(float a) { return isfinite(a); }
 __device__ __forceinline__ bool m_finite(double a) { return isfinite(a); }
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based random numbers: Philox4x32-10 (Salmon et al., SC'11), one 128-bit block per (seed, stream, id, step).
+// ---------------------------------------------------------------------------------------------
+enum { NOISE_STREAM_ACCEL = 0, NOISE_STREAM_DETECTOR = 1, NOISE_STREAM_LIDAR = 2, NOISE_STREAM_OMNI = 3 };
+
+__host__ __device__ inline uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = 0xD2511F53ull * c.x, p1 = 0xCD9E8D57ull * c.z;
+        c = make_uint4((unsigned)(p1 >> 32) ^ c.y ^ k.x, (unsigned)p1, (unsigned)(p0 >> 32) ^ c.w ^ k.y, (unsigned)p0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__host__ __device__ inline uint4 noise_block(unsigned long long seed, int stream, unsigned long long id, unsigned long long step)
+{
+    return philox4x32_10(make_uint4((unsigned)id, (unsigned)(id >> 32), (unsigned)step, (unsigned)(step >> 32) ^ ((unsigned)stream << 28)),
+                         make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+}
+// uniform in (0, 1): 32 random bits, centred in their cell
+__host__ __device__ inline double noise_uniform(unsigned bits) { return ((double)bits + 0.5) * (1.0 / 4294967296.0); }
+// two independent standard normals from two 32-bit words (Box-Muller, fp64: accurate far into the tails)
+static __device__ __noinline__ double2 noise_normal2(unsigned b0, unsigned b1)
+{
+    const double r = sqrt(-2.0 * log(noise_uniform(b0)));
+    double s, c;
+    sincospi(2.0 * noise_uniform(b1), &s, &c);
+    return make_double2(r * c, r * s);
+}
+// body-frame acceleration noise of pedestrian g at absolute step `step` (_hsfm.py:288-289)
+static __device__ __noinline__ double2 accel_noise_draw(const HsfmArgs &a, size_t g, long long step)
+{
+    const uint4 b = noise_block(a.noise_seed, NOISE_STREAM_ACCEL, g, (unsigned long long)step);
+    const double2 z = noise_normal2(b.x, b.y);
+    return make_double2(a.accel_noise_std * z.x, a.accel_noise_std * z.y);
+}
 
 // Python / numpy float modulo (sign of the divisor): _hsfm.py:98,189, util/_util.py:6.
 template <typename T>

@@ -6,11 +6,11 @@
 namespace pms {
 
 // Collision list + detector on the stored state (Simulation.__init__ sensor pass, core/_simulation.py:37).
-// One CTA per world, one thread per (padded) pedestrian.
+// Grid (world, block of 256 pedestrians), one thread per (padded) pedestrian.
 template <typename ST>
 __global__ void sense_kernel(const __grid_constant__ HsfmArgs a)
 {
-    const int w = blockIdx.x, i = threadIdx.x;
+    const int w = blockIdx.x, i = blockIdx.y * blockDim.x + threadIdx.x;
     const int N = a.N, words = (N + 31) >> 5;
     RobotSlot rb{a.robot_pose[3 * w], a.robot_pose[3 * w + 1], a.robot_pose[3 * w + 2], 0.0, 0.0};
     SenseOut so{false, false, 0.0, 0.0};
@@ -32,6 +32,87 @@ __global__ void sense_kernel(const __grid_constant__ HsfmArgs a)
         a.det_mask[(size_t)w * words + (i >> 5)] = dm;
         a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
     }
+}
+
+// PedestrianDetectorNoise on the device (sensors/_pedestrian_detector.py:104-112 + _convert_reading :114-134): every detected
+// pedestrian is dropped with probability misdetection_prob, the survivors get N(mu, sigma) added to distance and angle in
+// the polar frame and are then converted to the configured return type.  `vals_in` holds POLAR readings (the step kernels
+// are switched to polar while the noise is on).  Philox block per (world-pedestrian, absolute step): deterministic.
+struct DetNoise {
+    double p_miss, d_mu, d_sigma, a_mu, a_sigma;
+    unsigned long long seed;
+    int enabled, return_type;
+};
+__global__ void detector_noise_kernel(int W, int N, int words, const uint32_t *mask_in, const double2 *vals_in,
+                                      uint32_t *mask_out, double2 *vals_out, const double *robot_pose, DetNoise nz,
+                                      long long step)
+{
+    const int w = blockIdx.x, i = blockIdx.y * blockDim.x + threadIdx.x;      // one thread per padded pedestrian
+    const size_t g = (size_t)w * N + i;
+    bool det = i < N && ((mask_in[(size_t)w * words + (i >> 5)] >> (i & 31)) & 1u);
+    double2 v = make_double2(0.0, 0.0);
+    if (det) {
+        const uint4 b = noise_block(nz.seed, NOISE_STREAM_DETECTOR, g, (unsigned long long)step);
+        if (noise_uniform(b.x) < nz.p_miss) det = false;                 // np.random.binomial(1, 1 - p) == 0
+        else {
+            const double2 z = noise_normal2(b.y, b.z);
+            const double2 p = vals_in[g];
+            const double distance = p.x + (nz.d_mu + nz.d_sigma * z.x), angle = p.y + (nz.a_mu + nz.a_sigma * z.y);
+            if (nz.return_type == DET_POLAR) v = make_double2(distance, angle);
+            else {
+                double sa, ca;
+                sincos(angle, &sa, &ca);
+                const double xrr = distance * ca, yrr = distance * sa;
+                if (nz.return_type == DET_RELATIVE_ROTATED) v = make_double2(xrr, yrr);
+                else {
+                    double st, ct;
+                    sincos(robot_pose[3 * w + 2], &st, &ct);
+                    const double xr = xrr * ct - yrr * st, yr = xrr * st + yrr * ct;
+                    v = nz.return_type == DET_RELATIVE ? make_double2(xr, yr)
+                                                       : make_double2(xr + robot_pose[3 * w], yr + robot_pose[3 * w + 1]);
+                }
+            }
+        }
+    }
+    if (i < N) vals_out[g] = v;
+    const unsigned dm = __ballot_sync(0xffffffffu, det);
+    if ((i & 31) == 0 && (i >> 5) < words) mask_out[(size_t)w * words + (i >> 5)] = dm;
+}
+
+// LidarSensorNoise.noisify_reading (sensors/_lidar.py:79-87): every hit point is dropped with probability drop_prob (its
+// hit index becomes -1), the survivors get mean + L z added, L = Cholesky factor of point_cov, z ~ N(0, I).
+struct LidarNoise {
+    double drop_prob, mean_x, mean_y, l00, l10, l11;
+    unsigned long long seed;
+    int enabled;
+};
+__global__ void lidar_noise_kernel(size_t nb, int32_t *hit, double2 *points, LidarNoise nz, long long step)
+{
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= nb || hit[k] < 0) return;
+    const uint4 b = noise_block(nz.seed, NOISE_STREAM_LIDAR, k, (unsigned long long)step);
+    if (noise_uniform(b.x) < nz.drop_prob) { hit[k] = -1; points[k] = make_double2(0.0, 0.0); return; }
+    const double2 z = noise_normal2(b.y, b.z);
+    double2 p = points[k];
+    p.x += nz.mean_x + nz.l00 * z.x;
+    p.y += nz.mean_y + (nz.l10 * z.x + nz.l11 * z.y);
+    points[k] = p;
+}
+
+// OmniObstacleDetector._noisify_reading (sensors/_omni_obstacle_detector.py:64-69): inf with probability
+// misdetection_prob, else distance + N(mu, sigma).
+struct OmniNoise {
+    double p_miss, mu, sigma;
+    unsigned long long seed;
+    int enabled;
+};
+__global__ void omni_noise_kernel(int W, double *dist, OmniNoise nz, long long step)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const uint4 b = noise_block(nz.seed, NOISE_STREAM_OMNI, (unsigned long long)w, (unsigned long long)step);
+    if (noise_uniform(b.x) < nz.p_miss) { dist[w] = CUDART_INF; return; }
+    dist[w] += nz.mu + nz.sigma * noise_normal2(b.y, b.z).x;
 }
 
 struct LidarArgs {

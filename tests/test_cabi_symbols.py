@@ -94,3 +94,17 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "created" in out.stdout or "CUDA" in out.stdout or "fallback" in out.stdout
+
+
+def test_philox_known_answers():
+    """The device noise generator is Philox4x32-10: Random123's published known-answer vectors (kat_vectors: philox4x32 10)."""
+    lib = _capi.load()
+    u32x4, u32x2 = ctypes.c_uint32 * 4, ctypes.c_uint32 * 2
+    pi_ctr = (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344)
+    pi_key = (0xa4093822, 0x299f31d0)
+    for ctr, key, want in (((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+                           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+                           (pi_ctr, pi_key, (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))):
+        out = u32x4()
+        lib.pms_philox4x32_10(u32x4(*ctr), u32x2(*key), out)
+        assert tuple(out) == want, [hex(v) for v in out]
