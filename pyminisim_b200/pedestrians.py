@@ -17,7 +17,7 @@ from .core import (DEFAULT_ROBOT_RADIUS, PEDESTRIAN_RADIUS, AbstractPedestriansM
                    AbstractWaypointTracker, AbstractWaypointTrackerState)
 
 __all__ = ["HSFMParams", "HeadedSocialForceModelPolicy", "RandomWaypointTracker", "FixedWaypointTracker",
-           "ORCAParams", "ORCAPedestriansModel", "HSFMState", "ORCAState"]
+           "ORCAParams", "ORCAPedestriansModel", "HSFMState", "ORCAState", "ReplayPedestriansPolicy", "ReplayPedestriansState"]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -388,3 +388,53 @@ class ORCAPedestriansModel(AbstractPedestriansModel):
     def reset_to_state(self, state: ORCAState):
         self._state = state                       # like the reference, the agents themselves are not reset (:114-116)
         self._tracker.reset_to_state(state.waypoints)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ReplayPedestriansPolicy (pedestrians/_replay.py): recorded trajectories, one frame per step.  No dynamics: the
+# frames are handed to Simulation, whose collision list and sensors run on the device like for every other model.
+# ---------------------------------------------------------------------------------------------------------
+class ReplayPedestriansState(AbstractPedestriansModelState):
+    def __init__(self, step: int, pedestrians: Dict[int, Tuple[np.ndarray, np.ndarray]]):
+        super().__init__(pedestrians, None)
+        assert isinstance(step, int) and step >= 0, f"step must be int >= 0, got {step}"        # _replay.py:10
+        self._current_step = step
+
+    @property
+    def current_step(self) -> int:
+        return self._current_step
+
+
+class ReplayPedestriansPolicy(AbstractPedestriansModel):
+    def __init__(self, poses: np.ndarray, velocities: np.ndarray, loop: bool = False) -> None:
+        assert len(poses.shape) == 3 and poses.shape[2] == 3, \
+            f"Pedestrians poses must have shape (T, n_pedestrians, 3), got {poses.shape}"
+        assert len(velocities.shape) == 3 and velocities.shape[2] == 3, \
+            f"Pedestrians velocities must have shape (T, n_pedestrians, 3), got {velocities.shape}"
+        assert poses.shape[0] == velocities.shape[0] and poses.shape[1] == velocities.shape[1], \
+            (f"Poses and velocities must match in time and pedestrians dimension, "
+             f"got shapes {poses.shape} and {velocities.shape}")
+        self._poses, self._velocities, self._loop = poses.copy(), velocities.copy(), loop
+        self._max_step, self._n = poses.shape[0] - 1, poses.shape[1]
+        self._current_step = 0
+        self._state = self._frame(0)
+
+    def _frame(self, step: int) -> ReplayPedestriansState:
+        return ReplayPedestriansState(step, {i: (self._poses[step, i], self._velocities[step, i]) for i in range(self._n)})
+
+    @property
+    def state(self) -> ReplayPedestriansState:
+        return self._state
+
+    def step(self, dt: float = None, robot_pose: Optional[np.ndarray] = None, robot_velocity: Optional[np.ndarray] = None):
+        if self._current_step == self._max_step:        # _replay.py:46-52: stay on the last frame unless looping
+            if not self._loop:
+                return
+            self._current_step = 0
+        else:
+            self._current_step += 1
+        self._state = self._frame(self._current_step)
+
+    def reset_to_state(self, state: ReplayPedestriansState):
+        self._state = state
+        self._current_step = state.current_step

@@ -275,8 +275,42 @@ def gen_random_tracker():
              poses=np.array(poses), vels=np.array(vels), cur=np.array(curs), vmag=np.array([1.5, 2.5]))
 
 
+def gen_replay():
+    """ReplayPedestriansPolicy (pedestrians/_replay.py) under a Simulation with a unicycle robot and the detector:
+    recorded trajectories of 5 pedestrians over 12 frames, loop and no-loop, 30 simulation steps each."""
+    from pyminisim.pedestrians import ReplayPedestriansPolicy
+    rng = np.random.default_rng(21)
+    T, n = 12, 5
+    start = rng.uniform(-2.5, 2.5, (n, 2))
+    vel = rng.uniform(-1.0, 1.0, (n, 2))
+    poses = np.zeros((T, n, 3)); vels = np.zeros((T, n, 3))
+    for t in range(T):
+        poses[t, :, :2] = start + vel * (0.1 * t)
+        poses[t, :, 2] = np.arctan2(vel[:, 1], vel[:, 0])
+        vels[t, :, :2] = vel
+    res = {"rec_poses": poses, "rec_vels": vels}
+    for loop in (False, True):
+        model = ReplayPedestriansPolicy(poses.copy(), vels.copy(), loop=loop)
+        rm = UnicycleRobotModel(initial_pose=np.array([-1.0, 0.2, 0.3]), initial_control=np.array([0.8, 0.4]))
+        sensors = [PedestrianDetector(config=PedestrianDetectorConfig(max_dist=4.0, fov=np.deg2rad(140.0), return_type="relative"))]
+        sim = Simulation(world_map=EmptyWorld(), robot_model=rm, pedestrians_model=model, sensors=sensors, sim_dt=0.01, rt_factor=None)
+        steps, ps, masks, vals, colls = [], [], [], [], []
+        for _ in range(30):
+            st = sim.step()
+            steps.append(st.world.pedestrians.current_step)
+            p, _ = _ped_arrays(st.world.pedestrians)
+            ps.append(p)
+            m, v = _det_arrays(st.sensors["pedestrian_detector"].reading, n)
+            masks.append(m); vals.append(v)
+            colls.append(_mask(st.world.robot_to_pedestrians_collisions, n))
+        tag = "loop" if loop else "once"
+        res.update({f"{tag}_step": np.array(steps), f"{tag}_poses": np.array(ps), f"{tag}_det_mask": np.array(masks),
+                    f"{tag}_det_vals": np.array(vals), f"{tag}_coll_mask": np.array(colls)})
+    np.savez(os.path.join(HERE, "replay.npz"), **res)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random"]
+    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random", "replay"]
     if "pair" in which:
         gen_pair_forces()
     if "kat2" in which:
@@ -289,4 +323,6 @@ if __name__ == "__main__":
         gen_sensors()
     if "random" in which:
         gen_random_tracker()
+    if "replay" in which:
+        gen_replay()
     print("golden fixtures written to", HERE)

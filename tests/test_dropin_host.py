@@ -1,5 +1,6 @@
 """Host-side logic of the drop-in classes (no GPU): trackers, maps, robot models, sensor scheduler."""
 import numpy as np
+import pytest
 
 from pyminisim_b200.core import AbstractSensor, AbstractSensorReading, Simulation
 from pyminisim_b200.pedestrians import FixedWaypointTracker, RandomWaypointTracker
@@ -111,3 +112,24 @@ def test_sensor_scheduler_fires_every_eleven_steps(golden):
     import pytest
     with pytest.raises(RuntimeError):
         sim.set_pedestrians_enabled(False)
+
+
+def test_replay_policy_frame_sequence_matches_reference(golden):
+    """ReplayPedestriansPolicy (pedestrians/_replay.py:46-56): frame index and poses per step, loop and no-loop."""
+    from pyminisim_b200.pedestrians import ReplayPedestriansPolicy, ReplayPedestriansState
+    g = golden("replay")
+    for tag, loop in (("once", False), ("loop", True)):
+        model = ReplayPedestriansPolicy(g["rec_poses"], g["rec_vels"], loop=loop)
+        assert model.state.current_step == 0
+        for k in range(30):
+            model.step(0.01, None, None)
+            assert model.state.current_step == g[f"{tag}_step"][k]
+            assert np.array_equal(np.stack([model.state.poses[i] for i in range(5)]), g[f"{tag}_poses"][k])
+        snap = model.state
+        model.step()
+        model.reset_to_state(snap)
+        assert model.state.current_step == snap.current_step
+    with pytest.raises(AssertionError):
+        ReplayPedestriansPolicy(np.zeros((4, 3, 2)), np.zeros((4, 3, 3)))
+    with pytest.raises(AssertionError):
+        ReplayPedestriansState(-1, {})

@@ -176,3 +176,30 @@ def test_orca_dropin_model():
     assert np.array_equal(p[:, :2].astype(np.float32), o.pos[0])
     assert np.allclose(p[:, 2], o.heading[0], atol=1e-12)
     assert model.state.waypoints.current_indices == {i: int(o.wp_index[0, i]) for i in range(7)}
+
+
+def test_replay_policy_through_simulation(golden):
+    """Recorded pedestrians (pedestrians/_replay.py) under Simulation: the device collision list and detector see every frame."""
+    from pyminisim_b200.core import Simulation
+    from pyminisim_b200.pedestrians import ReplayPedestriansPolicy
+    from pyminisim_b200.robot import UnicycleRobotModel
+    from pyminisim_b200.sensors import PedestrianDetector, PedestrianDetectorConfig
+    from pyminisim_b200.world_map import EmptyWorld
+    g = golden("replay")
+    for tag, loop in (("once", False), ("loop", True)):
+        model = ReplayPedestriansPolicy(g["rec_poses"].copy(), g["rec_vels"].copy(), loop=loop)
+        sim = Simulation(world_map=EmptyWorld(), robot_model=UnicycleRobotModel(np.array([-1.0, 0.2, 0.3]), np.array([0.8, 0.4])),
+                         pedestrians_model=model, sensors=[PedestrianDetector(PedestrianDetectorConfig(4.0, np.deg2rad(140.0), "relative"))],
+                         sim_dt=0.01, rt_factor=None)
+        seen = 0
+        for k in range(30):
+            st = sim.step()
+            assert st.world.pedestrians.current_step == g[f"{tag}_step"][k]
+            det = st.sensors["pedestrian_detector"].reading.pedestrians
+            ref_ids = [i for i in range(5) if (int(g[f"{tag}_det_mask"][k][0]) >> i) & 1]
+            assert sorted(det.keys()) == ref_ids
+            for i in ref_ids:
+                assert np.allclose(det[i], g[f"{tag}_det_vals"][k][i], atol=1e-12)
+            assert st.world.robot_to_pedestrians_collisions == [i for i in range(5) if (int(g[f"{tag}_coll_mask"][k][0]) >> i) & 1]
+            seen += len(ref_ids)
+        assert seen > 30
