@@ -34,12 +34,11 @@ typedef enum {
 } pms_status;
 
 /* Arithmetic mode of the HSFM kernels.
- *   PMS_FP32  : pair forces and per-pedestrian math in fp32 (north-star production mode).  Worlds of up to 128
- *               pedestrians carry the state as unevaluated fp32 sums hi + lo with compensated Euler updates, so a
- *               step no longer rounds the full magnitude of the state to fp32 (the error that dominates plain fp32
- *               and that the crowd dynamics amplify ~1e6 x over 1000 steps); pair forces see the high parts.
- *   PMS_FP32_PLAIN : as PMS_FP32 with a plain fp32 state, one rounding per variable per step (what every kernel
- *               does for larger worlds).
+ *   PMS_FP32  : pair forces and per-pedestrian math in fp32 (north-star production mode).  The state is carried as
+ *               unevaluated fp32 sums hi + lo with compensated Euler updates, so a step no longer rounds the full
+ *               magnitude of the state to fp32 (the error that dominates plain fp32 and that the crowd dynamics
+ *               amplify by orders of magnitude over 1000 steps); pair forces see the high parts.
+ *   PMS_FP32_PLAIN : as PMS_FP32 with a plain fp32 state, one rounding per variable per step.
  *   PMS_MIXED : fp64 state and per-pedestrian math; pair forces in fp32 from hi/lo-split
  *               positions (differences exact to fp64).
  *   PMS_FP64  : everything fp64 -- verification mode, algorithmically identical to the reference.

@@ -34,6 +34,9 @@ constexpr int LARGE_STAGES = 4;      // j-tile buffers in shared memory (TMA run
 struct LargeArgs {
     // ping-pong state (element g = w*N + i); src is read, dst is written
     void *pos_src, *vel_src, *th_src, *pos_dst, *vel_dst, *th_dst;
+    // FP32 with the compensated state (a.comp): vel_* hold the float4 low parts of {x,y,vx,vy}, thlo_* the float2 low
+    // parts of {theta, omega}
+    void *thlo_src, *thlo_dst;
     // pair view, structure-of-arrays of PT: arrays x, y, vx, vy (+ float xlo, ylo), each Npad long per world
     const void *view_src;
     void *view_dst;
@@ -51,7 +54,7 @@ struct LargeArgs {
 };
 
 struct LargeScratch {
-    void *pos2 = nullptr, *vel2 = nullptr, *th2 = nullptr;
+    void *pos2 = nullptr, *vel2 = nullptr, *th2 = nullptr, *thlo2 = nullptr, *thlo3 = nullptr;
     void *view[2] = {nullptr, nullptr};
     RobotSlot *robot_slot = nullptr;
     RobotRegs *robot_regs = nullptr;
@@ -70,7 +73,7 @@ struct LargeScratch {
 
 inline void large_free(LargeScratch &s)
 {
-    void *p[] = {s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes,
+    void *p[] = {s.thlo2, s.thlo3, s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes,
                  s.pos3, s.vel3, s.th3, s.keys[0], s.keys[1], s.perm[0], s.perm[1], s.sort_tmp};
     for (void *q : p) if (q) cudaFree(q);
     s = LargeScratch{};
@@ -187,7 +190,8 @@ __global__ void large_sortkey_kernel(const __grid_constant__ HsfmArgs a, float i
 // sorted <- caller order (gather) or caller order <- sorted (scatter) of position / velocity / heading
 template <typename ST, bool GATHER>
 __global__ void large_permute_kernel(size_t n, const int *perm, const void *pos_in, const void *vel_in, const void *th_in,
-                                     void *pos_out, void *vel_out, void *th_out)
+                                     void *pos_out, void *vel_out, void *th_out, const void *thlo_in = nullptr,
+                                     void *thlo_out = nullptr)
 {
     using ST2 = typename Vec2<ST>::type;
     const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -195,6 +199,10 @@ __global__ void large_permute_kernel(size_t n, const int *perm, const void *pos_
     const size_t src = GATHER ? (size_t)perm[k] : k, dst = GATHER ? k : (size_t)perm[k];
     if constexpr (sizeof(ST) == 4) {
         reinterpret_cast<float4 *>(pos_out)[dst] = reinterpret_cast<const float4 *>(pos_in)[src];
+        if (thlo_in) {       // compensated state: the low parts travel with the pedestrian
+            reinterpret_cast<float4 *>(vel_out)[dst] = reinterpret_cast<const float4 *>(vel_in)[src];
+            reinterpret_cast<float2 *>(thlo_out)[dst] = reinterpret_cast<const float2 *>(thlo_in)[src];
+        }
     } else {
         reinterpret_cast<double2 *>(pos_out)[dst] = reinterpret_cast<const double2 *>(pos_in)[src];
         reinterpret_cast<double2 *>(vel_out)[dst] = reinterpret_cast<const double2 *>(vel_in)[src];
@@ -460,8 +468,24 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         ST nzx = 0, nzy = 0;
         if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
         else if (a.accel_noise_std > 0.0) { const double2 z = accel_noise_draw(a, g, a.steps_done + la.step); nzx = (ST)z.x; nzy = (ST)z.y; }
-        ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
-        const ST ex = wp.x - x, ey = wp.y - y;
+        StateLo lo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lo0 = lo;
+        bool comp = false;
+        if constexpr (sizeof(ST) == 4) comp = a.comp != 0;
+        if constexpr (sizeof(ST) == 4) {
+            if (comp) {
+                const float4 pl = __ldcg(reinterpret_cast<const float4 *>(la.vel_src) + gs);
+                const float2 tl = __ldcg(reinterpret_cast<const float2 *>(la.thlo_src) + gs);
+                lo = StateLo{pl.x, pl.y, pl.z, pl.w, tl.x, tl.y}; lo0 = lo;
+                const float s0 = sn;
+                sn = fmaf(c, tl.x, sn); c = fmaf(-s0, tl.x, c);
+                ped_integrate_comp(kc, fx, fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, lo, nzx, nzy);
+            } else {
+                ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
+            }
+        } else {
+            ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
+        }
+        const ST ex = (wp.x - x) - (ST)lo.x, ey = (wp.y - y) - (ST)lo.y;
         bool reached;
         if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
         else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
@@ -472,7 +496,7 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
                 if (ni >= a.n_table) { if (a.loop) ni = 0; else { ni = a.n_table - 1; steady = true; } }
                 a.wp_index[g] = ni;
                 wp = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
-                if (steady) { x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0; }
+                if (steady) { x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0; lo = StateLo{lo0.x, lo0.y, 0.f, 0.f, lo0.th, 0.f}; }
             } else {
                 const int cnt = a.q_count[g];
                 const int slot = atomicAdd(a.ev_count, 1);
@@ -491,6 +515,10 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         // new state -> destination buffers + destination pair view
         if constexpr (sizeof(ST) == 4) {
             reinterpret_cast<float4 *>(la.pos_dst)[gs] = make_float4(x, y, vx, vy);
+            if (comp) {
+                reinterpret_cast<float4 *>(la.vel_dst)[gs] = make_float4(lo.x, lo.y, lo.vx, lo.vy);
+                reinterpret_cast<float2 *>(la.thlo_dst)[gs] = make_float2(lo.th, lo.om);
+            }
         } else {
             reinterpret_cast<double2 *>(la.pos_dst)[gs] = make_double2(x, y);
             reinterpret_cast<double2 *>(la.vel_dst)[gs] = make_double2(vx, vy);
@@ -505,7 +533,14 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
             vdst[i] = (PT)x; vdst[vs + i] = (PT)y; vdst[2 * vs + i] = (PT)vx; vdst[3 * vs + i] = (PT)vy;
         }
         if (!m_finite(x + y + vx + vy + th + om)) atomicMin(&a.nonfinite[w], (int)(a.steps_done + la.step + 1));
-        if (has_robot) so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+        if (has_robot) {
+            if constexpr (sizeof(ST) == 4) {
+                if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, la.last != 0);
+                else so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+            } else {
+                so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+            }
+        }
         if (la.last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
     }
     if (has_robot) {
@@ -545,6 +580,10 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         if ((e = cudaMalloc(&s.pos2, n * 16)) != cudaSuccess) return -2;
         if ((e = cudaMalloc(&s.vel2, n * 16)) != cudaSuccess) return -2;
         if ((e = cudaMalloc(&s.th2, n * e2)) != cudaSuccess) return -2;
+        if (sizeof(ST) == 4) {
+            if ((e = cudaMalloc(&s.thlo2, n * 8)) != cudaSuccess) return -2;
+            if ((e = cudaMalloc(&s.thlo3, n * 8)) != cudaSuccess) return -2;
+        }
         s.view_bytes = nv * NARR * sizeof(PT);
         if ((e = cudaMalloc(&s.view[0], s.view_bytes)) != cudaSuccess) return -2;
         if ((e = cudaMalloc(&s.view[1], s.view_bytes)) != cudaSuccess) return -2;
@@ -578,8 +617,9 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
     const float inv_strip = 1.0f / sqrtf(a.warp_cut2);            // strips one cut-off distance wide
 
     // working state: the caller's arrays, or the spatially sorted copy (home[0] is then s.pos3 ...)
-    void *pos[2] = {a.pos, s.pos2}, *vel[2] = {a.vel, s.vel2}, *th[2] = {a.th, s.th2};
-    if (reorder) { pos[0] = s.pos3; vel[0] = s.vel3; th[0] = s.th3; }
+    const bool comp = sizeof(ST) == 4 && a.comp;                  // FP32: a.vel (= a.pos_lo) and a.th_lo hold the low parts
+    void *pos[2] = {a.pos, s.pos2}, *vel[2] = {a.vel, s.vel2}, *th[2] = {a.th, s.th2}, *thlo[2] = {a.th_lo, s.thlo2};
+    if (reorder) { pos[0] = s.pos3; vel[0] = s.vel3; th[0] = s.th3; thlo[0] = s.thlo3; }
     int cur = 0;                                                   // buffer that holds the current state
     for (int t0 = 0; t0 < a.n_steps; t0 += LARGE_RESORT) {
         const int t1 = t0 + LARGE_RESORT < a.n_steps ? t0 + LARGE_RESORT : a.n_steps;
@@ -587,7 +627,8 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             // sort by (world, strip, y) of the CURRENT positions (in the caller's arrays), gather the state
             large_sortkey_kernel<ST><<<gn, 256, 0, stream>>>(a, inv_strip, s.keys[0], s.perm[0]);
             cub::DeviceRadixSort::SortPairs(s.sort_tmp, s.sort_tmp_bytes, s.keys[0], s.keys[1], s.perm[0], s.perm[1], (int)n, 0, end_bit, stream);
-            large_permute_kernel<ST, true><<<gn, 256, 0, stream>>>(n, s.perm[1], a.pos, a.vel, a.th, pos[0], vel[0], th[0]);
+            large_permute_kernel<ST, true><<<gn, 256, 0, stream>>>(n, s.perm[1], a.pos, a.vel, a.th, pos[0], vel[0], th[0],
+                                                                   comp ? a.th_lo : nullptr, thlo[0]);
             *launches += 3;
             cur = 0;
         }
@@ -606,6 +647,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             LargeArgs la{};
             la.pos_src = pos[src]; la.vel_src = vel[src]; la.th_src = th[src];
             la.pos_dst = pos[dst]; la.vel_dst = vel[dst]; la.th_dst = th[dst];
+            la.thlo_src = thlo[src]; la.thlo_dst = thlo[dst];
             la.view_src = s.view[src]; la.view_dst = s.view[dst];
             la.view_stride = nv; la.Npad = Npad; la.tiles_i = tiles_i; la.tiles_j = tiles_j; la.cluster = cluster;
             la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = s.robot_slot;
@@ -628,14 +670,16 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             cur = dst;
         }
         if (reorder) {             // back to the caller's order (the next sort reads the caller's arrays)
-            large_permute_kernel<ST, false><<<gn, 256, 0, stream>>>(n, s.perm[1], pos[cur], vel[cur], th[cur], a.pos, a.vel, a.th);
+            large_permute_kernel<ST, false><<<gn, 256, 0, stream>>>(n, s.perm[1], pos[cur], vel[cur], th[cur], a.pos, a.vel, a.th,
+                                                                    comp ? thlo[cur] : nullptr, a.th_lo);
             ++*launches;
         }
     }
     // without re-ordering an odd number of steps leaves the newest state in the scratch buffers: copy it home
     if (!reorder && cur == 1) {
         cudaMemcpyAsync(a.pos, s.pos2, n * 16, cudaMemcpyDeviceToDevice, stream);
-        if (sizeof(ST) == 8) cudaMemcpyAsync(a.vel, s.vel2, n * 16, cudaMemcpyDeviceToDevice, stream);
+        if (sizeof(ST) == 8 || comp) cudaMemcpyAsync(a.vel, s.vel2, n * 16, cudaMemcpyDeviceToDevice, stream);
+        if (comp) cudaMemcpyAsync(a.th_lo, s.thlo2, n * 8, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(a.th, s.th2, n * e2, cudaMemcpyDeviceToDevice, stream);
     }
     *out_blocks = a.W * tiles_i;

@@ -187,6 +187,50 @@ __device__ __forceinline__ void ped_integrate(const PedConsts<ST> &k, ST fx, ST 
     vy = vy + (s * a_ + c * b_);
 }
 
+// Compensated sum hi + lo <- hi + p (the carry of the old lo is folded into p by the caller): s = fl(hi + p),
+// lo = p - (s - hi) (Fast2Sum: exact when |hi| >= |p|, which the Euler increments satisfy except around zero crossings,
+// where the loss is <= ulp(p)).
+__device__ __forceinline__ void comp_add(float &hi, float &lo, float p)
+{
+    const float s = hi + p;
+    lo = p - (s - hi);
+    hi = s;
+}
+
+// ped_integrate<float> on a state carried as unevaluated fp32 sums hi + lo (PMS_FP32, see hsfm_warp.cuh): same
+// arithmetic, compensated Euler sums, sincos(theta_hi) rotated to first order by theta_lo.
+struct StateLo { float x, y, vx, vy, th, om; };
+__device__ __forceinline__ void ped_integrate_comp(const PedConsts<float> &k, float fx, float fy, float wx, float wy, float vm,
+                                                   float &x, float &y, float &vx, float &vy, float &th, float &om,
+                                                   float &c, float &s, StateLo &lo, float noise_x, float noise_y)
+{
+    const float ddx = (wx - x) - lo.x, ddy = (wy - y) - lo.y;
+    const float n2 = ddx * ddx + ddy * ddy;
+    float ri = fast_rsqrt(n2);
+    ri = ri * fmaf(-0.5f * n2 * ri, ri, 1.5f);
+    const float sc = vm * ri;
+    const float vdx = ddx * sc, vdy = ddy * sc;
+    const float f0x = k.m_over_tau * ((vdx - vx) - lo.vx), f0y = k.m_over_tau * ((vdy - vy) - lo.vy);
+    const float vo = -s * vx + c * vy;
+    const float uf = (f0x + fx) * c + (f0y + fy) * s;
+    const float uo = k.ko * (fx * (-s) + fy * c) - k.kd * vo;
+    const float klf = k.kl * m_sqrt(f0x * f0x + f0y * f0y);
+    const float werr = m_atan2(s * vdx - c * vdy, c * vdx + s * vdy);
+    const float komega = k.one_alpha * m_sqrt(klf * k.inv_alpha);
+    const float dom = -klf * werr - komega * om;
+    const float dvbx = k.inv_m * uf + noise_x, dvby = k.inv_m * uo + noise_y;
+    comp_add(x, lo.x, fmaf(vx, k.dt, fmaf(lo.vx, k.dt, lo.x)));
+    comp_add(y, lo.y, fmaf(vy, k.dt, fmaf(lo.vy, k.dt, lo.y)));
+    comp_add(th, lo.th, fmaf(om, k.dt, fmaf(lo.om, k.dt, lo.th)));
+    comp_add(om, lo.om, fmaf(dom, k.dt, lo.om));
+    m_sincos(th, &s, &c);
+    const float s0 = s;
+    s = fmaf(c, lo.th, s); c = fmaf(-s0, lo.th, c);
+    const float a_ = dvbx * k.dt, b_ = dvby * k.dt;
+    comp_add(vx, lo.vx, (c * a_ + (-s) * b_) + lo.vx);
+    comp_add(vy, lo.vy, (s * a_ + c * b_) + lo.vy);
+}
+
 // ---- collision list + pedestrian detector for one pedestrian (fp64 predicates) -----------------
 // core/_simulation.py:141-143 and sensors/_pedestrian_detector.py:86-103,114-134.
 struct SenseOut {
@@ -234,8 +278,11 @@ __device__ __forceinline__ SenseOut sense_ped(const HsfmArgs &a, const RobotSlot
 template <typename ST> struct OwnerView {
     ST *x, *y, *vx, *vy, *th, *om, *wx, *wy, *vm, *c, *s;
     int *widx;
+    float *lo = nullptr;     // compensated FP32 state: low parts x y vx vy th om, Np floats each (else NULL)
+    int Np_ = 0;
     __device__ __forceinline__ explicit OwnerView(unsigned char *base, int Np, size_t off_widx)
     {
+        Np_ = Np;
         x = reinterpret_cast<ST *>(base); y = x + Np; vx = x + 2 * Np; vy = x + 3 * Np; th = x + 4 * Np; om = x + 5 * Np;
         wx = x + 6 * Np; wy = x + 7 * Np; vm = x + 8 * Np; c = x + 9 * Np; s = x + 10 * Np;
         widx = reinterpret_cast<int *>(base + off_widx);
@@ -261,9 +308,22 @@ __device__ __forceinline__ SenseOut owner_update(const HsfmArgs &a, const OwnerV
     ST nzx = 0, nzy = 0;
     if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
     else if (a.accel_noise_std > 0.0) { const double2 z = accel_noise_draw(a, g, a.steps_done + t); nzx = (ST)z.x; nzy = (ST)z.y; }
-    ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, nzx, nzy);
+    StateLo lo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lo0 = lo;
+    bool comp = false;
+    if constexpr (sizeof(ST) == 4) comp = ow.lo != nullptr;
+    if constexpr (sizeof(ST) == 4) {
+        if (comp) {
+            const float *l = ow.lo + i; const int Np = ow.Np_;
+            lo = StateLo{l[0], l[Np], l[2 * Np], l[3 * Np], l[4 * Np], l[5 * Np]}; lo0 = lo;
+            ped_integrate_comp(kc, fx, fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, lo, nzx, nzy);
+        } else {
+            ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, nzx, nzy);
+        }
+    } else {
+        ped_integrate<ST>(kc, (ST)fx, (ST)fy, wx, wy, o_vm[i], x, y, vx, vy, th, om, c, sn, nzx, nzy);
+    }
     // ---- waypoint tracker on the NEW pose (_hsfm.py:301) ----
-    const ST ex = wx - x, ey = wy - y;
+    const ST ex = (wx - x) - (ST)lo.x, ey = (wy - y) - (ST)lo.y;
     bool reached;
     if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
     else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
@@ -280,6 +340,13 @@ __device__ __forceinline__ SenseOut owner_update(const HsfmArgs &a, const OwnerV
             if (steady) {                            // _hsfm.py:302-304
                 x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0;
                 m_sincos(th, &sn, &c);
+                if constexpr (sizeof(ST) == 4) {
+                    if (comp) {
+                        lo = StateLo{lo0.x, lo0.y, 0.f, 0.f, lo0.th, 0.f};
+                        const float s0 = sn;
+                        sn = fmaf(c, lo.th, sn); c = fmaf(-s0, lo.th, c);
+                    }
+                }
             }
         } else {                                     // _random_waypoint_tracker.py:66-91
             const int cnt = a.q_count[g];
@@ -298,10 +365,23 @@ __device__ __forceinline__ SenseOut owner_update(const HsfmArgs &a, const OwnerV
         o_wx[i] = wx; o_wy[i] = wy;
     }
     o_x[i] = x; o_y[i] = y; o_vx[i] = vx; o_vy[i] = vy; o_th[i] = th; o_om[i] = om; o_c[i] = c; o_s[i] = sn;
+    if constexpr (sizeof(ST) == 4) {
+        if (comp) {
+            float *l = ow.lo + i; const int Np = ow.Np_;
+            l[0] = lo.x; l[Np] = lo.y; l[2 * Np] = lo.vx; l[3 * Np] = lo.vy; l[4 * Np] = lo.th; l[5 * Np] = lo.om;
+        }
+    }
     publish(x, y, vx, vy);
     if (!first_bad && !m_finite(x + y + vx + vy + th + om)) first_bad = (int)(a.steps_done + t + 1);
     // ---- collision list + detector on the new state ----
-    if (has_robot) so = sense_ped<ST>(a, rb, x, y, last);
+    if (has_robot) {
+        if constexpr (sizeof(ST) == 4) {
+            if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, last);
+            else so = sense_ped<ST>(a, rb, x, y, last);
+        } else {
+            so = sense_ped<ST>(a, rb, x, y, last);
+        }
+    }
     if (last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
     return so;
 }
@@ -367,7 +447,10 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
 
     // carve the shared memory of local world wl
     unsigned char *base = smem_raw + (size_t)(wl < a.wpc ? wl : 0) * L::bytes(Np, S);
-    const OwnerView<ST> ow(base, Np, L::off_widx(Np));
+    OwnerView<ST> ow(base, Np, L::off_widx(Np));
+    // compensated FP32 state: the low parts of all worlds of the CTA follow the per-world blocks (6 * Np floats each)
+    if constexpr (sizeof(ST) == 4)
+        if (a.comp) ow.lo = reinterpret_cast<float *>(smem_raw + (size_t)a.wpc * L::bytes(Np, S)) + (size_t)(wl < a.wpc ? wl : 0) * 6 * Np;
     ST *o_x = ow.x, *o_y = ow.y, *o_vx = ow.vx, *o_vy = ow.vy, *o_th = ow.th, *o_om = ow.om;
     ST *o_wx = ow.wx, *o_wy = ow.wy, *o_vm = ow.vm, *o_c = ow.c, *o_s = ow.s;
     int *o_widx = ow.widx;
@@ -402,6 +485,16 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
         const ST2 t = __ldcg(reinterpret_cast<const ST2 *>(a.th) + g);
         const ST2 q = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
         m_sincos(t.x, &sn, &c);
+        if constexpr (sizeof(ST) == 4) {
+            if (ow.lo) {
+                const float4 pl = __ldcg(reinterpret_cast<const float4 *>(a.pos_lo) + g);
+                const float2 tl = __ldcg(reinterpret_cast<const float2 *>(a.th_lo) + g);
+                float *l = ow.lo + i;
+                l[0] = pl.x; l[Np] = pl.y; l[2 * Np] = pl.z; l[3 * Np] = pl.w; l[4 * Np] = tl.x; l[5 * Np] = tl.y;
+                const float s0 = sn;
+                sn = fmaf(c, tl.x, sn); c = fmaf(-s0, tl.x, c);
+            }
+        }
         o_x[i] = x; o_y[i] = y; o_vx[i] = vx; o_vy[i] = vy; o_th[i] = t.x; o_om[i] = t.y;
         o_wx[i] = q.x; o_wy[i] = q.y; o_vm[i] = reinterpret_cast<const ST *>(a.vmag)[g]; o_c[i] = c; o_s[i] = sn;
         o_widx[i] = __ldcg(a.wp_index + g);
@@ -576,6 +669,13 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
         ST2 w2; w2.x = o_wx[i]; w2.y = o_wy[i];
         reinterpret_cast<ST2 *>(a.wp)[g] = w2;
         a.wp_index[g] = o_widx[i];
+        if constexpr (sizeof(ST) == 4) {
+            if (ow.lo) {
+                const float *l = ow.lo + i;
+                reinterpret_cast<float4 *>(a.pos_lo)[g] = make_float4(l[0], l[Np], l[2 * Np], l[3 * Np]);
+                reinterpret_cast<float2 *>(a.th_lo)[g] = make_float2(l[4 * Np], l[5 * Np]);
+            }
+        }
         if (first_bad) atomicMin(&a.nonfinite[w], first_bad);
     }
     if (owner_warp && has_robot && lane == 0) {

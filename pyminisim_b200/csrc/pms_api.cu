@@ -196,7 +196,7 @@ template <typename F> int by_state(pms_sim *h, F &&f)
 template <typename PT, typename ST, bool SPLIT, int S>
 int launch_small_t(pms_sim *h, int wpc, bool big)
 {
-    const size_t smem = SmallSmem<PT, ST, SPLIT>::bytes(h->Np, S) * wpc;
+    const size_t smem = (SmallSmem<PT, ST, SPLIT>::bytes(h->Np, S) + (sizeof(ST) == 4 && h->a.comp ? 6 * sizeof(float) * h->Np : 0)) * wpc;
     const int threads = wpc * S * h->Np + 32;
     const int groups = (h->W + wpc - 1) / wpc;
     int blocks = groups;
@@ -432,9 +432,10 @@ int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hs
     CKC(dalloc(&raw, n * (precision == PMS_FP32 ? 16 : 16))); a.pos = raw;
     CKC(dalloc(&raw, n * 16)); a.vel = raw;
     CKC(dalloc(&raw, n * e2)); a.th = raw;
-    if (precision == PMS_FP32) {
-        CKC(dalloc(&raw, n * 16)); a.pos_lo = raw;
+    if (precision == PMS_FP32) {        // low parts of the state: {x,y,vx,vy} in the (otherwise unused) vel array, {theta, omega}
+        a.pos_lo = a.vel;
         CKC(dalloc(&raw, n * 8)); a.th_lo = raw;
+        a.comp = compensated ? 1 : 0;
     }
     CKC(dalloc(&raw, n * e2)); a.wp = raw;
     CKC(dalloc(&raw, n * h->esz)); a.vmag = raw;
@@ -483,7 +484,7 @@ int pms_destroy(pms_sim *h)
     Guard gd(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     HsfmArgs &a = h->a;
-    void *ptrs[] = {a.pos_lo, a.th_lo, a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
+    void *ptrs[] = {a.th_lo, a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
                     a.events, a.ev_count, a.robot_pose, a.robot_vel, a.robot_ctrl, a.robot_rear,
                     a.robot_world_collision, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
                     a.nonfinite, h->noisy_mask, h->noisy_vals, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done, h->noise_dev};
@@ -861,7 +862,7 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     else if (warp_ok) rc = launch_warp(h);
     else rc = launch_small(h);
     if (rc) return rc;
-    if (h->precision == PMS_FP32 && (large_path || !warp_ok)) {   // these kernels carry a plain fp32 state
+    if (h->precision == PMS_FP32 && !h->compensated && (large_path || !warp_ok)) {   // plain fp32 state: low parts are gone
         const size_t n = (size_t)h->W * h->N;
         CK(cudaMemsetAsync(h->a.pos_lo, 0, n * 16, h->stream));
         CK(cudaMemsetAsync(h->a.th_lo, 0, n * 8, h->stream));
@@ -966,7 +967,7 @@ static void snapshot_regions(pms_sim *h, std::vector<std::pair<void *, size_t>> 
          {a.robot_pose, W * 24}, {a.robot_vel, W * 24}, {a.robot_ctrl, W * 16}, {a.robot_rear, W * 24},
          {a.robot_world_collision, W * 4}, {a.det_count, W * 8}, {a.coll_count, W * 8}, {a.nonfinite, W * 4}};
     if (a.queue) r.push_back({(void *)a.queue, n * a.q_cap * 2 * h->esz});
-    if (a.pos_lo) { r.push_back({a.pos_lo, n * 16}); r.push_back({a.th_lo, n * 8}); }
+    if (a.th_lo) r.push_back({a.th_lo, n * 8});      // (the {x,y,vx,vy} low parts live in a.vel)
 }
 
 int pms_snapshot_save(pms_sim *h)

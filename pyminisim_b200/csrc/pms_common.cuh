@@ -39,6 +39,7 @@ struct HsfmArgs {
     // hsfm_warp.cuh; the other kernels write high parts only and the API zeroes these after their launches)
     void *pos_lo;               // float4 {x,y,vx,vy} low parts
     void *th_lo;                // float2 {theta, omega} low parts
+    int comp;                   // 1: FP32 kernels carry the compensated state (PMS_FP32), 0: plain fp32 state (PMS_FP32_PLAIN)
     void *wp;                   // current waypoint float2 | double2
     void *vmag;                 // float | double
     int *wp_index;

@@ -102,3 +102,40 @@ def test_fp32_free_running_1000_steps_within_the_north_star_tolerance(n):
     assert ep.max() < 1e-4 and ev.max() < (1e-4 if n == 64 else 1e-3), (ep.max(), ev.max())
     assert np.median(ep) < 1e-5 and np.median(ev) < 1e-5
     assert np.median(ep) < np.median(errs["fp32_plain"][0])          # and the compensation is what buys it
+
+
+@pytest.mark.parametrize("path,tuning,kernel", [("directed-pair kernel", (-1, 0, 0, 0), 0), ("large-crowd kernel", (0, 0, 0, -4), 1)])
+def test_compensated_state_in_the_other_fp32_kernels(path, tuning, kernel):
+    """PMS_FP32 means the same thing in every kernel: the directed-pair kernel (129..992 pedestrians) and the large-crowd
+    kernel carry the hi + lo state too.  Forced onto the 64-pedestrian benchmark crowd, 1000 free-running steps."""
+    worlds, n = 16, 64
+    sc = make_bench_crowd(worlds, n)
+    o = make_oracle(sc)
+    o.rollout(0.01, 1000, n_threads=8)
+    errs = {}
+    for precision in ("fp32", "fp32_plain"):
+        c = make_cuda(sc, precision)
+        c.set_tuning(*tuning)
+        for _ in range(4):                       # several calls: the low parts survive the trip through HBM
+            c.step(0.01, 250)
+        assert c.launch_info()["kernel"] == kernel
+        p, v = c.get_state()
+        errs[precision] = max(rel_err(p[w], o.poses[w]) for w in range(worlds))
+        print(f"{path} {precision}: worst position error after 1000 steps {errs[precision]:.2e}")
+    assert errs["fp32"] < 1e-4
+    assert errs["fp32"] < 0.1 * errs["fp32_plain"]
+
+
+def test_compensated_state_natural_directed_pair_world():
+    """160 pedestrians per world: the directed-pair kernel is the natural choice; 300 steps against the oracle."""
+    sc = make_bench_crowd(6, 160)
+    o = make_oracle(sc)
+    o.rollout(0.01, 300, n_threads=6)
+    errs = {}
+    for precision in ("fp32", "fp32_plain"):
+        c = make_cuda(sc, precision)
+        c.step(0.01, 300)
+        assert c.launch_info()["kernel"] == 0
+        errs[precision] = rel_err(c.get_state()[0], o.poses)
+        print(f"160 pedestrians {precision}: position error after 300 steps {errs[precision]:.2e}")
+    assert errs["fp32"] < 1e-6 and errs["fp32"] < 0.3 * errs["fp32_plain"]
