@@ -259,6 +259,145 @@ __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ 
 }
 
 // ---- the step kernel --------------------------------------------------------------------------------
+// ---- robot term, O(1) dynamics, tracker, sensors of one pedestrian: shared by the tile-streaming kernel and the chunk kernel
+template <typename PT, typename ST, bool SPLIT>
+__device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &la, int w, int i, bool valid, size_t gs, size_t g, int ie,
+                                            int lane, PT mx, PT my, float mlx, float mly, PT mvx, PT mvy, PT fx, PT fy)
+{
+    using ST2 = typename Vec2<ST>::type;
+    const int N = a.N;
+    const size_t vs = la.view_stride;
+    const PairK<PT> &kpr = kpr_of(a, PT{});
+    // ---- robot term, O(1) dynamics, tracker, sensors: identical to the small-world owner phase ----
+    const bool has_robot = a.robot_model != ROBOT_NONE;
+    RobotSlot rb{0, 0, 0, 0, 0};
+    if (has_robot) rb = la.robot_slot[w];
+    SenseOut so{false, false, 0.0, 0.0};
+    PT *vdst = reinterpret_cast<PT *>(la.view_dst) + (size_t)w * la.Npad;
+    if (valid) {
+        if (has_robot && a.robot_visible) {
+            PT dx, dy;
+            if constexpr (SPLIT) {
+                const float rxh = (float)rb.x, ryh = (float)rb.y;
+                dx = (mx - rxh) + (mlx - (float)(rb.x - (double)rxh));
+                dy = (my - ryh) + (mly - (float)(rb.y - (double)ryh));
+            } else { dx = mx - (PT)rb.x; dy = my - (PT)rb.y; }
+            pair_accum(kpr, dx, dy, (PT)rb.vx - mvx, (PT)rb.vy - mvy, false, fx, fy);
+        }
+        const PedConsts<ST> &kc = kc_of(a, ST{});
+        ST x, y, vx, vy;
+        if constexpr (sizeof(ST) == 4) {
+            const float4 p = __ldcg(reinterpret_cast<const float4 *>(la.pos_src) + gs);
+            x = p.x; y = p.y; vx = p.z; vy = p.w;
+        } else {
+            const double2 p = __ldcg(reinterpret_cast<const double2 *>(la.pos_src) + gs);
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(la.vel_src) + gs);
+            x = p.x; y = p.y; vx = v.x; vy = v.y;
+        }
+        const ST2 tw = __ldcg(reinterpret_cast<const ST2 *>(la.th_src) + gs);
+        ST th = tw.x, om = tw.y, c, sn;
+        m_sincos(th, &sn, &c);
+        ST2 wp = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
+        const ST vm = reinterpret_cast<const ST *>(a.vmag)[g];
+        const ST x0 = x, y0 = y, th0 = th;
+        ST nzx = 0, nzy = 0;
+        if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
+        else if (a.accel_noise_std > 0.0) { const double2 z = accel_noise_draw(a, g, a.steps_done + la.step); nzx = (ST)z.x; nzy = (ST)z.y; }
+        StateLo lo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lo0 = lo;
+        bool comp = false;
+        if constexpr (sizeof(ST) == 4) comp = a.comp != 0;
+        if constexpr (sizeof(ST) == 4) {
+            if (comp) {
+                const float4 pl = __ldcg(reinterpret_cast<const float4 *>(la.vel_src) + gs);
+                const float2 tl = __ldcg(reinterpret_cast<const float2 *>(la.thlo_src) + gs);
+                lo = StateLo{pl.x, pl.y, pl.z, pl.w, tl.x, tl.y}; lo0 = lo;
+                const float s0 = sn;
+                sn = fmaf(c, tl.x, sn); c = fmaf(-s0, tl.x, c);
+                ped_integrate_comp(kc, fx, fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, lo, nzx, nzy);
+            } else {
+                ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
+            }
+        } else {
+            ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
+        }
+        const ST ex = (wp.x - x) - (ST)lo.x, ey = (wp.y - y) - (ST)lo.y;
+        bool reached;
+        if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
+        else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
+        if (reached) {
+            if (a.tracker_kind == TRACKER_FIXED) {
+                int ni = a.wp_index[g] + 1;
+                bool steady = false;
+                if (ni >= a.n_table) { if (a.loop) ni = 0; else { ni = a.n_table - 1; steady = true; } }
+                a.wp_index[g] = ni;
+                wp = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
+                if (steady) { x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0; lo = StateLo{lo0.x, lo0.y, 0.f, 0.f, lo0.th, 0.f}; }
+            } else {
+                const int cnt = a.q_count[g];
+                const int slot = atomicAdd(a.ev_count, 1);
+                if (cnt > 0) {
+                    const int head = a.q_head[g];
+                    wp = reinterpret_cast<const ST2 *>(a.queue)[g * a.q_cap + head];
+                    a.q_head[g] = (head + 1) % a.q_cap;
+                    a.q_count[g] = cnt - 1;
+                    if (slot < a.ev_cap) { a.events[3 * slot] = la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = ie; }
+                } else if (slot < a.ev_cap) {
+                    a.events[3 * slot] = -1 - la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = ie;
+                }
+            }
+            reinterpret_cast<ST2 *>(a.wp)[g] = wp;
+        }
+        // new state -> destination buffers + destination pair view
+        if constexpr (sizeof(ST) == 4) {
+            reinterpret_cast<float4 *>(la.pos_dst)[gs] = make_float4(x, y, vx, vy);
+            if (comp) {
+                reinterpret_cast<float4 *>(la.vel_dst)[gs] = make_float4(lo.x, lo.y, lo.vx, lo.vy);
+                reinterpret_cast<float2 *>(la.thlo_dst)[gs] = make_float2(lo.th, lo.om);
+            }
+        } else {
+            reinterpret_cast<double2 *>(la.pos_dst)[gs] = make_double2(x, y);
+            reinterpret_cast<double2 *>(la.vel_dst)[gs] = make_double2(vx, vy);
+        }
+        ST2 t2; t2.x = th; t2.y = om;
+        reinterpret_cast<ST2 *>(la.th_dst)[gs] = t2;
+        if constexpr (SPLIT) {
+            const float xh = (float)x, yh = (float)y;
+            vdst[i] = xh; vdst[vs + i] = yh; vdst[2 * vs + i] = (float)vx; vdst[3 * vs + i] = (float)vy;
+            vdst[4 * vs + i] = (float)(x - (double)xh); vdst[5 * vs + i] = (float)(y - (double)yh);
+        } else {
+            vdst[i] = (PT)x; vdst[vs + i] = (PT)y; vdst[2 * vs + i] = (PT)vx; vdst[3 * vs + i] = (PT)vy;
+        }
+        if (!m_finite(x + y + vx + vy + th + om)) atomicMin(&a.nonfinite[w], (int)(a.steps_done + la.step + 1));
+        if (has_robot) {
+            if constexpr (sizeof(ST) == 4) {
+                if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, la.last != 0);
+                else so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+            } else {
+                so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+            }
+        }
+        if (la.last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
+    }
+    if (has_robot) {
+        const unsigned dm = __ballot_sync(0xffffffffu, so.det);
+        const unsigned cm = __ballot_sync(0xffffffffu, so.coll);
+        if (lane == 0) {
+            if (dm) atomicAdd(&a.det_count[w], (unsigned long long)__popc(dm));
+            if (cm) atomicAdd(&a.coll_count[w], (unsigned long long)__popc(cm));
+            const int words = (N + 31) >> 5;
+            if (la.last && !la.perm && (i >> 5) < words) {
+                a.det_mask[(size_t)w * words + (i >> 5)] = dm;
+                a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
+            }
+        }
+        if (la.last && la.perm) {          // sorted slots: set the caller's bit (the masks were cleared before the call)
+            const int words = (N + 31) >> 5;
+            if (so.det) atomicOr(&a.det_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
+            if (so.coll) atomicOr(&a.coll_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
+        }
+    }
+}
+
 template <typename PT, typename ST, bool SPLIT>
 __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
 {
@@ -433,140 +572,123 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         fy += (fya.x + fya.y) + (fyb.x + fyb.y);
     }
 
-    // ---- robot term, O(1) dynamics, tracker, sensors: identical to the small-world owner phase ----
-    const bool has_robot = a.robot_model != ROBOT_NONE;
-    RobotSlot rb{0, 0, 0, 0, 0};
-    if (has_robot) rb = la.robot_slot[w];
-    SenseOut so{false, false, 0.0, 0.0};
-    PT *vdst = reinterpret_cast<PT *>(la.view_dst) + (size_t)w * la.Npad;
-    if (valid) {
-        if (has_robot && a.robot_visible) {
-            PT dx, dy;
-            if constexpr (SPLIT) {
-                const float rxh = (float)rb.x, ryh = (float)rb.y;
-                dx = (mx - rxh) + (mlx - (float)(rb.x - (double)rxh));
-                dy = (my - ryh) + (mly - (float)(rb.y - (double)ryh));
-            } else { dx = mx - (PT)rb.x; dy = my - (PT)rb.y; }
-            pair_accum(kpr, dx, dy, (PT)rb.vx - mvx, (PT)rb.vy - mvy, false, fx, fy);
+    large_owner<PT, ST, SPLIT>(a, la, w, i, valid, gs, g, ie, lane, mx, my, mlx, mly, mvx, mvy, fx, fy);
+}
+
+// ---- pruned regime: one warp per chunk, no cluster, no block barrier (FP32 pair view) ---------------------------------
+// With exact pruning on the sorted copy a pedestrian meets ~200 of the 65 536 others, and the tile-streaming kernel above
+// spends its time at the per-tile cluster barriers (ncu: 28 % issue, barrier + membar stalls).  Here every warp works alone:
+// it owns the 32 pedestrians of one chunk, finds the chunks within reach of its own box (tile boxes 32 per ballot, then the 16
+// chunk boxes of a near tile), gathers their indices in a per-warp list and walks it with a two-deep software pipeline -- the
+// coalesced loads of chunk k + 1 (x, y, vx, vy of pedestrian `lane`, 512 B from L2) are in flight while chunk k, staged in the
+// warp's own 512-byte shared-memory buffer, is evaluated with the broadcast LDS.128 / packed-FP32 pair code of the kernel above.
+// Same pairs, same arithmetic per pair; the order of summation is (tile, chunk, j) like above, so the result is bit-identical
+// to the tile-streaming kernel's.
+constexpr int CHUNK_LIST = 96;        // near chunks gathered per pass of the list
+
+__global__ void __launch_bounds__(LARGE_TI, 4) hsfm_chunk_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
+{
+    using PT = float;
+    __shared__ __align__(16) float stage[LARGE_TI / 32][2][4 * LARGE_CHUNK];
+    __shared__ int near_list[LARGE_TI / 32][CHUNK_LIST];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int w = blockIdx.x / la.tiles_i, it = blockIdx.x - w * la.tiles_i;
+    const int i = it * LARGE_TI + tid;
+    const int N = a.N;
+    const bool valid = i < N;
+    const size_t gs = (size_t)w * N + (valid ? i : 0);
+    const size_t g = la.perm ? (size_t)la.perm[gs] : gs;
+    const int ie = (int)(g - (size_t)w * N);
+    const PT *vsrc = reinterpret_cast<const PT *>(la.view_src) + (size_t)w * la.Npad;
+    const size_t vs = la.view_stride;
+    const int iv = valid ? i : 0;
+    const PT mx = vsrc[iv], my = vsrc[vs + iv], mvx = vsrc[2 * vs + iv], mvy = vsrc[3 * vs + iv];
+    const PairK<PT> &kpp = a.kpp_f;
+    const int i0 = i & ~31;
+    constexpr int CPT = LARGE_TJ / LARGE_CHUNK;                        // chunks per tile
+    const float4 *tile_box = la.boxes + (size_t)w * la.tiles_j;
+    const float4 *chunk_box = la.chunk_boxes + (size_t)w * la.Npad / LARGE_CHUNK;
+    const float4 wbox = __ldg(chunk_box + i0 / LARGE_CHUNK);          // box of this warp's 32 pedestrians
+    int *list = near_list[wid];
+
+    PT fx = 0, fy = 0;
+    float2 fxa = make_float2(0.f, 0.f), fya = fxa, fxb = fxa, fyb = fxa;
+    const float2 m2x = make_float2(mx, mx), m2y = make_float2(my, my);
+
+    auto near = [&](const float4 o) {                                 // NaN / infinite boxes are never skipped
+        const float gx = fmaxf(0.f, fmaxf(o.x - wbox.y, wbox.x - o.y)), gy = fmaxf(0.f, fmaxf(o.z - wbox.w, wbox.z - o.w));
+        return !(gx * gx + gy * gy > la.cut2);
+    };
+    auto load_chunk = [&](int jc) {                                   // pedestrian `lane` of chunk jc, coalesced
+        const int j = jc * LARGE_CHUNK + lane;
+        return make_float4(__ldcg(vsrc + j), __ldcg(vsrc + vs + j), __ldcg(vsrc + 2 * vs + j), __ldcg(vsrc + 3 * vs + j));
+    };
+    auto group = [&](const float *xs, int jl, int self) {             // 4 partners; self = index of j == i in the chunk, or -1
+        const float4 X = *reinterpret_cast<const float4 *>(xs + jl);
+        const float4 Y = *reinterpret_cast<const float4 *>(xs + LARGE_CHUNK + jl);
+        float2 dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
+        float2 dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
+        if (self >= 0) {
+            const int k = self - jl;
+            dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
+            dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
         }
-        const PedConsts<ST> &kc = kc_of(a, ST{});
-        ST x, y, vx, vy;
-        if constexpr (sizeof(ST) == 4) {
-            const float4 p = __ldcg(reinterpret_cast<const float4 *>(la.pos_src) + gs);
-            x = p.x; y = p.y; vx = p.z; vy = p.w;
-        } else {
-            const double2 p = __ldcg(reinterpret_cast<const double2 *>(la.pos_src) + gs);
-            const double2 v = __ldcg(reinterpret_cast<const double2 *>(la.vel_src) + gs);
-            x = p.x; y = p.y; vx = v.x; vy = v.y;
+        float2 inva, invb, sa, sb;
+        pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
+        pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
+        const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
+        if (__any_sync(0xffffffffu, smax > 0.0f)) {
+            const float4 VX = *reinterpret_cast<const float4 *>(xs + 2 * LARGE_CHUNK + jl);
+            const float4 VY = *reinterpret_cast<const float4 *>(xs + 3 * LARGE_CHUNK + jl);
+            pair_contact(kpp, dxa.x, dya.x, VX.x - mvx, VY.x - mvy, inva.x, sa.x, fx, fy);
+            pair_contact(kpp, dxa.y, dya.y, VX.y - mvx, VY.y - mvy, inva.y, sa.y, fx, fy);
+            pair_contact(kpp, dxb.x, dyb.x, VX.z - mvx, VY.z - mvy, invb.x, sb.x, fx, fy);
+            pair_contact(kpp, dxb.y, dyb.y, VX.w - mvx, VY.w - mvy, invb.y, sb.y, fx, fy);
         }
-        const ST2 tw = __ldcg(reinterpret_cast<const ST2 *>(la.th_src) + gs);
-        ST th = tw.x, om = tw.y, c, sn;
-        m_sincos(th, &sn, &c);
-        ST2 wp = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
-        const ST vm = reinterpret_cast<const ST *>(a.vmag)[g];
-        const ST x0 = x, y0 = y, th0 = th;
-        ST nzx = 0, nzy = 0;
-        if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
-        else if (a.accel_noise_std > 0.0) { const double2 z = accel_noise_draw(a, g, a.steps_done + la.step); nzx = (ST)z.x; nzy = (ST)z.y; }
-        StateLo lo{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lo0 = lo;
-        bool comp = false;
-        if constexpr (sizeof(ST) == 4) comp = a.comp != 0;
-        if constexpr (sizeof(ST) == 4) {
-            if (comp) {
-                const float4 pl = __ldcg(reinterpret_cast<const float4 *>(la.vel_src) + gs);
-                const float2 tl = __ldcg(reinterpret_cast<const float2 *>(la.thlo_src) + gs);
-                lo = StateLo{pl.x, pl.y, pl.z, pl.w, tl.x, tl.y}; lo0 = lo;
-                const float s0 = sn;
-                sn = fmaf(c, tl.x, sn); c = fmaf(-s0, tl.x, c);
-                ped_integrate_comp(kc, fx, fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, lo, nzx, nzy);
-            } else {
-                ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
-            }
-        } else {
-            ped_integrate<ST>(kc, (ST)fx, (ST)fy, wp.x, wp.y, vm, x, y, vx, vy, th, om, c, sn, nzx, nzy);
+    };
+    auto flush = [&](int K) {                                         // evaluate the K chunks of the list
+        __syncwarp();
+        if (K == 0) return;
+        float4 nxt = load_chunk(list[0]);
+        for (int k = 0; k < K; ++k) {
+            float *buf = stage[wid][k & 1];
+            buf[lane] = nxt.x; buf[LARGE_CHUNK + lane] = nxt.y; buf[2 * LARGE_CHUNK + lane] = nxt.z; buf[3 * LARGE_CHUNK + lane] = nxt.w;
+            __syncwarp();                   // chunk k staged; everybody is done with chunk k - 1 (the other buffer may be refilled)
+            const int jc = list[k];
+            if (k + 1 < K) nxt = load_chunk(list[k + 1]);
+            const int self = jc * LARGE_CHUNK == i0 ? i - i0 : -1;
+#pragma unroll
+            for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(buf, jl, self);
         }
-        const ST ex = (wp.x - x) - (ST)lo.x, ey = (wp.y - y) - (ST)lo.y;
-        bool reached;
-        if constexpr (sizeof(ST) == 8) reached = m_sqrt(ex * ex + ey * ey) <= kc.reach;
-        else reached = ex * ex + ey * ey <= kc.reach * kc.reach;
-        if (reached) {
-            if (a.tracker_kind == TRACKER_FIXED) {
-                int ni = a.wp_index[g] + 1;
-                bool steady = false;
-                if (ni >= a.n_table) { if (a.loop) ni = 0; else { ni = a.n_table - 1; steady = true; } }
-                a.wp_index[g] = ni;
-                wp = reinterpret_cast<const ST2 *>(a.table)[g * a.n_table + ni];
-                if (steady) { x = x0; y = y0; th = th0; vx = 0; vy = 0; om = 0; lo = StateLo{lo0.x, lo0.y, 0.f, 0.f, lo0.th, 0.f}; }
-            } else {
-                const int cnt = a.q_count[g];
-                const int slot = atomicAdd(a.ev_count, 1);
-                if (cnt > 0) {
-                    const int head = a.q_head[g];
-                    wp = reinterpret_cast<const ST2 *>(a.queue)[g * a.q_cap + head];
-                    a.q_head[g] = (head + 1) % a.q_cap;
-                    a.q_count[g] = cnt - 1;
-                    if (slot < a.ev_cap) { a.events[3 * slot] = la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = ie; }
-                } else if (slot < a.ev_cap) {
-                    a.events[3 * slot] = -1 - la.step; a.events[3 * slot + 1] = w; a.events[3 * slot + 2] = ie;
-                }
-            }
-            reinterpret_cast<ST2 *>(a.wp)[g] = wp;
-        }
-        // new state -> destination buffers + destination pair view
-        if constexpr (sizeof(ST) == 4) {
-            reinterpret_cast<float4 *>(la.pos_dst)[gs] = make_float4(x, y, vx, vy);
-            if (comp) {
-                reinterpret_cast<float4 *>(la.vel_dst)[gs] = make_float4(lo.x, lo.y, lo.vx, lo.vy);
-                reinterpret_cast<float2 *>(la.thlo_dst)[gs] = make_float2(lo.th, lo.om);
-            }
-        } else {
-            reinterpret_cast<double2 *>(la.pos_dst)[gs] = make_double2(x, y);
-            reinterpret_cast<double2 *>(la.vel_dst)[gs] = make_double2(vx, vy);
-        }
-        ST2 t2; t2.x = th; t2.y = om;
-        reinterpret_cast<ST2 *>(la.th_dst)[gs] = t2;
-        if constexpr (SPLIT) {
-            const float xh = (float)x, yh = (float)y;
-            vdst[i] = xh; vdst[vs + i] = yh; vdst[2 * vs + i] = (float)vx; vdst[3 * vs + i] = (float)vy;
-            vdst[4 * vs + i] = (float)(x - (double)xh); vdst[5 * vs + i] = (float)(y - (double)yh);
-        } else {
-            vdst[i] = (PT)x; vdst[vs + i] = (PT)y; vdst[2 * vs + i] = (PT)vx; vdst[3 * vs + i] = (PT)vy;
-        }
-        if (!m_finite(x + y + vx + vy + th + om)) atomicMin(&a.nonfinite[w], (int)(a.steps_done + la.step + 1));
-        if (has_robot) {
-            if constexpr (sizeof(ST) == 4) {
-                if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, la.last != 0);
-                else so = sense_ped<ST>(a, rb, x, y, la.last != 0);
-            } else {
-                so = sense_ped<ST>(a, rb, x, y, la.last != 0);
-            }
-        }
-        if (la.last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
-    }
-    if (has_robot) {
-        const unsigned dm = __ballot_sync(0xffffffffu, so.det);
-        const unsigned cm = __ballot_sync(0xffffffffu, so.coll);
-        if (lane == 0) {
-            if (dm) atomicAdd(&a.det_count[w], (unsigned long long)__popc(dm));
-            if (cm) atomicAdd(&a.coll_count[w], (unsigned long long)__popc(cm));
-            const int words = (N + 31) >> 5;
-            if (la.last && !la.perm && (i >> 5) < words) {
-                a.det_mask[(size_t)w * words + (i >> 5)] = dm;
-                a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
-            }
-        }
-        if (la.last && la.perm) {          // sorted slots: set the caller's bit (the masks were cleared before the call)
-            const int words = (N + 31) >> 5;
-            if (so.det) atomicOr(&a.det_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
-            if (so.coll) atomicOr(&a.coll_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
+        __syncwarp();
+    };
+
+    int K = 0;
+    for (int base = 0; base < la.tiles_j; base += 32) {
+        const int jt = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, jt < la.tiles_j && near(__ldg(tile_box + jt)));
+        while (m) {
+            const int t = base + __ffs(m) - 1;
+            m &= m - 1;
+            const bool keep = lane < CPT && near(__ldg(chunk_box + t * CPT + lane));
+            const unsigned mc = __ballot_sync(0xffffffffu, keep);
+            const int n = __popc(mc);
+            if (K + n > CHUNK_LIST) { flush(K); K = 0; }
+            if (keep) list[K + __popc(mc & ((1u << lane) - 1u))] = t * CPT + lane;
+            K += n;
         }
     }
+    flush(K);
+    fx += (fxa.x + fxa.y) + (fxb.x + fxb.y);
+    fy += (fya.x + fya.y) + (fyb.x + fyb.y);
+    large_owner<float, float, false>(a, la, w, i, valid, gs, g, ie, lane, mx, my, 0.f, 0.f, mvx, mvy, fx, fy);
 }
 
 // ---- host-side launch of n_steps large-crowd steps ---------------------------------------------------
 template <typename PT, typename ST, bool SPLIT>
 inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_tiles, bool reorder, cudaStream_t stream,
-                          long long *launches, int *out_blocks, int *out_smem)
+                          long long *launches, int *out_blocks, int *out_smem, bool chunk_kernel = false)
 {
     constexpr int NARR = SPLIT ? 6 : 4;
     const int Npad = (a.N + LARGE_TJ - 1) / LARGE_TJ * LARGE_TJ;
@@ -658,6 +780,15 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
                     large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes, s.chunk_boxes,
                                                                                      s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
                 ++*launches;
+            }
+            if constexpr (sizeof(ST) == 4) {
+                if (chunk_kernel && prune) {      // pruned FP32 regime: barrier-free warp-per-chunk kernel
+                    hsfm_chunk_kernel<<<(unsigned)(a.W * tiles_i), LARGE_TI, 0, stream>>>(a, la);
+                    if ((e = cudaGetLastError()) != cudaSuccess) return -2;
+                    ++*launches;
+                    cur = dst;
+                    continue;
+                }
             }
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)(a.W * tiles_i)); cfg.blockDim = dim3(LARGE_TI); cfg.dynamicSmemBytes = smem; cfg.stream = stream;

@@ -340,7 +340,9 @@ int launch_large(pms_sim *h)
     int blocks = 0, smem = 0, rc;
     long long launches = 0;
     switch (h->precision) {
-    case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, !h->no_prune, !h->no_reorder, h->stream, &launches, &blocks, &smem); break;
+    // FP32 with exact pruning runs the barrier-free chunk kernel unless a cluster size was asked for explicitly
+    case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, !h->no_prune, !h->no_reorder, h->stream, &launches, &blocks, &smem,
+                                                            h->tune_cluster == 0); break;
     case PMS_MIXED: rc = launch_large_t<float, double, true>(h->large, h->a, cluster, !h->no_prune, !h->no_reorder, h->stream, &launches, &blocks, &smem); break;
     default: rc = launch_large_t<double, double, false>(h->large, h->a, cluster, false, false, h->stream, &launches, &blocks, &smem); break;
     }
