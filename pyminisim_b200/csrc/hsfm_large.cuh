@@ -2,7 +2,8 @@
 //
 // One launch per simulation step (the step needs every pedestrian's state at time t, so the state is
 // double-buffered in HBM and the launch boundary is the grid-wide barrier):
-//   robot_step_kernel   : one thread per world, fp64 (tiny)
+//   robot_window_kernel : one thread per world, fp64: the robot of every step of a window of LARGE_RESORT steps (it does not
+//                         depend on the pedestrians), once per window
 //   hsfm_large_kernel   : grid = worlds x i-tiles.  A CTA owns TI pedestrians (one per thread) and streams
 //                         the whole world's "pair view" (structure-of-arrays x, y, vx, vy [, xlo, ylo])
 //                         through shared memory in j-tiles of TJ with cp.async.bulk (TMA 1-D bulk copy)
@@ -49,6 +50,11 @@ struct LargeArgs {
     const RobotSlot *robot_slot;     // (W) robot state for this step
     const float4 *boxes;             // (W, tiles_j) bounding box {xmin, xmax, ymin, ymax} of every j-tile of view_src, or NULL
     const float4 *chunk_boxes;       // (W, Npad / 32) the same per chunk of 32 pedestrians
+    // chunk kernel: the boxes of view_dst are produced by the step itself (no box launch between two steps)
+    float4 *boxes_dst;               // tile boxes of view_dst, merged with atomic min / max (reset to empty beforehand)
+    float4 *boxes_reset;             // the third tile-box buffer: reset to empty for the step after the next
+    float4 *chunk_boxes_dst;         // chunk boxes of view_dst
+    int tiles_c;                     // chunk-kernel CTAs per world
     float cut2;                      // squared distance beyond which the pair force is exactly 0 (fp32 pair arithmetic)
     const int *perm;                 // (W*N) sorted slot -> caller's global pedestrian index, or NULL (identity)
 };
@@ -58,13 +64,16 @@ struct LargeScratch {
     void *view[2] = {nullptr, nullptr};
     RobotSlot *robot_slot = nullptr;
     RobotRegs *robot_regs = nullptr;
-    float4 *boxes = nullptr, *chunk_boxes = nullptr;
+    float4 *boxes[3] = {nullptr, nullptr, nullptr}, *chunk_boxes[2] = {nullptr, nullptr};
     // spatially sorted working copy: sorted state (ping), keys / permutation double buffers, cub scratch
     void *pos3 = nullptr, *vel3 = nullptr, *th3 = nullptr;
     unsigned long long *keys[2] = {nullptr, nullptr};
     int *perm[2] = {nullptr, nullptr};
     void *sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
+    // the robots of a window are integrated on a side stream while the main stream sorts (fork / join events)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int Npad = 0;
     int parity = 0;                  // which view buffer holds the current state
     bool view_valid = false;
@@ -73,9 +82,12 @@ struct LargeScratch {
 
 inline void large_free(LargeScratch &s)
 {
-    void *p[] = {s.thlo2, s.thlo3, s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes, s.chunk_boxes,
+    void *p[] = {s.thlo2, s.thlo3, s.pos2, s.vel2, s.th2, s.view[0], s.view[1], s.robot_slot, s.robot_regs, s.boxes[0], s.boxes[1], s.boxes[2], s.chunk_boxes[0], s.chunk_boxes[1],
                  s.pos3, s.vel3, s.th3, s.keys[0], s.keys[1], s.perm[0], s.perm[1], s.sort_tmp};
     for (void *q : p) if (q) cudaFree(q);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.aux) cudaStreamDestroy(s.aux);
     s = LargeScratch{};
 }
 
@@ -131,9 +143,13 @@ __device__ __forceinline__ void large_robot_step(const HsfmArgs &a, int w, Robot
     slot[w] = RobotSlot{r.x, r.y, r.th, r.vx, r.vy};
     if (last) robot_store(a, w, r);
 }
-__global__ void robot_step_kernel(const __grid_constant__ HsfmArgs a, RobotRegs *regs, RobotSlot *slot, int step, int first, int last)
+// The robot's motion does not depend on the pedestrians (controls + map veto only): the slots of steps t0 .. t1-1 are
+// computed ahead, slot[(t - t0) * W + w].
+__global__ void robot_window_kernel(const __grid_constant__ HsfmArgs a, RobotRegs *regs, RobotSlot *slot, int t0, int t1)
 {
-    large_robot_step(a, blockIdx.x * blockDim.x + threadIdx.x, regs, slot, step, first, last);
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int t = t0; t < t1; ++t)
+        large_robot_step(a, w, regs, slot + (size_t)(t - t0) * a.W, t, t == 0, t == a.n_steps - 1);
 }
 
 // ---- pair view initialisation from the state (first step of a call) --------------------------------------
@@ -168,6 +184,9 @@ __global__ void large_view_kernel(const __grid_constant__ HsfmArgs a, PT *view, 
 // has an empty box, which is far from everything); a chunk that holds a non-finite coordinate gets an infinite box (never
 // skipped: its NaN must reach every other pedestrian like in the reference).
 constexpr int LARGE_RESORT = 128;     // steps between two spatial sorts
+// Strip width in units of the cut-off distance.  Wider than 1: the boxes of strip s and strip s +- 2 stay more than the
+// cut-off apart while the crowd drifts between two sorts (measured on C3, 256 steps: 31.0 us per step at 1.0, 26.0 at 1.25).
+constexpr float LARGE_STRIP_SCALE = 1.25f;
 
 // Sort key = world : strip : y.  Strips are columns as wide as the cut-off distance; inside a strip the pedestrians are
 // ordered by y, upwards in even strips and downwards in odd ones (a snake through the world).  32 consecutive pedestrians (a chunk) then fill a compact box of one strip width, 512 (a tile) a piece of
@@ -214,12 +233,11 @@ constexpr int LARGE_CHUNK = 32;       // pedestrians per chunk box (one warp's r
 
 template <typename PT>
 __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ HsfmArgs a, int Npad, int tiles_j, const PT *view,
-                                                        size_t stride, float4 *boxes, float4 *chunk_boxes, RobotRegs *regs,
-                                                        RobotSlot *slot, int step, int first, int last)
+                                                        size_t stride, float4 *boxes, float4 *chunk_boxes,
+                                                        float4 *chunk_boxes2, float4 *boxes_empty)
 {
-    // the robots ride along in the first CTA (one launch less per step)
-    if (blockIdx.x == 0)
-        for (int rw = threadIdx.x; rw < a.W; rw += 128) large_robot_step(a, rw, regs, slot, step, first, last);
+    // chunk_boxes2 (optional): second copy of the chunk boxes (the chunk kernel's destination buffer: its all-padding chunks
+    // are never rewritten); boxes_empty (optional): tile-box buffer reset to empty boxes for the chunk kernel's atomics
     const int N = a.N;
     const int w = blockIdx.x / tiles_j, jt = blockIdx.x - w * tiles_j;
     const PT *xs = view + (size_t)w * Npad + (size_t)jt * LARGE_TJ, *ys = xs + stride;
@@ -243,7 +261,10 @@ __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ 
         }
         float4 cb = make_float4(xmin, xmax, ymin, ymax);
         if (__any_sync(0xffffffffu, bad)) cb = make_float4(-inf, inf, -inf, inf);
-        if (lane == 0) chunk_boxes[((size_t)w * Npad + (size_t)jt * LARGE_TJ + k) / LARGE_CHUNK] = cb;
+        if (lane == 0) {
+            chunk_boxes[((size_t)w * Npad + (size_t)jt * LARGE_TJ + k) / LARGE_CHUNK] = cb;
+            if (chunk_boxes2) chunk_boxes2[((size_t)w * Npad + (size_t)jt * LARGE_TJ + k) / LARGE_CHUNK] = cb;
+        }
         tb.x = fminf(tb.x, cb.x); tb.y = fmaxf(tb.y, cb.y); tb.z = fminf(tb.z, cb.z); tb.w = fmaxf(tb.w, cb.w);
     }
     __shared__ float4 part[4];
@@ -255,6 +276,7 @@ __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ 
             bx.x = fminf(bx.x, part[q].x); bx.y = fmaxf(bx.y, part[q].y); bx.z = fminf(bx.z, part[q].z); bx.w = fmaxf(bx.w, part[q].w);
         }
         boxes[blockIdx.x] = bx;
+        if (boxes_empty) boxes_empty[blockIdx.x] = make_float4(inf, -inf, inf, -inf);
     }
 }
 
@@ -262,7 +284,8 @@ __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ 
 // ---- robot term, O(1) dynamics, tracker, sensors of one pedestrian: shared by the tile-streaming kernel and the chunk kernel
 template <typename PT, typename ST, bool SPLIT>
 __device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &la, int w, int i, bool valid, size_t gs, size_t g, int ie,
-                                            int lane, PT mx, PT my, float mlx, float mly, PT mvx, PT mvy, PT fx, PT fy)
+                                            int lane, PT mx, PT my, float mlx, float mly, PT mvx, PT mvy, PT fx, PT fy,
+                                            PT &view_x, PT &view_y)            // out: the new position as the pair view holds it
 {
     using ST2 = typename Vec2<ST>::type;
     const int N = a.N;
@@ -364,8 +387,10 @@ __device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &
             const float xh = (float)x, yh = (float)y;
             vdst[i] = xh; vdst[vs + i] = yh; vdst[2 * vs + i] = (float)vx; vdst[3 * vs + i] = (float)vy;
             vdst[4 * vs + i] = (float)(x - (double)xh); vdst[5 * vs + i] = (float)(y - (double)yh);
+            view_x = xh; view_y = yh;
         } else {
             vdst[i] = (PT)x; vdst[vs + i] = (PT)y; vdst[2 * vs + i] = (PT)vx; vdst[3 * vs + i] = (PT)vy;
+            view_x = (PT)x; view_y = (PT)y;
         }
         if (!m_finite(x + y + vx + vy + th + om)) atomicMin(&a.nonfinite[w], (int)(a.steps_done + la.step + 1));
         if (has_robot) {
@@ -572,7 +597,8 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
         fy += (fya.x + fya.y) + (fyb.x + fyb.y);
     }
 
-    large_owner<PT, ST, SPLIT>(a, la, w, i, valid, gs, g, ie, lane, mx, my, mlx, mly, mvx, mvy, fx, fy);
+    PT view_x = 0, view_y = 0;
+    large_owner<PT, ST, SPLIT>(a, la, w, i, valid, gs, g, ie, lane, mx, my, mlx, mly, mvx, mvy, fx, fy, view_x, view_y);
 }
 
 // ---- pruned regime: one warp per chunk, no cluster, no block barrier (FP32 pair view) ---------------------------------
@@ -584,17 +610,38 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
 // warp's own 512-byte shared-memory buffer, is evaluated with the broadcast LDS.128 / packed-FP32 pair code of the kernel above.
 // Same pairs, same arithmetic per pair; the order of summation is (tile, chunk, j) like above, so the result is bit-identical
 // to the tile-streaming kernel's.
+// The step also produces what the next step's pruning needs -- the box of the warp's 32 new positions (chunk box) and, merged
+// with atomic min / max, the box of their j-tile -- so that one launch per step remains.  min / max are exact in any order:
+// the boxes equal large_box_kernel's bit for bit.
 constexpr int CHUNK_LIST = 96;        // near chunks gathered per pass of the list
+constexpr int CHUNK_TI = 64;          // threads per CTA: two independent warps (small CTAs spread evenly over 148 SMs)
 
-__global__ void __launch_bounds__(LARGE_TI, 4) hsfm_chunk_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
+// atomic min / max of finite-or-infinite floats through their ordered integer images (+0.0f is added so that -0 counts as +0)
+__device__ __forceinline__ void atomic_min_float(float *p, float v)
+{
+    v += 0.0f;
+    if (v >= 0.f) atomicMin(reinterpret_cast<int *>(p), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned *>(p), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float *p, float v)
+{
+    v += 0.0f;
+    if (v >= 0.f) atomicMax(reinterpret_cast<int *>(p), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned *>(p), __float_as_uint(v));
+}
+
+#ifndef PMS_CHUNK_MINB
+#define PMS_CHUNK_MINB 8
+#endif
+__global__ void __launch_bounds__(CHUNK_TI, PMS_CHUNK_MINB) hsfm_chunk_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
 {
     using PT = float;
-    __shared__ __align__(16) float stage[LARGE_TI / 32][2][4 * LARGE_CHUNK];
-    __shared__ int near_list[LARGE_TI / 32][CHUNK_LIST];
+    __shared__ __align__(16) float stage[CHUNK_TI / 32][2][4 * LARGE_CHUNK];
+    __shared__ int near_list[CHUNK_TI / 32][CHUNK_LIST];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int w = blockIdx.x / la.tiles_i, it = blockIdx.x - w * la.tiles_i;
-    const int i = it * LARGE_TI + tid;
+    const int w = blockIdx.x / la.tiles_c, it = blockIdx.x - w * la.tiles_c;
+    const int i = it * CHUNK_TI + tid;
     const int N = a.N;
     const bool valid = i < N;
     const size_t gs = (size_t)w * N + (valid ? i : 0);
@@ -682,7 +729,37 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_chunk_kernel(const __grid_co
     flush(K);
     fx += (fxa.x + fxa.y) + (fxb.x + fxb.y);
     fy += (fya.x + fya.y) + (fyb.x + fyb.y);
-    large_owner<float, float, false>(a, la, w, i, valid, gs, g, ie, lane, mx, my, 0.f, 0.f, mvx, mvy, fx, fy);
+    float nx = 0.f, ny = 0.f;
+    large_owner<float, float, false>(a, la, w, i, valid, gs, g, ie, lane, mx, my, 0.f, 0.f, mvx, mvy, fx, fy, nx, ny);
+
+    // ---- boxes of the new positions (same rules as large_box_kernel) ----
+    {
+        const size_t gt = blockIdx.x * (size_t)CHUNK_TI + tid;
+        if (gt < (size_t)a.W * la.tiles_j) la.boxes_reset[gt] = make_float4(CUDART_INF_F, -CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F);
+        const float inf = CUDART_INF_F;
+        float xmin = inf, xmax = -inf, ymin = inf, ymax = -inf;
+        bool bad = false;
+        if (valid) {
+            bad = !(fabsf(nx) <= 3.0e38f) || !(fabsf(ny) <= 3.0e38f);
+            xmin = xmax = nx; ymin = ymax = ny;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        float4 cb = make_float4(xmin, xmax, ymin, ymax);
+        if (__any_sync(0xffffffffu, bad)) cb = make_float4(-inf, inf, -inf, inf);
+        if (i0 < N && lane < 4) {
+            if (lane == 0) la.chunk_boxes_dst[((size_t)w * la.Npad + i0) / LARGE_CHUNK] = cb;
+            float *tb = reinterpret_cast<float *>(la.boxes_dst + (size_t)w * la.tiles_j + i0 / LARGE_TJ);
+            // lane q merges component q of the tile box: x-min, x-max, y-min, y-max
+            if (lane == 0) atomic_min_float(tb, cb.x);
+            else if (lane == 1) atomic_max_float(tb + 1, cb.y);
+            else if (lane == 2) atomic_min_float(tb + 2, cb.z);
+            else atomic_max_float(tb + 3, cb.w);
+        }
+    }
 }
 
 // ---- host-side launch of n_steps large-crowd steps ---------------------------------------------------
@@ -709,10 +786,15 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         s.view_bytes = nv * NARR * sizeof(PT);
         if ((e = cudaMalloc(&s.view[0], s.view_bytes)) != cudaSuccess) return -2;
         if ((e = cudaMalloc(&s.view[1], s.view_bytes)) != cudaSuccess) return -2;
-        if ((e = cudaMalloc((void **)&s.robot_slot, sizeof(RobotSlot) * a.W)) != cudaSuccess) return -2;
+        if ((e = cudaMalloc((void **)&s.robot_slot, sizeof(RobotSlot) * a.W * LARGE_RESORT * 2)) != cudaSuccess) return -2;
+        if ((e = cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking)) != cudaSuccess) return -2;
+        if ((e = cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming)) != cudaSuccess) return -2;
+        if ((e = cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming)) != cudaSuccess) return -2;
         if ((e = cudaMalloc((void **)&s.robot_regs, sizeof(RobotRegs) * a.W)) != cudaSuccess) return -2;
-        if ((e = cudaMalloc((void **)&s.boxes, sizeof(float4) * (size_t)a.W * (Npad / LARGE_TJ))) != cudaSuccess) return -2;
-        if ((e = cudaMalloc((void **)&s.chunk_boxes, sizeof(float4) * (size_t)a.W * (Npad / LARGE_CHUNK))) != cudaSuccess) return -2;
+        for (int q = 0; q < 3; ++q)
+            if ((e = cudaMalloc((void **)&s.boxes[q], sizeof(float4) * (size_t)a.W * (Npad / LARGE_TJ))) != cudaSuccess) return -2;
+        for (int q = 0; q < 2; ++q)
+            if ((e = cudaMalloc((void **)&s.chunk_boxes[q], sizeof(float4) * (size_t)a.W * (Npad / LARGE_CHUNK))) != cudaSuccess) return -2;
         s.Npad = Npad;
     }
     int end_bit = 48;
@@ -729,14 +811,16 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         if ((e = cudaMalloc(&s.sort_tmp, s.sort_tmp_bytes ? s.sort_tmp_bytes : 1)) != cudaSuccess) return -2;
     }
 
-    const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ;
+    const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ, tiles_c = (a.N + CHUNK_TI - 1) / CHUNK_TI;
+    bool use_chunk = false;                                        // pruned FP32 regime: barrier-free warp-per-chunk kernel
+    if constexpr (sizeof(ST) == 4) use_chunk = chunk_kernel && prune;
     // grid must be a multiple of the cluster size and a cluster must stay inside one world
     while (cluster > 1 && (tiles_i % cluster != 0 || LARGE_TJ % cluster != 0)) cluster >>= 1;
     const size_t smem = LARGE_STAGES * NARR * LARGE_TJ * sizeof(PT) + LARGE_STAGES * sizeof(uint64_t) + sizeof(int) * (tiles_j + 1);
     auto kern = hsfm_large_kernel<PT, ST, SPLIT>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
     const unsigned gn = (unsigned)((n + 255) / 256), gv = (unsigned)((nv + 255) / 256);
-    const float inv_strip = 1.0f / sqrtf(a.warp_cut2);            // strips one cut-off distance wide
+    const float inv_strip = 1.0f / (LARGE_STRIP_SCALE * sqrtf(a.warp_cut2));
 
     // working state: the caller's arrays, or the spatially sorted copy (home[0] is then s.pos3 ...)
     const bool comp = sizeof(ST) == 4 && a.comp;                  // FP32: a.vel (= a.pos_lo) and a.th_lo hold the low parts
@@ -745,6 +829,15 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
     int cur = 0;                                                   // buffer that holds the current state
     for (int t0 = 0; t0 < a.n_steps; t0 += LARGE_RESORT) {
         const int t1 = t0 + LARGE_RESORT < a.n_steps ? t0 + LARGE_RESORT : a.n_steps;
+        // the robots of the whole window, ahead of the pedestrians, on the side stream (slot buffers alternate per window)
+        RobotSlot *const slots = s.robot_slot + (size_t)((t0 / LARGE_RESORT) & 1) * LARGE_RESORT * a.W;
+        if (a.robot_model != ROBOT_NONE) {
+            cudaEventRecord(s.ev_fork, stream);
+            cudaStreamWaitEvent(s.aux, s.ev_fork, 0);
+            robot_window_kernel<<<(a.W + 127) / 128, 128, 0, s.aux>>>(a, s.robot_regs, slots, t0, t1);
+            cudaEventRecord(s.ev_join, s.aux);
+            ++*launches;
+        }
         if (reorder) {
             // sort by (world, strip, y) of the CURRENT positions (in the caller's arrays), gather the state
             large_sortkey_kernel<ST><<<gn, 256, 0, stream>>>(a, inv_strip, s.keys[0], s.perm[0]);
@@ -760,30 +853,33 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur]), nv, Npad);
         if (t0 == 0) large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur ^ 1]), nv, Npad);
         *launches += 2;
+        if (a.robot_model != ROBOT_NONE) cudaStreamWaitEvent(stream, s.ev_join, 0);
         for (int t = t0; t < t1; ++t) {
             const int src = cur, dst = cur ^ 1;
-            if (a.robot_model != ROBOT_NONE && !prune) {      // with pruning the robots ride along in the box kernel
-                robot_step_kernel<<<(a.W + 127) / 128, 128, 0, stream>>>(a, s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
-                ++*launches;
-            }
+            // tile boxes rotate through three buffers in the chunk-kernel regime (read, merged into, reset), chunk boxes through two
+            const int bq = use_chunk ? (t - t0) % 3 : 0, cq = use_chunk ? (t - t0) & 1 : 0;
             LargeArgs la{};
             la.pos_src = pos[src]; la.vel_src = vel[src]; la.th_src = th[src];
             la.pos_dst = pos[dst]; la.vel_dst = vel[dst]; la.th_dst = th[dst];
             la.thlo_src = thlo[src]; la.thlo_dst = thlo[dst];
             la.view_src = s.view[src]; la.view_dst = s.view[dst];
             la.view_stride = nv; la.Npad = Npad; la.tiles_i = tiles_i; la.tiles_j = tiles_j; la.cluster = cluster;
-            la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = s.robot_slot;
-            la.boxes = prune ? s.boxes : nullptr; la.chunk_boxes = s.chunk_boxes; la.cut2 = a.warp_cut2;
+            la.step = t; la.last = (t == a.n_steps - 1); la.robot_slot = slots + (size_t)(t - t0) * a.W;
+            la.boxes = prune ? s.boxes[bq] : nullptr; la.chunk_boxes = s.chunk_boxes[cq]; la.cut2 = a.warp_cut2;
+            la.boxes_dst = s.boxes[(bq + 1) % 3]; la.boxes_reset = s.boxes[(bq + 2) % 3]; la.chunk_boxes_dst = s.chunk_boxes[cq ^ 1];
+            la.tiles_c = tiles_c;
             la.perm = reorder ? s.perm[1] : nullptr;
-            if (prune) {
+            if (prune && (!use_chunk || t == t0)) {       // the chunk kernel keeps the boxes up to date itself after the first step
                 if constexpr (sizeof(PT) == 4)
-                    large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv, s.boxes, s.chunk_boxes,
-                                                                                     s.robot_regs, s.robot_slot, t, t == 0, t == a.n_steps - 1);
+                    large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv,
+                                                                                     s.boxes[bq], s.chunk_boxes[cq],
+                                                                                     use_chunk ? s.chunk_boxes[cq ^ 1] : nullptr,
+                                                                                     use_chunk ? s.boxes[(bq + 1) % 3] : nullptr);
                 ++*launches;
             }
             if constexpr (sizeof(ST) == 4) {
-                if (chunk_kernel && prune) {      // pruned FP32 regime: barrier-free warp-per-chunk kernel
-                    hsfm_chunk_kernel<<<(unsigned)(a.W * tiles_i), LARGE_TI, 0, stream>>>(a, la);
+                if (use_chunk) {
+                    hsfm_chunk_kernel<<<(unsigned)(a.W * tiles_c), CHUNK_TI, 0, stream>>>(a, la);
                     if ((e = cudaGetLastError()) != cudaSuccess) return -2;
                     ++*launches;
                     cur = dst;
@@ -813,7 +909,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         if (comp) cudaMemcpyAsync(a.th_lo, s.thlo2, n * 8, cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(a.th, s.th2, n * e2, cudaMemcpyDeviceToDevice, stream);
     }
-    *out_blocks = a.W * tiles_i;
+    *out_blocks = use_chunk ? a.W * tiles_c : a.W * tiles_i;
     *out_smem = (int)smem;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -91,10 +91,9 @@ static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, 
     }
     const double *map = a.map_data ? a.map_data + (size_t)w * a.map_stride : nullptr;
     if (a.robot_model == ROBOT_UNICYCLE) {
-        double sn, cs_;
-        sincos(r.th, &sn, &cs_);
-        const double nx = r.x + u0 * cs_ * a.dt;
-        const double ny = r.y + u0 * sn * a.dt;
+        // r.cs, r.sn are sincos(r.th) already (robot_load / the previous step): one fp64 sincos per step, not two
+        const double nx = r.x + u0 * r.cs * a.dt;
+        const double ny = r.y + u0 * r.sn * a.dt;
         double nth = r.th + u1 * a.dt;
         nth = py_mod(nth + PMS_PI, PMS_TWO_PI) - PMS_PI;
         if (map_is_collision(a.map_kind, a.map_count, map, nx, ny, a.robot_radius)) {
@@ -102,10 +101,11 @@ static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, 
         } else {
             r.world_collision = 0;
             r.x = nx; r.y = ny; r.th = nth; r.c0 = u0; r.c1 = u1;
+            double sn, cs_;
+            sincos(nth, &sn, &cs_);
+            r.cs = cs_; r.sn = sn;
         }
-        sincos(r.th, &sn, &cs_);
-        r.cs = cs_; r.sn = sn;
-        r.vx = r.c0 * cs_; r.vy = r.c0 * sn; r.vw = r.c1;
+        r.vx = r.c0 * r.cs; r.vy = r.c0 * r.sn; r.vw = r.c1;
     } else {
         double sn, cs_;
         sincos(r.rth, &sn, &cs_);

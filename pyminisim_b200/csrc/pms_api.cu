@@ -348,7 +348,7 @@ int launch_large(pms_sim *h)
     }
     if (rc) return fail(PMS_ERR_CUDA, std::string("large-crowd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->info.kernel = 1;
-    h->info.threads_per_block = LARGE_TI;
+    h->info.threads_per_block = (h->precision == PMS_FP32 && h->tune_cluster == 0 && !h->no_prune) ? CHUNK_TI : LARGE_TI;
     h->info.blocks = blocks;
     h->info.worlds_per_block = 0;
     h->info.j_split = cluster;
