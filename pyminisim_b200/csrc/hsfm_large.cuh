@@ -282,9 +282,45 @@ __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ 
 
 // ---- the step kernel --------------------------------------------------------------------------------
 // ---- robot term, O(1) dynamics, tracker, sensors of one pedestrian: shared by the tile-streaming kernel and the chunk kernel
+// The per-pedestrian inputs of the owner step.  They are read in ONE batch (the L2 latencies overlap instead of queueing up
+// behind the sincos / the robot term): by owner_load right before the step (tile-streaming kernel), or by cp.async into
+// shared memory at the start of the chunk kernel, where they arrive while the pairs are evaluated.
+template <typename ST>
+struct OwnerIn {
+    ST x, y, vx, vy, th, om, wpx, wpy, vm;
+    float4 pl;      // FP32 compensated state: low parts of x y vx vy
+    float2 tl;      //                          low parts of theta, omega
+};
+template <typename ST>
+__device__ __forceinline__ OwnerIn<ST> owner_load(const HsfmArgs &a, const LargeArgs &la, size_t gs, size_t g)
+{
+    using ST2 = typename Vec2<ST>::type;
+    OwnerIn<ST> in;
+    in.pl = make_float4(0.f, 0.f, 0.f, 0.f); in.tl = make_float2(0.f, 0.f);
+    if constexpr (sizeof(ST) == 4) {
+        const float4 p = __ldcg(reinterpret_cast<const float4 *>(la.pos_src) + gs);
+        in.x = p.x; in.y = p.y; in.vx = p.z; in.vy = p.w;
+        if (a.comp) {
+            in.pl = __ldcg(reinterpret_cast<const float4 *>(la.vel_src) + gs);
+            in.tl = __ldcg(reinterpret_cast<const float2 *>(la.thlo_src) + gs);
+        }
+    } else {
+        const double2 p = __ldcg(reinterpret_cast<const double2 *>(la.pos_src) + gs);
+        const double2 v = __ldcg(reinterpret_cast<const double2 *>(la.vel_src) + gs);
+        in.x = p.x; in.y = p.y; in.vx = v.x; in.vy = v.y;
+    }
+    const ST2 tw = __ldcg(reinterpret_cast<const ST2 *>(la.th_src) + gs);
+    in.th = tw.x; in.om = tw.y;
+    const ST2 wp = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
+    in.wpx = wp.x; in.wpy = wp.y;
+    in.vm = reinterpret_cast<const ST *>(a.vmag)[g];
+    return in;
+}
+
 template <typename PT, typename ST, bool SPLIT>
 __device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &la, int w, int i, bool valid, size_t gs, size_t g, int ie,
                                             int lane, PT mx, PT my, float mlx, float mly, PT mvx, PT mvy, PT fx, PT fy,
+                                            const OwnerIn<ST> &in,
                                             PT &view_x, PT &view_y)            // out: the new position as the pair view holds it
 {
     using ST2 = typename Vec2<ST>::type;
@@ -308,20 +344,11 @@ __device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &
             pair_accum(kpr, dx, dy, (PT)rb.vx - mvx, (PT)rb.vy - mvy, false, fx, fy);
         }
         const PedConsts<ST> &kc = kc_of(a, ST{});
-        ST x, y, vx, vy;
-        if constexpr (sizeof(ST) == 4) {
-            const float4 p = __ldcg(reinterpret_cast<const float4 *>(la.pos_src) + gs);
-            x = p.x; y = p.y; vx = p.z; vy = p.w;
-        } else {
-            const double2 p = __ldcg(reinterpret_cast<const double2 *>(la.pos_src) + gs);
-            const double2 v = __ldcg(reinterpret_cast<const double2 *>(la.vel_src) + gs);
-            x = p.x; y = p.y; vx = v.x; vy = v.y;
-        }
-        const ST2 tw = __ldcg(reinterpret_cast<const ST2 *>(la.th_src) + gs);
-        ST th = tw.x, om = tw.y, c, sn;
+        ST x = in.x, y = in.y, vx = in.vx, vy = in.vy;
+        ST th = in.th, om = in.om, c, sn;
         m_sincos(th, &sn, &c);
-        ST2 wp = __ldcg(reinterpret_cast<const ST2 *>(a.wp) + g);
-        const ST vm = reinterpret_cast<const ST *>(a.vmag)[g];
+        ST2 wp; wp.x = in.wpx; wp.y = in.wpy;
+        const ST vm = in.vm;
         const ST x0 = x, y0 = y, th0 = th;
         ST nzx = 0, nzy = 0;
         if (a.accel_noise) { nzx = (ST)a.accel_noise[2 * g]; nzy = (ST)a.accel_noise[2 * g + 1]; }
@@ -331,8 +358,8 @@ __device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &
         if constexpr (sizeof(ST) == 4) comp = a.comp != 0;
         if constexpr (sizeof(ST) == 4) {
             if (comp) {
-                const float4 pl = __ldcg(reinterpret_cast<const float4 *>(la.vel_src) + gs);
-                const float2 tl = __ldcg(reinterpret_cast<const float2 *>(la.thlo_src) + gs);
+                const float4 pl = in.pl;
+                const float2 tl = in.tl;
                 lo = StateLo{pl.x, pl.y, pl.z, pl.w, tl.x, tl.y}; lo0 = lo;
                 const float s0 = sn;
                 sn = fmaf(c, tl.x, sn); c = fmaf(-s0, tl.x, c);
@@ -598,7 +625,9 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
     }
 
     PT view_x = 0, view_y = 0;
-    large_owner<PT, ST, SPLIT>(a, la, w, i, valid, gs, g, ie, lane, mx, my, mlx, mly, mvx, mvy, fx, fy, view_x, view_y);
+    OwnerIn<ST> in{};
+    if (valid) in = owner_load<ST>(a, la, gs, g);
+    large_owner<PT, ST, SPLIT>(a, la, w, i, valid, gs, g, ie, lane, mx, my, mlx, mly, mvx, mvy, fx, fy, in, view_x, view_y);
 }
 
 // ---- pruned regime: one warp per chunk, no cluster, no block barrier (FP32 pair view) ---------------------------------
@@ -614,7 +643,12 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
 // with atomic min / max, the box of their j-tile -- so that one launch per step remains.  min / max are exact in any order:
 // the boxes equal large_box_kernel's bit for bit.
 constexpr int CHUNK_LIST = 96;        // near chunks gathered per pass of the list
-constexpr int CHUNK_TI = 64;          // threads per CTA: two independent warps (small CTAs spread evenly over 148 SMs)
+constexpr int CHUNK_TI = 64;          // KS = 1: threads per CTA, two independent warps (small CTAs spread evenly over 148 SMs)
+// KS > 1 (j-split): KS warps share one chunk of 32 pedestrians -- a 65 536-pedestrian world is only 2048 warps (3.5 per
+// scheduler), too few to hide the MUFU / L2 latency of the pair chains.  Warp q takes the near chunks at list positions
+// q, q + KS, ...; the partial sums meet in shared memory and are added in warp order by warp 0, which then runs the
+// per-pedestrian step.  Deterministic, but the order of summation differs from KS = 1 (same pairs, same per-pair arithmetic).
+// KS is chosen by the number of chunks (launch_large_t): 1 from about 1200 chunks (38 000 pedestrians) upwards.
 
 // atomic min / max of finite-or-infinite floats through their ordered integer images (+0.0f is added so that -0 counts as +0)
 __device__ __forceinline__ void atomic_min_float(float *p, float v)
@@ -631,17 +665,29 @@ __device__ __forceinline__ void atomic_max_float(float *p, float v)
 }
 
 #ifndef PMS_CHUNK_MINB
-#define PMS_CHUNK_MINB 8
+#define PMS_CHUNK_MINB 8              // resident 64-thread CTAs per SM the register budget is set for (16 warps per SM)
 #endif
-__global__ void __launch_bounds__(CHUNK_TI, PMS_CHUNK_MINB) hsfm_chunk_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int KS, int CPB>       // warps per chunk, chunks per CTA
+__global__ void __launch_bounds__(32 * KS * CPB, PMS_CHUNK_MINB * 2 / (KS * CPB)) hsfm_chunk_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
 {
     using PT = float;
-    __shared__ __align__(16) float stage[CHUNK_TI / 32][2][4 * LARGE_CHUNK];
-    __shared__ int near_list[CHUNK_TI / 32][CHUNK_LIST];
+    constexpr int NW = KS * CPB;
+    __shared__ __align__(16) float stage[NW][2][4 * LARGE_CHUNK];
+    __shared__ int near_list[NW][CHUNK_LIST];
+    __shared__ float2 part[KS > 1 ? NW : 1][32];
+    __shared__ __align__(16) float4 own16[CPB][2][32];                 // owner inputs: {x y vx vy}, their low parts
+    __shared__ __align__(8) float2 own8[CPB][3][32];                   //               {theta omega}, low parts, waypoint
+    __shared__ float own4[CPB][32];                                    //               speed
+    __shared__ unsigned short near_tiles[NW][128];                     // near tiles of the current group of 128
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int q = wid % KS;                                            // this warp's share of the near list
     const int w = blockIdx.x / la.tiles_c, it = blockIdx.x - w * la.tiles_c;
-    const int i = it * CHUNK_TI + tid;
+    const int i = (it * CPB + wid / KS) * LARGE_CHUNK + lane;
     const int N = a.N;
     const bool valid = i < N;
     const size_t gs = (size_t)w * N + (valid ? i : 0);
@@ -658,6 +704,19 @@ __global__ void __launch_bounds__(CHUNK_TI, PMS_CHUNK_MINB) hsfm_chunk_kernel(co
     const float4 *chunk_box = la.chunk_boxes + (size_t)w * la.Npad / LARGE_CHUNK;
     const float4 wbox = __ldg(chunk_box + i0 / LARGE_CHUNK);          // box of this warp's 32 pedestrians
     int *list = near_list[wid];
+    // the per-pedestrian step's inputs travel into shared memory (cp.async, no registers held) while the pairs are evaluated;
+    // every thread reads back only what it copied itself
+    const int oc = wid / KS;                                           // chunk of this CTA
+    if (q == 0 && valid) {
+        cp_async16(&own16[oc][0][lane], reinterpret_cast<const float4 *>(la.pos_src) + gs);
+        cp_async8(&own8[oc][0][lane], reinterpret_cast<const float2 *>(la.th_src) + gs);
+        if (a.comp) {
+            cp_async16(&own16[oc][1][lane], reinterpret_cast<const float4 *>(la.vel_src) + gs);
+            cp_async8(&own8[oc][1][lane], reinterpret_cast<const float2 *>(la.thlo_src) + gs);
+        }
+        cp_async8(&own8[oc][2][lane], reinterpret_cast<const float2 *>(a.wp) + g);
+        cp_async4(&own4[oc][lane], reinterpret_cast<const float *>(a.vmag) + g);
+    }
 
     PT fx = 0, fy = 0;
     float2 fxa = make_float2(0.f, 0.f), fya = fxa, fxb = fxa, fyb = fxa;
@@ -711,30 +770,81 @@ __global__ void __launch_bounds__(CHUNK_TI, PMS_CHUNK_MINB) hsfm_chunk_kernel(co
         __syncwarp();
     };
 
-    int K = 0;
-    for (int base = 0; base < la.tiles_j; base += 32) {
-        const int jt = base + lane;
-        unsigned m = __ballot_sync(0xffffffffu, jt < la.tiles_j && near(__ldg(tile_box + jt)));
-        while (m) {
-            const int t = base + __ffs(m) - 1;
-            m &= m - 1;
-            const bool keep = lane < CPT && near(__ldg(chunk_box + t * CPT + lane));
-            const unsigned mc = __ballot_sync(0xffffffffu, keep);
-            const int n = __popc(mc);
-            if (K + n > CHUNK_LIST) { flush(K); K = 0; }
-            if (keep) list[K + __popc(mc & ((1u << lane) - 1u))] = t * CPT + lane;
-            K += n;
+    // The scan is a chain of dependent L2 reads (tile boxes, then the chunk boxes of the near tiles), so the reads are issued in
+    // batches: 128 tile boxes at a time, then the chunk boxes of up to 8 near tiles (two tiles per warp-wide load, 16 lanes each).
+    static_assert(CPT == 16, "two tiles per warp-wide chunk-box load");
+    int K = 0, P = 0;                                                  // entries in this warp's list; near chunks seen so far
+    for (int base0 = 0; base0 < la.tiles_j; base0 += 128) {
+        float4 tb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jt = base0 + 32 * u + lane;
+            tb[u] = jt < la.tiles_j ? __ldg(tile_box + jt) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        unsigned tm[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tm[u] = __ballot_sync(0xffffffffu, base0 + 32 * u + lane < la.tiles_j && near(tb[u]));
+        int cnt = 0;                                                   // near tiles of this group, ascending, in shared memory
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if ((tm[u] >> lane) & 1u) near_tiles[wid][cnt + __popc(tm[u] & ((1u << lane) - 1u))] = (unsigned short)(32 * u + lane);
+            cnt += __popc(tm[u]);
+        }
+        __syncwarp();
+        for (int r = 0; r < cnt; r += 8) {                             // near tiles of rank r .. r + 7: 16 lanes per tile
+            float4 cbx[4];
+            int cid[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int rk = r + 2 * v + (lane >> 4);
+                cid[v] = rk < cnt ? (base0 + (int)near_tiles[wid][rk]) * CPT + (lane & 15) : -1;
+                cbx[v] = cid[v] >= 0 ? __ldg(chunk_box + cid[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                if (r + 2 * v >= cnt) break;                           // uniform
+                bool keep = cid[v] >= 0 && near(cbx[v]);
+                unsigned mc = __ballot_sync(0xffffffffu, keep);
+                if constexpr (KS > 1) {                                // position P + rank in the common list decides the owner warp
+                    const int pos = P + __popc(mc & ((1u << lane) - 1u));
+                    P += __popc(mc);
+                    keep = keep && (pos % KS == q);
+                    mc = __ballot_sync(0xffffffffu, keep);
+                }
+                const int n = __popc(mc);
+                if (K + n > CHUNK_LIST) { flush(K); K = 0; }
+                if (keep) list[K + __popc(mc & ((1u << lane) - 1u))] = cid[v];
+                K += n;
+            }
         }
     }
     flush(K);
     fx += (fxa.x + fxa.y) + (fxb.x + fxb.y);
     fy += (fya.x + fya.y) + (fyb.x + fyb.y);
+    if constexpr (KS > 1) {
+        part[wid][lane] = make_float2(fx, fy);
+        __syncthreads();
+        if (q != 0) return;
+        fx = part[wid][lane].x; fy = part[wid][lane].y;
+#pragma unroll
+        for (int r = 1; r < KS; ++r) { fx += part[wid + r][lane].x; fy += part[wid + r][lane].y; }
+    }
     float nx = 0.f, ny = 0.f;
-    large_owner<float, float, false>(a, la, w, i, valid, gs, g, ie, lane, mx, my, 0.f, 0.f, mvx, mvy, fx, fy, nx, ny);
+    OwnerIn<float> in{};
+    cp_async_wait_all();
+    if (valid) {
+        const float4 p = own16[oc][0][lane];
+        const float2 tw = own8[oc][0][lane], wp = own8[oc][2][lane];
+        in.x = p.x; in.y = p.y; in.vx = p.z; in.vy = p.w; in.th = tw.x; in.om = tw.y; in.wpx = wp.x; in.wpy = wp.y; in.vm = own4[oc][lane];
+        in.pl = make_float4(0.f, 0.f, 0.f, 0.f); in.tl = make_float2(0.f, 0.f);
+        if (a.comp) { in.pl = own16[oc][1][lane]; in.tl = own8[oc][1][lane]; }
+    }
+    large_owner<float, float, false>(a, la, w, i, valid, gs, g, ie, lane, mx, my, 0.f, 0.f, mvx, mvy, fx, fy, in, nx, ny);
 
     // ---- boxes of the new positions (same rules as large_box_kernel) ----
     {
-        const size_t gt = blockIdx.x * (size_t)CHUNK_TI + tid;
+        const size_t gt = (blockIdx.x * (size_t)CPB + wid / KS) * LARGE_CHUNK + lane;
         if (gt < (size_t)a.W * la.tiles_j) la.boxes_reset[gt] = make_float4(CUDART_INF_F, -CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F);
         const float inf = CUDART_INF_F;
         float xmin = inf, xmax = -inf, ymin = inf, ymax = -inf;
@@ -765,7 +875,8 @@ __global__ void __launch_bounds__(CHUNK_TI, PMS_CHUNK_MINB) hsfm_chunk_kernel(co
 // ---- host-side launch of n_steps large-crowd steps ---------------------------------------------------
 template <typename PT, typename ST, bool SPLIT>
 inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_tiles, bool reorder, cudaStream_t stream,
-                          long long *launches, int *out_blocks, int *out_smem, bool chunk_kernel = false)
+                          long long *launches, int *out_blocks, int *out_smem, bool chunk_kernel = false, int chunk_split = 0,
+                          int *out_threads = nullptr)
 {
     constexpr int NARR = SPLIT ? 6 : 4;
     const int Npad = (a.N + LARGE_TJ - 1) / LARGE_TJ * LARGE_TJ;
@@ -811,7 +922,13 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         if ((e = cudaMalloc(&s.sort_tmp, s.sort_tmp_bytes ? s.sort_tmp_bytes : 1)) != cudaSuccess) return -2;
     }
 
-    const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ, tiles_c = (a.N + CHUNK_TI - 1) / CHUNK_TI;
+    // j-split of the chunk kernel: asked for, or by the number of chunks (measured on one B200, 148 SMs: 512 chunks 15.0 / 13.2 /
+    // 11.6 us per step with 1 / 2 / 4 warps per chunk, 1024 chunks 16.9 / 16.6 / 17.9, 2048 chunks 23.0 / 25.8 / 29.7)
+    const long long n_chunks_all = (long long)a.W * ((a.N + LARGE_CHUNK - 1) / LARGE_CHUNK);
+    const int ks = chunk_split == 1 || chunk_split == 2 || chunk_split == 4 ? chunk_split
+                   : (n_chunks_all <= 4 * 148 ? 4 : (n_chunks_all <= 8 * 148 ? 2 : 1));
+    const int cpb = ks == 1 ? CHUNK_TI / LARGE_CHUNK : 1;          // chunks per chunk-kernel CTA
+    const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ, tiles_c = (a.N + cpb * LARGE_CHUNK - 1) / (cpb * LARGE_CHUNK);
     bool use_chunk = false;                                        // pruned FP32 regime: barrier-free warp-per-chunk kernel
     if constexpr (sizeof(ST) == 4) use_chunk = chunk_kernel && prune;
     // grid must be a multiple of the cluster size and a cluster must stay inside one world
@@ -879,7 +996,10 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             }
             if constexpr (sizeof(ST) == 4) {
                 if (use_chunk) {
-                    hsfm_chunk_kernel<<<(unsigned)(a.W * tiles_c), CHUNK_TI, 0, stream>>>(a, la);
+                    const unsigned gc = (unsigned)(a.W * tiles_c);
+                    if (ks == 1) hsfm_chunk_kernel<1, CHUNK_TI / LARGE_CHUNK><<<gc, CHUNK_TI, 0, stream>>>(a, la);
+                    else if (ks == 2) hsfm_chunk_kernel<2, 1><<<gc, 64, 0, stream>>>(a, la);
+                    else hsfm_chunk_kernel<4, 1><<<gc, 128, 0, stream>>>(a, la);
                     if ((e = cudaGetLastError()) != cudaSuccess) return -2;
                     ++*launches;
                     cur = dst;
@@ -910,6 +1030,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         cudaMemcpyAsync(a.th, s.th2, n * e2, cudaMemcpyDeviceToDevice, stream);
     }
     *out_blocks = use_chunk ? a.W * tiles_c : a.W * tiles_i;
+    if (out_threads) *out_threads = use_chunk ? 32 * ks * cpb : LARGE_TI;
     *out_smem = (int)smem;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -337,18 +337,18 @@ int launch_large(pms_sim *h)
 {
     int cluster = h->tune_cluster > 0 ? h->tune_cluster : 4;
     if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) return fail(PMS_ERR_INVALID, "cluster size must be 1, 2, 4 or 8");
-    int blocks = 0, smem = 0, rc;
+    int blocks = 0, smem = 0, threads = LARGE_TI, rc;
     long long launches = 0;
     switch (h->precision) {
     // FP32 with exact pruning runs the barrier-free chunk kernel unless a cluster size was asked for explicitly
     case PMS_FP32: rc = launch_large_t<float, float, false>(h->large, h->a, cluster, !h->no_prune, !h->no_reorder, h->stream, &launches, &blocks, &smem,
-                                                            h->tune_cluster == 0); break;
+                                                            h->tune_cluster == 0, h->tune_S, &threads); break;
     case PMS_MIXED: rc = launch_large_t<float, double, true>(h->large, h->a, cluster, !h->no_prune, !h->no_reorder, h->stream, &launches, &blocks, &smem); break;
     default: rc = launch_large_t<double, double, false>(h->large, h->a, cluster, false, false, h->stream, &launches, &blocks, &smem); break;
     }
     if (rc) return fail(PMS_ERR_CUDA, std::string("large-crowd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->info.kernel = 1;
-    h->info.threads_per_block = (h->precision == PMS_FP32 && h->tune_cluster == 0 && !h->no_prune) ? CHUNK_TI : LARGE_TI;
+    h->info.threads_per_block = threads;
     h->info.blocks = blocks;
     h->info.worlds_per_block = 0;
     h->info.j_split = cluster;

@@ -379,7 +379,7 @@ def test_large_crowd_tile_pruning_is_bit_identical(precision):
         outs = []
         for n_chunks in (-2, -1):         # -2: pruning in the caller's order, -1: every j-tile visited
             c = make_cuda(sc, precision)
-            c.set_tuning(0, 0, n_chunks, 0)
+            c.set_tuning(1, 0, n_chunks, 0)   # j_split 1: the chunk kernel sums in the cluster kernel's order
             c.step(0.01, 7)
             assert c.launch_info()["kernel"] == 1
             outs.append(c.get_state() + c.get_detector() + (c.get_collisions(),) + c.get_stats())
@@ -388,9 +388,10 @@ def test_large_crowd_tile_pruning_is_bit_identical(precision):
 
 
 def test_large_crowd_chunk_kernel_equals_cluster_kernel():
-    """FP32 with exact pruning runs the barrier-free warp-per-chunk kernel by default; asking for a cluster size selects the
-    tile-streaming cluster kernel.  Same pairs, same per-pair arithmetic, same order of summation: same bits, with the sorted
-    working copy (shuffled crowd, robot inside it, re-sort inside the call) and in the caller's order."""
+    """FP32 with exact pruning runs the barrier-free chunk kernel by default; asking for a cluster size selects the
+    tile-streaming cluster kernel.  With one warp per chunk (j_split 1): same pairs, same per-pair arithmetic, same order of
+    summation, hence the same bits -- with the sorted working copy (shuffled crowd, robot inside it, re-sort inside the call)
+    and in the caller's order."""
     n = 5000
     sc = make_crowd(2, n, side=2.0 * np.sqrt(n), local_goals=1.2)
     perm = np.random.default_rng(11).permutation(n)
@@ -400,12 +401,39 @@ def test_large_crowd_chunk_kernel_equals_cluster_kernel():
         outs = []
         for cluster in (0, 4):
             c = make_cuda(sc, "fp32", det=(6.0, 200.0, 0))
-            c.set_tuning(0, 0, n_chunks, cluster)
+            c.set_tuning(1, 0, n_chunks, cluster)
             c.step(0.01, 3); c.step(0.01, steps)
             assert c.launch_info()["kernel"] == 1
             outs.append(c.get_state() + c.get_detector() + (c.get_collisions(),) + c.get_stats() + (c.get_waypoints()[1],))
         for a, b in zip(*outs):
             assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("j_split", [2, 4])
+def test_large_crowd_chunk_kernel_j_split(j_split):
+    """Default chunk kernel: 4 (or 2) warps share a chunk and split its near list; the partial sums are added in warp order.
+    Same pairs and per-pair arithmetic as one warp per chunk, another order of summation: equal to rounding after a few
+    steps, deterministic (two runs give the same bits), and within the fp32 tolerance of the fp64 oracle."""
+    n = 5000
+    sc = make_crowd(2, n, side=2.0 * np.sqrt(n), local_goals=1.2)
+    perm = np.random.default_rng(11).permutation(n)
+    sc.poses, sc.table, sc.vmag, sc.vels = sc.poses[:, perm], sc.table[:, perm], sc.vmag[:, perm], sc.vels[:, perm]
+    sc.robot_pose[:, :2] = [3.0, -2.0]
+    o = make_oracle(sc, det=(6.0, 200.0, 0))
+    o.rollout(0.01, 12, n_threads=8)
+    outs = []
+    for js in (1, j_split, j_split):
+        c = make_cuda(sc, "fp32", det=(6.0, 200.0, 0))
+        c.set_tuning(js, 0, 0, 0)
+        c.step(0.01, 5); c.step(0.01, 7)
+        info = c.launch_info()
+        assert info["kernel"] == 1 and info["threads_per_block"] == (64 if js == 1 else 32 * js)
+        outs.append(c.get_state() + c.get_detector() + (c.get_collisions(),) + c.get_stats() + (c.get_waypoints()[1],))
+    for a, b in zip(outs[1], outs[2]):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert rel_err(outs[1][0], outs[0][0]) < 1e-6 and np.abs(outs[1][1] - outs[0][1]).max() < 1e-3
+    assert rel_err(outs[1][0], o.poses) < 2e-6
+    assert (outs[1][-1] == outs[0][-1]).all()
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-6), ("mixed", 1e-9)])   # fp32 beyond 100 steps: hand-off timing, see below
