@@ -75,7 +75,14 @@ struct LargeScratch {
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int Npad = 0;
-    int parity = 0;                  // which view buffer holds the current state
+    // The sorted working copy outlives a call: while the caller's state arrays have not been written by the host
+    // (pms_api.cu clears sorted_valid) and the last sort is less than LARGE_RESORT steps old, the next call goes on in it
+    // -- a loop of one-step calls pays one sort per LARGE_RESORT steps, not one per call.
+    bool sorted_valid = false;
+    int since_sort = 0;              // steps taken in the current sorted copy
+    int cur = 0;                     // which ping-pong buffer holds the newest sorted state (and its pair view)
+    int bq = 0, cq = 0;              // chunk kernel: tile- / chunk-box buffers that hold the boxes of that state
+    unsigned window = 0;             // windows so far (robot slot buffers alternate)
     bool view_valid = false;
     size_t view_bytes = 0;
 };
@@ -944,10 +951,14 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
     void *pos[2] = {a.pos, s.pos2}, *vel[2] = {a.vel, s.vel2}, *th[2] = {a.th, s.th2}, *thlo[2] = {a.th_lo, s.thlo2};
     if (reorder) { pos[0] = s.pos3; vel[0] = s.vel3; th[0] = s.th3; thlo[0] = s.thlo3; }
     int cur = 0;                                                   // buffer that holds the current state
-    for (int t0 = 0; t0 < a.n_steps; t0 += LARGE_RESORT) {
-        const int t1 = t0 + LARGE_RESORT < a.n_steps ? t0 + LARGE_RESORT : a.n_steps;
+    if (!reorder) s.sorted_valid = false;
+    for (int t0 = 0, t1 = 0; t0 < a.n_steps; t0 = t1) {
+        // go on in the existing sorted copy while it is fresh, else sort again
+        const bool cont = reorder && s.sorted_valid && s.since_sort < LARGE_RESORT;
+        const int room = cont ? LARGE_RESORT - s.since_sort : LARGE_RESORT;
+        t1 = t0 + room < a.n_steps ? t0 + room : a.n_steps;
         // the robots of the whole window, ahead of the pedestrians, on the side stream (slot buffers alternate per window)
-        RobotSlot *const slots = s.robot_slot + (size_t)((t0 / LARGE_RESORT) & 1) * LARGE_RESORT * a.W;
+        RobotSlot *const slots = s.robot_slot + (size_t)(s.window++ & 1) * LARGE_RESORT * a.W;
         if (a.robot_model != ROBOT_NONE) {
             cudaEventRecord(s.ev_fork, stream);
             cudaStreamWaitEvent(s.aux, s.ev_fork, 0);
@@ -955,7 +966,8 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             cudaEventRecord(s.ev_join, s.aux);
             ++*launches;
         }
-        if (reorder) {
+        if (cont) cur = s.cur;
+        if (reorder && !cont) {
             // sort by (world, strip, y) of the CURRENT positions (in the caller's arrays), gather the state
             large_sortkey_kernel<ST><<<gn, 256, 0, stream>>>(a, inv_strip, s.keys[0], s.perm[0]);
             cub::DeviceRadixSort::SortPairs(s.sort_tmp, s.sort_tmp_bytes, s.keys[0], s.keys[1], s.perm[0], s.perm[1], (int)n, 0, end_bit, stream);
@@ -963,18 +975,24 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
                                                                    comp ? a.th_lo : nullptr, thlo[0]);
             *launches += 3;
             cur = 0;
+            s.since_sort = 0;
         }
-        // the pair view is rebuilt from the working state (the host may have changed it between calls)
-        HsfmArgs av = a;
-        av.pos = pos[cur]; av.vel = vel[cur]; av.th = th[cur];
-        large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur]), nv, Npad);
-        if (t0 == 0) large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur ^ 1]), nv, Npad);
-        *launches += 2;
+        // the pair view is rebuilt from the working state (the host may have changed it between calls) -- unless the call goes
+        // on in the sorted copy of the previous one, whose last step left the view (and, chunk kernel, the boxes) up to date
+        const bool keep_boxes = cont && use_chunk && s.view_valid;
+        if (!(cont && s.view_valid)) {
+            HsfmArgs av = a;
+            av.pos = pos[cur]; av.vel = vel[cur]; av.th = th[cur];
+            large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur]), nv, Npad);
+            if (t0 == 0) large_view_kernel<PT, ST, SPLIT><<<gv, 256, 0, stream>>>(av, reinterpret_cast<PT *>(s.view[cur ^ 1]), nv, Npad);
+            *launches += 2;
+        }
+        const int bq0 = keep_boxes ? s.bq : 0, cq0 = keep_boxes ? s.cq : 0;
         if (a.robot_model != ROBOT_NONE) cudaStreamWaitEvent(stream, s.ev_join, 0);
         for (int t = t0; t < t1; ++t) {
             const int src = cur, dst = cur ^ 1;
             // tile boxes rotate through three buffers in the chunk-kernel regime (read, merged into, reset), chunk boxes through two
-            const int bq = use_chunk ? (t - t0) % 3 : 0, cq = use_chunk ? (t - t0) & 1 : 0;
+            const int bq = use_chunk ? (bq0 + t - t0) % 3 : 0, cq = use_chunk ? (cq0 + t - t0) & 1 : 0;
             LargeArgs la{};
             la.pos_src = pos[src]; la.vel_src = vel[src]; la.th_src = th[src];
             la.pos_dst = pos[dst]; la.vel_dst = vel[dst]; la.th_dst = th[dst];
@@ -986,7 +1004,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             la.boxes_dst = s.boxes[(bq + 1) % 3]; la.boxes_reset = s.boxes[(bq + 2) % 3]; la.chunk_boxes_dst = s.chunk_boxes[cq ^ 1];
             la.tiles_c = tiles_c;
             la.perm = reorder ? s.perm[1] : nullptr;
-            if (prune && (!use_chunk || t == t0)) {       // the chunk kernel keeps the boxes up to date itself after the first step
+            if (prune && (!use_chunk || (t == t0 && !keep_boxes))) {   // the chunk kernel keeps the boxes up to date itself after the first step
                 if constexpr (sizeof(PT) == 4)
                     large_box_kernel<PT><<<(unsigned)(a.W * tiles_j), 128, 0, stream>>>(a, Npad, tiles_j, reinterpret_cast<const PT *>(s.view[src]), nv,
                                                                                      s.boxes[bq], s.chunk_boxes[cq],
@@ -1016,10 +1034,12 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             ++*launches;
             cur = dst;
         }
-        if (reorder) {             // back to the caller's order (the next sort reads the caller's arrays)
+        if (reorder) {             // back to the caller's order (host reads and the next sort use the caller's arrays)
             large_permute_kernel<ST, false><<<gn, 256, 0, stream>>>(n, s.perm[1], pos[cur], vel[cur], th[cur], a.pos, a.vel, a.th,
                                                                     comp ? thlo[cur] : nullptr, a.th_lo);
             ++*launches;
+            s.sorted_valid = true; s.view_valid = true; s.cur = cur; s.since_sort += t1 - t0;
+            s.bq = (bq0 + t1 - t0) % 3; s.cq = (cq0 + t1 - t0) & 1;
         }
     }
     // without re-ordering an odd number of steps leaves the newest state in the scratch buffers: copy it home

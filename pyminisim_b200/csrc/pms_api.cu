@@ -532,6 +532,7 @@ int pms_set_ped_state(pms_sim *h, const double *poses, const double *vels)
     if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a, h->compensated);
     else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a, false);
     CK(cudaGetLastError());
+    h->large.sorted_valid = false;            // the large-crowd kernel's sorted working copy no longer mirrors the state
     IO_DONE(h);
     return PMS_OK;
 }
@@ -998,6 +999,7 @@ int pms_snapshot_restore(pms_sim *h)
         CK(cudaMemcpyAsync(h->snap_src[k].first, h->snap_dst[k], h->snap_src[k].second, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemsetAsync(h->a.ev_count, 0, sizeof(int), h->stream));
     h->a.steps_done = h->snap_steps;
+    h->large.sorted_valid = false;
     return PMS_OK;
 }
 
@@ -1074,6 +1076,7 @@ int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, 
     h->no_reorder = n_chunks < 0;                     // -1, -2: no sorted working copy
     h->force_large = cluster_size < 0;               // negative: force the large-crowd kernel (tests)
     h->tune_cluster = cluster_size < 0 ? -cluster_size : cluster_size;
+    h->large.sorted_valid = false;
     return PMS_OK;
 }
 

@@ -409,6 +409,35 @@ def test_large_crowd_chunk_kernel_equals_cluster_kernel():
             assert np.array_equal(a, b, equal_nan=True)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "mixed"])
+def test_large_crowd_sorted_copy_survives_calls(precision):
+    """The sorted working copy outlives a call: 140 one-step calls sort at steps 0 and 128 like one 140-step call does, so
+    both give the same bits (and far fewer launches than a sort per call); a host write to the state (snapshot_restore)
+    makes the next call sort again instead of going on in the stale copy."""
+    n = 3000
+    sc = make_crowd(2, n, side=2.0 * np.sqrt(n), local_goals=1.2)
+    perm = np.random.default_rng(5).permutation(n)
+    sc.poses, sc.table, sc.vmag, sc.vels = sc.poses[:, perm], sc.table[:, perm], sc.vmag[:, perm], sc.vels[:, perm]
+    sc.robot_pose[:, :2] = [3.0, -2.0]
+    one = make_cuda(sc, precision, det=(6.0, 200.0, 0))
+    one.step(0.01, 140)
+    many = make_cuda(sc, precision, det=(6.0, 200.0, 0))
+    for _ in range(140):
+        many.step(0.01, 1)
+    grab = lambda c: c.get_state() + (c.get_detector()[0], c.get_collisions(), c.get_waypoints()[1], c.get_robot()[0]) + c.get_stats()
+    for a, b in zip(grab(one), grab(many)):
+        assert np.array_equal(a, b, equal_nan=True)
+    # per call: robots + step + scatter (+ boxes with the cluster kernel); a sort per call would add 8 or more launches
+    assert many.launch_info()["kernel"] == 1 and many.launch_info()["kernel_launches"] < 140 * (4 if precision == "fp32" else 5)
+    many.snapshot_save()
+    many.step(0.01, 5)
+    first = many.get_state()
+    many.snapshot_restore()
+    many.step(0.01, 5)
+    again = many.get_state()
+    assert rel_err(again[0], first[0]) < (2e-6 if precision == "fp32" else 1e-9)
+
+
 @pytest.mark.parametrize("j_split", [2, 4])
 def test_large_crowd_chunk_kernel_j_split(j_split):
     """Default chunk kernel: 4 (or 2) warps share a chunk and split its near list; the partial sums are added in warp order.
