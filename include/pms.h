@@ -164,6 +164,18 @@ int pms_hsfm_step(pms_sim *h, double dt, int n_steps);
 /* same, asynchronous on the handle's stream (no host synchronisation); pair with pms_sync */
 int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps);
 int pms_sync(pms_sim *h);
+/* One tick of the reference's step loop in one call and one host synchronisation -- what Simulation.step does between
+ * two readings (core/_simulation.py:60-73,119-160): AbstractPedestriansModel.step(dt, robot_pose, robot_velocity)
+ * (pedestrians/_hsfm.py:250-306) with the robot supplied by the caller (model EXTERNAL; NULL pose = no robot,
+ * _hsfm.py:279-284), then the state, the waypoint indices, the robot-pedestrian collision list, the detector reading, the
+ * non-finite flag and the number of logged waypoint events.  Equivalent to pms_set_robot + pms_hsfm_step +
+ * pms_get_ped_state + pms_get_waypoints + pms_get_collisions + pms_get_detector + pms_get_stats; every output pointer may
+ * be NULL.  `robot_radius` is AbstractRobotMotionModel.radius (collision list). */
+int pms_step_tick(pms_sim *h, double dt, int n_steps, const double *robot_pose /*(W,3) or NULL*/,
+                  const double *robot_velocity /*(W,3) or NULL*/, double robot_radius, int visible,
+                  double *poses /*(W,N,3)*/, double *vels /*(W,N,3)*/, int32_t *wp_index /*(W,N)*/,
+                  uint32_t *coll_mask /*(W,ceil(N/32))*/, uint32_t *det_mask /*(W,ceil(N/32))*/, double *det_vals /*(W,N,2)*/,
+                  int32_t *first_nonfinite_step /*(W)*/, int32_t *n_events /*(1)*/);
 /* CUDA stream of the handle as an opaque pointer (cudaStream_t), for event timing by the caller */
 void *pms_stream(pms_sim *h);
 /* evaluate collision list + detector on the current state without stepping (Simulation.__init__

@@ -199,6 +199,31 @@ class BatchedSimulation:
     def sync(self):
         check(self._lib.pms_sync(self._h))
 
+    def step_tick(self, dt: float, n_steps: int = 1, robot_pose=None, robot_velocity=None, robot_radius: float = 0.35,
+                  visible: bool = True) -> dict:
+        """One tick in one call and one host synchronisation (``pms_step_tick``): upload the robot the caller supplies
+        (``None`` = no robot), step, and fetch state, waypoint indices, collision list, detector reading, non-finite flag and
+        the number of logged waypoint events.  The output arrays are reused from tick to tick: copy what you keep."""
+        if not hasattr(self, "_tick"):
+            self._tick = dict(poses=np.empty((self.W, self.N, 3)), vels=np.empty((self.W, self.N, 3)),
+                              wp_index=np.empty((self.W, self.N), dtype=np.int32),
+                              coll_mask=np.empty((self.W, self.words), dtype=np.uint32),
+                              det_mask=np.empty((self.W, self.words), dtype=np.uint32), det_vals=np.empty((self.W, self.N, 2)),
+                              nonfinite=np.empty(self.W, dtype=np.int32), n_events=np.zeros(1, dtype=np.int32))
+            t = self._tick
+            self._tick_ptrs = (dptr(t["poses"]), dptr(t["vels"]), iptr(t["wp_index"]), uptr(t["coll_mask"]), uptr(t["det_mask"]),
+                               dptr(t["det_vals"]), iptr(t["nonfinite"]), iptr(t["n_events"]))
+        if robot_pose is None:
+            self.robot_model = capi.ROBOT_NONE
+            rp = rv = None
+        else:
+            self.robot_model = capi.ROBOT_EXTERNAL
+            rp = f64(robot_pose, (self.W, 3))
+            rv = None if robot_velocity is None else f64(robot_velocity, (self.W, 3))
+        check(self._lib.pms_step_tick(self._h, float(dt), int(n_steps), dptr(rp), dptr(rv), float(robot_radius), int(bool(visible)),
+                                      *self._tick_ptrs))
+        return self._tick
+
     @property
     def stream(self) -> int:
         return int(self._lib.pms_stream(self._h) or 0)

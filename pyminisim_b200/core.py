@@ -265,6 +265,13 @@ class Simulation:
         self._backup_pedestrians_model = None
         self._robot_to_world_collision = False
         self._sense = _GpuSenseContext()
+        if robot_model is not None and hasattr(pedestrians_model, "_collision_radius"):
+            pedestrians_model._collision_radius = robot_model.radius      # the fused step evaluates the collision list with it
+            for sensor in sensors:          # ... and the reading of the (first) pedestrian detector
+                if getattr(sensor, "sensor_name", None) == "pedestrian_detector" and hasattr(sensor, "_fused_config") \
+                        and hasattr(pedestrians_model, "configure_fused_detector"):
+                    pedestrians_model.configure_fused_detector(*sensor._fused_config())
+                    break
         self._current_state = self._make_state({})       # the constructor runs the sensor pass once (:37)
 
     @property
@@ -345,8 +352,12 @@ class Simulation:
         ped_state = self._pedestrians_model.state if self._pedestrians_model is not None else None
         collisions = None
         if robot_state is not None and ped_state is not None:
-            ids, coll, _, _ = self._sense.run(ped_state.poses, robot_state.pose, self._robot_model.radius)
-            collisions = [k for k, c in zip(ids, coll) if c]
+            # the fused step already evaluated the list for this robot pose (HSFM policy); else a sense pass of its own
+            fused = getattr(self._pedestrians_model, "fused_collisions", None)
+            collisions = fused(robot_state.pose, self._robot_model.radius) if fused is not None else None
+            if collisions is None:
+                ids, coll, _, _ = self._sense.run(ped_state.poses, robot_state.pose, self._robot_model.radius)
+                collisions = [k for k, c in zip(ids, coll) if c]
         return WorldState(world_map=self._world_map.current_state, robot=robot_state, pedestrians=ped_state,
                           robot_to_pedestrians_collisions=collisions,
                           robot_to_world_collision=self._robot_to_world_collision)

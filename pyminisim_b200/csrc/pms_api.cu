@@ -82,6 +82,16 @@ __global__ void convert_array_kernel(size_t n, const double *src, ST *dst)
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g < n) dst[g] = (ST)src[g];
 }
+// pms_step_tick: detector values, waypoint indices, masks, flags and the event count into the tick block
+__global__ void tick_gather_kernel(size_t n, int W, int words, HsfmArgs a, double2 *vals, int *wp_index, uint32_t *coll, uint32_t *det,
+                                   int *nonfinite, int *n_events)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g < n) { vals[g] = a.det_vals[g]; wp_index[g] = a.wp_index ? a.wp_index[g] : 0; }
+    if (g < (size_t)W * words) { coll[g] = a.coll_mask[g]; det[g] = a.det_mask[g]; }
+    if (g < (size_t)W) nonfinite[g] = a.nonfinite[g];
+    if (g == 0) *n_events = a.ev_count ? *a.ev_count : 0;
+}
 template <typename ST>
 __global__ void convert_back_kernel(size_t n, const ST *src, double *dst)
 {
@@ -139,6 +149,9 @@ struct pms_sim {
     HsfmArgs a{};          // device pointers + configuration (the kernel argument block)
     // staging (device, fp64) for host <-> device marshalling
     double *stage = nullptr;
+    // pms_step_tick: one device block + one pinned host block that carry every output of a tick in ONE transfer
+    unsigned char *tick_dev = nullptr, *tick_host = nullptr;
+    size_t tick_bytes = 0;
     size_t stage_elems = 0;
     double *controls_dev = nullptr;
     size_t controls_cap = 0;
@@ -492,6 +505,8 @@ int pms_destroy(pms_sim *h)
                     a.nonfinite, h->noisy_mask, h->noisy_vals, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done, h->noise_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->snap_dst) if (p) cudaFree(p);
+    if (h->tick_dev) cudaFree(h->tick_dev);
+    if (h->tick_host) cudaFreeHost(h->tick_host);
     large_free(h->large);
     orca_free(h->orca);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -890,6 +905,76 @@ int pms_hsfm_step(pms_sim *h, double dt, int n_steps)
 }
 
 void *pms_stream(pms_sim *h) { return h ? (void *)h->stream : nullptr; }
+
+// One tick of the drop-in classes in one call and ONE host synchronisation: robot upload (pinned staging, asynchronous),
+// n_steps fused steps, every output gathered into one device block, one device-to-host copy.
+int pms_step_tick(pms_sim *h, double dt, int n_steps, const double *robot_pose, const double *robot_velocity, double robot_radius,
+                  int visible, double *poses, double *vels, int32_t *wp_index, uint32_t *coll_mask, uint32_t *det_mask,
+                  double *det_vals, int32_t *first_nonfinite_step, int32_t *n_events)
+{
+    HCHECK(h);
+    if (n_steps < 1) return fail(PMS_ERR_INVALID, "n_steps < 1");
+    HsfmArgs &a = h->a;
+    const int W = h->W;
+    const size_t n = (size_t)W * h->N, nm = (size_t)W * h->words;
+    // layout of the tick block: poses | vels | det_vals (doubles) | wp_index | nonfinite | n_events (ints) | coll | det (u32);
+    // the head of the host block doubles as the staging area of the robot upload (pose | velocity | control | rear: 11 W doubles)
+    const size_t o_pose = 0, o_vel = o_pose + n * 24, o_vals = o_vel + n * 24, o_idx = o_vals + n * 16, o_nf = o_idx + n * 4,
+                 o_ev = o_nf + (size_t)W * 4, o_coll = o_ev + 4, o_det = o_coll + nm * 4, total = o_det + nm * 4;
+    const size_t need = total > (size_t)W * 88 ? total : (size_t)W * 88;
+    if (need > h->tick_bytes) {
+        if (h->tick_dev) cudaFree(h->tick_dev);
+        if (h->tick_host) cudaFreeHost(h->tick_host);
+        h->tick_dev = h->tick_host = nullptr; h->tick_bytes = 0;
+        CK(cudaMalloc((void **)&h->tick_dev, need));
+        CK(cudaMallocHost((void **)&h->tick_host, need));
+        h->tick_bytes = need;
+    }
+    if (!robot_pose) {
+        a.robot_model = PMS_ROBOT_NONE;
+    } else {
+        if (!(robot_radius > 0.0)) return fail(PMS_ERR_INVALID, "robot radius must be > 0");
+        a.robot_model = PMS_ROBOT_EXTERNAL; a.robot_visible = visible ? 1 : 0; a.robot_radius = robot_radius;
+        double *st = reinterpret_cast<double *>(h->tick_host);       // the previous tick was synchronised: the block is free
+        double *s_pose = st, *s_vel = st + 3 * W, *s_ctrl = st + 6 * W, *s_rear = st + 8 * W;
+        for (int w = 0; w < W; ++w) {
+            const double th = robot_pose[3 * w + 2];
+            for (int k = 0; k < 3; ++k) { s_pose[3 * w + k] = robot_pose[3 * w + k]; s_vel[3 * w + k] = robot_velocity ? robot_velocity[3 * w + k] : 0.0; }
+            s_ctrl[2 * w] = s_ctrl[2 * w + 1] = 0.0;
+            s_rear[3 * w] = robot_pose[3 * w] - (a.wheel_base / 2.0) * std::cos(th);
+            s_rear[3 * w + 1] = robot_pose[3 * w + 1] - (a.wheel_base / 2.0) * std::sin(th);
+            s_rear[3 * w + 2] = th;
+        }
+        CK(cudaMemcpyAsync(a.robot_pose, s_pose, sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(a.robot_vel, s_vel, sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(a.robot_ctrl, s_ctrl, sizeof(double) * W * 2, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(a.robot_rear, s_rear, sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemsetAsync(a.robot_world_collision, 0, sizeof(int) * W, h->stream));
+    }
+    int rc = pms_hsfm_step_async(h, dt, n_steps);
+    if (rc) return rc;
+    unsigned char *d = h->tick_dev;
+    if (h->precision == PMS_FP32) unpack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, (double *)(d + o_pose), (double *)(d + o_vel), a);
+    else unpack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, (double *)(d + o_pose), (double *)(d + o_vel), a);
+    tick_gather_kernel<<<nblk(n > nm ? n : nm), 256, 0, h->stream>>>(n, W, h->words, a, (double2 *)(d + o_vals), (int *)(d + o_idx), (uint32_t *)(d + o_coll),
+                                                                      (uint32_t *)(d + o_det), (int *)(d + o_nf), (int *)(d + o_ev));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->tick_host, d, total, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const unsigned char *q = h->tick_host;
+    if (poses) std::memcpy(poses, q + o_pose, n * 24);
+    if (vels) std::memcpy(vels, q + o_vel, n * 24);
+    if (det_vals) std::memcpy(det_vals, q + o_vals, n * 16);
+    if (wp_index) std::memcpy(wp_index, q + o_idx, n * 4);
+    if (coll_mask) std::memcpy(coll_mask, q + o_coll, nm * 4);
+    if (det_mask) std::memcpy(det_mask, q + o_det, nm * 4);
+    if (n_events) std::memcpy(n_events, q + o_ev, 4);
+    if (first_nonfinite_step) {
+        std::memcpy(first_nonfinite_step, q + o_nf, (size_t)W * 4);
+        for (int w = 0; w < W; ++w) if (first_nonfinite_step[w] == 0x7fffffff) first_nonfinite_step[w] = 0;
+    }
+    return PMS_OK;
+}
 
 int pms_sense(pms_sim *h)
 {

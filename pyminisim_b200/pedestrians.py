@@ -249,8 +249,11 @@ class _TrackerLink:
             idx = np.array([st.current_indices[i] for i in range(self.n)], dtype=np.int32)[None]
             sim.set_waypoints_fixed(table[None], start_index=idx, reach_distance=self.tracker.reach_distance, loop=self.tracker.loop)
 
-    def after_step(self, sim):
+    def after_step(self, sim, tick=None):
+        """``tick`` (BatchedSimulation.step_tick): event count and waypoint indices arrived with the state already."""
         if self.random:
+            if tick is not None and int(tick["n_events"][0]) == 0:
+                return
             events = sim.pop_waypoint_events()
             if len(events) == 0:
                 return
@@ -266,7 +269,7 @@ class _TrackerLink:
             self.tracker.reset_to_state(RandomWaypointTrackerState(cur, nxt))
             sim.append_waypoints(np.array(appended_ids, dtype=np.int32), np.array(appended_pts))
         else:
-            _, idx = sim.get_waypoints()
+            idx = tick["wp_index"] if tick is not None else sim.get_waypoints()[1]
             self.tracker._set_indices(idx[0])
 
 
@@ -300,33 +303,63 @@ class HeadedSocialForceModelPolicy(AbstractPedestriansModel):
         self._link = _TrackerLink(self._tracker, self._n)
         self._link.upload(self._sim)
         self._state = HSFMState({i: (poses[i].copy(), vels[i].copy()) for i in range(self._n)}, self._tracker.state)
+        self._collision_radius = None     # Simulation sets it to its robot model's radius (collision list of the fused step)
+        self._fused = None
+        self._det_cfg = None              # (max_dist, fov, return code) of the detector the fused step evaluates, if any
 
     @property
     def state(self) -> HSFMState:
         return self._state
+
+    def configure_fused_detector(self, max_dist: float, fov: float, code: int):
+        """Simulation hands over the configuration of its PedestrianDetector: the step kernel's epilogue then evaluates the
+        reading for the robot pose of every step, and the sensor picks it up from the state object (``_fused_sense``)."""
+        self._det_cfg = (float(max_dist), float(fov), int(code))
+        self._sim.set_detector(self._det_cfg[0], self._det_cfg[1], self._det_cfg[2], enabled=True)
+
+    def fused_collisions(self, robot_pose: np.ndarray, radius: float):
+        """Robot-pedestrian collision list (core/_simulation.py:141-143) of the step just taken, if the kernel's fused
+        epilogue evaluated it for exactly this robot pose and radius; else None (the caller runs its own pass)."""
+        f = self._fused
+        if f is None or f[1] != radius or not np.array_equal(f[0], robot_pose):
+            return None
+        return list(f[2])
 
     def step(self, dt: float, robot_pose: Optional[np.ndarray], robot_velocity: Optional[np.ndarray]):
         if robot_pose is None:
             assert robot_velocity is None
         elif robot_velocity is None:
             assert robot_pose is None
-        if robot_pose is not None and self._robot_visible:     # _hsfm.py:279-284
-            self._sim.set_robot(capi.ROBOT_EXTERNAL, np.asarray(robot_pose, dtype=np.float64)[None],
-                                velocity=np.asarray(robot_velocity, dtype=np.float64)[None], radius=self._robot_radius)
-        else:
-            self._sim.set_robot(capi.ROBOT_NONE)
         if self._noise_std is not None:                        # :288-289, same global RNG draw
             self._sim.set_accel_noise(np.random.normal(0, self._noise_std, (self._n, 2))[None])
-        self._sim.step(dt, 1)
-        _, _, nonfinite = self._sim.get_stats()
-        if nonfinite[0]:   # the reference's numba inverse raises on non-finite headings
+        # one call, one synchronisation: robot upload, step, state + indices + collision list + flags back.  The robot is
+        # handed over even when the pedestrians do not see it (_hsfm.py:279-284: visible = False keeps it out of the
+        # forces) so that the fused epilogue can evaluate the collision list Simulation asks for next.
+        radius = self._collision_radius if self._collision_radius is not None else self._robot_radius
+        if robot_pose is not None:
+            rp = np.asarray(robot_pose, dtype=np.float64)
+            tick = self._sim.step_tick(dt, 1, rp[None], np.asarray(robot_velocity, dtype=np.float64)[None], radius,
+                                       self._robot_visible)
+        else:
+            tick = self._sim.step_tick(dt, 1, None)
+        if tick["nonfinite"][0]:   # the reference's numba inverse raises on non-finite headings
             raise np.linalg.LinAlgError("Array must not contain infs or NaNs")
-        self._link.after_step(self._sim)
-        poses, vels = self._sim.get_state()
-        self._state = HSFMState({i: (poses[0, i].copy(), vels[0, i].copy()) for i in range(self._n)}, self._tracker.state)
+        self._link.after_step(self._sim, tick)
+        poses, vels = tick["poses"][0].copy(), tick["vels"][0].copy()
+        self._state = HSFMState({i: (poses[i], vels[i]) for i in range(self._n)}, self._tracker.state)
+        if robot_pose is not None:
+            words = tick["coll_mask"][0]
+            self._fused = (rp.copy(), radius, [i for i in range(self._n) if (int(words[i >> 5]) >> (i & 31)) & 1])
+            if self._det_cfg is not None:
+                dw = tick["det_mask"][0]
+                hits = [i for i in range(self._n) if (int(dw[i >> 5]) >> (i & 31)) & 1]
+                self._state._fused_sense = (self._fused[0], self._det_cfg, hits, tick["det_vals"][0].copy())
+        else:
+            self._fused = None
 
     def reset_to_state(self, state: HSFMState):
         self._state = state
+        self._fused = None
         self._tracker.reset_to_state(state.waypoints)
         poses, vels = state.poses, state.velocities
         self._sim.set_state(np.stack([poses[i] for i in range(self._n)])[None], np.stack([vels[i] for i in range(self._n)])[None])

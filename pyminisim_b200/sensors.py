@@ -69,18 +69,28 @@ class PedestrianDetector(AbstractSensor):
     def sensor_config(self) -> AbstractSensorConfig:
         return self._config
 
+    def _fused_config(self):
+        """(max_dist, fov, device return code) for a pedestrians model that evaluates the reading inside its step."""
+        code = capi.DET_POLAR if self._noise is not None else self._config._CODES[self._config.return_type]
+        return self._config.max_dist, self._config.fov, code
+
     def get_reading(self, world_state: WorldState, world_map: AbstractWorldMap) -> AbstractSensorReading:
         if world_state.pedestrians is None or world_state.robot is None:
             return PedestrianDetectorReading({})
         robot_pose = world_state.robot.pose
         # with noise the device returns polar readings; noise and the frame conversion follow on the host
         code = capi.DET_POLAR if self._noise is not None else self._config._CODES[self._config.return_type]
-        ids, _, det, vals = self._ctx.run(world_state.pedestrians.poses, robot_pose, 0.35,
-                                          (self._config.max_dist, self._config.fov, code))
+        # the fused step may have evaluated this very reading already (same robot pose, same configuration)
+        fs = getattr(world_state.pedestrians, "_fused_sense", None)
+        if fs is not None and fs[1] == (float(self._config.max_dist), float(self._config.fov), int(code)) \
+                and np.array_equal(fs[0], robot_pose):
+            hits = [(k, fs[3][k]) for k in fs[2]]
+        else:
+            ids, _, det, vals = self._ctx.run(world_state.pedestrians.poses, robot_pose, 0.35,
+                                              (self._config.max_dist, self._config.fov, code))
+            hits = [(k, v) for k, hit, v in zip(ids, det, vals) if hit]
         readings = {}
-        for k, hit, v in zip(ids, det, vals):
-            if not hit:
-                continue
+        for k, v in hits:
             if self._noise is None:
                 readings[k] = (float(v[0]), float(v[1]))
                 continue

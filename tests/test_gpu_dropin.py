@@ -203,3 +203,42 @@ def test_replay_policy_through_simulation(golden):
             assert st.world.robot_to_pedestrians_collisions == [i for i in range(5) if (int(g[f"{tag}_coll_mask"][k][0]) >> i) & 1]
             seen += len(ref_ids)
         assert seen > 30
+
+
+@pytest.mark.parametrize("visible", [True, False])
+def test_fused_tick_equals_separate_sense_pass(visible):
+    """Simulation.step takes the collision list and the detector reading from the fused epilogue of the HSFM step
+    (pms_step_tick: one call, one synchronisation per tick).  They must equal what a stand-alone sense pass over the
+    returned state gives -- the path the reference's own step order describes (core/_simulation.py:138-160)."""
+    from pyminisim_b200.core import Simulation, _GpuSenseContext
+    from pyminisim_b200.pedestrians import FixedWaypointTracker, HeadedSocialForceModelPolicy
+    from pyminisim_b200.robot import UnicycleRobotModel
+    from pyminisim_b200.sensors import PedestrianDetector, PedestrianDetectorConfig
+    from pyminisim_b200.world_map import EmptyWorld
+    from pyminisim_b200 import _capi as capi
+    n = 12
+    ang = np.linspace(0.0, 2.0 * np.pi, n, endpoint=False)
+    start = np.stack([1.7 * np.cos(ang), 1.7 * np.sin(ang)], axis=1)
+    poses = np.concatenate([start, (ang + np.pi)[:, None]], axis=1)
+    goals = np.stack([-start, start], axis=1)                       # through the robot at the origin and back
+    tracker = FixedWaypointTracker(initial_positions=start.copy(), waypoints=goals.copy(), loop=True)
+    model = HeadedSocialForceModelPolicy(waypoint_tracker=tracker, n_pedestrians=n, initial_poses=poses.copy(),
+                                         robot_visible=visible)
+    robot = UnicycleRobotModel(np.array([0.9, 0., 0.]), np.array([0.05, 0.3]))   # in the path of pedestrian 0
+    cfg = PedestrianDetectorConfig(5.0, np.deg2rad(120.), "relative")
+    sim = Simulation(world_map=EmptyWorld(), robot_model=robot, pedestrians_model=model, sensors=[PedestrianDetector(cfg)],
+                     sim_dt=0.01, rt_factor=None)
+    check = _GpuSenseContext()
+    n_det = n_coll = 0
+    for _ in range(250):
+        st = sim.step()
+        assert model._fused is not None and hasattr(st.world.pedestrians, "_fused_sense")
+        ids, coll, det, vals = check.run(st.world.pedestrians.poses, st.world.robot.pose, robot.radius,
+                                         (5.0, np.deg2rad(120.), capi.DET_RELATIVE))
+        assert st.world.robot_to_pedestrians_collisions == [k for k, c in zip(ids, coll) if c]
+        reading = st.sensors["pedestrian_detector"].reading.pedestrians
+        assert list(reading.keys()) == [k for k, d in zip(ids, det) if d]
+        for k in reading:
+            assert reading[k] == (float(vals[k][0]), float(vals[k][1]))
+        n_det += len(reading); n_coll += len(st.world.robot_to_pedestrians_collisions)
+    assert n_det > 0 and (n_coll > 0 or visible)
