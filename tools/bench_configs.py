@@ -3,6 +3,7 @@
   C3  1 world x 65536 pedestrians HSFM (large-crowd kernel), 20 steps
   C4  4096 worlds x 64 pedestrians HSFM + detector, 1000 steps (bench.py's workload)
   C5  2048 worlds x 64 agents ORCA, 200 steps
+  sensors: stand-alone collision/detector, lidar and omni passes over 4096 worlds (wall clock, results on the host)
 CUDA events on the handle's stream, best of 3 after one warm-up.  Prints one JSON line per case."""
 import json
 import os
@@ -75,8 +76,46 @@ def time_orca(name, W, N, steps, reps=3):
     return out
 
 
+def time_sensors(W=4096, N=64, n_circles=8, n_beams=100, reps=3):
+    """Stand-alone sensor passes over W worlds, through the C ABI with host result buffers (their calls synchronise):
+    collision list + pedestrian detector (`pms_sense`), lidar against a per-world CirclesWorld (`pms_lidar_scan`: 100 beams,
+    8 m, 1 cm samples like sensors/_lidar.py), omni obstacle detector (`pms_omni_scan`).  Wall clock around the call."""
+    import time
+    sc = make_bench_crowd(W, N)
+    sim = BatchedSimulation(W, N, precision="fp32")
+    sim.set_state(sc.poses, sc.vels); sim.set_speeds(sc.vmag); sim.set_waypoints_fixed(sc.table, loop=True)
+    sim.set_robot(capi.ROBOT_UNICYCLE, sc.robot_pose, control=sc.robot_control)
+    sim.set_detector(5.0, np.deg2rad(120.0), capi.DET_POLAR)
+    rng = np.random.default_rng(3)
+    circles = np.concatenate([sc.robot_pose[:, None, :2] + rng.uniform(-6.0, 6.0, (W, n_circles, 2)),
+                              rng.uniform(0.3, 1.0, (W, n_circles, 1))], axis=2)
+    circles[:, :, 0] += 2.0 * np.sign(circles[:, :, 0] - sc.robot_pose[:, None, 0] + 1e-9)   # keep the robot outside
+    sim.set_map(capi.MAP_CIRCLES, circles)
+    mask = np.empty((W, sim.words), dtype=np.uint32); vals = np.empty((W, N, 2))
+
+    def best_of(f):
+        f(); torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(reps):
+            t0 = time.perf_counter(); f(); best = min(best, time.perf_counter() - t0)
+        return best
+
+    t = best_of(lambda: (sim.sense(), sim.get_detector(mask, vals), sim.get_collisions()))
+    print(json.dumps(dict(case="sense: collision list + detector, results on the host", worlds=W, peds=N, ms=1e3 * t,
+                          ped_checks_per_s=W * N / t)), flush=True)
+    hits = sim.lidar_scan(n_beams, 8.0, 0.01)[0]
+    t = best_of(lambda: sim.lidar_scan(n_beams, 8.0, 0.01))
+    print(json.dumps(dict(case="lidar: 100 beams x 800 samples, CirclesWorld of 8 per world, results on the host", worlds=W,
+                          beams=n_beams, circles=n_circles, ms=1e3 * t, beams_per_s=W * n_beams / t,
+                          reference_point_tests_per_s=W * n_beams * 800 * n_circles / t,
+                          beams_with_hit=float((hits >= 0).mean()))), flush=True)
+    t = best_of(lambda: sim.omni_scan())
+    print(json.dumps(dict(case="omni obstacle detector", worlds=W, circles=n_circles, ms=1e3 * t, worlds_per_s=W / t)), flush=True)
+    sim.close()
+
+
 def main():
-    which = set(sys.argv[1:]) or {"c2", "c3", "c4", "c5"}
+    which = set(sys.argv[1:]) or {"c2", "c3", "c4", "c5", "sensors"}
     if "c2" in which:
         time_hsfm("C2 warp kernel", 1024, 32, 1000)
         time_hsfm("C2 warp kernel, plain fp32 state", 1024, 32, 1000, precision="fp32_plain")
@@ -101,6 +140,8 @@ def main():
         time_hsfm("C3 large crowd, MIXED", 1, 65536, 20, large=True, precision="mixed")
     if "c5" in which:
         time_orca("C5 ORCA", 2048, 64, 200)
+    if "sensors" in which:
+        time_sensors()
 
 
 if __name__ == "__main__":
