@@ -176,6 +176,12 @@ int pms_step_tick(pms_sim *h, double dt, int n_steps, const double *robot_pose /
                   double *poses /*(W,N,3)*/, double *vels /*(W,N,3)*/, int32_t *wp_index /*(W,N)*/,
                   uint32_t *coll_mask /*(W,ceil(N/32))*/, uint32_t *det_mask /*(W,ceil(N/32))*/, double *det_vals /*(W,N,2)*/,
                   int32_t *first_nonfinite_step /*(W)*/, int32_t *n_events /*(1)*/);
+/* The sensor pass of one tick for pedestrians that were moved elsewhere (ORCA handle, ReplayPedestriansPolicy, a custom
+ * model): Simulation._get_world_state's collision list (core/_simulation.py:138-160) and PedestrianDetector.get_reading
+ * (sensors/_pedestrian_detector.py:78-134) for the given poses and robot pose, in one call and one host synchronisation.
+ * Equivalent to pms_set_ped_state + pms_set_robot(EXTERNAL) + pms_sense + pms_get_collisions + pms_get_detector. */
+int pms_sense_tick(pms_sim *h, const double *poses /*(W,N,3)*/, const double *robot_pose /*(W,3)*/, double robot_radius,
+                   uint32_t *coll_mask /*(W,ceil(N/32)) or NULL*/, uint32_t *det_mask /*or NULL*/, double *det_vals /*(W,N,2) or NULL*/);
 /* CUDA stream of the handle as an opaque pointer (cudaStream_t), for event timing by the caller */
 void *pms_stream(pms_sim *h);
 /* evaluate collision list + detector on the current state without stepping (Simulation.__init__

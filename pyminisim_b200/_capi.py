@@ -80,6 +80,7 @@ PROTOTYPES = {
     "pms_hsfm_step": (C.c_int, [_h, C.c_double, C.c_int]),
     "pms_hsfm_step_async": (C.c_int, [_h, C.c_double, C.c_int]),
     "pms_sync": (C.c_int, [_h]),
+    "pms_sense_tick": (C.c_int, [_h, _dp, _dp, C.c_double, _up, _up, _dp]),
     "pms_step_tick": (C.c_int, [_h, C.c_double, C.c_int, _dp, _dp, C.c_double, C.c_int, _dp, _dp, _ip, _up, _up, _dp, _ip, _ip]),
     "pms_stream": (C.c_void_p, [_h]),
     "pms_sense": (C.c_int, [_h]),

@@ -231,6 +231,16 @@ class BatchedSimulation:
     def sense(self):
         check(self._lib.pms_sense(self._h))
 
+    def sense_tick(self, poses, robot_pose, robot_radius: float = 0.35):
+        """Collision list + detector reading for the given poses and robot pose in one call (``pms_sense_tick``)."""
+        self.robot_model = capi.ROBOT_EXTERNAL
+        coll = np.empty((self.W, self.words), dtype=np.uint32)
+        det = np.empty((self.W, self.words), dtype=np.uint32)
+        vals = np.empty((self.W, self.N, 2))
+        check(self._lib.pms_sense_tick(self._h, dptr(f64(poses, (self.W, self.N, 3))), dptr(f64(robot_pose, (self.W, 3))),
+                                       float(robot_radius), uptr(coll), uptr(det), dptr(vals)))
+        return coll, det, vals
+
     def get_detector(self, out_mask=None, out_vals=None) -> Tuple[np.ndarray, np.ndarray]:
         mask = np.empty((self.W, self.words), dtype=np.uint32) if out_mask is None else out_mask
         vals = np.empty((self.W, self.N, 2)) if out_vals is None else out_vals

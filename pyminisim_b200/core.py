@@ -233,18 +233,15 @@ class _GpuSenseContext:
             self._sim = BatchedSimulation(1, n, precision="fp64")
             self._n = n
         poses = np.stack([ped_poses[k] for k in ids])[None]
-        self._sim.set_state(poses)
-        self._sim.set_robot(capi.ROBOT_EXTERNAL, np.asarray(robot_pose, dtype=np.float64)[None], velocity=np.zeros((1, 3)),
-                            radius=robot_radius)
         if detector is None:
             self._sim.set_detector(enabled=False)
         else:
             self._sim.set_detector(detector[0], detector[1], detector[2], enabled=True)
-        self._sim.sense()
-        coll = self._sim.get_collisions()[0]
-        mask, vals = self._sim.get_detector()
-        bits = lambda m: np.array([(int(m[i >> 5]) >> (i & 31)) & 1 for i in range(n)], dtype=bool)  # noqa: E731
-        return ids, bits(coll), bits(mask[0]), vals[0]
+        # one call, one synchronisation: poses + robot in, collision list + reading out
+        coll, mask, vals = self._sim.sense_tick(poses, np.asarray(robot_pose, dtype=np.float64)[None], robot_radius)
+        k = np.arange(n)
+        bits = lambda m: ((m[k >> 5] >> (k & 31).astype(np.uint32)) & 1).astype(bool)  # noqa: E731
+        return ids, bits(coll[0]), bits(mask[0]), vals[0]
 
 
 # ---- the orchestrator (core/_simulation.py:16-185) -----------------------------------------------------------
@@ -265,13 +262,15 @@ class Simulation:
         self._backup_pedestrians_model = None
         self._robot_to_world_collision = False
         self._sense = _GpuSenseContext()
+        self._detector_cfg = None           # (max_dist, fov, device return code) of the first pedestrian detector
+        for sensor in sensors:
+            if getattr(sensor, "sensor_name", None) == "pedestrian_detector" and hasattr(sensor, "_fused_config"):
+                self._detector_cfg = sensor._fused_config()
+                break
         if robot_model is not None and hasattr(pedestrians_model, "_collision_radius"):
             pedestrians_model._collision_radius = robot_model.radius      # the fused step evaluates the collision list with it
-            for sensor in sensors:          # ... and the reading of the (first) pedestrian detector
-                if getattr(sensor, "sensor_name", None) == "pedestrian_detector" and hasattr(sensor, "_fused_config") \
-                        and hasattr(pedestrians_model, "configure_fused_detector"):
-                    pedestrians_model.configure_fused_detector(*sensor._fused_config())
-                    break
+            if self._detector_cfg is not None and hasattr(pedestrians_model, "configure_fused_detector"):
+                pedestrians_model.configure_fused_detector(*self._detector_cfg)   # ... and the detector's reading
         self._current_state = self._make_state({})       # the constructor runs the sensor pass once (:37)
 
     @property
@@ -356,8 +355,18 @@ class Simulation:
             fused = getattr(self._pedestrians_model, "fused_collisions", None)
             collisions = fused(robot_state.pose, self._robot_model.radius) if fused is not None else None
             if collisions is None:
-                ids, coll, _, _ = self._sense.run(ped_state.poses, robot_state.pose, self._robot_model.radius)
+                # one pass serves the collision list and the (first) pedestrian detector: its reading travels with the
+                # state object like the fused step's does
+                cfg = self._detector_cfg
+                ids, coll, det, vals = self._sense.run(ped_state.poses, robot_state.pose, self._robot_model.radius, cfg)
                 collisions = [k for k, c in zip(ids, coll) if c]
+                if cfg is not None and ids == list(range(len(ids))):
+                    try:
+                        ped_state._fused_sense = (np.array(robot_state.pose, dtype=np.float64),
+                                                  (float(cfg[0]), float(cfg[1]), int(cfg[2])),
+                                                  [k for k, d in zip(ids, det) if d], vals)
+                    except AttributeError:        # a foreign state class with __slots__: the detector runs its own pass
+                        pass
         return WorldState(world_map=self._world_map.current_state, robot=robot_state, pedestrians=ped_state,
                           robot_to_pedestrians_collisions=collisions,
                           robot_to_world_collision=self._robot_to_world_collision)

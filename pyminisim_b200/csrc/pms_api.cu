@@ -833,6 +833,62 @@ void pms_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+// The sensor pass of one tick for a pedestrians model that runs elsewhere (ORCA handle, replayed trajectories, a custom
+// model): poses + robot in, collision list + detector reading out, one call and one host synchronisation.
+int pms_sense_tick(pms_sim *h, const double *poses, const double *robot_pose, double robot_radius, uint32_t *coll_mask,
+                   uint32_t *det_mask, double *det_vals)
+{
+    HCHECK(h);
+    if (!poses || !robot_pose) return fail(PMS_ERR_INVALID, "poses / robot_pose is NULL");
+    if (!(robot_radius > 0.0)) return fail(PMS_ERR_INVALID, "robot radius must be > 0");
+    if (h->det_noise.enabled) return fail(PMS_ERR_STATE, "pms_sense_tick returns the exact reading: switch the detector noise off");
+    HsfmArgs &a = h->a;
+    const int W = h->W;
+    const size_t n = (size_t)W * h->N, nm = (size_t)W * h->words;
+    // host block: poses (3n doubles) | robot pose (3W) -- then reused for the results: det_vals (2n doubles) | coll | det
+    const size_t in_bytes = (n * 3 + (size_t)W * 3) * 8, o_coll = n * 16, o_det = o_coll + nm * 4, out_bytes = o_det + nm * 4;
+    const size_t need = in_bytes > out_bytes ? in_bytes : out_bytes;
+    if (need > h->tick_bytes) {
+        if (h->tick_dev) cudaFree(h->tick_dev);
+        if (h->tick_host) cudaFreeHost(h->tick_host);
+        h->tick_dev = h->tick_host = nullptr; h->tick_bytes = 0;
+        CK(cudaMalloc((void **)&h->tick_dev, need));
+        CK(cudaMallocHost((void **)&h->tick_host, need));
+        h->tick_bytes = need;
+    }
+    if (ensure_stage(h, n * 6)) return PMS_ERR_CUDA;
+    double *st = reinterpret_cast<double *>(h->tick_host);
+    std::memcpy(st, poses, n * 24);
+    std::memcpy(st + n * 3, robot_pose, (size_t)W * 24);
+    a.robot_model = PMS_ROBOT_EXTERNAL; a.robot_radius = robot_radius;
+    CK(cudaMemcpyAsync(h->stage, st, n * 24, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->stage + n * 3, 0, n * 24, h->stream));
+    CK(cudaMemcpyAsync(a.robot_pose, st + n * 3, (size_t)W * 24, cudaMemcpyHostToDevice, h->stream));
+    if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, a, h->compensated);
+    else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, a, false);
+    h->large.sorted_valid = false;
+    int rc = clear_sensor_outputs(h);
+    if (rc) return rc;
+    fill_consts(a);
+    const dim3 grid(W, (h->Np + 255) / 256);
+    const int threads = h->Np < 256 ? h->Np : 256;
+    if (h->precision == PMS_FP32) sense_kernel<float><<<grid, threads, 0, h->stream>>>(a);
+    else sense_kernel<double><<<grid, threads, 0, h->stream>>>(a);
+    h->info.kernel_launches++;
+    unsigned char *d = h->tick_dev;
+    CK(cudaMemcpyAsync(d, a.det_vals, n * 16, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + o_coll, a.coll_mask, nm * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + o_det, a.det_mask, nm * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->tick_host, d, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const unsigned char *q = h->tick_host;
+    if (det_vals) std::memcpy(det_vals, q, n * 16);
+    if (coll_mask) std::memcpy(coll_mask, q + o_coll, nm * 4);
+    if (det_mask) std::memcpy(det_mask, q + o_det, nm * 4);
+    return PMS_OK;
+}
+
 int pms_detector_config(pms_sim *h, int enabled, double max_dist, double fov, int return_type)
 {
     HCHECK(h);

@@ -58,6 +58,8 @@ class FixedWaypointTracker(AbstractWaypointTracker):
         self._all_waypoints = {k: np.concatenate((np.asarray(initial_positions[k], dtype=float)[None, :],
                                                    np.asarray(waypoints[k], dtype=float)), axis=0) for k in ids}
         self._current_indices = {k: 1 for k in self._all_waypoints}
+        rows = {v.shape[0] for v in self._all_waypoints.values()}
+        self._stacked = (list(self._all_waypoints.keys()), np.stack(list(self._all_waypoints.values()))) if len(rows) == 1 else None
 
     # -- device hand-off helpers --
     @property
@@ -87,6 +89,18 @@ class FixedWaypointTracker(AbstractWaypointTracker):
     def update_waypoints(self, agents_poses):
         assert agents_poses.keys() == self._all_waypoints.keys()
         out = {}
+        if self._stacked is not None:      # same rule, one distance evaluation for all pedestrians
+            keys, tabs = self._stacked
+            idx = np.fromiter((self._current_indices[k] for k in keys), dtype=np.int64, count=len(keys))
+            pos = np.stack([agents_poses[k][:2] for k in keys])
+            reached = np.sqrt(((tabs[np.arange(len(keys)), idx] - pos) ** 2).sum(axis=1)) <= self._reach_distance
+            for j in np.nonzero(reached)[0]:
+                k, nxt, steady = keys[j], int(idx[j]) + 1, False
+                if nxt >= tabs.shape[1]:
+                    nxt, steady = (0, False) if self._loop else (tabs.shape[1] - 1, True)
+                self._current_indices[k] = nxt
+                out[k] = (self._all_waypoints[k][nxt], steady)
+            return out
         for k, pose in agents_poses.items():
             tab, idx = self._all_waypoints[k], self._current_indices[k]
             if np.linalg.norm(tab[idx] - pose[:2]) <= self._reach_distance:

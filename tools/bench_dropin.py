@@ -56,6 +56,33 @@ def run(n, steps, warm):
                 us_per_step=1e6 * dt / steps, ped_updates_per_s=n * steps / dt, finite=bool(np.isfinite(p).all()))
 
 
+def run_orca(n, steps, warm):
+    """ORCAPedestriansModel in the same loop (this package only: the reference's ORCA needs the absent rvo2).  The sensor
+    pass is the stand-alone one (pms_sense_tick), as for every model without a fused epilogue."""
+    from pyminisim_b200.pedestrians import FixedWaypointTracker, ORCAPedestriansModel
+    side = max(7.0, 2.0 * np.sqrt(n))
+    g = int(np.ceil(np.sqrt(n)))
+    xs = (np.arange(g) + 0.5) / g * side - side / 2
+    pos = np.array([[x, y] for x in xs for y in xs])[:n]
+    tracker = FixedWaypointTracker(initial_positions=pos.copy(), waypoints=np.stack([-pos, pos], axis=1), loop=True)
+    model = ORCAPedestriansModel(dt=0.01, waypoint_tracker=tracker, n_pedestrians=n,
+                                 initial_poses=np.concatenate([pos, np.zeros((n, 1))], axis=1))
+    sim = Simulation(world_map=EmptyWorld(),
+                     robot_model=UnicycleRobotModel(initial_pose=np.array([-side / 2 - 1.0, 0.0, 0.0]),
+                                                    initial_control=np.array([0.5, 0.0])),
+                     pedestrians_model=model, sensors=[PedestrianDetector()], sim_dt=0.01, rt_factor=None)
+    for _ in range(warm):
+        sim.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step()
+    dt = time.perf_counter() - t0
+    return dict(impl="pyminisim_b200", model="orca", n_pedestrians=n, steps=steps, us_per_step=1e6 * dt / steps)
+
+
 if __name__ == "__main__":
     for n in (2, 8, 32, 64):
         print(json.dumps(run(n, 300 if REFERENCE and n >= 32 else 1000, 50)), flush=True)
+    if not REFERENCE:
+        for n in (8, 64):
+            print(json.dumps(run_orca(n, 1000, 50)), flush=True)
