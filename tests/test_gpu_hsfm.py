@@ -522,3 +522,42 @@ def test_ragged_sizes_at_the_kernel_boundaries(n, kernel):
             assert (c.get_waypoints()[1] == o.wp_index).all()
             det, col, nf = c.get_stats()
             assert (det == o.det_count).all() and (col == o.coll_count).all() and (nf == 0).all()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_step_tick_and_sense_tick_equal_the_separate_calls(precision):
+    """pms_step_tick (robot in, step, every output out: one synchronisation) against pms_set_robot + pms_hsfm_step + the
+    individual getters, three worlds, several ticks, with and without a robot; pms_sense_tick against pms_set_ped_state +
+    pms_set_robot + pms_sense + getters.  Same kernels underneath: same bits."""
+    from pyminisim_b200 import _capi as capi
+    sc = make_bench_crowd(3, 40)
+    rng = np.random.default_rng(4)
+    a = make_cuda(sc, precision, det=(6.0, 200.0, 2), robot=0)
+    b = make_cuda(sc, precision, det=(6.0, 200.0, 2), robot=0)
+    for t in range(12):
+        pose = np.concatenate([sc.poses[:, 5 + t, :2] + rng.uniform(0.2, 0.6, (3, 2)), rng.uniform(-3, 3, (3, 1))], axis=1)
+        vel = rng.uniform(-1, 1, (3, 3))
+        if t % 5 == 4:
+            tick = a.step_tick(0.01, 1, None)
+            b.set_robot(capi.ROBOT_NONE); b.step(0.01, 1)
+        else:
+            tick = a.step_tick(0.01, 1, pose, vel, 0.4, visible=(t % 3 != 0))
+            b.set_robot(capi.ROBOT_EXTERNAL, pose, velocity=vel, radius=0.4, visible=(t % 3 != 0)); b.step(0.01, 1)
+        p, v = b.get_state()
+        assert np.array_equal(tick["poses"], p) and np.array_equal(tick["vels"], v)
+        assert np.array_equal(tick["wp_index"], b.get_waypoints()[1])
+        assert np.array_equal(tick["nonfinite"], b.get_stats()[2])
+        if t % 5 != 4:
+            m, vals = b.get_detector()
+            assert np.array_equal(tick["det_mask"], m) and np.array_equal(tick["coll_mask"], b.get_collisions())
+            hit = np.array([[(int(m[w, i >> 5]) >> (i & 31)) & 1 for i in range(40)] for w in range(3)], dtype=bool)
+            assert np.array_equal(tick["det_vals"][hit], vals[hit])
+    assert tick["det_mask"].any()
+    # sense_tick on foreign poses
+    poses = sc.poses + rng.uniform(-0.3, 0.3, sc.poses.shape)
+    coll, det, vals = a.sense_tick(poses, pose, 0.5)
+    b.set_state(poses); b.set_robot(capi.ROBOT_EXTERNAL, pose, velocity=np.zeros((3, 3)), radius=0.5); b.sense()
+    m, v2 = b.get_detector()
+    assert np.array_equal(det, m) and np.array_equal(coll, b.get_collisions()) and det.any()
+    hit = np.array([[(int(m[w, i >> 5]) >> (i & 31)) & 1 for i in range(40)] for w in range(3)], dtype=bool)
+    assert np.array_equal(vals[hit], v2[hit])
