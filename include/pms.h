@@ -231,6 +231,7 @@ int pms_get_launch_info(pms_sim *h, pms_launch_info *out);
  *   n_chunks       : 1 forces the static grid; for the large-crowd kernel -2 keeps the caller's pedestrian order (no
  *                    sorted working copy) and -1 also visits every j-tile (no exact pruning).
  *   cluster_size   : (1,2,4,8) multicast width of the large-crowd kernel; a negative value also forces that kernel
+ *                    (-100: forces the large-crowd path with its default kernel choice)
  *                    for small N. */
 int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, int cluster_size);
 

@@ -929,7 +929,11 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     int rc;
     // j_split < 0 selects the directed-pair kernel for small worlds too (tests, comparisons)
     const bool warp_ok = h->precision != PMS_FP64 && h->Np <= 32 * WARP_MAX_TILES && h->tune_S >= 0;
-    const bool large_path = h->force_large || (!warp_ok && h->Np + 32 > 1024);
+    // FP32 worlds of 512 pedestrians and more take the pruned large-crowd path (sorted copy + chunk kernel) although they would
+    // fit the directed-pair kernel: measured 64 x 992: 77 -> 18 us per step, 256 x 512: 50 -> 30 (bench crowd, 100-step calls);
+    // below 512 the all-pairs kernel wins when the world is dense (nothing to prune).  j_split < 0 keeps the directed-pair kernel.
+    const bool mid_fp32 = h->precision == PMS_FP32 && h->N >= 512 && !h->no_prune && !h->no_reorder && h->tune_S >= 0 && h->tune_cluster == 0;
+    const bool large_path = h->force_large || (!warp_ok && (h->Np + 32 > 1024 || mid_fp32));
     // the large-crowd kernel sets mask bits with atomicOr when it works on the sorted copy: start from zero
     if ((h->a.robot_model == ROBOT_NONE || large_path) && (rc = clear_sensor_outputs(h))) return rc;
     if (large_path) rc = launch_large(h);
@@ -1216,7 +1220,7 @@ int pms_set_tuning(pms_sim *h, int j_split, int worlds_per_block, int n_chunks, 
     h->no_prune = n_chunks == -1;                     // -1: the large-crowd kernel visits every j-tile
     h->no_reorder = n_chunks < 0;                     // -1, -2: no sorted working copy
     h->force_large = cluster_size < 0;               // negative: force the large-crowd kernel (tests)
-    h->tune_cluster = cluster_size < 0 ? -cluster_size : cluster_size;
+    h->tune_cluster = cluster_size == -100 ? 0 : (cluster_size < 0 ? -cluster_size : cluster_size);   // -100: forced, default kernel choice
     h->large.sorted_valid = false;
     return PMS_OK;
 }
