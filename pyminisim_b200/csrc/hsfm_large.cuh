@@ -678,8 +678,15 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) { as
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(dst_smem)), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-template <int KS, int CPB>       // warps per chunk, chunks per CTA
-__global__ void __launch_bounds__(32 * KS * CPB, PMS_CHUNK_MINB * 2 / (KS * CPB)) hsfm_chunk_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
+#ifndef PMS_CHUNK_MINB_HI
+#define PMS_CHUNK_MINB_HI 14          // the same for crowds of several waves: 28 warps per SM at 72 registers
+#endif
+// MINB: register budget as resident 64-thread CTAs per SM.  One wave of warps (C3: 2048 warps, 13.8 per SM) runs fastest with
+// 128 registers (23.1 vs 24.1 us per step at 80); several waves (1024 worlds x 512 pedestrians: 16 384 warps) gain 9-14 % from
+// more resident warps (us per step at 128 / 80 / 72 / 64 registers: 1024 x 512: 93.4 / 84.9 / 83.0 / 81.5; 4096 x 512: 355 / 316 /
+// 306 / 294; 256 x 992: 47.3 / 45.1 / 43.6 / 44.7).  launch_large_t chooses by the chunk count.
+template <int KS, int CPB, int MINB = PMS_CHUNK_MINB>       // warps per chunk, chunks per CTA, register budget
+__global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chunk_kernel(const __grid_constant__ HsfmArgs a, const __grid_constant__ LargeArgs la)
 {
     using PT = float;
     constexpr int NW = KS * CPB;
@@ -1015,7 +1022,8 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             if constexpr (sizeof(ST) == 4) {
                 if (use_chunk) {
                     const unsigned gc = (unsigned)(a.W * tiles_c);
-                    if (ks == 1) hsfm_chunk_kernel<1, CHUNK_TI / LARGE_CHUNK><<<gc, CHUNK_TI, 0, stream>>>(a, la);
+                    if (ks == 1 && n_chunks_all > 16 * 148) hsfm_chunk_kernel<1, CHUNK_TI / LARGE_CHUNK, PMS_CHUNK_MINB_HI><<<gc, CHUNK_TI, 0, stream>>>(a, la);
+                    else if (ks == 1) hsfm_chunk_kernel<1, CHUNK_TI / LARGE_CHUNK><<<gc, CHUNK_TI, 0, stream>>>(a, la);
                     else if (ks == 2) hsfm_chunk_kernel<2, 1><<<gc, 64, 0, stream>>>(a, la);
                     else hsfm_chunk_kernel<4, 1><<<gc, 128, 0, stream>>>(a, la);
                     if ((e = cudaGetLastError()) != cudaSuccess) return -2;

@@ -387,21 +387,21 @@ def test_large_crowd_tile_pruning_is_bit_identical(precision):
             assert np.array_equal(a, b, equal_nan=True)
 
 
-def test_large_crowd_chunk_kernel_equals_cluster_kernel():
+@pytest.mark.parametrize("worlds,n", [(2, 5000), (90, 900)])      # 90 x 900: more than one wave of chunks, 72-register variant
+def test_large_crowd_chunk_kernel_equals_cluster_kernel(worlds, n):
     """FP32 with exact pruning runs the barrier-free chunk kernel by default; asking for a cluster size selects the
     tile-streaming cluster kernel.  With one warp per chunk (j_split 1): same pairs, same per-pair arithmetic, same order of
     summation, hence the same bits -- with the sorted working copy (shuffled crowd, robot inside it, re-sort inside the call)
     and in the caller's order."""
-    n = 5000
-    sc = make_crowd(2, n, side=2.0 * np.sqrt(n), local_goals=1.2)
+    sc = make_crowd(worlds, n, side=2.0 * np.sqrt(n), local_goals=1.2)
     perm = np.random.default_rng(11).permutation(n)
     sc.poses, sc.table, sc.vmag, sc.vels = sc.poses[:, perm], sc.table[:, perm], sc.vmag[:, perm], sc.vels[:, perm]
     sc.robot_pose[:, :2] = [3.0, -2.0]
-    for n_chunks, steps in ((0, 133), (-2, 9)):
+    for n_chunks, steps in ((0, 133 if worlds == 2 else 20), (-2, 9)):
         outs = []
         for cluster in (0, 4):
             c = make_cuda(sc, "fp32", det=(6.0, 200.0, 0))
-            c.set_tuning(1, 0, n_chunks, cluster)
+            c.set_tuning(1, 0, n_chunks, -cluster if cluster else -100)   # large-crowd path also below 993 pedestrians
             c.step(0.01, 3); c.step(0.01, steps)
             assert c.launch_info()["kernel"] == 1
             outs.append(c.get_state() + c.get_detector() + (c.get_collisions(),) + c.get_stats() + (c.get_waypoints()[1],))
