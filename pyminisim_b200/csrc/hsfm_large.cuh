@@ -237,6 +237,37 @@ __global__ void large_permute_kernel(size_t n, const int *perm, const void *pos_
 }
 
 constexpr int LARGE_CHUNK = 32;       // pedestrians per chunk box (one warp's rows / one warp-level skip unit)
+constexpr int LARGE_HALF = 16;        // pedestrians per half-chunk box (the chunk kernel's skip unit on the partner side)
+
+// Boxes of one chunk from the lanes' positions (empty lanes pass +-inf): the chunk box goes to out[ci], the boxes of its two
+// halves (lanes 0-15 / 16-31) to out[n_chunks + 2 ci], out[n_chunks + 2 ci + 1] -- the half boxes live behind the chunk boxes in
+// the same allocation.  A non-finite coordinate makes its boxes infinite (never skipped).  Returns the chunk box.
+__device__ __forceinline__ float4 chunk_and_half_boxes(float xmin, float xmax, float ymin, float ymax, bool bad, int lane, size_t ci,
+                                                       size_t n_chunks, float4 *out, float4 *out2)
+{
+    const float inf = CUDART_INF_F;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    const unsigned badm = __ballot_sync(0xffffffffu, bad);
+    float4 hb = make_float4(xmin, xmax, ymin, ymax);
+    if (badm & (lane < 16 ? 0x0000ffffu : 0xffff0000u)) hb = make_float4(-inf, inf, -inf, inf);
+    xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, 16)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, 16));
+    ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, 16)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, 16));
+    float4 cb = make_float4(xmin, xmax, ymin, ymax);
+    if (badm) cb = make_float4(-inf, inf, -inf, inf);
+    if ((lane & 15) == 0) {
+        out[n_chunks + 2 * ci + (lane >> 4)] = hb;
+        if (out2) out2[n_chunks + 2 * ci + (lane >> 4)] = hb;
+    }
+    if (lane == 0) {
+        out[ci] = cb;
+        if (out2) out2[ci] = cb;
+    }
+    return cb;
+}
 
 template <typename PT>
 __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ HsfmArgs a, int Npad, int tiles_j, const PT *view,
@@ -261,17 +292,8 @@ __global__ void __launch_bounds__(128) large_box_kernel(const __grid_constant__ 
             bad = !(fabsf(x) <= 3.0e38f) || !(fabsf(y) <= 3.0e38f);
             xmin = xmax = x; ymin = ymax = y;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-            ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-        }
-        float4 cb = make_float4(xmin, xmax, ymin, ymax);
-        if (__any_sync(0xffffffffu, bad)) cb = make_float4(-inf, inf, -inf, inf);
-        if (lane == 0) {
-            chunk_boxes[((size_t)w * Npad + (size_t)jt * LARGE_TJ + k) / LARGE_CHUNK] = cb;
-            if (chunk_boxes2) chunk_boxes2[((size_t)w * Npad + (size_t)jt * LARGE_TJ + k) / LARGE_CHUNK] = cb;
-        }
+        const size_t ci = ((size_t)w * Npad + (size_t)jt * LARGE_TJ + k) / LARGE_CHUNK;     // this warp's chunk
+        const float4 cb = chunk_and_half_boxes(xmin, xmax, ymin, ymax, bad, lane, ci, (size_t)a.W * Npad / LARGE_CHUNK, chunk_boxes, chunk_boxes2);
         tb.x = fminf(tb.x, cb.x); tb.y = fmaxf(tb.y, cb.y); tb.z = fminf(tb.z, cb.z); tb.w = fmaxf(tb.w, cb.w);
     }
     __shared__ float4 part[4];
@@ -649,7 +671,7 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
 // The step also produces what the next step's pruning needs -- the box of the warp's 32 new positions (chunk box) and, merged
 // with atomic min / max, the box of their j-tile -- so that one launch per step remains.  min / max are exact in any order:
 // the boxes equal large_box_kernel's bit for bit.
-constexpr int CHUNK_LIST = 96;        // near chunks gathered per pass of the list
+constexpr int CHUNK_LIST = 128;       // near half-chunks gathered per pass of the list
 constexpr int CHUNK_TI = 64;          // KS = 1: threads per CTA, two independent warps (small CTAs spread evenly over 148 SMs)
 // KS > 1 (j-split): KS warps share one chunk of 32 pedestrians -- a 65 536-pedestrian world is only 2048 warps (3.5 per
 // scheduler), too few to hide the MUFU / L2 latency of the pair chains.  Warp q takes the near chunks at list positions
@@ -740,16 +762,20 @@ __global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chu
         const float gx = fmaxf(0.f, fmaxf(o.x - wbox.y, wbox.x - o.y)), gy = fmaxf(0.f, fmaxf(o.z - wbox.w, wbox.z - o.w));
         return !(gx * gx + gy * gy > la.cut2);
     };
-    auto load_chunk = [&](int jc) {                                   // pedestrian `lane` of chunk jc, coalesced
-        const int j = jc * LARGE_CHUNK + lane;
+    // list entries are HALF-chunks (16 pedestrians); a stage holds two of them: entry k in slots 0-15, entry k + 1 in 16-31
+    auto load_pair = [&](int k, int K) {
+        const int e = k + (lane >> 4);
+        if (e >= K) return make_float4(1e18f, 1e18f, 0.f, 0.f);        // odd tail: a partner far away contributes exactly 0
+        const int j = list[e] * LARGE_HALF + (lane & 15);
         return make_float4(__ldcg(vsrc + j), __ldcg(vsrc + vs + j), __ldcg(vsrc + 2 * vs + j), __ldcg(vsrc + 3 * vs + j));
     };
-    auto group = [&](const float *xs, int jl, int self) {             // 4 partners; self = index of j == i in the chunk, or -1
+    const int my_half = i0 / LARGE_HALF + (lane >> 4);                 // the half-chunk this lane's own pedestrian sits in
+    auto group = [&](const float *xs, int jl, int self) {             // 4 partners; self = slot of j == i in the stage, or < 0
         const float4 X = *reinterpret_cast<const float4 *>(xs + jl);
         const float4 Y = *reinterpret_cast<const float4 *>(xs + LARGE_CHUNK + jl);
         float2 dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
         float2 dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
-        if (self >= 0) {
+        if (self != -1) {                                             // uniform: -1 on every lane, or the own slot / -1000
             const int k = self - jl;
             dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
             dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
@@ -770,14 +796,18 @@ __global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chu
     auto flush = [&](int K) {                                         // evaluate the K chunks of the list
         __syncwarp();
         if (K == 0) return;
-        float4 nxt = load_chunk(list[0]);
-        for (int k = 0; k < K; ++k) {
-            float *buf = stage[wid][k & 1];
+        float4 nxt = load_pair(0, K);
+        for (int k = 0; k < K; k += 2) {
+            float *buf = stage[wid][(k >> 1) & 1];
             buf[lane] = nxt.x; buf[LARGE_CHUNK + lane] = nxt.y; buf[2 * LARGE_CHUNK + lane] = nxt.z; buf[3 * LARGE_CHUNK + lane] = nxt.w;
-            __syncwarp();                   // chunk k staged; everybody is done with chunk k - 1 (the other buffer may be refilled)
-            const int jc = list[k];
-            if (k + 1 < K) nxt = load_chunk(list[k + 1]);
-            const int self = jc * LARGE_CHUNK == i0 ? i - i0 : -1;
+            __syncwarp();                   // pair k staged; everybody is done with pair k - 2 (the other buffer may be refilled)
+            const int ea = list[k], eb = k + 1 < K ? list[k + 1] : -1;
+            if (k + 2 < K) nxt = load_pair(k + 2, K);
+            // own pedestrian among the staged partners?  (uniform test on the warp's two halves, then the lane's own slot)
+            const int h0 = i0 / LARGE_HALF;
+            int self = -1;
+            if (ea == h0 || ea == h0 + 1 || eb == h0 || eb == h0 + 1)
+                self = ea == my_half ? (lane & 15) : (eb == my_half ? LARGE_HALF + (lane & 15) : -1000);
 #pragma unroll
             for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(buf, jl, self);
         }
@@ -786,7 +816,8 @@ __global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chu
 
     // The scan is a chain of dependent L2 reads (tile boxes, then the chunk boxes of the near tiles), so the reads are issued in
     // batches: 128 tile boxes at a time, then the chunk boxes of up to 8 near tiles (two tiles per warp-wide load, 16 lanes each).
-    static_assert(CPT == 16, "two tiles per warp-wide chunk-box load");
+    static_assert(CPT * 2 == 32, "one tile = 32 half-chunks per warp-wide box load");
+    const float4 *half_box = la.chunk_boxes + (size_t)a.W * la.Npad / LARGE_CHUNK + (size_t)w * la.Npad / LARGE_HALF;
     int K = 0, P = 0;                                                  // entries in this warp's list; near chunks seen so far
     for (int base0 = 0; base0 < la.tiles_j; base0 += 128) {
         float4 tb[4];
@@ -806,18 +837,17 @@ __global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chu
             cnt += __popc(tm[u]);
         }
         __syncwarp();
-        for (int r = 0; r < cnt; r += 8) {                             // near tiles of rank r .. r + 7: 16 lanes per tile
+        for (int r = 0; r < cnt; r += 4) {                             // near tiles of rank r .. r + 3: lane = half-chunk of the tile
             float4 cbx[4];
             int cid[4];
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const int rk = r + 2 * v + (lane >> 4);
-                cid[v] = rk < cnt ? (base0 + (int)near_tiles[wid][rk]) * CPT + (lane & 15) : -1;
-                cbx[v] = cid[v] >= 0 ? __ldg(chunk_box + cid[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cid[v] = r + v < cnt ? (base0 + (int)near_tiles[wid][r + v]) * (2 * CPT) + lane : -1;
+                cbx[v] = cid[v] >= 0 ? __ldg(half_box + cid[v]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                if (r + 2 * v >= cnt) break;                           // uniform
+                if (r + v >= cnt) break;                               // uniform
                 bool keep = cid[v] >= 0 && near(cbx[v]);
                 unsigned mc = __ballot_sync(0xffffffffu, keep);
                 if constexpr (KS > 1) {                                // position P + rank in the common list decides the owner warp
@@ -867,15 +897,10 @@ __global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chu
             bad = !(fabsf(nx) <= 3.0e38f) || !(fabsf(ny) <= 3.0e38f);
             xmin = xmax = nx; ymin = ymax = ny;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-            ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-        }
-        float4 cb = make_float4(xmin, xmax, ymin, ymax);
-        if (__any_sync(0xffffffffu, bad)) cb = make_float4(-inf, inf, -inf, inf);
-        if (i0 < N && lane < 4) {
-            if (lane == 0) la.chunk_boxes_dst[((size_t)w * la.Npad + i0) / LARGE_CHUNK] = cb;
+        if (i0 >= N) return;                                      // an all-padding chunk keeps the empty boxes of the box kernel
+        const float4 cb = chunk_and_half_boxes(xmin, xmax, ymin, ymax, bad, lane, ((size_t)w * la.Npad + i0) / LARGE_CHUNK,
+                                               (size_t)a.W * la.Npad / LARGE_CHUNK, la.chunk_boxes_dst, nullptr);
+        if (lane < 4) {
             float *tb = reinterpret_cast<float *>(la.boxes_dst + (size_t)w * la.tiles_j + i0 / LARGE_TJ);
             // lane q merges component q of the tile box: x-min, x-max, y-min, y-max
             if (lane == 0) atomic_min_float(tb, cb.x);
@@ -919,7 +944,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
         for (int q = 0; q < 3; ++q)
             if ((e = cudaMalloc((void **)&s.boxes[q], sizeof(float4) * (size_t)a.W * (Npad / LARGE_TJ))) != cudaSuccess) return -2;
         for (int q = 0; q < 2; ++q)
-            if ((e = cudaMalloc((void **)&s.chunk_boxes[q], sizeof(float4) * (size_t)a.W * (Npad / LARGE_CHUNK))) != cudaSuccess) return -2;
+            if ((e = cudaMalloc((void **)&s.chunk_boxes[q], sizeof(float4) * 3 * (size_t)a.W * (Npad / LARGE_CHUNK))) != cudaSuccess) return -2;   // + half boxes
         s.Npad = Npad;
     }
     int end_bit = 48;
