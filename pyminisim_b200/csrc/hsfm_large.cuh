@@ -770,21 +770,43 @@ __global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chu
         return make_float4(__ldcg(vsrc + j), __ldcg(vsrc + vs + j), __ldcg(vsrc + 2 * vs + j), __ldcg(vsrc + 3 * vs + j));
     };
     const int my_half = i0 / LARGE_HALF + (lane >> 4);                 // the half-chunk this lane's own pedestrian sits in
-    auto group = [&](const float *xs, int jl, int self) {             // 4 partners; self = slot of j == i in the stage, or < 0
+    // (x_i - x_j) of the 4 partners at slots jl .. jl + 3; self = slot of j == i in the stage, -1000 if it is not staged, or -1 on
+    // every lane (uniform) when neither of the warp's own halves is staged
+    auto deltas = [&](const float *xs, int jl, int self, float2 &dxa, float2 &dxb, float2 &dya, float2 &dyb) {
         const float4 X = *reinterpret_cast<const float4 *>(xs + jl);
         const float4 Y = *reinterpret_cast<const float4 *>(xs + LARGE_CHUNK + jl);
-        float2 dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
-        float2 dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
-        if (self != -1) {                                             // uniform: -1 on every lane, or the own slot / -1000
+        dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)); dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
+        dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)); dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
+        if (self != -1) {
             const int k = self - jl;
             dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
             dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
         }
-        float2 inva, invb, sa, sb;
-        pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
-        pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
-        const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
-        if (__any_sync(0xffffffffu, smax > 0.0f)) {
+    };
+    // far-field term of a stage in straight-line code (no vote, no branch between the 8 groups: their MUFU chains overlap);
+    // the largest overlap r_ij - d of the stage tells whether the rare body-contact pass has anything to do
+    auto stage_far = [&](const float *xs, int self) {
+        float smax = -CUDART_INF_F;
+#pragma unroll
+        for (int jl = 0; jl < LARGE_CHUNK; jl += 4) {
+            float2 dxa, dxb, dya, dyb, inva, invb, sa, sb;
+            deltas(xs, jl, self, dxa, dxb, dya, dyb);
+            pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
+            pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
+            smax = fmaxf(smax, fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y)));
+        }
+        return smax;
+    };
+    // body-contact terms of a stage: 1 / d and the overlap are re-derived with the same operations (bit for bit), groups and
+    // partners in the same order as the far pass
+    auto stage_contact = [&](const float *xs, int self) {
+        for (int jl = 0; jl < LARGE_CHUNK; jl += 4) {
+            float2 dxa, dxb, dya, dyb, inva, invb, sa, sb;
+            deltas(xs, jl, self, dxa, dxb, dya, dyb);
+            pair_geom2(kpp, dxa, dya, inva, sa);
+            pair_geom2(kpp, dxb, dyb, invb, sb);
+            const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
+            if (!__any_sync(0xffffffffu, smax > 0.0f)) continue;
             const float4 VX = *reinterpret_cast<const float4 *>(xs + 2 * LARGE_CHUNK + jl);
             const float4 VY = *reinterpret_cast<const float4 *>(xs + 3 * LARGE_CHUNK + jl);
             pair_contact(kpp, dxa.x, dya.x, VX.x - mvx, VY.x - mvy, inva.x, sa.x, fx, fy);
@@ -808,8 +830,8 @@ __global__ void __launch_bounds__(32 * KS * CPB, MINB * 2 / (KS * CPB)) hsfm_chu
             int self = -1;
             if (ea == h0 || ea == h0 + 1 || eb == h0 || eb == h0 + 1)
                 self = ea == my_half ? (lane & 15) : (eb == my_half ? LARGE_HALF + (lane & 15) : -1000);
-#pragma unroll
-            for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(buf, jl, self);
+            const float smax = stage_far(buf, self);
+            if (__any_sync(0xffffffffu, smax > 0.0f)) stage_contact(buf, self);
         }
         __syncwarp();
     };

@@ -400,8 +400,8 @@ __device__ __forceinline__ void world_barrier(int wl, int count)
 
 // fp32 far-field pair force for TWO pairs at once on the Blackwell packed-FP32 pipe (FFMA2 / FMUL2 /
 // FADD2): 8 packed FMA-pipe instructions + 4 MUFU for 2 pairs.  Same arithmetic as pair_far.
-__device__ __forceinline__ void pair_far2(const PairK<float> &k, float2 dx, float2 dy, float2 &inv, float2 &sg,
-                                          float2 &fx, float2 &fy)
+// 1 / d and the overlap r_ij - d of two pairs (the part of pair_far2 a contact pass re-derives, bit for bit)
+__device__ __forceinline__ void pair_geom2(const PairK<float> &k, float2 dx, float2 dy, float2 &inv, float2 &sg)
 {
     const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
     inv.x = fast_rsqrt(d2.x); inv.y = fast_rsqrt(d2.y);
@@ -411,6 +411,11 @@ __device__ __forceinline__ void pair_far2(const PairK<float> &k, float2 dx, floa
     d = __ffma2_rn(err, __fmul2_rn(inv, make_float2(0.5f, 0.5f)), d);
 #endif
     sg = __fadd2_rn(make_float2(k.rij, k.rij), make_float2(-d.x, -d.y));
+}
+__device__ __forceinline__ void pair_far2(const PairK<float> &k, float2 dx, float2 dy, float2 &inv, float2 &sg,
+                                          float2 &fx, float2 &fy)
+{
+    pair_geom2(k, dx, dy, inv, sg);
     const float2 arg = __fmul2_rn(sg, make_float2(k.cexp, k.cexp));
     float2 e; e.x = fast_ex2(arg.x); e.y = fast_ex2(arg.y);
     const float2 a = __fmul2_rn(e, __fmul2_rn(inv, make_float2(k.A, k.A)));
