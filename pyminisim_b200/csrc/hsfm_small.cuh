@@ -588,7 +588,11 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
                     pair_contact(kpp, dxb.y, dyb.y, VX.w - mvx, VY.w - mvy, invb.y, sb.y, fx, fy);
                 };
                 auto groups = [&](int jb, const int je, auto masked) {
-                    // 8 pairs per trip (four independent packed chains), then a 4-pair tail
+                    // Far-field pass over the whole range without a vote or branch between the trips (8 pairs per trip: four
+                    // independent packed chains; consecutive trips overlap), then one vote on the largest overlap r_ij - d:
+                    // the rare body-contact pass re-derives 1 / d and the overlap with the same operations, bit for bit.
+                    const int j0 = jb;
+                    float smax = -CUDART_INF_F;
                     for (; jb + 8 <= je; jb += 8) {
                         float2 dxa, dya, dxb, dyb, dxc, dyc, dxd, dyd, inva, invb, invc, invd, sa, sb, sc, sd;
                         load_group(jb, masked, dxa, dya, dxb, dyb);
@@ -597,20 +601,24 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
                         pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
                         pair_far2(kpp, dxc, dyc, invc, sc, fxa, fya);
                         pair_far2(kpp, dxd, dyd, invd, sd, fxb, fyb);
-                        const float smax = fmaxf(fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y)),
-                                                 fmaxf(fmaxf(sc.x, sc.y), fmaxf(sd.x, sd.y)));
-                        if (__any_sync(0xffffffffu, smax > 0.0f)) {      // somebody in the warp touches somebody
-                            contact_group(jb, dxa, dya, dxb, dyb, inva, invb, sa, sb);
-                            contact_group(jb + 4, dxc, dyc, dxd, dyd, invc, invd, sc, sd);
-                        }
+                        smax = fmaxf(smax, fmaxf(fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y)),
+                                                 fmaxf(fmaxf(sc.x, sc.y), fmaxf(sd.x, sd.y))));
                     }
                     for (; jb < je; jb += 4) {
                         float2 dxa, dya, dxb, dyb, inva, invb, sa, sb;
                         load_group(jb, masked, dxa, dya, dxb, dyb);
                         pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
                         pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
-                        const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
-                        if (__any_sync(0xffffffffu, smax > 0.0f)) contact_group(jb, dxa, dya, dxb, dyb, inva, invb, sa, sb);
+                        smax = fmaxf(smax, fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y)));
+                    }
+                    if (!__any_sync(0xffffffffu, smax > 0.0f)) return;   // nobody in the warp touches anybody of this range
+                    for (jb = j0; jb < je; jb += 4) {
+                        float2 dxa, dya, dxb, dyb, inva, invb, sa, sb;
+                        load_group(jb, masked, dxa, dya, dxb, dyb);
+                        pair_geom2(kpp, dxa, dya, inva, sa);
+                        pair_geom2(kpp, dxb, dyb, invb, sb);
+                        const float s4 = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
+                        if (__any_sync(0xffffffffu, s4 > 0.0f)) contact_group(jb, dxa, dya, dxb, dyb, inva, invb, sa, sb);
                     }
                 };
                 const int m_lo = max(j_lo, min(j_hi, i0)), m_hi = min(j_hi, max(j_lo, i0 + 32));
