@@ -586,11 +586,11 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
             const float *xlo = reinterpret_cast<const float *>(xs + 4 * LARGE_TJ), *ylo = xlo + LARGE_TJ;
             const float2 m2x = make_float2(mx, mx), m2y = make_float2(my, my);
             const float2 l2x = make_float2(mlx, mlx), l2y = make_float2(mly, mly);
-            auto group = [&](int jl, auto masked) {
+            auto deltas = [&](int jl, auto masked, float2 &dxa, float2 &dxb, float2 &dya, float2 &dyb) {
                 const float4 X = *reinterpret_cast<const float4 *>(xs + jl);
                 const float4 Y = *reinterpret_cast<const float4 *>(ys + jl);
-                float2 dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)), dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
-                float2 dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)), dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
+                dxa = __fadd2_rn(m2x, make_float2(-X.x, -X.y)); dxb = __fadd2_rn(m2x, make_float2(-X.z, -X.w));
+                dya = __fadd2_rn(m2y, make_float2(-Y.x, -Y.y)); dyb = __fadd2_rn(m2y, make_float2(-Y.z, -Y.w));
                 if constexpr (SPLIT) {
                     const float4 XL = *reinterpret_cast<const float4 *>(xlo + jl);
                     const float4 YL = *reinterpret_cast<const float4 *>(ylo + jl);
@@ -604,11 +604,27 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
                     dxa.x = k == 0 ? 1e18f : dxa.x; dxa.y = k == 1 ? 1e18f : dxa.y;
                     dxb.x = k == 2 ? 1e18f : dxb.x; dxb.y = k == 3 ? 1e18f : dxb.y;
                 }
-                float2 inva, invb, sa, sb;
-                pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
-                pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
-                const float smax = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
-                if (__any_sync(0xffffffffu, smax > 0.0f)) {
+            };
+            // one chunk of 32 partners: far-field pass in straight-line code (no vote between the 8 groups), one vote on the
+            // largest overlap, then the rare contact pass with 1 / d and the overlap re-derived bit for bit (like hsfm_chunk_kernel)
+            auto chunk = [&](int jc, auto masked) {
+                float smax = -CUDART_INF_F;
+#pragma unroll
+                for (int jl = jc; jl < jc + LARGE_CHUNK; jl += 4) {
+                    float2 dxa, dxb, dya, dyb, inva, invb, sa, sb;
+                    deltas(jl, masked, dxa, dxb, dya, dyb);
+                    pair_far2(kpp, dxa, dya, inva, sa, fxa, fya);
+                    pair_far2(kpp, dxb, dyb, invb, sb, fxb, fyb);
+                    smax = fmaxf(smax, fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y)));
+                }
+                if (!__any_sync(0xffffffffu, smax > 0.0f)) return;
+                for (int jl = jc; jl < jc + LARGE_CHUNK; jl += 4) {
+                    float2 dxa, dxb, dya, dyb, inva, invb, sa, sb;
+                    deltas(jl, masked, dxa, dxb, dya, dyb);
+                    pair_geom2(kpp, dxa, dya, inva, sa);
+                    pair_geom2(kpp, dxb, dyb, invb, sb);
+                    const float s4 = fmaxf(fmaxf(sa.x, sa.y), fmaxf(sb.x, sb.y));
+                    if (!__any_sync(0xffffffffu, s4 > 0.0f)) continue;
                     const float4 VX = *reinterpret_cast<const float4 *>(vxs + jl);
                     const float4 VY = *reinterpret_cast<const float4 *>(vys + jl);
                     pair_contact(kpp, dxa.x, dya.x, VX.x - mvx, VY.x - mvy, inva.x, sa.x, fx, fy);
@@ -632,13 +648,8 @@ __global__ void __launch_bounds__(LARGE_TI, 4) hsfm_large_kernel(const __grid_co
             while (near) {
                 const int jc = (__ffs(near) - 1) * LARGE_CHUNK;
                 near &= near - 1;
-                if (jbase + jc == i0) {
-#pragma unroll
-                    for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(jc + jl, std::true_type{});
-                } else {
-#pragma unroll
-                    for (int jl = 0; jl < LARGE_CHUNK; jl += 4) group(jc + jl, std::false_type{});
-                }
+                if (jbase + jc == i0) chunk(jc, std::true_type{});
+                else chunk(jc, std::false_type{});
             }
         } else {
             const int jn = min(LARGE_TJ, N - jbase);
