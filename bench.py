@@ -4,7 +4,9 @@
 A bench "step" = one pass of the hot path over one batch of synthetic worlds: `--sim-steps` fused
 simulation steps (robot -> HSFM forces + Euler -> waypoints -> collision list + detector) of
 `--worlds` worlds x `--peds` pedestrians per GPU.  Default workload = BASELINE config C4
-(4096 worlds x 64 pedestrians + detector, dt = 0.01, 1000 simulation steps) per GPU.
+(4096 worlds x 64 pedestrians + detector, dt = 0.01, 1000 simulation steps) IN TOTAL, sharded over the GPUs of the run
+(`--scaling strong`, BASELINE.json: "4096 worlds x 64 pedestrians ... sharded across 1/2/4/8 B200"); with more than one GPU
+the line also carries `weak_scaling` = the same metric with 4096 worlds PER GPU (`--scaling weak` makes that the headline).
 
   value : whole-job pedestrian-updates/s with state resident in HBM (CUDA events around the kernel,
           L2 flushed between timed steps, max over ranks).
@@ -42,11 +44,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU (weak scaling)")
+    ap.add_argument("--worlds", type=int, default=4096, help="worlds in total (strong scaling) / per GPU (weak scaling)")
     ap.add_argument("--peds", type=int, default=64)
     ap.add_argument("--sim-steps", type=int, default=1000, help="fused simulation steps per bench step")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_plain", "mixed", "fp64"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--j-split", type=int, default=0)
     ap.add_argument("--wpc", type=int, default=0)
     ap.add_argument("--chunks", type=int, default=0)
@@ -56,9 +58,22 @@ def parse_args():
     return ap.parse_args()
 
 
-KERNEL_NAMES = {0: "hsfm_small_kernel", 1: "hsfm_large_kernel", 3: "hsfm_warp_kernel"}
-# DRAM bytes per launch of the default workload from the committed ncu capture (None: not captured for that kernel)
-TRAFFIC_BYTES_PER_LAUNCH = {(3, "fp32"): 24788992, (3, "fp32_plain"): 17762304}
+KERNEL_NAMES = {0: "hsfm_small_kernel", 1: "hsfm_large_kernel", 3: "hsfm_warp_kernel", 4: "hsfm_duo_kernel"}
+# Figures that only a profiler can measure -- DRAM bytes of the launch, executed FMA-pipe / XU-pipe / issue-slot utilisation --
+# are read from profiles/ncu_captures.json: records written by `tools/ncu_summary.py --json` from an `ncu --set full` capture of
+# exactly this command (kernel, worlds per GPU, pedestrians, fused steps, precision).  No matching record -> null.
+def ncu_capture(kernel_name, worlds, peds, sim_steps, precision):
+    path = os.path.join(ROOT, "profiles", "ncu_captures.json")
+    try:
+        with open(path) as f:
+            recs = json.load(f)
+    except Exception:
+        return None
+    for r in reversed(recs):            # the latest capture of this launch wins
+        if (r.get("kernel") == kernel_name and r.get("worlds") == worlds and r.get("peds") == peds
+                and r.get("sim_steps") == sim_steps and r.get("precision") == precision):
+            return r
+    return None
 
 
 def flops_per_update(n_peds: int) -> float:
@@ -137,14 +152,14 @@ def cpu_reference_run(args, n_steps_timed: int, warmup: int):
             "ms_per_step": 1e3 * t_total / n_steps_timed}
 
 
-def config_dict(args, world_size):
+def config_dict(args, world_size, precision=None):
     per = "per GPU" if args.scaling == "weak" else f"in total over {world_size} GPU(s)"
     return {"workload": f"C4: {args.worlds} worlds x {args.peds} pedestrians {per}, HSFM + unicycle robot + "
                         f"pedestrian detector (5 m, 120 deg) + collision list, jittered grid with local looped goals "
                         f"(scenarios.make_bench_crowd), {args.sim_steps} fused sim-steps "
                         f"of dt=0.01 per bench step",
             "worlds": args.worlds, "worlds_are": "per GPU" if args.scaling == "weak" else "total", "peds_per_world": args.peds, "sim_steps_per_step": args.sim_steps,
-            "dt": 0.01, "precision": args.precision, "parallelism": f"worlds sharded over {world_size} GPU(s), "
+            "dt": 0.01, "precision": precision or args.precision, "parallelism": f"worlds sharded over {world_size} GPU(s), "
             "no collective on the step path", "l2": "256 MiB L2 flush between timed steps (state is 16 MB and "
             "lives on-chip during a step)"}
 
@@ -157,7 +172,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, args.gpus),
+            "config": config_dict(args, args.gpus, precision="fp64 (C port of the reference's algorithm)"),
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -274,6 +289,39 @@ def main():
     updates_total = float(total_worlds) * N * K * args.steps
     value = updates_total / (ms_max * 1e-3)
 
+    # ---- the other scaling mode as an extra key (N > 1): strong = BASELINE's split of 4096 worlds, weak = 4096 worlds per GPU ----
+    other = None
+    if world_size > 1:
+        o_first, o_worlds = (rank * args.worlds, args.worlds) if args.scaling == "strong" else shard_worlds(args.worlds, rank, world_size)
+        sc_o = make_bench_crowd(o_worlds, args.peds, first_world=o_first)
+        sim_o = BatchedSimulation(o_worlds, N, precision=args.precision, device=local_rank)
+        sim_o.set_state(sc_o.poses, sc_o.vels); sim_o.set_speeds(sc_o.vmag); sim_o.set_waypoints_fixed(sc_o.table, loop=True)
+        sim_o.set_robot(capi.ROBOT_UNICYCLE, sc_o.robot_pose, control=sc_o.robot_control)
+        sim_o.set_detector(5.0, np.deg2rad(120.0), capi.DET_POLAR)
+        sim_o.snapshot_save()
+        st_o = torch.cuda.ExternalStream(sim_o.stream, device=torch.device("cuda", local_rank))
+
+        def timed_other(n):
+            total = 0.0
+            for _ in range(n):
+                sim_o.snapshot_restore()
+                with torch.cuda.stream(st_o):
+                    flush.zero_()
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(st_o); sim_o.step_async(0.01, K); e1.record(st_o)
+                e1.synchronize()
+                total += e0.elapsed_time(e1)
+            return total
+        timed_other(3)
+        barrier()
+        ms_o = max_over_ranks(timed_other(args.steps), device="cuda")
+        barrier()
+        tot_o = args.worlds * world_size if args.scaling == "strong" else args.worlds
+        other = {"scaling": "weak" if args.scaling == "strong" else "strong", "value": float(tot_o) * N * K * args.steps / (ms_o * 1e-3),
+                 "unit": UNIT, "worlds_total": tot_o, "worlds_per_gpu": o_worlds, "ms_per_step": ms_o / args.steps,
+                 "kernel": KERNEL_NAMES.get(sim_o.launch_info()["kernel"])}
+        sim_o.close()
+
     # ---- end-to-end through the public API with host buffers ----
     # Every step: H2D of the step's initial state from pinned memory, the fused launch, D2H of the final state, the
     # detector reading, the collision list and the episode statistics.  Two handles alternate in asynchronous-I/O mode
@@ -386,6 +434,7 @@ def main():
     if rank == 0:
         info = sim.launch_info()
         kernel_ms = ms / max(launches, 1)
+        cap = ncu_capture(KERNEL_NAMES.get(info["kernel"], str(info["kernel"])), W, N, K, args.precision)
         achieved_tflops = float(W) * N * K * flops_per_update(N) / (kernel_ms * 1e-3) / 1e12
         peak = fp32_peak if fp32_peak and fp32_peak > 0 else 148 * 128 * 2 * 1.965e9 / 1e12
         cpu = None
@@ -404,7 +453,12 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak,
-                         "traffic": TRAFFIC_BYTES_PER_LAUNCH.get((info["kernel"], args.precision)) if (W, N, K) == (4096, 64, 1000) else None,
+                         "traffic": cap["dram_bytes"] if cap else None,
+                         "fma_pipe_pct": cap["fma_pipe_cycles_pct"] if cap else None,
+                         "xu_pipe_pct": cap["xu_pipe_pct"] if cap else None,
+                         "issue_slots_pct": cap["issue_slots_pct"] if cap else None,
+                         "executed_pipe_source": (cap["source"] + " (ncu --set full of this launch; executed, not algorithmic: "
+                                                  "every unordered pair is evaluated once)") if cap else None,
                          "peak_source": "FP32 FMA-chain microbenchmark measured in this run (pms_measure_fp32_tflops); "
                                         "MEASURED_PEAKS.json has no non-tensor FP32 figure",
                          "kernel": KERNEL_NAMES.get(info["kernel"], str(info["kernel"])),
@@ -413,10 +467,11 @@ def main():
                                  "hsfm_warp_kernel evaluates every UNORDERED pair once (f_ij = -f_ji), i.e. executes about "
                                  "half of the algorithmic flops, so frac can exceed what the FMA pipe executes; the binding "
                                  "unit is the XU (MUFU) pipe: one rsqrt + one ex2 per unordered pair (profiles/)",
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                           "of this command (profiles/r1_warp_kernel_comp_ncu.md, fp32_plain: r1_warp_kernel_ncu.md); bytes per launch"},
+                         "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum per launch, " + cap["source"]) if cap else None},
             "cpu_baseline": cpu, "clocks": clocks, "launch": info, "episode_stats": episode,
         }
+        if other is not None:
+            line[other["scaling"] + "_scaling"] = other
         line.update(extra)
         emit(line)
     sim.close()

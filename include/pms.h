@@ -210,6 +210,14 @@ int pms_orca_set_agents(pms_sim *h, const double *positions /*(W,N,2)*/, const d
  * flag is ignored like _orca.py:106-107 does) */
 int pms_orca_set_waypoints_fixed(pms_sim *h, const double *table /*(W,N,n_rows,2)*/, int n_rows,
                                  const int32_t *start_index /*(W,N) or NULL*/, double reach_distance, int loop);
+/* Any other tracker (AbstractWaypointTracker, e.g. RandomWaypointTracker: _orca.py:106-107 accepts them all): the tracker runs
+ * on the host, the caller hands over tracker.state.current_waypoints after every update; the device hand-off is off and
+ * the preferred velocities (_orca.py:118-127) are recomputed from the given waypoints and the current positions. */
+int pms_orca_set_waypoints_current(pms_sim *h, const double *current /*(W,N,2)*/);
+/* enabled = 0: the waypoint setters above leave the agents' preferred velocities untouched -- the semantics of
+ * ORCAPedestriansModel.reset_to_state (_orca.py:114-116), which resets the tracker only: the next doStep still runs on the old
+ * preferred velocities and _update_preferred_velocities (:118-127) follows after it.  Default 1 (constructor semantics, :86). */
+int pms_orca_set_pref_refresh(pms_sim *h, int enabled);
 int pms_orca_step(pms_sim *h, int n_steps);
 int pms_orca_get_agents(pms_sim *h, double *poses /*(W,N,3)*/, double *velocities /*(W,N,3)*/);
 

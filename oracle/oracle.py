@@ -98,6 +98,14 @@ def lib():
         _lib.orc_orca_rollout.restype = C.c_int
         _lib.orc_orca_update_pref.argtypes = [C.POINTER(_OrcaBatch)]
         _lib.orc_orca_update_pref.restype = None
+        _lib.orc_orca_solve_batch.argtypes = [C.c_int, C.c_int, _fp, _fp, _fp, _fp, _ip]
+        _lib.orc_orca_solve_batch.restype = None
+        _lib.orc_orca_halfplane_batch.argtypes = [C.c_int, _fp, _fp, _fp, _fp, C.c_float, C.c_float, C.c_float, _fp]
+        _lib.orc_orca_halfplane_batch.restype = None
+        _lib.orc_orca_solve_batch_f64.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _ip]
+        _lib.orc_orca_solve_batch_f64.restype = None
+        _lib.orc_orca_halfplane_batch_f64.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, _dp]
+        _lib.orc_orca_halfplane_batch_f64.restype = None
     return _lib
 
 
@@ -363,3 +371,30 @@ class OracleOrca:
     def rollout(self, n_steps, n_threads=1):
         lib().orc_orca_rollout(C.byref(self._struct()), int(n_steps), int(n_threads))
         return self
+
+
+def orca_solve_batch(lines, max_speed, pref, fp64=False):
+    """Test hook: the oracle's 2-D program + relaxed fallback for m problems of n half-planes {point, dir} each.  fp32 is the
+    oracle; fp64=True runs the fp64 instantiation of the same code (tests only).
+    Returns (v (m,2), fail (m,) int32: index of the half-plane the 2-D program failed at, n = feasible)."""
+    dt, pt = (np.float64, _dp) if fp64 else (np.float32, _fp)
+    lines = np.ascontiguousarray(lines, dtype=dt)
+    m, n = lines.shape[:2]
+    ms = np.ascontiguousarray(np.broadcast_to(max_speed, (m,)), dtype=dt)
+    pr = np.ascontiguousarray(pref, dtype=dt).reshape(m, 2)
+    v = np.zeros((m, 2), dtype=dt)
+    fail = np.zeros(m, dtype=np.int32)
+    f = lib().orc_orca_solve_batch_f64 if fp64 else lib().orc_orca_solve_batch
+    f(m, n, _ptr(lines, pt), _ptr(ms, pt), _ptr(pr, pt), _ptr(v, pt), _ptr(fail, _ip))
+    return v, fail
+
+
+def orca_halfplane_batch(pa, po, va, vo, radius=0.3, time_horizon=2.0, time_step=0.01, fp64=False):
+    """Test hook: the ORCA half-plane {point, dir} agent a (pa, va) takes on for neighbour o (po, vo), m pairs."""
+    dt, pt = (np.float64, _dp) if fp64 else (np.float32, _fp)
+    arrs = [np.ascontiguousarray(x, dtype=dt).reshape(-1, 2) for x in (pa, po, va, vo)]
+    m = arrs[0].shape[0]
+    out = np.zeros((m, 4), dtype=dt)
+    f = lib().orc_orca_halfplane_batch_f64 if fp64 else lib().orc_orca_halfplane_batch
+    f(m, *[_ptr(x, pt) for x in arrs], float(radius), float(time_horizon), float(time_step), _ptr(out, pt))
+    return out

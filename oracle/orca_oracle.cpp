@@ -35,68 +35,72 @@
 
 namespace {
 
-constexpr float kEps = 1e-5f;
-
-struct V2 {
-    float x, y;
+/* The algorithm is written once over the scalar type F.  F = float IS the oracle (rvo2 computes in single precision); the
+ * F = double instantiation exists only for tests/test_oracle_orca_independent.py, which separates "is the algorithm right"
+ * (fp64 instantiation against brute-force solvers, 1e-9) from "what does single precision cost" (fp32 against fp64). */
+template <typename F> struct V2T {
+    F x, y;
 };
-inline V2 operator+(V2 a, V2 b) { return {a.x + b.x, a.y + b.y}; }
-inline V2 operator-(V2 a, V2 b) { return {a.x - b.x, a.y - b.y}; }
-inline V2 operator-(V2 a) { return {-a.x, -a.y}; }
-inline V2 operator*(float s, V2 a) { return {s * a.x, s * a.y}; }
-inline V2 operator/(V2 a, float s) {
-    const float inv = 1.0f / s; /* the library divides through a reciprocal */
+template <typename F> inline V2T<F> operator+(V2T<F> a, V2T<F> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename F> inline V2T<F> operator-(V2T<F> a, V2T<F> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename F> inline V2T<F> operator-(V2T<F> a) { return {-a.x, -a.y}; }
+template <typename F> inline V2T<F> operator*(F s, V2T<F> a) { return {s * a.x, s * a.y}; }
+template <typename F> inline V2T<F> operator/(V2T<F> a, F s) {
+    const F inv = F(1) / s; /* the library divides through a reciprocal */
     return {a.x * inv, a.y * inv};
 }
-inline float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
-inline float det(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
-inline float norm2(V2 a) { return dot(a, a); }
-inline float norm(V2 a) { return std::sqrt(norm2(a)); }
-inline V2 unit(V2 a) { return a / norm(a); }
+template <typename F> inline F dot(V2T<F> a, V2T<F> b) { return a.x * b.x + a.y * b.y; }
+template <typename F> inline F det(V2T<F> a, V2T<F> b) { return a.x * b.y - a.y * b.x; }
+template <typename F> inline F norm2(V2T<F> a) { return dot(a, a); }
+template <typename F> inline F norm(V2T<F> a) { return std::sqrt(norm2(a)); }
+template <typename F> inline V2T<F> unit(V2T<F> a) { return a / norm(a); }
 
-struct HalfPlane {
-    V2 point, dir;
+template <typename F> struct HalfPlaneT {
+    V2T<F> point, dir;
 };
 
 /* 1-D LP along half-plane `k`, constrained by the speed disc and half-planes 0..k-1. */
-bool lp_line(const HalfPlane *hp, int k, float radius, V2 opt, bool direction_opt, V2 &result)
+template <typename F>
+bool lp_line(const HalfPlaneT<F> *hp, int k, F radius, V2T<F> opt, bool direction_opt, V2T<F> &result)
 {
-    const float dp = dot(hp[k].point, hp[k].dir);
-    const float disc = dp * dp + radius * radius - norm2(hp[k].point);
-    if (disc < 0.0f) return false;
-    const float sq = std::sqrt(disc);
-    float t_lo = -dp - sq, t_hi = -dp + sq;
+    const F kEps = F(1e-5f);
+    const F dp = dot(hp[k].point, hp[k].dir);
+    const F disc = dp * dp + radius * radius - norm2(hp[k].point);
+    if (disc < F(0)) return false;
+    const F sq = std::sqrt(disc);
+    F t_lo = -dp - sq, t_hi = -dp + sq;
     for (int i = 0; i < k; ++i) {
-        const float den = det(hp[k].dir, hp[i].dir);
-        const float num = det(hp[i].dir, hp[k].point - hp[i].point);
+        const F den = det(hp[k].dir, hp[i].dir);
+        const F num = det(hp[i].dir, hp[k].point - hp[i].point);
         if (std::fabs(den) <= kEps) {
-            if (num < 0.0f) return false;
+            if (num < F(0)) return false;
             continue;
         }
-        const float t = num / den;
-        if (den >= 0.0f) t_hi = std::fmin(t_hi, t);
+        const F t = num / den;
+        if (den >= F(0)) t_hi = std::fmin(t_hi, t);
         else t_lo = std::fmax(t_lo, t);
         if (t_lo > t_hi) return false;
     }
     if (direction_opt) {
-        result = hp[k].point + (dot(opt, hp[k].dir) > 0.0f ? t_hi : t_lo) * hp[k].dir;
+        result = hp[k].point + (dot(opt, hp[k].dir) > F(0) ? t_hi : t_lo) * hp[k].dir;
     } else {
-        const float t = dot(hp[k].dir, opt - hp[k].point);
-        const float tc = t < t_lo ? t_lo : (t > t_hi ? t_hi : t);
+        const F t = dot(hp[k].dir, opt - hp[k].point);
+        const F tc = t < t_lo ? t_lo : (t > t_hi ? t_hi : t);
         result = hp[k].point + tc * hp[k].dir;
     }
     return true;
 }
 
 /* 2-D incremental LP. Returns the index of the first half-plane that made it infeasible, or n. */
-int lp_plane(const HalfPlane *hp, int n, float radius, V2 opt, bool direction_opt, V2 &result)
+template <typename F>
+int lp_plane(const HalfPlaneT<F> *hp, int n, F radius, V2T<F> opt, bool direction_opt, V2T<F> &result)
 {
     if (direction_opt) result = radius * opt;
     else if (norm2(opt) > radius * radius) result = radius * unit(opt);
     else result = opt;
     for (int i = 0; i < n; ++i) {
-        if (det(hp[i].dir, hp[i].point - result) > 0.0f) {
-            const V2 keep = result;
+        if (det(hp[i].dir, hp[i].point - result) > F(0)) {
+            const V2T<F> keep = result;
             if (!lp_line(hp, i, radius, opt, direction_opt, result)) {
                 result = keep;
                 return i;
@@ -107,33 +111,81 @@ int lp_plane(const HalfPlane *hp, int n, float radius, V2 opt, bool direction_op
 }
 
 /* Fallback: minimise the maximum penetration (no obstacle half-planes on this path). */
-void lp_relax(const HalfPlane *hp, int n, int begin, float radius, V2 &result)
+template <typename F>
+void lp_relax(const HalfPlaneT<F> *hp, int n, int begin, F radius, V2T<F> &result)
 {
-    float distance = 0.0f;
-    std::vector<HalfPlane> proj;
+    const F kEps = F(1e-5f);
+    F distance = F(0);
+    std::vector<HalfPlaneT<F>> proj;
     for (int i = begin; i < n; ++i) {
         if (det(hp[i].dir, hp[i].point - result) > distance) {
             proj.clear();
             for (int j = 0; j < i; ++j) {
-                HalfPlane l;
-                const float d = det(hp[i].dir, hp[j].dir);
+                HalfPlaneT<F> l;
+                const F d = det(hp[i].dir, hp[j].dir);
                 if (std::fabs(d) <= kEps) {
-                    if (dot(hp[i].dir, hp[j].dir) > 0.0f) continue;
-                    l.point = 0.5f * (hp[i].point + hp[j].point);
+                    if (dot(hp[i].dir, hp[j].dir) > F(0)) continue;
+                    l.point = F(0.5) * (hp[i].point + hp[j].point);
                 } else {
                     l.point = hp[i].point + (det(hp[j].dir, hp[i].point - hp[j].point) / d) * hp[i].dir;
                 }
                 l.dir = unit(hp[j].dir - hp[i].dir);
                 proj.push_back(l);
             }
-            const V2 keep = result;
-            if (lp_plane(proj.data(), (int)proj.size(), radius, V2{-hp[i].dir.y, hp[i].dir.x}, true, result) <
+            const V2T<F> keep = result;
+            if (lp_plane(proj.data(), (int)proj.size(), radius, V2T<F>{-hp[i].dir.y, hp[i].dir.x}, true, result) <
                 (int)proj.size())
                 result = keep;
             distance = det(hp[i].dir, hp[i].point - result);
         }
     }
 }
+
+/* The ORCA half-plane agent `a` takes on for neighbour `o`: u is the smallest change of the relative velocity that leaves
+ * the velocity obstacle truncated at the time horizon (or, when the discs already overlap, at one time step); the agent
+ * takes half of it (reciprocity): point = v_a + u / 2, the line runs along `dir` with the permitted side on its left. */
+template <typename F>
+HalfPlaneT<F> orca_halfplane(V2T<F> pa, V2T<F> po, V2T<F> va, V2T<F> vo, F radius, F inv_th, F time_step)
+{
+    const V2T<F> rp = po - pa;
+    const V2T<F> rv = va - vo;
+    const F d2 = norm2(rp);
+    const F R = radius + radius;
+    const F R2 = R * R;
+    V2T<F> u;
+    HalfPlaneT<F> l;
+    if (d2 > R2) {
+        const V2T<F> wv = rv - inv_th * rp;
+        const F w2 = norm2(wv);
+        const F dp1 = dot(wv, rp);
+        if (dp1 < F(0) && dp1 * dp1 > R2 * w2) {
+            const F wl = std::sqrt(w2);
+            const V2T<F> uw = wv / wl;
+            l.dir = V2T<F>{uw.y, -uw.x};
+            u = (R * inv_th - wl) * uw;
+        } else {
+            const F leg = std::sqrt(d2 - R2);
+            if (det(rp, wv) > F(0))
+                l.dir = V2T<F>{rp.x * leg - rp.y * R, rp.x * R + rp.y * leg} / d2;
+            else
+                l.dir = -(V2T<F>{rp.x * leg + rp.y * R, -rp.x * R + rp.y * leg} / d2);
+            const F dp2 = dot(rv, l.dir);
+            u = dp2 * l.dir - rv;
+        }
+    } else {
+        const F inv_dt = F(1) / time_step;
+        const V2T<F> wv = rv - inv_dt * rp;
+        const F wl = norm(wv);
+        const V2T<F> uw = wv / wl;
+        l.dir = V2T<F>{uw.y, -uw.x};
+        u = (R * inv_dt - wl) * uw;
+    }
+    l.point = va + F(0.5) * u;
+    return l;
+}
+
+using V2 = V2T<float>;
+using HalfPlane = HalfPlaneT<float>;
 
 } // namespace
 
@@ -198,41 +250,7 @@ static void orca_world_step(const orc_orca_batch *b, int w, std::vector<V2> &new
         /* one ORCA half-plane per neighbour */
         for (int k = 0; k < cnt; ++k) {
             const int o = ni[k];
-            const V2 rp = pos[o] - pos[a];
-            const V2 rv = vel[a] - vel[o];
-            const float d2 = norm2(rp);
-            const float R = b->radius + b->radius;
-            const float R2 = R * R;
-            V2 u;
-            HalfPlane l;
-            if (d2 > R2) {
-                const V2 wv = rv - inv_th * rp;
-                const float w2 = norm2(wv);
-                const float dp1 = dot(wv, rp);
-                if (dp1 < 0.0f && dp1 * dp1 > R2 * w2) {
-                    const float wl = std::sqrt(w2);
-                    const V2 uw = wv / wl;
-                    l.dir = V2{uw.y, -uw.x};
-                    u = (R * inv_th - wl) * uw;
-                } else {
-                    const float leg = std::sqrt(d2 - R2);
-                    if (det(rp, wv) > 0.0f)
-                        l.dir = V2{rp.x * leg - rp.y * R, rp.x * R + rp.y * leg} / d2;
-                    else
-                        l.dir = -(V2{rp.x * leg + rp.y * R, -rp.x * R + rp.y * leg} / d2);
-                    const float dp2 = dot(rv, l.dir);
-                    u = dp2 * l.dir - rv;
-                }
-            } else {
-                const float inv_dt = 1.0f / b->time_step;
-                const V2 wv = rv - inv_dt * rp;
-                const float wl = norm(wv);
-                const V2 uw = wv / wl;
-                l.dir = V2{uw.y, -uw.x};
-                u = (R * inv_dt - wl) * uw;
-            }
-            l.point = vel[a] + 0.5f * u;
-            hp[k] = l;
+            hp[k] = orca_halfplane(pos[a], pos[o], vel[a], vel[o], b->radius, inv_th, b->time_step);
         }
         V2 res;
         const int fail = lp_plane(hp.data(), cnt, vmax[a], pref[a], false, res);
@@ -308,6 +326,72 @@ int orc_orca_rollout(orc_orca_batch *b, int n_steps, int n_threads)
     worker();
     for (auto &t : pool) t.join();
     return 0;
+}
+
+
+/* ---- test hooks (tests/test_oracle_orca_independent.py): the two building blocks on their own ---- */
+/* out = {point.x, point.y, dir.x, dir.y} of the half-plane agent a takes on for agent o */
+void orc_orca_halfplane(const float *pa, const float *po, const float *va, const float *vo, float radius, float time_horizon,
+                        float time_step, float *out)
+{
+    const HalfPlane l = orca_halfplane(V2{pa[0], pa[1]}, V2{po[0], po[1]}, V2{va[0], va[1]}, V2{vo[0], vo[1]}, radius,
+                                       1.0f / time_horizon, time_step);
+    out[0] = l.point.x; out[1] = l.point.y; out[2] = l.dir.x; out[3] = l.dir.y;
+}
+
+/* new velocity for n half-planes lines = (n,4) {point, dir}, speed limit and preferred velocity; returns the index of the
+ * first half-plane the 2-D program failed at (n = feasible; < n = the relaxed program ran) */
+int orc_orca_solve(int n, const float *lines, float max_speed, const float *pref, float *out_v)
+{
+    std::vector<HalfPlane> hp(n > 0 ? n : 1);
+    for (int k = 0; k < n; ++k) hp[k] = HalfPlane{V2{lines[4 * k], lines[4 * k + 1]}, V2{lines[4 * k + 2], lines[4 * k + 3]}};
+    V2 res;
+    const int fail = lp_plane(hp.data(), n, max_speed, V2{pref[0], pref[1]}, false, res);
+    if (fail < n) lp_relax(hp.data(), n, fail, max_speed, res);
+    out_v[0] = res.x; out_v[1] = res.y;
+    return fail;
+}
+
+/* fp64 instantiation of the same algorithm -- NOT the oracle (rvo2 is single precision); test use only */
+int orc_orca_solve_f64(int n, const double *lines, double max_speed, const double *pref, double *out_v)
+{
+    using H = HalfPlaneT<double>;
+    using V = V2T<double>;
+    std::vector<H> hp(n > 0 ? n : 1);
+    for (int k = 0; k < n; ++k) hp[k] = H{V{lines[4 * k], lines[4 * k + 1]}, V{lines[4 * k + 2], lines[4 * k + 3]}};
+    V res;
+    const int fail = lp_plane(hp.data(), n, max_speed, V{pref[0], pref[1]}, false, res);
+    if (fail < n) lp_relax(hp.data(), n, fail, max_speed, res);
+    out_v[0] = res.x; out_v[1] = res.y;
+    return fail;
+}
+void orc_orca_solve_batch_f64(int m, int n, const double *lines, const double *max_speed, const double *pref, double *out_v, int *out_fail)
+{
+    for (int q = 0; q < m; ++q)
+        out_fail[q] = orc_orca_solve_f64(n, lines + (size_t)q * n * 4, max_speed[q], pref + 2 * q, out_v + 2 * q);
+}
+void orc_orca_halfplane_batch_f64(int m, const double *pa, const double *po, const double *va, const double *vo, double radius,
+                                  double time_horizon, double time_step, double *out)
+{
+    using V = V2T<double>;
+    for (int q = 0; q < m; ++q) {
+        const HalfPlaneT<double> l = orca_halfplane(V{pa[2 * q], pa[2 * q + 1]}, V{po[2 * q], po[2 * q + 1]}, V{va[2 * q], va[2 * q + 1]},
+                                                   V{vo[2 * q], vo[2 * q + 1]}, radius, 1.0 / time_horizon, time_step);
+        out[4 * q] = l.point.x; out[4 * q + 1] = l.point.y; out[4 * q + 2] = l.dir.x; out[4 * q + 3] = l.dir.y;
+    }
+}
+
+/* the same for m independent problems of n half-planes each (lines (m,n,4), max_speed (m), pref (m,2)) */
+void orc_orca_solve_batch(int m, int n, const float *lines, const float *max_speed, const float *pref, float *out_v, int *out_fail)
+{
+    for (int q = 0; q < m; ++q)
+        out_fail[q] = orc_orca_solve(n, lines + (size_t)q * n * 4, max_speed[q], pref + 2 * q, out_v + 2 * q);
+}
+void orc_orca_halfplane_batch(int m, const float *pa, const float *po, const float *va, const float *vo, float radius,
+                              float time_horizon, float time_step, float *out)
+{
+    for (int q = 0; q < m; ++q)
+        orc_orca_halfplane(pa + 2 * q, po + 2 * q, va + 2 * q, vo + 2 * q, radius, time_horizon, time_step, out + 4 * q);
 }
 
 } // extern "C"

@@ -93,6 +93,8 @@ PROTOTYPES = {
     "pms_orca_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(OrcaParamsC), C.POINTER(_h)]),
     "pms_orca_set_agents": (C.c_int, [_h, _dp, _dp, _dp, _dp]),
     "pms_orca_set_waypoints_fixed": (C.c_int, [_h, _dp, C.c_int, _ip, C.c_double, C.c_int]),
+    "pms_orca_set_waypoints_current": (C.c_int, [_h, _dp]),
+    "pms_orca_set_pref_refresh": (C.c_int, [_h, C.c_int]),
     "pms_orca_step": (C.c_int, [_h, C.c_int]),
     "pms_orca_get_agents": (C.c_int, [_h, _dp, _dp]),
     "pms_get_launch_info": (C.c_int, [_h, C.POINTER(LaunchInfoC)]),

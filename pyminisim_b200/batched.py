@@ -338,6 +338,16 @@ class BatchedOrca:
             si = np.ascontiguousarray(np.broadcast_to(np.asarray(start_index, dtype=np.int32), (self.W, self.N)))
         check(self._lib.pms_orca_set_waypoints_fixed(self._h, dptr(table), n_rows, iptr(si), float(reach_distance), int(bool(loop))))
 
+    def set_waypoints_current(self, current):
+        """Waypoints of a tracker that runs on the host (any AbstractWaypointTracker): hand over its current waypoints after
+        every update; the device-side hand-off is off (_orca.py:106-107,118-127)."""
+        cur = f64(np.asarray(current, dtype=np.float64)[..., :2], (self.W, self.N, 2))
+        check(self._lib.pms_orca_set_waypoints_current(self._h, dptr(cur)))
+
+    def set_pref_refresh(self, enabled: bool):
+        """False: the waypoint setters keep the preferred velocities (ORCAPedestriansModel.reset_to_state, _orca.py:114-116)."""
+        check(self._lib.pms_orca_set_pref_refresh(self._h, int(bool(enabled))))
+
     def step(self, n_steps: int = 1):
         check(self._lib.pms_orca_step(self._h, int(n_steps)))
 

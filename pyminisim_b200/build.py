@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpms_b200.so")
-SOURCES = ["pms_api.cu", "hsfm_warp.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
-HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_warp.cuh", "hsfm_warp_api.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
+SOURCES = ["pms_api.cu", "hsfm_warp.cu", "hsfm_duo.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
+HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_warp.cuh", "hsfm_warp_api.cuh", "hsfm_duo.cuh", "hsfm_duo_api.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
 
 
 def nvcc_path() -> str:
@@ -46,7 +46,6 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
             raise subprocess.CalledProcessError(pr.returncode, f"nvcc {src}")
     subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, check=True)
     return out
-    return LIB
 
 
 if __name__ == "__main__":

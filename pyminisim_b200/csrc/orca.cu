@@ -380,7 +380,19 @@ int orca_set_waypoints(OrcaState &s, const double *table, int n_rows, const int3
     s.n_table = n_rows; s.reach = reach; s.loop = loop ? 1 : 0;
     orca_gather_wp_kernel<<<nb(n), 256, 0, stream>>>(n, n_rows, s.table, s.wp_index, s.cur_wp);
     s.waypoints_set = true;
-    if (s.agents_set) orca_pref_kernel<<<nb(n), 256, 0, stream>>>(make_args(s, 0));
+    if (s.agents_set && s.refresh_pref) orca_pref_kernel<<<nb(n), 256, 0, stream>>>(make_args(s, 0));
+    return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : -2;
+}
+
+// Waypoints supplied by the caller (any tracker that runs on the host, e.g. RandomWaypointTracker): the device hand-off is
+// switched off (n_table = 0) and the preferred velocities follow the given current waypoints (_orca.py:118-127).
+int orca_set_current_waypoints(OrcaState &s, const double *current, cudaStream_t stream)
+{
+    const size_t n = (size_t)s.W * s.N;
+    cudaMemcpyAsync(s.cur_wp, current, n * sizeof(double2), cudaMemcpyHostToDevice, stream);
+    s.n_table = 0;
+    s.waypoints_set = true;
+    if (s.agents_set && s.refresh_pref) orca_pref_kernel<<<nb(n), 256, 0, stream>>>(make_args(s, 0));
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : -2;
 }
 

@@ -28,6 +28,7 @@ struct OrcaState {
     double *stage = nullptr;
     size_t stage_elems = 0;
     bool agents_set = false, waypoints_set = false;
+    bool refresh_pref = true;   // waypoint setters recompute the preferred velocities (off: ORCAPedestriansModel.reset_to_state)
 };
 
 int orca_alloc(OrcaState &s, int W, int N, double time_step, double neighbor_dist, int max_neighbors,
@@ -37,6 +38,7 @@ int orca_set_agents(OrcaState &s, const double *pos, const double *vel, const do
                     const double *pref_speeds, cudaStream_t stream);
 int orca_set_waypoints(OrcaState &s, const double *table, int n_rows, const int32_t *start_index, double reach,
                        int loop, cudaStream_t stream);
+int orca_set_current_waypoints(OrcaState &s, const double *current, cudaStream_t stream);
 int orca_step(OrcaState &s, int n_steps, cudaStream_t stream, long long *launches);
 int orca_get_agents(OrcaState &s, double *poses, double *vels, int32_t *n_constraints, cudaStream_t stream);
 

@@ -11,6 +11,7 @@
 
 #include "hsfm_small.cuh"
 #include "hsfm_warp_api.cuh"
+#include "hsfm_duo_api.cuh"
 #include "hsfm_large.cuh"
 #include "sensors.cuh"
 #include "orca.cuh"
@@ -297,7 +298,7 @@ int launch_warp(pms_sim *h)
     if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
     if (wpc > h->W) wpc = h->W;
     // register budget of the instantiation (WarpCfg in hsfm_warp.cuh): j_split 0 = 128 registers, 1 = 96, 2 = 80, 3 = 80 (256 threads)
-    const int T = h->Np / 32, minb = h->tune_S >= 1 && h->tune_S <= 3 ? h->tune_S : 0;
+    const int T = h->Np / 32, minb = h->tune_S >= 1 && h->tune_S <= 3 ? h->tune_S : 0;   // 4..7 select / exclude hsfm_duo
     if ((minb == 1 || minb == 2) && wpc > 4) wpc = 4;
     const bool split = h->precision == PMS_MIXED;
     const bool comp = h->precision == PMS_FP32 && h->compensated;
@@ -340,6 +341,54 @@ int launch_warp(pms_sim *h)
     h->info.j_split = 0;
     h->info.smem_bytes = (int)smem;
     h->info.n_chunks = h->a.n_chunks;
+    h->info.blocks_per_sm = occ;
+    h->info.kernel_launches++;
+    return 0;
+}
+
+// ---- launch of the pair-warp / owner-warp kernel (hsfm_duo.cu): FP32 modes, N <= 64, batches that leave the schedulers
+// under-filled with one warp per world ----
+bool duo_eligible(const pms_sim *h)
+{
+    return h->precision == PMS_FP32 && h->Np <= 32 * DUO_MAX_TILES;
+}
+
+// automatic choice: the warp-per-world kernel brings ONE warp per world to the schedulers; below ~2 warps per scheduler its
+// dependent chain per step is exposed and the pair-warp / owner-warp kernel (3T + 1 warps per world, one world per CTA,
+// 7 / 4 CTAs resident per SM for N <= 32 / 64) wins.  Measured cross-over on one B200 (profiles/r2_duo.md): N <= 32: one
+// wave of CTAs (1024 worlds: 1.04 vs 1.46 ms per 1000 steps, 2048: 1.97 vs 1.97); N <= 64: up to ~2.5 waves (512: 1.48 vs
+// 2.81, 1024: 2.52 vs 3.27; 2048 worlds would take 4 waves and lose to the 4.8 ms of the warp-per-world kernel).
+bool duo_preferred(const pms_sim *h)
+{
+    if (h->tune_S == 5) return false;                      // forced: warp-per-world kernel
+    if (h->tune_S == 4) return true;                       // forced: pair-warp / owner-warp kernel
+    if (h->tune_S != 0) return false;
+    const long long wave = (long long)(h->Np <= 32 ? 7 : 4) * h->sm_count;
+    return h->Np <= 32 ? h->W <= wave : 2LL * h->W <= 5 * wave;
+}
+
+int launch_duo(pms_sim *h)
+{
+    const int T = h->Np / 32;
+    const bool comp = h->compensated;
+    int occ = 0;
+    size_t smem = 0;
+    h->a.wpc = 1;
+    h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
+    CK(duo_kernel_prepare(comp, T, &occ, &smem));
+    CK(duo_kernel_launch(comp, T, h->a, h->W, smem, h->stream));
+    if (!comp) {        // plain fp32 state: the low parts a set_state left are gone
+        const size_t n = (size_t)h->W * h->N;
+        CK(cudaMemsetAsync(h->a.pos_lo, 0, n * 16, h->stream));
+        CK(cudaMemsetAsync(h->a.th_lo, 0, n * 8, h->stream));
+    }
+    h->info.kernel = 4;
+    h->info.threads_per_block = 96 * T + 32;
+    h->info.blocks = h->W;
+    h->info.worlds_per_block = 1;
+    h->info.j_split = 0;
+    h->info.smem_bytes = (int)smem;
+    h->info.n_chunks = 1;
     h->info.blocks_per_sm = occ;
     h->info.kernel_launches++;
     return 0;
@@ -937,6 +986,7 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     // the large-crowd kernel sets mask bits with atomicOr when it works on the sorted copy: start from zero
     if ((h->a.robot_model == ROBOT_NONE || large_path) && (rc = clear_sensor_outputs(h))) return rc;
     if (large_path) rc = launch_large(h);
+    else if (warp_ok && duo_eligible(h) && duo_preferred(h)) rc = launch_duo(h);
     else if (warp_ok) rc = launch_warp(h);
     else rc = launch_small(h);
     if (rc) return rc;
@@ -1337,6 +1387,21 @@ int pms_orca_set_waypoints_fixed(pms_sim *h, const double *table, int n_rows, co
         for (size_t k = 0; k < (size_t)h->W * h->N; ++k)
             if (start_index[k] < 0 || start_index[k] >= n_rows) return fail(PMS_ERR_INVALID, "start_index out of range");
     if (orca_set_waypoints(h->orca, table, n_rows, start_index, reach, loop, h->stream)) return fail(PMS_ERR_CUDA, "orca_set_waypoints failed");
+    return PMS_OK;
+}
+
+int pms_orca_set_waypoints_current(pms_sim *h, const double *current)
+{
+    OCHECK(h);
+    if (!current) return fail(PMS_ERR_INVALID, "current is NULL");
+    if (orca_set_current_waypoints(h->orca, current, h->stream)) return fail(PMS_ERR_CUDA, "orca_set_current_waypoints failed");
+    return PMS_OK;
+}
+
+int pms_orca_set_pref_refresh(pms_sim *h, int enabled)
+{
+    OCHECK(h);
+    h->orca.refresh_pref = enabled != 0;
     return PMS_OK;
 }
 

@@ -409,17 +409,25 @@ class ORCAPedestriansModel(AbstractPedestriansModel):
             preferred_speeds = max_speeds.copy()
         self._n = poses.shape[0]
         self._tracker = waypoint_tracker
-        if not isinstance(waypoint_tracker, FixedWaypointTracker):
-            raise TypeError("the accelerated ORCA path supports FixedWaypointTracker")
         if self._tracker.state is None:
             self._tracker.resample_all({i: poses[i] for i in range(self._n)})
         self._robot_visible = robot_visible
         self._sim = BatchedOrca(dt, 1, self._n, params, device=device)
         self._sim.set_agents(poses[None, :, :2], vels[None, :, :2], max_speeds[None], preferred_speeds[None])
-        ids, table = self._tracker.table()
-        idx = np.array([self._tracker.state.current_indices[i] for i in range(self._n)], dtype=np.int32)[None]
-        self._sim.set_waypoints_fixed(table[None], start_index=idx, reach_distance=self._tracker.reach_distance, loop=self._tracker.loop)
+        # FixedWaypointTracker: the hand-off runs on the device (table upload); any other tracker (the reference accepts every
+        # AbstractWaypointTracker, _orca.py:30-39,106-107) runs on the host and hands its current waypoints over every step
+        self._device_tracker = isinstance(waypoint_tracker, FixedWaypointTracker)
+        self._upload_waypoints()
         self._state = ORCAState({i: (poses[i].copy(), vels[i].copy()) for i in range(self._n)}, self._tracker.state)
+
+    def _upload_waypoints(self):
+        if self._device_tracker:
+            ids, table = self._tracker.table()
+            idx = np.array([self._tracker.state.current_indices[i] for i in range(self._n)], dtype=np.int32)[None]
+            self._sim.set_waypoints_fixed(table[None], start_index=idx, reach_distance=self._tracker.reach_distance, loop=self._tracker.loop)
+        else:
+            cur = self._tracker.state.current_waypoints
+            self._sim.set_waypoints_current(np.stack([np.asarray(cur[i], dtype=np.float64)[:2] for i in range(self._n)])[None])
 
     @property
     def state(self) -> ORCAState:
@@ -429,12 +437,23 @@ class ORCAPedestriansModel(AbstractPedestriansModel):
         self._sim.step(1)
         poses, vels = self._sim.get_agents()
         if self._tracker.state is not None:
-            self._tracker.update_waypoints({i: poses[0, i] for i in range(self._n)})   # host mirror of the device hand-off
+            # FixedWaypointTracker: host mirror of the device hand-off; any other tracker: THE hand-off (_orca.py:106-107),
+            # followed by _update_preferred_velocities (:118-127) on the device from the new current waypoints
+            self._tracker.update_waypoints({i: poses[0, i] for i in range(self._n)})
+            if not self._device_tracker:
+                self._upload_waypoints()
         self._state = ORCAState({i: (poses[0, i].copy(), vels[0, i].copy()) for i in range(self._n)}, self._tracker.state)
 
     def reset_to_state(self, state: ORCAState):
-        self._state = state                       # like the reference, the agents themselves are not reset (:114-116)
+        # like the reference, the rvo2 agents themselves are not reset (_orca.py:114-116); the tracker is: the next doStep
+        # still runs on the old preferred velocities, the hand-off and _update_preferred_velocities (:106-112,118-127) that
+        # follow it see the reset tracker -- so the device copy of the tracker (indices, current waypoints) is re-uploaded
+        # with the preferred velocities left as they are
+        self._state = state
         self._tracker.reset_to_state(state.waypoints)
+        self._sim.set_pref_refresh(False)
+        self._upload_waypoints()
+        self._sim.set_pref_refresh(True)
 
 
 # ---------------------------------------------------------------------------------------------------------

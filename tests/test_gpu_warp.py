@@ -8,13 +8,37 @@ import numpy as np
 import pytest
 
 from conftest import rel_err
-from helpers import make_cuda, make_oracle
+from helpers import make_oracle
+import helpers
 from oracle import oracle as orc
 from pyminisim_b200.scenarios import make_bench_crowd, make_crowd
 
 pytestmark = pytest.mark.gpu
 
-KERNEL_WARP, KERNEL_SMALL = 3, 0
+KERNEL_WARP, KERNEL_SMALL, KERNEL_DUO = 3, 0, 4
+# Every test of this file runs twice: on the warp-per-world kernel (j_split 5) and on the pair-warp / owner-warp kernel
+# (csrc/hsfm_duo.cuh, j_split 4: FP32 modes, N <= 64; other cases fall back to the warp-per-world kernel).  Without a
+# forced choice the library picks by batch size (pms_api.cu:duo_preferred).
+FORCE = {"j_split": 5}
+
+
+@pytest.fixture(autouse=True, params=["warp", "duo"])
+def kernel_family(request):
+    FORCE["j_split"] = 5 if request.param == "warp" else 4
+    yield request.param
+    FORCE["j_split"] = 5
+
+
+def expected_kernel(c):
+    duo = FORCE["j_split"] == 4 and c.precision in ("fp32", "fp32_plain") and c.N <= 64
+    return KERNEL_DUO if duo else KERNEL_WARP
+
+
+def make_cuda(sc, precision, **kw):
+    c = helpers.make_cuda(sc, precision, **kw)
+    c.set_tuning(FORCE["j_split"])
+    return c
+
 
 
 @pytest.mark.parametrize("precision", ["fp32", "mixed"])
@@ -29,7 +53,7 @@ def test_warp_kernel_vs_oracle(precision, n):
         o.rollout(0.01, h - done, n_threads=4)
         c.step(0.01, h - done)
         done = h
-        assert c.launch_info()["kernel"] == KERNEL_WARP
+        assert c.launch_info()["kernel"] == expected_kernel(c)
         p, v = c.get_state()
         assert rel_err(p, o.poses) < t, (precision, n, h, rel_err(p, o.poses))
         assert rel_err(v, o.vels) < t * 20, (precision, n, h, rel_err(v, o.vels))
@@ -50,7 +74,7 @@ def test_warp_kernel_dense_contact_scenes(n, side):
     for precision, tol in (("fp32", 3e-5), ("mixed", 1e-5)):
         c = make_cuda(sc, precision)
         c.step(0.01, 120)
-        assert c.launch_info()["kernel"] == KERNEL_WARP
+        assert c.launch_info()["kernel"] == expected_kernel(c)
         p, v = c.get_state()
         assert rel_err(p, o.poses) < tol, (precision, n, rel_err(p, o.poses))
     # and the directed-pair kernel agrees to the same level on the same input
@@ -88,10 +112,11 @@ def test_warp_kernel_tuning_is_bit_identical(precision):
     outs = []
     for wpc, chunks in ((0, 1), (1, 1), (3, 1), (8, 4), (5, 3)):
         sim = make_cuda(sc, precision)
-        sim.set_tuning(0, wpc, chunks)
+        sim.set_tuning(FORCE["j_split"], wpc, chunks)
         sim.step(0.01, 130)
         info = sim.launch_info()
-        assert info["kernel"] == KERNEL_WARP and info["n_chunks"] == chunks
+        # (the pair-warp / owner-warp kernel runs one world per CTA on a static grid: wpc / chunks do not apply)
+        assert info["kernel"] == expected_kernel(sim) and info["n_chunks"] == (chunks if info["kernel"] == KERNEL_WARP else 1)
         outs.append(sim.get_state() + sim.get_detector() + (sim.get_collisions(),) + sim.get_stats() + sim.get_robot())
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
@@ -105,6 +130,7 @@ def test_warp_kernel_newton_third_law_momentum():
     n = 64
     sc = make_crowd(4, n, side=9.0)
     sim = BatchedSimulation(4, n, precision="fp32", hsfm_params=HSFMParams(tau=1e9, k_d=0.0, k_o=1.0))
+    sim.set_tuning(FORCE["j_split"])
     sim.set_state(sc.poses)
     sim.set_speeds(np.zeros((4, n)))
     sim.set_waypoints_fixed(sc.table, loop=True)
@@ -122,6 +148,7 @@ def _pair(sc, precision, robot_model, det=(5.0, 120.0, 0), loop=True, visible=Tr
     W, N = sc.poses.shape[:2]
     o = orc.OracleBatch(sc.poses, vels=sc.vels, vmag=sc.vmag)
     c = BatchedSimulation(W, N, precision=precision)
+    c.set_tuning(FORCE["j_split"])
     c.set_state(sc.poses, sc.vels)
     c.set_speeds(sc.vmag)
     if tracker == "fixed":
@@ -137,7 +164,7 @@ def _pair(sc, precision, robot_model, det=(5.0, 120.0, 0), loop=True, visible=Tr
 
 def _check(o, c, tol, robot=True):
     p, v = c.get_state()
-    assert c.launch_info()["kernel"] == KERNEL_WARP
+    assert c.launch_info()["kernel"] == expected_kernel(c)
     assert rel_err(p, o.poses) < tol, rel_err(p, o.poses)
     assert rel_err(v, o.vels) < 20 * tol, rel_err(v, o.vels)
     if robot:

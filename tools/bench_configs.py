@@ -130,6 +130,10 @@ def main():
         time_hsfm("4096 x 128 warp kernel", 4096, 128, 300)
         time_hsfm("4096 x 128 directed-pair kernel", 4096, 128, 300, tuning=(-1, 0, 0, 0))
         time_hsfm("16384 x 32 warp kernel", 16384, 32, 1000)
+    if "duo" in which:      # warp-per-world kernel (j_split 5) vs pair-warp / owner-warp kernel (j_split 4)
+        for W, N in ((1024, 32), (512, 64), (256, 64), (592, 64), (1024, 64), (512, 32), (2048, 32), (128, 64), (512, 48), (1024, 20)):
+            time_hsfm(f"{W} x {N} warp-per-world kernel", W, N, 1000, tuning=(5, 0, 0, 0))
+            time_hsfm(f"{W} x {N} duo kernel", W, N, 1000, tuning=(4, 0, 0, 0))
     if "c3" in which:
         time_hsfm("C3 large crowd", 1, 65536, 20, large=True)
         time_hsfm("C3 large crowd, 200 steps per call", 1, 65536, 200, large=True)

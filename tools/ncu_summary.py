@@ -1,6 +1,8 @@
 """Turn an `ncu --set full --import-source on` report into the markdown summary kept under profiles/.
 
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep "<title>" "<capture command>" [units-per-launch] > profiles/xx.md
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep --json kernel=hsfm_warp_kernel worlds=4096 peds=64 sim_steps=1000 \
+        precision=fp32 source=profiles/xx.md      # appends the record bench.py reads to profiles/ncu_captures.json
 
 Reads the raw page (pipe utilisation, stalls, DRAM traffic, occupancy limits) and the source page (executed
 warp-instructions per opcode; `units-per-launch`, e.g. worlds x steps, turns them into a per-unit count).
@@ -43,7 +45,35 @@ def page(rep, name):
     return list(csv.reader(out.splitlines()))
 
 
+def to_bytes(unit, val):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return float(val) * scale[unit]
+
+
+def json_record():
+    import json
+    import os
+    rep = sys.argv[1]
+    kv = dict(a.split("=", 1) for a in sys.argv[3:])
+    rows = page(rep, "raw")
+    m = {h: (u, v) for h, u, v in zip(rows[0], rows[1], rows[2])}
+    rec = {"kernel": kv["kernel"], "worlds": int(kv["worlds"]), "peds": int(kv["peds"]), "sim_steps": int(kv["sim_steps"]),
+           "precision": kv["precision"], "source": kv.get("source", rep), "kernel_name": m["Kernel Name"][1],
+           "duration_ms": float(m["gpu__time_duration.sum"][1]) * {"ms": 1.0, "us": 1e-3, "s": 1e3}[m["gpu__time_duration.sum"][0]],
+           "dram_bytes": int(to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])),
+           "fma_pipe_cycles_pct": float(m["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"][1]),
+           "xu_pipe_pct": float(m["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"][1]),
+           "issue_slots_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][1])}
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_captures.json")
+    recs = json.load(open(path)) if os.path.exists(path) else []
+    recs.append(rec)
+    json.dump(recs, open(path, "w"), indent=1)
+    print(json.dumps(rec))
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[2] == "--json":
+        return json_record()
     rep, title, cmd = sys.argv[1], sys.argv[2], sys.argv[3]
     units = float(sys.argv[4]) if len(sys.argv) > 4 else None
     rows = page(rep, "raw")
