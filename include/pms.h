@@ -89,6 +89,8 @@ int pms_set_ped_speeds(pms_sim *h, const double *vmag /*(W,N)*/); /* pedestrian_
  * first_nonfinite_step instead of 0. */
 int pms_set_async_io(pms_sim *h, int enabled);
 /* device-side snapshot of the complete simulation state (checkpoint / resume) */
+/* (pms_set_waypoints_fixed and pms_set_waypoint_queue replace device tables a snapshot refers to: they discard a saved
+ * snapshot, pms_snapshot_restore then fails with PMS_ERR_STATE until the next pms_snapshot_save) */
 int pms_snapshot_save(pms_sim *h);
 int pms_snapshot_restore(pms_sim *h);
 
@@ -223,7 +225,8 @@ int pms_orca_get_agents(pms_sim *h, double *poses /*(W,N,3)*/, double *velocitie
 
 /* ---- launch introspection (bench / tests) ---- */
 typedef struct {
-    int kernel;            /* 0 = directed-pair small-world kernel, 1 = large-crowd kernel, 2 = ORCA, 3 = warp-per-world kernel */
+    int kernel;            /* 0 = directed-pair small-world kernel, 1 = large-crowd kernel, 2 = ORCA, 3 = warp-per-world kernel,
+                              4 = pair-warp / owner-warp kernel (under-filled batches, N <= 64) */
     int threads_per_block, blocks, worlds_per_block, j_split; /* large kernel: j_split = cluster size */
     int smem_bytes;
     int n_chunks;          /* > 1: persistent CTAs pull (chunk, world-group) items dynamically */
@@ -236,6 +239,12 @@ int pms_get_launch_info(pms_sim *h, pms_launch_info *out);
  *                    j_split 1..3 selects a smaller register budget (96 / 80 / 80 registers per thread, more resident warps), and a negative
  *                    value selects the directed-pair kernel instead (-1: automatic j-slices, -1-S: S slices).  For the
  *                    directed-pair kernel (FP64, larger worlds) j_split = 1, 2, 4, 8 is the number of j-slices.
+ *                    FP32 batches of up to 64 pedestrians per world that fit about one wave of CTAs (one world per CTA) run the
+ *                    pair-warp / owner-warp kernel instead (kernel 4: 3T + 1 warps per world, the pair pass of step t + 1
+ *                    overlaps the dynamics of step t); j_split 4 forces it, j_split 5 forces the warp-per-world kernel, and so
+ *                    does any explicit worlds_per_block / n_chunks.  The two kernels add the same pair forces in a different
+ *                    order: results agree to fp32 rounding, not bit for bit -- pin one of them (4 / 5) when the bits of a world
+ *                    must not depend on the size of the batch it is in.
  *   n_chunks       : 1 forces the static grid; for the large-crowd kernel -2 keeps the caller's pedestrian order (no
  *                    sorted working copy) and -1 also visits every j-tile (no exact pruning).
  *   cluster_size   : (1,2,4,8) multicast width of the large-crowd kernel; a negative value also forces that kernel

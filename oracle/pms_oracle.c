@@ -83,15 +83,23 @@ void orc_pair_force(double radius_i, double radius_j, const double *r_i, const d
     f_out[1] = fy;
 }
 
-/* One world, one HSFM step without tracker: _hsfm.py:250-299 calling :146-158 and :46-110. */
-void orc_hsfm_world_step(const orc_batch *p, int n, double *poses, double *vels, const double *wps,
-                         const double *vmag, const double *robot4, double dt)
+/* Forces and body-frame accelerations of pedestrians [64 blk, 64 blk + 64) of one world: _hsfm.py:146-158 and :46-110.
+ * Pedestrians are independent within a step (each sums its own forces in j order), so blocks of rows can be shared among
+ * threads without changing a bit of the result (large single crowds, orc_rollout with one world). */
+typedef struct {
+    const orc_batch *p; int n; const double *poses, *vels, *wps, *vmag, *robot4; double *dvb, *dom;
+} row_ctx;
+static void hsfm_rows(void *vctx, int blk)
 {
-    double *dvb = (double *)malloc(sizeof(double) * 2 * (size_t)n);
-    double *dom = (double *)malloc(sizeof(double) * (size_t)n);
+    const row_ctx *q = (const row_ctx *)vctx;
+    const orc_batch *p = q->p;
+    const int n = q->n;
+    const double *poses = q->poses, *vels = q->vels, *wps = q->wps, *vmag = q->vmag, *robot4 = q->robot4;
+    double *dvb = q->dvb, *dom = q->dom;
     const double m = p->mass;
     const double I = 0.5 * (p->ped_radius * p->ped_radius); /* :239 */
-    for (int i = 0; i < n; ++i) {
+    const int i_end = 64 * blk + 64 < n ? 64 * blk + 64 : n;
+    for (int i = 64 * blk; i < i_end; ++i) {
         const double *ri = poses + 3 * i, *vi = vels + 3 * i;
         double theta = ri[2], omega = vi[2];
         /* _calc_desired_velocities :146-158 */
@@ -130,6 +138,18 @@ void orc_hsfm_world_step(const orc_batch *p, int n, double *poses, double *vels,
         dvb[2 * i + 1] = 1.0 / m * u_o;
         dom[i] = u_theta / I;                            /* :107 */
     }
+}
+
+static int g_row_threads = 1;   /* threads that share the rows of ONE world (set by orc_rollout when it has a single world) */
+
+/* One world, one HSFM step without tracker: _hsfm.py:250-299 calling :146-158 and :46-110. */
+void orc_hsfm_world_step(const orc_batch *p, int n, double *poses, double *vels, const double *wps,
+                         const double *vmag, const double *robot4, double dt)
+{
+    double *dvb = (double *)malloc(sizeof(double) * 2 * (size_t)n);
+    double *dom = (double *)malloc(sizeof(double) * (size_t)n);
+    row_ctx rc = {p, n, poses, vels, wps, vmag, robot4, dvb, dom};
+    parallel_for_worlds((n + 63) / 64, n >= 1024 ? g_row_threads : 1, hsfm_rows, &rc);
     /* explicit Euler :290-294 */
     for (int i = 0; i < n; ++i) {
         double *ri = poses + 3 * i, *vi = vels + 3 * i;
@@ -406,7 +426,9 @@ static void rollout_fn(void *ctx, int w)
 int orc_rollout(orc_batch *b, double dt, int n_steps, int n_threads)
 {
     rollout_ctx c = {b, dt, n_steps};
+    g_row_threads = b->n_worlds == 1 ? n_threads : 1;
     parallel_for_worlds(b->n_worlds, n_threads, rollout_fn, &c);
+    g_row_threads = 1;
     if (b->events && b->ev_count) {
         int cnt = *b->ev_count < b->ev_cap ? *b->ev_count : b->ev_cap;
         qsort(b->events, (size_t)cnt, 3 * sizeof(int), ev_cmp);

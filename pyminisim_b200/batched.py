@@ -47,6 +47,7 @@ class BatchedSimulation:
         cp = capi.HsfmParamsC(float(p.tau), float(p.A), float(p.B), float(p.k_1), float(p.k_2), float(p.k_o),
                               float(p.k_d), float(p.k_lambda), float(p.alpha), float(pedestrian_mass),
                               float(pedestrian_radius), float(hsfm_robot_radius))
+        self._async_io, self._pending_nf = False, []
         self._h = C.c_void_p()
         check(self._lib.pms_create(int(device), self.W, self.N, capi.PRECISIONS[precision], C.byref(cp), C.byref(self._h)))
         self.robot_model = capi.ROBOT_NONE
@@ -82,6 +83,7 @@ class BatchedSimulation:
         enqueued on the handle's stream and complete at ``sync()``.  Host arrays must be page-locked (``_capi.pinned_array``)
         and must not be touched before ``sync()``.  Lets several handles overlap copies with each other's kernels."""
         check(self._lib.pms_set_async_io(self._h, int(bool(enabled))))
+        self._async_io = bool(enabled)
 
     def snapshot_save(self):
         check(self._lib.pms_snapshot_save(self._h))
@@ -198,6 +200,11 @@ class BatchedSimulation:
 
     def sync(self):
         check(self._lib.pms_sync(self._h))
+        # asynchronous-I/O mode: pms_get_stats left the raw "never" sentinel (INT32_MAX) in the buffers it filled; after the
+        # synchronisation they read like the blocking call's (0 = the world stayed finite)
+        for nf in self._pending_nf:
+            nf[nf == np.iinfo(np.int32).max] = 0
+        self._pending_nf.clear()
 
     def step_tick(self, dt: float, n_steps: int = 1, robot_pose=None, robot_velocity=None, robot_radius: float = 0.35,
                   visible: bool = True) -> dict:
@@ -256,6 +263,8 @@ class BatchedSimulation:
         det, col, nf = out if out is not None else (np.empty(self.W, dtype=np.int64), np.empty(self.W, dtype=np.int64),
                                                     np.empty(self.W, dtype=np.int32))
         check(self._lib.pms_get_stats(self._h, lptr(det), lptr(col), iptr(nf)))
+        if self._async_io:
+            self._pending_nf.append(nf)
         return det, col, nf
 
     def reset_stats(self):

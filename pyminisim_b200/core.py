@@ -18,197 +18,233 @@ DEFAULT_ROBOT_RADIUS: float = 0.35   # core/_constants.py:1
 PEDESTRIAN_RADIUS: float = 0.3       # core/_constants.py:2
 
 
-# ---- world map (core/_world_map.py:7-71) ------------------------------------------------------------
-class AbstractWorldMapState(ABC):
-    pass
+# ---------------------------------------------------------------------------------------------------------------
+# The abstract interfaces and value types of pyminisim.core.  When the reference package itself is importable its OWN
+# classes are used, so everything in this package subclasses the reference's ABCs (isinstance checks, type hints and the
+# reference's own Simulation / renderer accept the accelerated models and sensors).  Otherwise -- the GPU box has no
+# reference -- the definitions below stand in for them: same names, members and assertion behaviour.
+# ---------------------------------------------------------------------------------------------------------------
+def _load_reference_core():
+    import importlib
+    import sys
+    try:
+        pkg = importlib.import_module("pyminisim")
+        if getattr(pkg, "__pms_b200_alias__", False):       # our own alias (pyminisim_b200.alias), not the reference
+            return None
+        core = importlib.import_module("pyminisim.core")
+        sensor = importlib.import_module("pyminisim.core._sensor")
+        return core, sensor
+    except Exception:
+        for name in [m for m in sys.modules if m == "pyminisim" or m.startswith("pyminisim.")]:
+            if not getattr(sys.modules.get("pyminisim"), "__pms_b200_alias__", False):
+                sys.modules.pop(name, None)                   # a half-imported reference must not linger
+        return None
 
 
-class AbstractWorldMap(ABC):
-    def __init__(self, initial_state: AbstractWorldMapState):
-        self._state = initial_state
+_REF = _load_reference_core()
+USING_REFERENCE_ABCS = _REF is not None
 
-    @property
-    def current_state(self) -> AbstractWorldMapState:
-        return self._state
-
-    def reset_to_state(self, state: AbstractWorldMapState):
-        self._state = state
-
-    @abstractmethod
-    def step(self, dt: float) -> None: ...
-
-    @abstractmethod
-    def closest_distance_to_obstacle(self, point: np.ndarray) -> Union[float, np.ndarray]: ...
-
-    @abstractmethod
-    def is_occupied(self, point: np.ndarray) -> Union[bool, np.ndarray]: ...
-
-    @abstractmethod
-    def is_collision(self, agent_points: np.ndarray, agent_radii, eps_margin: float = 0.05): ...
+if _REF is not None:
+    _c, _s = _REF
+    AbstractWorldMapState, AbstractWorldMap, AbstractStaticWorldMap = _c.AbstractWorldMapState, _c.AbstractWorldMap, _c.AbstractStaticWorldMap
+    AbstractRobotMotionModelState, AbstractRobotMotionModel = _c.AbstractRobotMotionModelState, _c.AbstractRobotMotionModel
+    AbstractWaypointTrackerState, AbstractWaypointTracker = _c.AbstractWaypointTrackerState, _c.AbstractWaypointTracker
+    AbstractPedestriansModelState, AbstractPedestriansModel = _c.AbstractPedestriansModelState, _c.AbstractPedestriansModel
+    AbstractSensorConfig, AbstractSensorReading, AbstractSensor = _c.AbstractSensorConfig, _c.AbstractSensorReading, _c.AbstractSensor
+    SensorState, WorldState, SimulationState = _s.SensorState, _c.WorldState, _c.SimulationState
+else:
+    # ---- world map (core/_world_map.py:7-71) ------------------------------------------------------------
+    class AbstractWorldMapState(ABC):
+        pass
 
 
-class AbstractStaticWorldMap(AbstractWorldMap, ABC):
-    def step(self, dt: float) -> None:
-        return
+    class AbstractWorldMap(ABC):
+        def __init__(self, initial_state: AbstractWorldMapState):
+            self._state = initial_state
+
+        @property
+        def current_state(self) -> AbstractWorldMapState:
+            return self._state
+
+        def reset_to_state(self, state: AbstractWorldMapState):
+            self._state = state
+
+        @abstractmethod
+        def step(self, dt: float) -> None: ...
+
+        @abstractmethod
+        def closest_distance_to_obstacle(self, point: np.ndarray) -> Union[float, np.ndarray]: ...
+
+        @abstractmethod
+        def is_occupied(self, point: np.ndarray) -> Union[bool, np.ndarray]: ...
+
+        @abstractmethod
+        def is_collision(self, agent_points: np.ndarray, agent_radii, eps_margin: float = 0.05): ...
 
 
-# ---- robot (core/_motion_state.py:6-42, core/_motion.py:10-32) ---------------------------------------
-class AbstractRobotMotionModelState(ABC):
-    @property
-    @abstractmethod
-    def pose(self) -> np.ndarray: ...
-
-    @property
-    @abstractmethod
-    def velocity(self) -> np.ndarray: ...
-
-    @property
-    @abstractmethod
-    def state(self) -> np.ndarray: ...
-
-    @property
-    @abstractmethod
-    def control(self) -> np.ndarray: ...
+    class AbstractStaticWorldMap(AbstractWorldMap, ABC):
+        def step(self, dt: float) -> None:
+            return
 
 
-class AbstractRobotMotionModel(ABC):
-    def __init__(self, initial_state: AbstractRobotMotionModelState, radius: float = DEFAULT_ROBOT_RADIUS):
-        assert radius > 0.
-        self._state = initial_state
-        self._radius = radius
+    # ---- robot (core/_motion_state.py:6-42, core/_motion.py:10-32) ---------------------------------------
+    class AbstractRobotMotionModelState(ABC):
+        @property
+        @abstractmethod
+        def pose(self) -> np.ndarray: ...
 
-    @property
-    def state(self) -> AbstractRobotMotionModelState:
-        return self._state
+        @property
+        @abstractmethod
+        def velocity(self) -> np.ndarray: ...
 
-    @property
-    def radius(self) -> float:
-        return self._radius
+        @property
+        @abstractmethod
+        def state(self) -> np.ndarray: ...
 
-    def reset_to_state(self, state: AbstractRobotMotionModelState):
-        self._state = state
-
-    @abstractmethod
-    def step(self, dt: float, world_map: AbstractWorldMap, control: Optional[np.ndarray] = None) -> bool: ...
+        @property
+        @abstractmethod
+        def control(self) -> np.ndarray: ...
 
 
-# ---- waypoints (core/_waypoints.py:7-40) ---------------------------------------------------------------
-class AbstractWaypointTrackerState(ABC):
-    def __init__(self, current_waypoints: Dict[int, np.ndarray]):
-        self._current_waypoints = {}
-        for ped_id, wp in current_waypoints.items():
-            assert wp.shape == (2,), f"Waypoints must be array of shape (2,), the {wp.shape} array was passed for pedestrian {ped_id}"
-            self._current_waypoints[ped_id] = wp.copy()
+    class AbstractRobotMotionModel(ABC):
+        def __init__(self, initial_state: AbstractRobotMotionModelState, radius: float = DEFAULT_ROBOT_RADIUS):
+            assert radius > 0.
+            self._state = initial_state
+            self._radius = radius
 
-    @property
-    def current_waypoints(self) -> Dict[int, np.ndarray]:
-        return self._current_waypoints
+        @property
+        def state(self) -> AbstractRobotMotionModelState:
+            return self._state
 
+        @property
+        def radius(self) -> float:
+            return self._radius
 
-class AbstractWaypointTracker(ABC):
-    @property
-    def state(self) -> AbstractWaypointTrackerState:
-        raise NotImplementedError()
+        def reset_to_state(self, state: AbstractRobotMotionModelState):
+            self._state = state
 
-    @abstractmethod
-    def resample_all(self, agents_poses: Dict[int, np.ndarray]) -> Dict[int, np.ndarray]: ...
-
-    @abstractmethod
-    def update_waypoints(self, agents_poses: Dict[int, np.ndarray]) -> Dict[int, Tuple[np.ndarray, bool]]: ...
-
-    @abstractmethod
-    def reset_to_state(self, state: AbstractWaypointTrackerState): ...
-
-    @abstractmethod
-    def sample_independent_points(self, n_points: int, min_cross_distance: Optional[float] = None): ...
+        @abstractmethod
+        def step(self, dt: float, world_map: AbstractWorldMap, control: Optional[np.ndarray] = None) -> bool: ...
 
 
-# ---- pedestrians (core/_pedestrians_model.py:9-47) -------------------------------------------------------
-class AbstractPedestriansModelState(ABC):
-    def __init__(self, pedestrians: Dict[int, Tuple[np.ndarray, np.ndarray]],
-                 waypoints_state: Optional[AbstractWaypointTrackerState]):
-        for ped_id, (pose, velocity) in pedestrians.items():
-            assert pose.shape == (3,), f"Each pedestrian pose must be a 3-dim array, but {pose.shape} array was passed for pedestrian {ped_id}"
-            assert velocity.shape == (3,), f"Each pedestrian velocity must be a 3-dim array, but {velocity.shape} array was passed for pedestrian {ped_id}"
-        self._pedestrians = pedestrians
-        self._waypoints = waypoints_state
+    # ---- waypoints (core/_waypoints.py:7-40) ---------------------------------------------------------------
+    class AbstractWaypointTrackerState(ABC):
+        def __init__(self, current_waypoints: Dict[int, np.ndarray]):
+            self._current_waypoints = {}
+            for ped_id, wp in current_waypoints.items():
+                assert wp.shape == (2,), f"Waypoints must be array of shape (2,), the {wp.shape} array was passed for pedestrian {ped_id}"
+                self._current_waypoints[ped_id] = wp.copy()
 
-    @property
-    def poses(self) -> Dict[int, np.ndarray]:
-        return {k: v[0].copy() for k, v in self._pedestrians.items()}      # fresh copies, like the reference
-
-    @property
-    def velocities(self) -> Dict[int, np.ndarray]:
-        return {k: v[1].copy() for k, v in self._pedestrians.items()}
-
-    @property
-    def waypoints(self) -> Optional[AbstractWaypointTrackerState]:
-        return self._waypoints
+        @property
+        def current_waypoints(self) -> Dict[int, np.ndarray]:
+            return self._current_waypoints
 
 
-class AbstractPedestriansModel(ABC):
-    @property
-    @abstractmethod
-    def state(self) -> AbstractPedestriansModelState: ...
+    class AbstractWaypointTracker(ABC):
+        @property
+        def state(self) -> AbstractWaypointTrackerState:
+            raise NotImplementedError()
 
-    @abstractmethod
-    def step(self, dt: float, robot_pose: Optional[np.ndarray], robot_velocity: Optional[np.ndarray]): ...
+        @abstractmethod
+        def resample_all(self, agents_poses: Dict[int, np.ndarray]) -> Dict[int, np.ndarray]: ...
 
-    @abstractmethod
-    def reset_to_state(self, state: AbstractPedestriansModelState): ...
+        @abstractmethod
+        def update_waypoints(self, agents_poses: Dict[int, np.ndarray]) -> Dict[int, Tuple[np.ndarray, bool]]: ...
 
+        @abstractmethod
+        def reset_to_state(self, state: AbstractWaypointTrackerState): ...
 
-# ---- sensors (core/_sensor.py:8-44) ----------------------------------------------------------------------
-class AbstractSensorConfig(ABC):
-    pass
-
-
-class AbstractSensorReading(ABC):
-    pass
+        @abstractmethod
+        def sample_independent_points(self, n_points: int, min_cross_distance: Optional[float] = None): ...
 
 
-class AbstractSensor(ABC):
-    def __init__(self, name: str, period: float):
-        assert period >= 0.
-        self._name = name
-        self._period = period
+    # ---- pedestrians (core/_pedestrians_model.py:9-47) -------------------------------------------------------
+    class AbstractPedestriansModelState(ABC):
+        def __init__(self, pedestrians: Dict[int, Tuple[np.ndarray, np.ndarray]],
+                     waypoints_state: Optional[AbstractWaypointTrackerState]):
+            for ped_id, (pose, velocity) in pedestrians.items():
+                assert pose.shape == (3,), f"Each pedestrian pose must be a 3-dim array, but {pose.shape} array was passed for pedestrian {ped_id}"
+                assert velocity.shape == (3,), f"Each pedestrian velocity must be a 3-dim array, but {velocity.shape} array was passed for pedestrian {ped_id}"
+            self._pedestrians = pedestrians
+            self._waypoints = waypoints_state
 
-    @property
-    def sensor_name(self) -> str:
-        return self._name
+        @property
+        def poses(self) -> Dict[int, np.ndarray]:
+            return {k: v[0].copy() for k, v in self._pedestrians.items()}      # fresh copies, like the reference
 
-    @property
-    def period(self) -> float:
-        return self._period
+        @property
+        def velocities(self) -> Dict[int, np.ndarray]:
+            return {k: v[1].copy() for k, v in self._pedestrians.items()}
 
-    @property
-    @abstractmethod
-    def sensor_config(self) -> AbstractSensorConfig: ...
-
-    @abstractmethod
-    def get_reading(self, world_state: "WorldState", world_map: AbstractWorldMap) -> AbstractSensorReading: ...
-
-
-@dataclass
-class SensorState:
-    reading: AbstractSensorReading
-    hold_time: float
+        @property
+        def waypoints(self) -> Optional[AbstractWaypointTrackerState]:
+            return self._waypoints
 
 
-# ---- state containers (core/_world_state.py:11-17, core/_simulation_state.py:10-13) -----------------------
-@dataclass
-class WorldState:
-    world_map: AbstractWorldMapState
-    robot: Optional[AbstractRobotMotionModelState]
-    pedestrians: Optional[AbstractPedestriansModelState]
-    robot_to_pedestrians_collisions: Optional[List[int]]
-    robot_to_world_collision: bool
+    class AbstractPedestriansModel(ABC):
+        @property
+        @abstractmethod
+        def state(self) -> AbstractPedestriansModelState: ...
+
+        @abstractmethod
+        def step(self, dt: float, robot_pose: Optional[np.ndarray], robot_velocity: Optional[np.ndarray]): ...
+
+        @abstractmethod
+        def reset_to_state(self, state: AbstractPedestriansModelState): ...
 
 
-@dataclass
-class SimulationState:
-    world: WorldState
-    sensors: Dict[str, SensorState]
+    # ---- sensors (core/_sensor.py:8-44) ----------------------------------------------------------------------
+    class AbstractSensorConfig(ABC):
+        pass
+
+
+    class AbstractSensorReading(ABC):
+        pass
+
+
+    class AbstractSensor(ABC):
+        def __init__(self, name: str, period: float):
+            assert period >= 0.
+            self._name = name
+            self._period = period
+
+        @property
+        def sensor_name(self) -> str:
+            return self._name
+
+        @property
+        def period(self) -> float:
+            return self._period
+
+        @property
+        @abstractmethod
+        def sensor_config(self) -> AbstractSensorConfig: ...
+
+        @abstractmethod
+        def get_reading(self, world_state: "WorldState", world_map: AbstractWorldMap) -> AbstractSensorReading: ...
+
+
+    @dataclass
+    class SensorState:
+        reading: AbstractSensorReading
+        hold_time: float
+
+
+    # ---- state containers (core/_world_state.py:11-17, core/_simulation_state.py:10-13) -----------------------
+    @dataclass
+    class WorldState:
+        world_map: AbstractWorldMapState
+        robot: Optional[AbstractRobotMotionModelState]
+        pedestrians: Optional[AbstractPedestriansModelState]
+        robot_to_pedestrians_collisions: Optional[List[int]]
+        robot_to_world_collision: bool
+
+
+    @dataclass
+    class SimulationState:
+        world: WorldState
+        sensors: Dict[str, SensorState]
+
 
 
 class _GpuSenseContext:

@@ -60,6 +60,7 @@ struct LargeArgs {
 };
 
 struct LargeScratch {
+    int sm_count = 148;                 // SMs of the device (set by the API from cudaDeviceProp): launch heuristics
     void *pos2 = nullptr, *vel2 = nullptr, *th2 = nullptr, *thlo2 = nullptr, *thlo3 = nullptr;
     void *view[2] = {nullptr, nullptr};
     RobotSlot *robot_slot = nullptr;
@@ -998,7 +999,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
     // 11.6 us per step with 1 / 2 / 4 warps per chunk, 1024 chunks 16.9 / 16.6 / 17.9, 2048 chunks 23.0 / 25.8 / 29.7)
     const long long n_chunks_all = (long long)a.W * ((a.N + LARGE_CHUNK - 1) / LARGE_CHUNK);
     const int ks = chunk_split == 1 || chunk_split == 2 || chunk_split == 4 ? chunk_split
-                   : (n_chunks_all <= 4 * 148 ? 4 : (n_chunks_all <= 8 * 148 ? 2 : 1));
+                   : (n_chunks_all <= 4LL * s.sm_count ? 4 : (n_chunks_all <= 8LL * s.sm_count ? 2 : 1));
     const int cpb = ks == 1 ? CHUNK_TI / LARGE_CHUNK : 1;          // chunks per chunk-kernel CTA
     const int tiles_i = (a.N + LARGE_TI - 1) / LARGE_TI, tiles_j = Npad / LARGE_TJ, tiles_c = (a.N + cpb * LARGE_CHUNK - 1) / (cpb * LARGE_CHUNK);
     bool use_chunk = false;                                        // pruned FP32 regime: barrier-free warp-per-chunk kernel
@@ -1080,7 +1081,7 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             if constexpr (sizeof(ST) == 4) {
                 if (use_chunk) {
                     const unsigned gc = (unsigned)(a.W * tiles_c);
-                    if (ks == 1 && n_chunks_all > 16 * 148) hsfm_chunk_kernel<1, CHUNK_TI / LARGE_CHUNK, PMS_CHUNK_MINB_HI><<<gc, CHUNK_TI, 0, stream>>>(a, la);
+                    if (ks == 1 && n_chunks_all > 16LL * s.sm_count) hsfm_chunk_kernel<1, CHUNK_TI / LARGE_CHUNK, PMS_CHUNK_MINB_HI><<<gc, CHUNK_TI, 0, stream>>>(a, la);
                     else if (ks == 1) hsfm_chunk_kernel<1, CHUNK_TI / LARGE_CHUNK><<<gc, CHUNK_TI, 0, stream>>>(a, la);
                     else if (ks == 2) hsfm_chunk_kernel<2, 1><<<gc, 64, 0, stream>>>(a, la);
                     else hsfm_chunk_kernel<4, 1><<<gc, 128, 0, stream>>>(a, la);

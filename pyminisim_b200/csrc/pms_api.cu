@@ -83,12 +83,27 @@ __global__ void convert_array_kernel(size_t n, const double *src, ST *dst)
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g < n) dst[g] = (ST)src[g];
 }
-// pms_step_tick: detector values, waypoint indices, masks, flags and the event count into the tick block
-__global__ void tick_gather_kernel(size_t n, int W, int words, HsfmArgs a, double2 *vals, int *wp_index, uint32_t *coll, uint32_t *det,
-                                   int *nonfinite, int *n_events)
+// pms_step_tick: state (fp64, hi + lo), detector values, waypoint indices, masks, flags and the event count into the tick block
+template <typename ST>
+__global__ void tick_pack_kernel(size_t n, int W, int words, HsfmArgs a, double *poses, double *vels, double2 *vals, int *wp_index,
+                                 uint32_t *coll, uint32_t *det, int *nonfinite, int *n_events)
 {
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (g < n) { vals[g] = a.det_vals[g]; wp_index[g] = a.wp_index ? a.wp_index[g] : 0; }
+    if (g < n) {
+        using ST2 = typename Vec2<ST>::type;
+        ST x, y, vx, vy;
+        load_pv(a, g, x, y, vx, vy);
+        const ST2 t = reinterpret_cast<const ST2 *>(a.th)[g];
+        double px = (double)x, py = (double)y, pt = (double)t.x, qx = (double)vx, qy = (double)vy, qt = (double)t.y;
+        if constexpr (sizeof(ST) == 4) {
+            const float4 pl = reinterpret_cast<const float4 *>(a.pos_lo)[g];
+            const float2 tl = reinterpret_cast<const float2 *>(a.th_lo)[g];
+            px += (double)pl.x; py += (double)pl.y; pt += (double)tl.x; qx += (double)pl.z; qy += (double)pl.w; qt += (double)tl.y;
+        }
+        poses[3 * g] = px; poses[3 * g + 1] = py; poses[3 * g + 2] = pt;
+        vels[3 * g] = qx; vels[3 * g + 1] = qy; vels[3 * g + 2] = qt;
+        vals[g] = a.det_vals[g]; wp_index[g] = a.wp_index ? a.wp_index[g] : 0;
+    }
     if (g < (size_t)W * words) { coll[g] = a.coll_mask[g]; det[g] = a.det_mask[g]; }
     if (g < (size_t)W) nonfinite[g] = a.nonfinite[g];
     if (g == 0) *n_events = a.ev_count ? *a.ev_count : 0;
@@ -160,6 +175,7 @@ struct pms_sim {
     size_t map_cap = 0;
     int *overflow_dev = nullptr;
     double *noise_dev = nullptr;
+    double *robot_block = nullptr;   // pose (3W) | velocity (3W) | control (2W) | rear axle (3W) doubles | world-collision (W ints)
     // snapshot
     std::vector<std::pair<void *, size_t>> snap_src;
     std::vector<void *> snap_dst;
@@ -268,8 +284,8 @@ int launch_small(pms_sim *h)
     const int Np = h->Np;
     int S = h->tune_S < 0 ? -h->tune_S - 1 : h->tune_S;   // j_split = -1: automatic, -1-S: forced S
     if (S <= 0) {
-        // enough threads to fill 148 SMs; every slice keeps >= 8 pairs for ILP
-        const long long target = 148LL * 1536;
+        // enough threads to fill the SMs; every slice keeps >= 8 pairs for ILP
+        const long long target = (long long)h->sm_count * 1536;
         S = 1;
         while (S < 8 && (long long)h->W * Np * S * 2 <= target && h->N / (S * 2) >= 8) S *= 2;
     }
@@ -362,7 +378,7 @@ bool duo_preferred(const pms_sim *h)
 {
     if (h->tune_S == 5) return false;                      // forced: warp-per-world kernel
     if (h->tune_S == 4) return true;                       // forced: pair-warp / owner-warp kernel
-    if (h->tune_S != 0) return false;
+    if (h->tune_S != 0 || h->tune_wpc > 0 || h->tune_chunks > 0) return false;   // explicit launch knobs of the other kernels
     const long long wave = (long long)(h->Np <= 32 ? 7 : 4) * h->sm_count;
     return h->Np <= 32 ? h->W <= wave : 2LL * h->W <= 5 * wave;
 }
@@ -509,11 +525,11 @@ int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hs
     a.ev_cap = 1 << 16;
     CKC(dalloc(&a.events, (size_t)a.ev_cap * 3));
     CKC(dalloc(&a.ev_count, 1));
-    CKC(dalloc(&a.robot_pose, (size_t)n_worlds * 3));
-    CKC(dalloc(&a.robot_vel, (size_t)n_worlds * 3));
-    CKC(dalloc(&a.robot_ctrl, (size_t)n_worlds * 2));
-    CKC(dalloc(&a.robot_rear, (size_t)n_worlds * 3));
-    CKC(dalloc(&a.robot_world_collision, (size_t)n_worlds));
+    // robot pose | velocity | control | rear axle | world-collision flag in ONE allocation: pms_step_tick uploads them in one copy
+    CKC(dalloc(&h->robot_block, (size_t)n_worlds * 12));
+    a.robot_pose = h->robot_block; a.robot_vel = a.robot_pose + 3 * (size_t)n_worlds; a.robot_ctrl = a.robot_vel + 3 * (size_t)n_worlds;
+    a.robot_rear = a.robot_ctrl + 2 * (size_t)n_worlds;
+    a.robot_world_collision = reinterpret_cast<int *>(a.robot_rear + 3 * (size_t)n_worlds);
     CKC(dalloc(&a.det_mask, (size_t)n_worlds * h->words));
     CKC(dalloc(&a.coll_mask, (size_t)n_worlds * h->words));
     CKC(dalloc(&a.det_vals, n));
@@ -526,6 +542,7 @@ int pms_create(int device, int n_worlds, int n_peds, int precision, const pms_hs
         cudaDeviceProp prop;
         CKC(cudaGetDeviceProperties(&prop, device));
         h->sm_count = prop.multiProcessorCount;
+        h->large.sm_count = h->sm_count;
     }
     fill_int_kernel<<<nblk(n_worlds), 256, 0, h->stream>>>((size_t)n_worlds, a.nonfinite, 0x7fffffff);
     // default speed 1.5 (_hsfm.py:205) and a waypoint table of one row (set properly by the caller)
@@ -549,8 +566,7 @@ int pms_destroy(pms_sim *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     HsfmArgs &a = h->a;
     void *ptrs[] = {a.th_lo, a.pos, a.vel, a.th, a.wp, a.vmag, a.wp_index, (void *)a.table, (void *)a.queue, a.q_head, a.q_count,
-                    a.events, a.ev_count, a.robot_pose, a.robot_vel, a.robot_ctrl, a.robot_rear,
-                    a.robot_world_collision, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
+                    a.events, a.ev_count, h->robot_block, a.det_mask, a.coll_mask, a.det_vals, a.det_count, a.coll_count,
                     a.nonfinite, h->noisy_mask, h->noisy_vals, h->stage, h->controls_dev, h->map_dev, h->overflow_dev, a.work_counter, a.group_done, h->noise_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : h->snap_dst) if (p) cudaFree(p);
@@ -639,15 +655,18 @@ int pms_set_waypoints_fixed(pms_sim *h, const double *table, int n_rows, const i
     if (!table || n_rows < 1) return fail(PMS_ERR_INVALID, "table is NULL or n_rows < 1");
     const size_t n = (size_t)h->W * h->N;
     HsfmArgs &a = h->a;
-    if (a.table) { cudaFree((void *)a.table); a.table = nullptr; }
-    unsigned char *raw;
-    CK(dalloc(&raw, n * n_rows * 2 * h->esz));
-    a.table = raw;
-    int rc = upload_converted(h, table, n * n_rows * 2, raw);
-    if (rc) return rc;
-    if (start_index) {
+    // validate everything before the handle is touched: a failed call leaves the old table, row count and indices in place
+    if (start_index)
         for (size_t k = 0; k < n; ++k)
             if (start_index[k] < 0 || start_index[k] >= n_rows) return fail(PMS_ERR_INVALID, "start_index out of range");
+    unsigned char *raw = nullptr;
+    CK(dalloc(&raw, n * n_rows * 2 * h->esz));
+    int rc = upload_converted(h, table, n * n_rows * 2, raw);
+    if (rc) { cudaFree(raw); return rc; }
+    if (a.table) cudaFree((void *)a.table);
+    a.table = raw;
+    h->has_snapshot = false;        // a saved snapshot holds indices into the old table
+    if (start_index) {
         CK(cudaMemcpyAsync(a.wp_index, start_index, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     } else {
         fill_int_kernel<<<nblk(n), 256, 0, h->stream>>>(n, a.wp_index, n_rows > 1 ? 1 : 0);
@@ -669,12 +688,13 @@ int pms_set_waypoint_queue(pms_sim *h, const double *current, const double *queu
     if (!current || !queue || q_len < 1) return fail(PMS_ERR_INVALID, "current/queue NULL or q_len < 1");
     const size_t n = (size_t)h->W * h->N;
     HsfmArgs &a = h->a;
-    if (a.queue) { cudaFree((void *)a.queue); a.queue = nullptr; }
-    unsigned char *raw;
+    unsigned char *raw = nullptr;
     CK(dalloc(&raw, n * q_len * 2 * h->esz));
-    a.queue = raw;
     int rc = upload_converted(h, queue, n * q_len * 2, raw);
-    if (rc) return rc;
+    if (rc) { cudaFree(raw); return rc; }
+    if (a.queue) cudaFree((void *)a.queue);
+    a.queue = raw;
+    h->has_snapshot = false;        // a saved snapshot points at the old queue allocation and capacity
     rc = upload_converted(h, current, n * 2, a.wp);
     if (rc) return rc;
     CK(cudaMemsetAsync(a.q_head, 0, n * sizeof(int), h->stream));
@@ -1028,10 +1048,10 @@ int pms_step_tick(pms_sim *h, double dt, int n_steps, const double *robot_pose, 
     const int W = h->W;
     const size_t n = (size_t)W * h->N, nm = (size_t)W * h->words;
     // layout of the tick block: poses | vels | det_vals (doubles) | wp_index | nonfinite | n_events (ints) | coll | det (u32);
-    // the head of the host block doubles as the staging area of the robot upload (pose | velocity | control | rear: 11 W doubles)
+    // the head of the host block doubles as the staging area of the robot upload (pose | velocity | control | rear: 11 W doubles, W ints)
     const size_t o_pose = 0, o_vel = o_pose + n * 24, o_vals = o_vel + n * 24, o_idx = o_vals + n * 16, o_nf = o_idx + n * 4,
                  o_ev = o_nf + (size_t)W * 4, o_coll = o_ev + 4, o_det = o_coll + nm * 4, total = o_det + nm * 4;
-    const size_t need = total > (size_t)W * 88 ? total : (size_t)W * 88;
+    const size_t need = total > (size_t)W * 96 ? total : (size_t)W * 96;
     if (need > h->tick_bytes) {
         if (h->tick_dev) cudaFree(h->tick_dev);
         if (h->tick_host) cudaFreeHost(h->tick_host);
@@ -1055,19 +1075,22 @@ int pms_step_tick(pms_sim *h, double dt, int n_steps, const double *robot_pose, 
             s_rear[3 * w + 1] = robot_pose[3 * w + 1] - (a.wheel_base / 2.0) * std::sin(th);
             s_rear[3 * w + 2] = th;
         }
-        CK(cudaMemcpyAsync(a.robot_pose, s_pose, sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(a.robot_vel, s_vel, sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(a.robot_ctrl, s_ctrl, sizeof(double) * W * 2, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(a.robot_rear, s_rear, sizeof(double) * W * 3, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemsetAsync(a.robot_world_collision, 0, sizeof(int) * W, h->stream));
+        std::memset(st + 11 * W, 0, sizeof(int) * W);                 // world-collision flags
+        // the device block has the same layout: one copy instead of four copies and a memset
+        CK(cudaMemcpyAsync(h->robot_block, st, sizeof(double) * W * 11 + sizeof(int) * W, cudaMemcpyHostToDevice, h->stream));
     }
     int rc = pms_hsfm_step_async(h, dt, n_steps);
     if (rc) return rc;
     unsigned char *d = h->tick_dev;
-    if (h->precision == PMS_FP32) unpack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, (double *)(d + o_pose), (double *)(d + o_vel), a);
-    else unpack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, (double *)(d + o_pose), (double *)(d + o_vel), a);
-    tick_gather_kernel<<<nblk(n > nm ? n : nm), 256, 0, h->stream>>>(n, W, h->words, a, (double2 *)(d + o_vals), (int *)(d + o_idx), (uint32_t *)(d + o_coll),
-                                                                      (uint32_t *)(d + o_det), (int *)(d + o_nf), (int *)(d + o_ev));
+    {
+        const unsigned nb_ = nblk(n > nm ? n : nm);
+        if (h->precision == PMS_FP32)
+            tick_pack_kernel<float><<<nb_, 256, 0, h->stream>>>(n, W, h->words, a, (double *)(d + o_pose), (double *)(d + o_vel), (double2 *)(d + o_vals),
+                                                                (int *)(d + o_idx), (uint32_t *)(d + o_coll), (uint32_t *)(d + o_det), (int *)(d + o_nf), (int *)(d + o_ev));
+        else
+            tick_pack_kernel<double><<<nb_, 256, 0, h->stream>>>(n, W, h->words, a, (double *)(d + o_pose), (double *)(d + o_vel), (double2 *)(d + o_vals),
+                                                                 (int *)(d + o_idx), (uint32_t *)(d + o_coll), (uint32_t *)(d + o_det), (int *)(d + o_nf), (int *)(d + o_ev));
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->tick_host, d, total, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -224,8 +224,69 @@ class RandomWaypointTracker(AbstractWaypointTracker):
 # ---------------------------------------------------------------------------------------------------------
 # HSFM
 # ---------------------------------------------------------------------------------------------------------
-class HSFMState(AbstractPedestriansModelState):
+class _ArrayBackedState(AbstractPedestriansModelState):
+    """State object of the accelerated models.  Takes the reference's signature -- a dict ``{id: (pose, velocity)}``
+    (core/_pedestrians_model.py:12-19) -- or, from the models themselves, a pair of ``(N, 3)`` arrays that the state owns.
+    In the second case nothing per-pedestrian is built until somebody asks: ``poses`` / ``velocities`` return a fresh dict of
+    copies on every access like the reference (:21-27), ``pose_array`` / ``velocity_array`` hand out the arrays without the dict."""
+
+    def __init__(self, pedestrians, waypoints_state):
+        if isinstance(pedestrians, dict):
+            self._arrays = None
+            super().__init__(pedestrians, waypoints_state)
+        else:
+            poses, velocities = pedestrians
+            assert poses.ndim == 2 and poses.shape[1] == 3 and velocities.shape == poses.shape
+            self._arrays = (poses, velocities)
+            self._dict = None
+            self._waypoints = waypoints_state
+
+    @property
+    def _pedestrians(self):                       # what the base class (and code written against it) reads
+        if self._dict is None:
+            p, v = self._arrays
+            self._dict = {i: (p[i], v[i]) for i in range(p.shape[0])}
+        return self._dict
+
+    @_pedestrians.setter
+    def _pedestrians(self, value):
+        self._dict = value
+
+    @property
+    def poses(self):
+        if self._arrays is None:
+            return {k: v[0].copy() for k, v in self._dict.items()}
+        p = self._arrays[0].copy()
+        return {i: p[i] for i in range(p.shape[0])}
+
+    @property
+    def velocities(self):
+        if self._arrays is None:
+            return {k: v[1].copy() for k, v in self._dict.items()}
+        v = self._arrays[1].copy()
+        return {i: v[i] for i in range(v.shape[0])}
+
+    @property
+    def pose_array(self) -> np.ndarray:
+        """(N, 3) copy of the poses in pedestrian-id order (ids of the accelerated models are 0..N-1)."""
+        if self._arrays is None:
+            return np.stack([self._dict[k][0] for k in sorted(self._dict)])
+        return self._arrays[0].copy()
+
+    @property
+    def velocity_array(self) -> np.ndarray:
+        if self._arrays is None:
+            return np.stack([self._dict[k][1] for k in sorted(self._dict)])
+        return self._arrays[1].copy()
+
+
+class HSFMState(_ArrayBackedState):
     pass
+
+
+def _mask_ids(words: np.ndarray, n: int):
+    """Pedestrian ids whose bit is set in a (ceil(n/32),) uint32 mask, ascending (the reference's list order)."""
+    return np.flatnonzero(np.unpackbits(np.ascontiguousarray(words).view(np.uint8), bitorder="little")[:n]).tolist()
 
 
 def _initial_arrays(tracker, n, initial_poses, initial_velocities):
@@ -316,7 +377,7 @@ class HeadedSocialForceModelPolicy(AbstractPedestriansModel):
         self._sim.set_state(poses[None], vels[None])
         self._link = _TrackerLink(self._tracker, self._n)
         self._link.upload(self._sim)
-        self._state = HSFMState({i: (poses[i].copy(), vels[i].copy()) for i in range(self._n)}, self._tracker.state)
+        self._state = HSFMState((poses.copy(), vels.copy()), self._tracker.state)
         self._collision_radius = None     # Simulation sets it to its robot model's radius (collision list of the fused step)
         self._fused = None
         self._det_cfg = None              # (max_dist, fov, return code) of the detector the fused step evaluates, if any
@@ -359,15 +420,13 @@ class HeadedSocialForceModelPolicy(AbstractPedestriansModel):
         if tick["nonfinite"][0]:   # the reference's numba inverse raises on non-finite headings
             raise np.linalg.LinAlgError("Array must not contain infs or NaNs")
         self._link.after_step(self._sim, tick)
-        poses, vels = tick["poses"][0].copy(), tick["vels"][0].copy()
-        self._state = HSFMState({i: (poses[i], vels[i]) for i in range(self._n)}, self._tracker.state)
+        # the state object owns copies of the two (N, 3) arrays of the tick block; per-pedestrian dicts are built on access
+        self._state = HSFMState((tick["poses"][0].copy(), tick["vels"][0].copy()), self._tracker.state)
         if robot_pose is not None:
-            words = tick["coll_mask"][0]
-            self._fused = (rp.copy(), radius, [i for i in range(self._n) if (int(words[i >> 5]) >> (i & 31)) & 1])
+            self._fused = (rp.copy(), radius, _mask_ids(tick["coll_mask"][0], self._n))
             if self._det_cfg is not None:
-                dw = tick["det_mask"][0]
-                hits = [i for i in range(self._n) if (int(dw[i >> 5]) >> (i & 31)) & 1]
-                self._state._fused_sense = (self._fused[0], self._det_cfg, hits, tick["det_vals"][0].copy())
+                self._state._fused_sense = (self._fused[0], self._det_cfg, _mask_ids(tick["det_mask"][0], self._n),
+                                            tick["det_vals"][0].copy())
         else:
             self._fused = None
 
@@ -384,7 +443,7 @@ class HeadedSocialForceModelPolicy(AbstractPedestriansModel):
 # ---------------------------------------------------------------------------------------------------------
 # ORCA
 # ---------------------------------------------------------------------------------------------------------
-class ORCAState(AbstractPedestriansModelState):
+class ORCAState(_ArrayBackedState):
     pass
 
 
@@ -418,7 +477,7 @@ class ORCAPedestriansModel(AbstractPedestriansModel):
         # AbstractWaypointTracker, _orca.py:30-39,106-107) runs on the host and hands its current waypoints over every step
         self._device_tracker = isinstance(waypoint_tracker, FixedWaypointTracker)
         self._upload_waypoints()
-        self._state = ORCAState({i: (poses[i].copy(), vels[i].copy()) for i in range(self._n)}, self._tracker.state)
+        self._state = ORCAState((poses.copy(), vels.copy()), self._tracker.state)
 
     def _upload_waypoints(self):
         if self._device_tracker:
@@ -442,7 +501,7 @@ class ORCAPedestriansModel(AbstractPedestriansModel):
             self._tracker.update_waypoints({i: poses[0, i] for i in range(self._n)})
             if not self._device_tracker:
                 self._upload_waypoints()
-        self._state = ORCAState({i: (poses[0, i].copy(), vels[0, i].copy()) for i in range(self._n)}, self._tracker.state)
+        self._state = ORCAState((poses[0], vels[0]), self._tracker.state)      # get_agents returned fresh arrays
 
     def reset_to_state(self, state: ORCAState):
         # like the reference, the rvo2 agents themselves are not reset (_orca.py:114-116); the tracker is: the next doStep

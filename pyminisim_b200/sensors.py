@@ -201,7 +201,9 @@ class LidarSensor(AbstractSensor):
             self._ctx = _GpuMapContext()
         sim = self._ctx.place(world_map, world_state.robot.pose)
         hit, pts = sim.lidar_scan(self._config.n_beams, self._config.max_dist, self._config.resolution)
-        reading = LidarSensorReading(pts[0][hit[0] >= 0])          # beam order, misses dropped (:117-120)
+        hits = pts[0][hit[0] >= 0]                                  # beam order, misses dropped (:117-120)
+        # no beam hit anything: the reference's list of points is empty and np.array([]) has shape (0,), not (0, 2) (:121)
+        reading = LidarSensorReading(hits if hits.shape[0] else np.array([]))
         if self._noise is not None:
             reading = self._noise.noisify_reading(reading)
         return reading

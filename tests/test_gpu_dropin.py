@@ -178,6 +178,88 @@ def test_orca_dropin_model():
     assert model.state.waypoints.current_indices == {i: int(o.wp_index[0, i]) for i in range(7)}
 
 
+def _orca_host_loop(o, tracker, steps):
+    """The reference's ORCAPedestriansModel.step around the ORACLE's rvo2 restatement: doStep, tracker hand-off on the new
+    poses, preferred velocities from the tracker's current waypoints (_orca.py:95-112,118-127).  The oracle's own table tracker
+    is disabled (reach < 0); `tracker` is the drop-in's host-side tracker class."""
+    from oracle import oracle as orc
+    n = o.N
+    for _ in range(steps):
+        o.rollout(1)
+        poses = np.concatenate([o.pos[0].astype(np.float64), o.heading[0][:, None]], axis=1)
+        tracker.update_waypoints({i: poses[i] for i in range(n)})
+        cur = tracker.state.current_waypoints
+        o.cur_wp[0] = np.stack([np.asarray(cur[i], dtype=np.float64)[:2] for i in range(n)])
+        orc.lib().orc_orca_update_pref(__import__("ctypes").byref(o._struct()))
+
+
+def test_orca_dropin_accepts_random_waypoint_tracker():
+    """_orca.py:30-39,106-107 take any AbstractWaypointTracker: with RandomWaypointTracker the hand-off runs on the host (global
+    numpy RNG, reference call order) and the device follows the tracker's current waypoints -- bit-identical to the same loop
+    around the oracle."""
+    from oracle import oracle as orc
+    from pyminisim_b200.core import Simulation
+    from pyminisim_b200.pedestrians import ORCAParams, ORCAPedestriansModel, RandomWaypointTracker
+    n = 9
+    rng = np.random.default_rng(5)
+    init = np.concatenate([rng.uniform(-3.0, 3.0, (n, 2)), np.zeros((n, 1))], axis=1)
+    ms = rng.uniform(1.0, 1.8, n)
+    runs = []
+    for which in ("cuda", "oracle"):
+        Simulation.seed(11)
+        tracker = RandomWaypointTracker(world_size=(7.0, 7.0))
+        if which == "cuda":
+            model = ORCAPedestriansModel(0.01, tracker, n, initial_poses=init.copy(), params=ORCAParams(default_max_speed=2.), max_speeds=ms)
+            for _ in range(400):
+                model.step()
+            p, v = _ped_arrays(model.state)
+            runs.append((p[:, :2].astype(np.float32), v[:, :2].astype(np.float32),
+                         np.stack([tracker.state.current_waypoints[i] for i in range(n)])))
+        else:
+            tracker.resample_all({i: init[i] for i in range(n)})
+            cur = np.stack([np.asarray(tracker.state.current_waypoints[i], dtype=np.float64)[:2] for i in range(n)])
+            table = np.stack([init[:, :2], cur], axis=1)[None]
+            o = orc.OracleOrca(0.01, init[None], table, loop=True, max_speed=ms[None], default_max_speed=2.0, reach=-1.0)
+            _orca_host_loop(o, tracker, 400)
+            runs.append((o.pos[0].copy(), o.vel[0].copy(), np.stack([tracker.state.current_waypoints[i] for i in range(n)])))
+    assert np.array_equal(runs[0][2], runs[1][2])            # the same waypoints were drawn and handed off
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert np.abs(runs[0][0] - init[:, :2].astype(np.float32)).max() > 1.0      # and the agents went somewhere
+
+
+def test_orca_reset_to_state_reuploads_the_tracker():
+    """ORCAPedestriansModel.reset_to_state resets the tracker only (_orca.py:114-116): the next doStep still runs on the old
+    preferred velocities, the hand-off and the preferred velocities after it use the reset tracker.  The device copy of the
+    tracker must follow (it kept steering to the stale index)."""
+    from oracle import oracle as orc
+    from pyminisim_b200.pedestrians import (FixedWaypointTracker, FixedWaypointTrackerState, ORCAParams, ORCAPedestriansModel, ORCAState)
+    n = 6
+    rng = np.random.default_rng(2)
+    init = np.concatenate([rng.uniform(-2.5, 2.5, (n, 2)), np.zeros((n, 1))], axis=1)
+    goals = rng.uniform(-3.0, 3.0, (n, 3, 2))
+    ms = np.full(n, 1.6)
+    tracker = FixedWaypointTracker(initial_positions=init[:, :2].copy(), waypoints=goals, loop=True)
+    model = ORCAPedestriansModel(0.01, tracker, n, initial_poses=init.copy(), params=ORCAParams(default_max_speed=2.), max_speeds=ms)
+    table = np.concatenate([init[:, None, :2], goals], axis=1)[None]
+    o = orc.OracleOrca(0.01, init[None], table, loop=True, max_speed=ms[None], default_max_speed=2.0)
+    for _ in range(120):
+        model.step()
+    o.rollout(120)
+    # reset: every pedestrian is sent to another row of its table
+    new_idx = {i: int((o.wp_index[0, i] + 2) % 4) for i in range(n)}
+    new_state = FixedWaypointTrackerState({i: table[0, i, new_idx[i]].copy() for i in range(n)}, dict(new_idx))
+    model.reset_to_state(ORCAState({i: (model.state.poses[i], model.state.velocities[i]) for i in range(n)}, new_state))
+    for i in range(n):                                        # the oracle: tracker reset, preferred velocities untouched
+        o.wp_index[0, i] = new_idx[i]
+        o.cur_wp[0, i] = table[0, i, new_idx[i]]
+    for _ in range(150):
+        model.step()
+    o.rollout(150)
+    p, v = _ped_arrays(model.state)
+    assert np.array_equal(p[:, :2].astype(np.float32), o.pos[0])
+    assert model.state.waypoints.current_indices == {i: int(o.wp_index[0, i]) for i in range(n)}
+
+
 def test_replay_policy_through_simulation(golden):
     """Recorded pedestrians (pedestrians/_replay.py) under Simulation: the device collision list and detector see every frame."""
     from pyminisim_b200.core import Simulation

@@ -31,13 +31,31 @@ def test_c4_full_size_independence_determinism_and_sampled_oracle():
     out_b = b.get_state() + b.get_detector() + (b.get_collisions(),) + b.get_stats()
     for x, y in zip(out_a, out_b):
         assert np.array_equal(x, y)
-    # independence: worlds 0, 1234 and 4095 run alone give the bits they have inside the batch
+    # independence: worlds 0, 1234 and 4095 run alone give the bits they have inside the batch -- under the same kernel:
+    # a batch this small would be routed to the pair-warp / owner-warp kernel (another summation order, last-bit differences),
+    # set_tuning(5) pins the warp-per-world kernel that ran the batch
+    assert a.launch_info()["kernel"] == 3
     for w in (0, 1234, 4095):
         one = make_cuda(sc, "fp32", worlds=slice(w, w + 1))
+        one.set_tuning(5)
         one.step(0.01, K)
         p1, v1 = one.get_state()
         assert np.array_equal(p1[0], pa[w]) and np.array_equal(v1[0], va[w])
         assert np.array_equal(one.get_detector()[0][0], out_a[2][w])
+    # the same property for the pair-warp / owner-warp kernel: 512 worlds (one shard of C4 on 8 GPUs) against worlds run alone
+    d = make_cuda(sc, "fp32", worlds=slice(1024, 1536))
+    d.step(0.01, K)
+    assert d.launch_info()["kernel"] == 4
+    pd, vd = d.get_state()
+    for w in (0, 300, 511):
+        one = make_cuda(sc, "fp32", worlds=slice(1024 + w, 1025 + w))
+        one.step(0.01, K)
+        assert one.launch_info()["kernel"] == 4
+        p1, v1 = one.get_state()
+        assert np.array_equal(p1[0], pd[w]) and np.array_equal(v1[0], vd[w])
+        assert np.array_equal(one.get_detector()[0][0], d.get_detector()[0][w])
+    # and the two kernels agree to the fp32 tolerance of the free-running horizon (test_gpu_trajectory.py states it per world)
+    assert rel_err(pd[..., :2], pa[1024:1536, :, :2]) < 1e-4
     # sampled worlds against the fp64 oracle at 300 steps (fp32 tolerance of test_gpu_hsfm.py: 1e-4 @300)
     sel = np.array([7, 511, 2048, 3333])
     sub = make_bench_crowd(W, N)

@@ -299,5 +299,5 @@ def test_async_io_pipeline_equals_blocking_calls():
             assert np.array_equal(o["p"], p_ref) and np.array_equal(o["v"], v_ref)
             assert np.array_equal(o["m"], m_ref) and np.array_equal(o["d"], d_ref)
             assert np.array_equal(o["det"], det_ref) and np.array_equal(o["col"], col_ref)
-            assert (o["nf"] == np.iinfo(np.int32).max).all() and (nf_ref == 0).all()   # async: the raw "never" sentinel
+            assert (o["nf"] == 0).all() and (nf_ref == 0).all()   # sync() maps the raw "never" sentinel of the async copy to 0
     sims[1].sync()

@@ -36,3 +36,26 @@ def test_reference_dynamics_amplify_an_fp32_rounding_of_the_initial_state():
     assert per_world[100].max() <= per_world[300].max() * 1.5 <= per_world[1000].max() * 2.25
     print("fp64-vs-fp64 divergence from an fp32 rounding of the initial positions:",
           {h: (float(np.median(v)), float(v.max())) for h, v in per_world.items()})
+
+
+def test_velocity_amplification_bounds_what_fp32_arithmetic_can_reach():
+    """The north star quotes <= 1e-4 on positions / velocities after 1000 steps in fp32.  One relative perturbation of 1e-10 of
+    the initial positions (fp64 oracle against itself, 48 benchmark worlds x 32 pedestrians) is amplified in the LINEAR VELOCITIES
+    by a median factor of ~90 and by more than 1e3 in the most sensitive world: an fp32 kernel commits 6e-8 per operation, every
+    step, so 1e-4 on velocities cannot hold in every world -- tests/test_gpu_trajectory.py states it per component with the
+    measured exceptions.  Positions are amplified ~10 x less."""
+    worlds, n, eps = 48, 32, 1e-10
+    sc = make_bench_crowd(worlds, n)
+    a = make_oracle(sc)
+    rng = np.random.default_rng(0)
+    sc.poses[..., :2] += eps * rng.uniform(-1, 1, sc.poses[..., :2].shape) * np.abs(sc.poses[..., :2])
+    b = make_oracle(sc)
+    a.rollout(0.01, 1000, n_threads=8)
+    b.rollout(0.01, 1000, n_threads=8)
+    lin = np.array([rel_err(b.vels[w, :, :2], a.vels[w, :, :2]) for w in range(worlds)]) / eps
+    xy = np.array([rel_err(b.poses[w, :, :2], a.poses[w, :, :2]) for w in range(worlds)]) / eps
+    print(f"amplification after 1000 steps, N = {n}: linear velocity median {np.median(lin):.0f} worst {lin.max():.0f}; "
+          f"position median {np.median(xy):.0f} worst {xy.max():.0f}")
+    assert lin.max() > 1e3 and np.median(lin) > 10
+    assert 6e-8 * lin.max() > 1e-4            # one fp32 rounding, amplified: already beyond the quoted tolerance
+    assert np.median(xy) < np.median(lin)

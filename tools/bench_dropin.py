@@ -81,6 +81,15 @@ def run_orca(n, steps, warm):
 
 
 if __name__ == "__main__":
+    if "--profile" in sys.argv:          # where the Python side of a tick goes (cProfile, N = 64)
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        run(64, 2000, 50)
+        pr.disable()
+        pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+        sys.exit(0)
     for n in (2, 8, 32, 64):
         print(json.dumps(run(n, 300 if REFERENCE and n >= 32 else 1000, 50)), flush=True)
     if not REFERENCE:
