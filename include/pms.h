@@ -82,6 +82,33 @@ int pms_n_peds(const pms_sim *h);
  *      (core/_pedestrians_model.py:9-31) and reset_to_state (_hsfm.py:308-310) ---- */
 int pms_set_ped_state(pms_sim *h, const double *poses /*(W,N,3)*/, const double *vels /*(W,N,3)*/);
 int pms_get_ped_state(pms_sim *h, double *poses /*(W,N,3)*/, double *vels /*(W,N,3)*/);
+/* The same with float32 host arrays: half the PCIe bytes for callers that do not need more than the FP32 kernels compute in
+ * (the state of PMS_FP32 is hi + lo: the getter returns the correctly rounded sum, the setter starts from lo = 0). */
+int pms_set_ped_state_f32(pms_sim *h, const float *poses /*(W,N,3)*/, const float *vels /*(W,N,3) or NULL = 0*/);
+int pms_get_ped_state_f32(pms_sim *h, float *poses /*(W,N,3) or NULL*/, float *vels /*(W,N,3) or NULL*/);
+/* Device-resident I/O: `poses` / `vels` are DEVICE pointers to caller-owned (W,N,3) arrays of float64 (is_f32 = 0) or
+ * float32 (is_f32 = 1) on the handle's device -- e.g. the data_ptr() of a torch tensor.  One conversion kernel on the handle's
+ * stream, no host synchronisation and no PCIe traffic: order the consumer after pms_sync or after the handle's stream. */
+int pms_set_ped_state_device(pms_sim *h, const void *poses, const void *vels /*or NULL = 0*/, int is_f32);
+int pms_get_ped_state_device(pms_sim *h, void *poses /*or NULL*/, void *vels /*or NULL*/, int is_f32);
+/* Raw device pointers of the handle's result buffers (zero-copy for callers that stay on the GPU): valid until the handle is
+ * destroyed or -- the PMS_BUF_REC_* record buffers -- until the next launch grows them; written by the launches on the
+ * handle's stream.  bytes = current extent (records: the readings of the last launch).  *ptr = NULL when the buffer does not
+ * exist (kind not scheduled). */
+typedef enum {
+    PMS_BUF_DET_MASK = 0,        /* uint32 (W, ceil(N/32)): detector membership after the last step */
+    PMS_BUF_COLL_MASK = 1,       /* uint32 (W, ceil(N/32)): robot-pedestrian collision list after the last step */
+    PMS_BUF_DET_VALUES = 2,      /* float64 (W, N, 2) */
+    PMS_BUF_ROBOT_POSE = 3,      /* float64 (W, 3) */
+    PMS_BUF_ROBOT_VELOCITY = 4,  /* float64 (W, 3) */
+    PMS_BUF_DETECTIONS = 5,      /* uint64 (W): episode counter */
+    PMS_BUF_COLLISIONS = 6,      /* uint64 (W): episode counter */
+    PMS_BUF_FIRST_NONFINITE = 7, /* int32 (W): 1-based step of the first non-finite state, INT32_MAX = never */
+    PMS_BUF_WAYPOINT_INDEX = 8,  /* int32 (W, N) */
+    PMS_BUF_REC_DET_MASK = 16, PMS_BUF_REC_DET_VALUES = 17, PMS_BUF_REC_COLL_MASK = 18, PMS_BUF_REC_LIDAR_HIT = 19,
+    PMS_BUF_REC_LIDAR_POINTS = 20, PMS_BUF_REC_OMNI = 21   /* the records of pms_sensor_schedule, layouts as in pms_get_*_records */
+} pms_buffer;
+int pms_device_buffer(pms_sim *h, int which, void **ptr, uint64_t *bytes /*or NULL*/);
 int pms_set_ped_speeds(pms_sim *h, const double *vmag /*(W,N)*/); /* pedestrian_linear_velocity_magnitude */
 /* Asynchronous I/O mode (pipelining several handles): pms_set_ped_state, pms_get_ped_state, pms_get_detector,
  * pms_get_collisions and pms_get_stats enqueue their copies on the handle's stream and return; the host buffers must be
@@ -192,6 +219,7 @@ int pms_sense(pms_sim *h);
 
 /* readings for the latest state */
 int pms_get_detector(pms_sim *h, uint32_t *mask /*(W,ceil(N/32))*/, double *values /*(W,N,2)*/);
+int pms_get_detector_f32(pms_sim *h, uint32_t *mask /*(W,ceil(N/32))*/, float *values /*(W,N,2)*/);   /* exact reading, float32 values */
 int pms_get_collisions(pms_sim *h, uint32_t *mask /*(W,ceil(N/32))*/);
 /* per-world episode statistics accumulated over all steps since the last pms_reset_stats */
 int pms_get_stats(pms_sim *h, int64_t *detections /*(W)*/, int64_t *collisions /*(W)*/, int32_t *first_nonfinite_step /*(W)*/);
@@ -203,6 +231,38 @@ int pms_lidar_scan(pms_sim *h, int n_beams, double max_dist, double resolution,
                    int32_t *hit_index /*(W,n_beams)*/, double *points /*(W,n_beams,2)*/);
 /* OmniObstacleDetector (sensors/_omni_obstacle_detector.py:58-62): min distance robot -> map */
 int pms_omni_scan(pms_sim *h, double *min_dist /*(W)*/);
+
+/* ---- sensors inside a fused launch: the hold-time scheduler of Simulation._update_sensors_state
+ *      (core/_simulation.py:162-185) on the device ----
+ * The reference keeps one hold_time per sensor: every step hold += dt, and when hold >= period the sensor is read and
+ * hold = 0 (dt = 0.01: a 10 Hz sensor fires every ELEVEN steps).  A sensor kind registered here is scheduled the same way
+ * inside pms_hsfm_step / pms_hsfm_step_async / pms_step_tick: a tiny kernel replays the fp64 recurrence for the n_steps of
+ * the launch, the step kernel takes the reading after every firing step and appends it to the RECORDS of the launch --
+ * record k of a kind is its k-th reading of the LAST launch, taken after launch step steps[k] (0-based).  hold_time
+ * persists from launch to launch (and through pms_snapshot_save / restore), so an episode split into several launches
+ * fires at the same steps as one long launch.  The kinds:
+ *   PMS_SENSOR_DETECTOR   PedestrianDetector.get_reading (sensors/_pedestrian_detector.py:78-134): membership mask per
+ *                         record, plus the (W,N,2) values when flags has PMS_SENSOR_VALUES (exact, no device noise)
+ *   PMS_SENSOR_LIDAR      LidarSensor.get_reading (sensors/_lidar.py:105-129) with the pms_lidar_config geometry, taken by
+ *                         the warp that integrates the robot; LidarSensorNoise as set by pms_set_lidar_noise
+ *   PMS_SENSOR_OMNI       OmniObstacleDetector.get_reading (sensors/_omni_obstacle_detector.py:58-62), pms_set_omni_noise
+ *   PMS_SENSOR_COLLISIONS WorldState.robot_to_pedestrians_collisions (core/_simulation.py:141-143); not a sensor in the
+ *                         reference (every step carries it): schedule it with period 0 for a per-step history
+ * period = AbstractSensor.period (1 / frequency; 0 = a reading after every step); hold_time = SensorState.hold_time to
+ * start from (0 right after Simulation.__init__, whose own first reading is pms_sense / pms_lidar_scan / pms_omni_scan).
+ * Without a robot (PMS_ROBOT_NONE) the detector / collision records are empty masks and lidar / omni records are not
+ * written (the reference returns no sensor state at all, core/_simulation.py:164-165). */
+typedef enum { PMS_SENSOR_DETECTOR = 0, PMS_SENSOR_LIDAR = 1, PMS_SENSOR_OMNI = 2, PMS_SENSOR_COLLISIONS = 3 } pms_sensor_kind;
+#define PMS_SENSOR_VALUES 1
+int pms_lidar_config(pms_sim *h, int n_beams, double max_dist, double resolution);   /* LidarSensorConfig, _lidar.py:8-23 */
+int pms_sensor_schedule(pms_sim *h, int kind, int enabled, double period, double hold_time, int flags);
+/* the readings of the last launch: how many, after which launch steps, and the hold_time the scheduler is left with */
+int pms_get_sensor_fires(pms_sim *h, int kind, int32_t *steps /*(cap) or NULL*/, int cap, int *n_fires, double *hold_time /*or NULL*/);
+/* records first .. first + count - 1 of the last launch (host arrays, record-major) */
+int pms_get_detector_records(pms_sim *h, int first, int count, uint32_t *mask /*(count,W,ceil(N/32))*/, double *values /*(count,W,N,2) or NULL*/);
+int pms_get_collision_records(pms_sim *h, int first, int count, uint32_t *mask /*(count,W,ceil(N/32))*/);
+int pms_get_lidar_records(pms_sim *h, int first, int count, int32_t *hit_index /*(count,W,n_beams)*/, double *points /*(count,W,n_beams,2) or NULL*/);
+int pms_get_omni_records(pms_sim *h, int first, int count, double *min_dist /*(count,W)*/);
 
 /* ---- ORCA (pedestrians/_orca.py:95-127 around rvo2.doStep) ---- */
 int pms_orca_create(int device, int n_worlds, int n_agents, const pms_orca_params *params, pms_sim **out);

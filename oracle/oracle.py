@@ -306,6 +306,39 @@ class OracleBatch:
         lib().orc_omni(C.byref(b), _ptr(out, _dp))
         return out
 
+    def episode(self, dt: float, n_steps: int, schedule: dict, lidar=(100, 8.0, 0.01), controls=None):
+        """n_steps single steps with the reference's sensor scheduler (Simulation._update_sensors_state,
+        core/_simulation.py:162-185): per scheduled kind, hold += dt after every step; hold >= period -> reading, hold = 0.
+        schedule: {"detector" | "lidar" | "omni" | "collisions": [period, hold_time]} (hold_time is updated in place).
+        Returns {kind: {"steps": [...], records...}} with one record per reading, in firing order."""
+        out = {k: {"steps": []} for k in schedule}
+        ctr = None if controls is None else _f64(controls).reshape(-1, self.W, 2)
+        for t in range(n_steps):
+            if ctr is not None:
+                self.set_controls(ctr[min(t, len(ctr) - 1)][None])
+            self.rollout(dt, 1)
+            for kind, ph in schedule.items():
+                ph[1] = ph[1] + dt
+                if not ph[1] >= ph[0]:
+                    continue
+                ph[1] = 0.0
+                rec = out[kind]
+                rec["steps"].append(t)
+                if kind == "detector":
+                    rec.setdefault("mask", []).append(self.det_mask.copy())
+                    rec.setdefault("vals", []).append(self.det_vals.copy())
+                elif kind == "collisions":
+                    rec.setdefault("mask", []).append(self.coll_mask.copy())
+                elif kind == "lidar":
+                    hit, pts = self.lidar(*lidar)
+                    rec.setdefault("hit", []).append(hit)
+                    rec.setdefault("points", []).append(pts)
+                elif kind == "omni":
+                    rec.setdefault("dist", []).append(self.omni())
+        if ctr is not None:
+            self.set_controls(None)
+        return {k: {n: np.asarray(v) for n, v in rec.items()} for k, rec in out.items()}
+
     def map_is_collision(self, w, x, y, radius):
         b = self._struct()
         return bool(lib().orc_map_is_collision(C.byref(b), int(w), float(x), float(y), float(radius)))

@@ -14,6 +14,12 @@ PMS_FP32, PMS_MIXED, PMS_FP64, PMS_FP32_PLAIN = 0, 1, 2, 3
 ROBOT_NONE, ROBOT_EXTERNAL, ROBOT_UNICYCLE, ROBOT_BICYCLE = 0, 1, 2, 3
 MAP_EMPTY, MAP_CIRCLES, MAP_AABB = 0, 1, 2
 DET_POLAR, DET_RELATIVE_ROTATED, DET_RELATIVE, DET_ABSOLUTE = 0, 1, 2, 3
+SENSOR_DETECTOR, SENSOR_LIDAR, SENSOR_OMNI, SENSOR_COLLISIONS = 0, 1, 2, 3
+SENSOR_VALUES = 1
+# pms_buffer: name -> (id, numpy dtype, trailing shape builder)
+BUF_DET_MASK, BUF_COLL_MASK, BUF_DET_VALUES, BUF_ROBOT_POSE, BUF_ROBOT_VELOCITY = 0, 1, 2, 3, 4
+BUF_DETECTIONS, BUF_COLLISIONS, BUF_FIRST_NONFINITE, BUF_WAYPOINT_INDEX = 5, 6, 7, 8
+BUF_REC_DET_MASK, BUF_REC_DET_VALUES, BUF_REC_COLL_MASK, BUF_REC_LIDAR_HIT, BUF_REC_LIDAR_POINTS, BUF_REC_OMNI = 16, 17, 18, 19, 20, 21
 PRECISIONS = {"fp32": PMS_FP32, "mixed": PMS_MIXED, "fp64": PMS_FP64, "fp32_plain": PMS_FP32_PLAIN}
 
 
@@ -40,6 +46,7 @@ class LaunchInfoC(C.Structure):
 
 
 _dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int32)
 _up = C.POINTER(C.c_uint32)
 _lp = C.POINTER(C.c_int64)
@@ -57,6 +64,12 @@ PROTOTYPES = {
     "pms_n_peds": (C.c_int, [_h]),
     "pms_set_ped_state": (C.c_int, [_h, _dp, _dp]),
     "pms_get_ped_state": (C.c_int, [_h, _dp, _dp]),
+    "pms_set_ped_state_f32": (C.c_int, [_h, _fp, _fp]),
+    "pms_get_ped_state_f32": (C.c_int, [_h, _fp, _fp]),
+    "pms_set_ped_state_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, C.c_int]),
+    "pms_get_ped_state_device": (C.c_int, [_h, C.c_void_p, C.c_void_p, C.c_int]),
+    "pms_device_buffer": (C.c_int, [_h, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "pms_get_detector_f32": (C.c_int, [_h, _up, _fp]),
     "pms_set_ped_speeds": (C.c_int, [_h, _dp]),
     "pms_set_async_io": (C.c_int, [_h, C.c_int]),
     "pms_snapshot_save": (C.c_int, [_h]),
@@ -90,6 +103,13 @@ PROTOTYPES = {
     "pms_reset_stats": (C.c_int, [_h]),
     "pms_lidar_scan": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, _ip, _dp]),
     "pms_omni_scan": (C.c_int, [_h, _dp]),
+    "pms_lidar_config": (C.c_int, [_h, C.c_int, C.c_double, C.c_double]),
+    "pms_sensor_schedule": (C.c_int, [_h, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]),
+    "pms_get_sensor_fires": (C.c_int, [_h, C.c_int, _ip, C.c_int, C.POINTER(C.c_int), _dp]),
+    "pms_get_detector_records": (C.c_int, [_h, C.c_int, C.c_int, _up, _dp]),
+    "pms_get_collision_records": (C.c_int, [_h, C.c_int, C.c_int, _up]),
+    "pms_get_lidar_records": (C.c_int, [_h, C.c_int, C.c_int, _ip, _dp]),
+    "pms_get_omni_records": (C.c_int, [_h, C.c_int, C.c_int, _dp]),
     "pms_orca_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(OrcaParamsC), C.POINTER(_h)]),
     "pms_orca_set_agents": (C.c_int, [_h, _dp, _dp, _dp, _dp]),
     "pms_orca_set_waypoints_fixed": (C.c_int, [_h, _dp, C.c_int, _ip, C.c_double, C.c_int]),
@@ -130,6 +150,10 @@ def check(rc: int):
 
 def dptr(a):
     return None if a is None else a.ctypes.data_as(_dp)
+
+
+def fptr(a):
+    return None if a is None else a.ctypes.data_as(_fp)
 
 
 def iptr(a):

@@ -12,7 +12,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import _capi as capi
-from ._capi import check, dptr, f64, iptr, lptr, uptr
+from ._capi import check, dptr, f64, fptr, iptr, lptr, uptr
 
 
 @dataclass
@@ -43,6 +43,7 @@ class BatchedSimulation:
         self.W, self.N = int(n_worlds), int(n_peds)
         self.words = (self.N + 31) // 32
         self.precision = precision
+        self.device = int(device)
         p = hsfm_params or HSFMParams()
         cp = capi.HsfmParamsC(float(p.tau), float(p.A), float(p.B), float(p.k_1), float(p.k_2), float(p.k_o),
                               float(p.k_d), float(p.k_lambda), float(p.alpha), float(pedestrian_mass),
@@ -65,15 +66,80 @@ class BatchedSimulation:
 
     # ---- state ----------------------------------------------------------------------------------
     def set_state(self, poses, velocities=None):
+        """Host arrays (W, N, 3).  float32 input takes the float32 interface (half the bytes over PCIe), anything else
+        the reference's float64."""
+        if getattr(poses, "dtype", None) == np.float32 and (velocities is None or getattr(velocities, "dtype", None) == np.float32):
+            p32 = np.ascontiguousarray(poses, dtype=np.float32).reshape(self.W, self.N, 3)
+            v32 = None if velocities is None else np.ascontiguousarray(velocities, dtype=np.float32).reshape(self.W, self.N, 3)
+            check(self._lib.pms_set_ped_state_f32(self._h, fptr(p32), fptr(v32)))
+            return
         poses = f64(poses, (self.W, self.N, 3))
         vels = None if velocities is None else f64(velocities, (self.W, self.N, 3))
         check(self._lib.pms_set_ped_state(self._h, dptr(poses), dptr(vels)))
 
-    def get_state(self, out_poses=None, out_vels=None) -> Tuple[np.ndarray, np.ndarray]:
-        poses = np.empty((self.W, self.N, 3)) if out_poses is None else out_poses
-        vels = np.empty((self.W, self.N, 3)) if out_vels is None else out_vels
-        check(self._lib.pms_get_ped_state(self._h, dptr(poses), dptr(vels)))
+    def get_state(self, out_poses=None, out_vels=None, dtype=np.float64) -> Tuple[np.ndarray, np.ndarray]:
+        """(poses, velocities) as host arrays (W, N, 3) of ``dtype`` (float64 like the reference, or float32); output arrays
+        passed in decide the dtype themselves."""
+        if out_poses is not None:
+            dtype = out_poses.dtype
+        elif out_vels is not None:
+            dtype = out_vels.dtype
+        poses = np.empty((self.W, self.N, 3), dtype=dtype) if out_poses is None else out_poses
+        vels = np.empty((self.W, self.N, 3), dtype=dtype) if out_vels is None else out_vels
+        if np.dtype(dtype) == np.float32:
+            check(self._lib.pms_get_ped_state_f32(self._h, fptr(poses), fptr(vels)))
+        else:
+            check(self._lib.pms_get_ped_state(self._h, dptr(poses), dptr(vels)))
         return poses, vels
+
+    # ---- device-resident I/O (callers that stay on the GPU: torch tensors, CuPy arrays, raw pointers) --------------------
+    def set_state_device(self, poses_ptr: int, vels_ptr: Optional[int], f32: bool):
+        """``poses_ptr`` / ``vels_ptr``: device addresses of (W, N, 3) float32 / float64 arrays on this handle's device."""
+        check(self._lib.pms_set_ped_state_device(self._h, C.c_void_p(poses_ptr), C.c_void_p(vels_ptr or 0) if vels_ptr else None, int(bool(f32))))
+
+    def get_state_device(self, poses_ptr: Optional[int], vels_ptr: Optional[int], f32: bool):
+        check(self._lib.pms_get_ped_state_device(self._h, C.c_void_p(poses_ptr) if poses_ptr else None,
+                                                 C.c_void_p(vels_ptr) if vels_ptr else None, int(bool(f32))))
+
+    def set_state_torch(self, poses, velocities=None):
+        """State from CUDA torch tensors (W, N, 3), float32 or float64, no host round trip.  The conversion kernel runs on
+        the handle's stream: the tensors must be complete (synchronise or order the producer stream first)."""
+        import torch
+        assert poses.is_cuda and poses.is_contiguous() and poses.shape == (self.W, self.N, 3) and poses.dtype in (torch.float32, torch.float64)
+        if velocities is not None:
+            assert velocities.is_cuda and velocities.is_contiguous() and velocities.shape == poses.shape and velocities.dtype == poses.dtype
+        self.set_state_device(poses.data_ptr(), None if velocities is None else velocities.data_ptr(), poses.dtype == torch.float32)
+
+    def get_state_torch(self, dtype=None, out=None):
+        """(poses, velocities) as CUDA torch tensors (W, N, 3); written on the handle's stream -- call ``sync()`` (or order
+        your stream after ``stream``) before reading them."""
+        import torch
+        if out is None:
+            dtype = dtype or torch.float32
+            dev = torch.device("cuda", self.device)
+            out = (torch.empty((self.W, self.N, 3), dtype=dtype, device=dev), torch.empty((self.W, self.N, 3), dtype=dtype, device=dev))
+        poses, vels = out
+        self.get_state_device(poses.data_ptr(), vels.data_ptr(), poses.dtype == torch.float32)
+        return poses, vels
+
+    def device_buffer(self, which: int) -> Tuple[int, int]:
+        """(device address, bytes) of one of the handle's result buffers (``capi.BUF_*``), zero-copy."""
+        p, b = C.c_void_p(), C.c_uint64(0)
+        check(self._lib.pms_device_buffer(self._h, int(which), C.byref(p), C.byref(b)))
+        return int(p.value or 0), int(b.value)
+
+    def device_tensor(self, which: int, dtype, shape=None):
+        """A torch tensor that ALIASES a result buffer (``capi.BUF_*``): no copy, valid as documented for pms_device_buffer."""
+        import torch
+        ptr, nbytes = self.device_buffer(which)
+        if not ptr or not nbytes:
+            return None
+        np_dt = np.dtype(dtype)
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (nbytes // np_dt.itemsize,), "typestr": np_dt.str, "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(_Alias(), device=torch.device("cuda", self.device))
+        return t if shape is None else t.view(*shape)
 
     def set_speeds(self, vmag):
         check(self._lib.pms_set_ped_speeds(self._h, dptr(f64(vmag, (self.W, self.N)))))
@@ -254,6 +320,13 @@ class BatchedSimulation:
         check(self._lib.pms_get_detector(self._h, uptr(mask), dptr(vals)))
         return mask, vals
 
+    def get_detector_f32(self, out_mask=None, out_vals=None) -> Tuple[np.ndarray, np.ndarray]:
+        """The exact reading with float32 values (half the bytes of ``get_detector``)."""
+        mask = np.empty((self.W, self.words), dtype=np.uint32) if out_mask is None else out_mask
+        vals = np.empty((self.W, self.N, 2), dtype=np.float32) if out_vals is None else out_vals
+        check(self._lib.pms_get_detector_f32(self._h, uptr(mask), fptr(vals)))
+        return mask, vals
+
     def get_collisions(self, out_mask=None) -> np.ndarray:
         mask = np.empty((self.W, self.words), dtype=np.uint32) if out_mask is None else out_mask
         check(self._lib.pms_get_collisions(self._h, uptr(mask)))
@@ -279,6 +352,63 @@ class BatchedSimulation:
     def omni_scan(self) -> np.ndarray:
         out = np.empty(self.W)
         check(self._lib.pms_omni_scan(self._h, dptr(out)))
+        return out
+
+    # ---- sensors inside a fused launch (the reference's hold-time scheduler on the device) -----------
+    def set_lidar(self, n_beams: int = 100, max_dist: float = 8.0, resolution: float = 0.01):
+        """LidarSensorConfig (sensors/_lidar.py:8-23) of the lidar readings taken inside fused launches."""
+        check(self._lib.pms_lidar_config(self._h, int(n_beams), float(max_dist), float(resolution)))
+        self._lidar_beams = int(n_beams)
+
+    def schedule_sensor(self, kind: int, period: float = 0.0, hold_time: float = 0.0, values: bool = False,
+                        enabled: bool = True):
+        """Schedule a sensor kind (``capi.SENSOR_*``) inside ``step`` with the reference's hold-time rule
+        (core/_simulation.py:162-185): after every step ``hold += dt``; ``hold >= period`` -> reading, ``hold = 0``.
+        ``period`` = ``AbstractSensor.period`` (1 / frequency, 0 = every step).  The readings of the last launch are the
+        *records* returned by ``sensor_fires`` / ``*_records``.  ``values``: detector records keep the (W, N, 2) values."""
+        check(self._lib.pms_sensor_schedule(self._h, int(kind), int(bool(enabled)), float(period), float(hold_time),
+                                            capi.SENSOR_VALUES if values else 0))
+
+    def sensor_fires(self, kind: int) -> Tuple[np.ndarray, float]:
+        """(0-based launch steps after which the kind was read in the last launch, hold_time left in the scheduler)."""
+        n, hold = C.c_int(0), C.c_double(0.0)
+        check(self._lib.pms_get_sensor_fires(self._h, int(kind), None, 0, C.byref(n), C.byref(hold)))
+        steps = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            check(self._lib.pms_get_sensor_fires(self._h, int(kind), iptr(steps), n.value, C.byref(n), C.byref(hold)))
+        return steps, hold.value
+
+    def _n_records(self, kind: int, first: int, count: Optional[int]) -> int:
+        if count is not None:
+            return int(count)
+        n = C.c_int(0)
+        check(self._lib.pms_get_sensor_fires(self._h, int(kind), None, 0, C.byref(n), None))
+        return n.value - first
+
+    def detector_records(self, first: int = 0, count: Optional[int] = None, values: bool = False):
+        count = self._n_records(capi.SENSOR_DETECTOR, first, count)
+        mask = np.empty((count, self.W, self.words), dtype=np.uint32)
+        vals = np.empty((count, self.W, self.N, 2)) if values else None
+        check(self._lib.pms_get_detector_records(self._h, int(first), count, uptr(mask), dptr(vals)))
+        return (mask, vals) if values else mask
+
+    def collision_records(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self._n_records(capi.SENSOR_COLLISIONS, first, count)
+        mask = np.empty((count, self.W, self.words), dtype=np.uint32)
+        check(self._lib.pms_get_collision_records(self._h, int(first), count, uptr(mask)))
+        return mask
+
+    def lidar_records(self, first: int = 0, count: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+        count = self._n_records(capi.SENSOR_LIDAR, first, count)
+        hit = np.empty((count, self.W, self._lidar_beams), dtype=np.int32)
+        pts = np.empty((count, self.W, self._lidar_beams, 2))
+        check(self._lib.pms_get_lidar_records(self._h, int(first), count, iptr(hit), dptr(pts)))
+        return hit, pts
+
+    def omni_records(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        count = self._n_records(capi.SENSOR_OMNI, first, count)
+        out = np.empty((count, self.W))
+        check(self._lib.pms_get_omni_records(self._h, int(first), count, dptr(out)))
         return out
 
     def launch_info(self) -> dict:

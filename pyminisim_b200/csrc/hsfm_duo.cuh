@@ -183,7 +183,8 @@ __device__ __forceinline__ void duo_contact(const HsfmArgs &a, const float2 *pl,
     }
 }
 
-template <int T, bool COMP>
+// SENS: the instantiation that serves a sensor plan (see warp_robot_block in hsfm_warp.cuh)
+template <int T, bool COMP, bool SENS>
 __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(const __grid_constant__ HsfmArgs a)
 {
     using L = DuoSmem<T>;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
         if (has_robot) {
             if (lane == 0) robot_load(a, w, *rrp);
             __syncwarp();
-            warp_robot_block(a, w, t_begin, min(WARP_ROBOT_BLOCK, t_end - t_begin), rrp, ring, lane);
+            warp_robot_block<SENS>(a, w, t_begin, min(WARP_ROBOT_BLOCK, t_end - t_begin), rrp, ring, lane);   // SENS: + lidar / omni readings
         }
         world_sync();                                                   // #1
         world_sync();                                                   // #2
@@ -255,9 +256,17 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
             const int k = t - t_begin, b = k & 1, nb = b ^ 1;
             if (contact_flag(b)) world_sync();
             if (has_robot) {
-                if ((k & (WARP_ROBOT_BLOCK - 1)) == 0 && t + WARP_ROBOT_BLOCK < t_end)
-                    warp_robot_block(a, w, t + WARP_ROBOT_BLOCK, min(WARP_ROBOT_BLOCK, t_end - t - WARP_ROBOT_BLOCK), rrp,
+                if ((k & (WARP_ROBOT_BLOCK - 1)) == 0 && t + WARP_ROBOT_BLOCK < t_end)   // (+ lidar / omni readings of the block's firing steps)
+                    warp_robot_block<SENS>(a, w, t + WARP_ROBOT_BLOCK, min(WARP_ROBOT_BLOCK, t_end - t - WARP_ROBOT_BLOCK), rrp,
                                      ring + ((k + WARP_ROBOT_BLOCK) & (DUO_RING - 1)), lane);
+                int dslot = -1, cslot = -1;          // sensor plan: records of the detector / collision list after this step
+                if constexpr (SENS) {
+                    if (a.sp.ped_on) {
+                        if (a.sp.fire[SENSOR_DETECTOR]) dslot = a.sp.fire[SENSOR_DETECTOR][t];
+                        if (a.sp.fire[SENSOR_COLLISIONS]) cslot = a.sp.fire[SENSOR_COLLISIONS][t];
+                    }
+                }
+                const bool rec_vals = SENS && dslot >= 0 && a.sp.det_vals != nullptr;
                 // ---- collision list + detector of step t: r_{t+1} against the robot after its step t; the tiles side by side
                 //      (one vote for the rare exact path of all of them) ----
                 const WarpRobotSlot &rb = ring[k & (DUO_RING - 1)];
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
                     det[s_] = d2[s_] < a.sn_det_lo2 && u[s_] > m[s_];   // sn_det_*: negative when the detector is off
                     coll[s_] = d2[s_] < a.sn_coll_lo2;
                     const bool unsure = (!coll[s_] && d2[s_] <= a.sn_coll_hi2) || (!det[s_] && d2[s_] <= a.sn_det_hi2 && !(u[s_] < -m[s_]));
-                    exact[s_] = unsure || (last && det[s_]);
+                    exact[s_] = unsure || ((last || rec_vals) && det[s_]);
                     any_exact = any_exact || exact[s_];
                 }
                 double2 dvals[T];
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
                         if (exact[s_]) {
                             SenseOut so{false, false, 0.0, 0.0};
                             const RobotSlot r64{rb.x, rb.y, rb.th, 0.0, 0.0};
-                            sense_ped_exact(a, r64, (double)px[s_] + (double)pxl[s_], (double)py[s_] + (double)pyl[s_], last, so);
+                            sense_ped_exact(a, r64, (double)px[s_] + (double)pxl[s_], (double)py[s_] + (double)pyl[s_], last || rec_vals, so);
                             det[s_] = so.det; coll[s_] = so.coll; dvals[s_] = make_double2(so.v0, so.v1);
                         }
                     }
@@ -302,12 +311,19 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
                     const unsigned cm = __ballot_sync(0xffffffffu, coll[s_]);
                     det_acc += __popc(dm);
                     coll_acc += __popc(cm);
+                    const int si = 32 * s_ + lane;
                     if (last) {
-                        const int si = 32 * s_ + lane;
                         if (a.det_enabled && si < N) a.det_vals[(size_t)w * N + si] = dvals[s_];
                         if (lane == 0 && s_ < words) {
                             a.det_mask[(size_t)w * words + s_] = dm;
                             a.coll_mask[(size_t)w * words + s_] = cm;
+                        }
+                    }
+                    if constexpr (SENS) {
+                        if (rec_vals && si < N) a.sp.det_vals[((size_t)dslot * a.W + w) * N + si] = dvals[s_];
+                        if (lane == 0 && s_ < words) {
+                            if (dslot >= 0) a.sp.det_mask[((size_t)dslot * a.W + w) * words + s_] = dm;
+                            if (cslot >= 0) a.sp.coll_mask[((size_t)cslot * a.W + w) * words + s_] = cm;
                         }
                     }
                 }

@@ -159,6 +159,13 @@ __global__ void robot_window_kernel(const __grid_constant__ HsfmArgs a, RobotReg
     for (int t = t0; t < t1; ++t)
         large_robot_step(a, w, regs, slot + (size_t)(t - t0) * a.W, t, t == 0, t == a.n_steps - 1);
 }
+// lidar / omni readings of the firing steps of the window (sensor plan): one warp per world, behind robot_window_kernel on
+// the side stream
+__global__ void sensor_window_kernel(const __grid_constant__ HsfmArgs a, const RobotSlot *slot, int t0, int t1)
+{
+    const int w = blockIdx.x, lane = threadIdx.x;
+    for (int t = t0; t < t1; ++t) sensor_fires_block(a, w, t, 1, slot + (size_t)(t - t0) * a.W + w, lane);
+}
 
 // ---- pair view initialisation from the state (first step of a call) --------------------------------------
 template <typename PT, typename ST, bool SPLIT>
@@ -362,6 +369,11 @@ __device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &
     RobotSlot rb{0, 0, 0, 0, 0};
     if (has_robot) rb = la.robot_slot[w];
     SenseOut so{false, false, 0.0, 0.0};
+    int dslot = -1, cslot = -1;               // sensor plan: records of the detector / collision list after this step
+    if (a.sp.ped_on) {
+        if (a.sp.fire[SENSOR_DETECTOR]) dslot = a.sp.fire[SENSOR_DETECTOR][la.step];
+        if (a.sp.fire[SENSOR_COLLISIONS]) cslot = a.sp.fire[SENSOR_COLLISIONS][la.step];
+    }
     PT *vdst = reinterpret_cast<PT *>(la.view_dst) + (size_t)w * la.Npad;
     if (valid) {
         if (has_robot && a.robot_visible) {
@@ -451,31 +463,40 @@ __device__ __forceinline__ void large_owner(const HsfmArgs &a, const LargeArgs &
         }
         if (!m_finite(x + y + vx + vy + th + om)) atomicMin(&a.nonfinite[w], (int)(a.steps_done + la.step + 1));
         if (has_robot) {
+            const bool want = la.last != 0 || (dslot >= 0 && a.sp.det_vals != nullptr);
             if constexpr (sizeof(ST) == 4) {
-                if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, la.last != 0);
-                else so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+                if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, want);
+                else so = sense_ped<ST>(a, rb, x, y, want);
             } else {
-                so = sense_ped<ST>(a, rb, x, y, la.last != 0);
+                so = sense_ped<ST>(a, rb, x, y, want);
             }
         }
         if (la.last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
+        if (dslot >= 0 && has_robot && a.sp.det_vals) a.sp.det_vals[(size_t)dslot * a.W * N + g] = make_double2(so.v0, so.v1);
     }
     if (has_robot) {
         const unsigned dm = __ballot_sync(0xffffffffu, so.det);
         const unsigned cm = __ballot_sync(0xffffffffu, so.coll);
+        const int words = (N + 31) >> 5;
         if (lane == 0) {
             if (dm) atomicAdd(&a.det_count[w], (unsigned long long)__popc(dm));
             if (cm) atomicAdd(&a.coll_count[w], (unsigned long long)__popc(cm));
-            const int words = (N + 31) >> 5;
-            if (la.last && !la.perm && (i >> 5) < words) {
-                a.det_mask[(size_t)w * words + (i >> 5)] = dm;
-                a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
+            if (!la.perm && (i >> 5) < words) {
+                if (la.last) {
+                    a.det_mask[(size_t)w * words + (i >> 5)] = dm;
+                    a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
+                }
+                if (dslot >= 0) a.sp.det_mask[((size_t)dslot * a.W + w) * words + (i >> 5)] = dm;
+                if (cslot >= 0) a.sp.coll_mask[((size_t)cslot * a.W + w) * words + (i >> 5)] = cm;
             }
         }
-        if (la.last && la.perm) {          // sorted slots: set the caller's bit (the masks were cleared before the call)
-            const int words = (N + 31) >> 5;
-            if (so.det) atomicOr(&a.det_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
-            if (so.coll) atomicOr(&a.coll_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
+        if (la.perm) {          // sorted slots: set the caller's bit (the masks / records were cleared before the call)
+            if (la.last) {
+                if (so.det) atomicOr(&a.det_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
+                if (so.coll) atomicOr(&a.coll_mask[(size_t)w * words + (ie >> 5)], 1u << (ie & 31));
+            }
+            if (dslot >= 0 && so.det) atomicOr(&a.sp.det_mask[((size_t)dslot * a.W + w) * words + (ie >> 5)], 1u << (ie & 31));
+            if (cslot >= 0 && so.coll) atomicOr(&a.sp.coll_mask[((size_t)cslot * a.W + w) * words + (ie >> 5)], 1u << (ie & 31));
         }
     }
 }
@@ -1029,8 +1050,9 @@ inline int launch_large_t(LargeScratch &s, HsfmArgs &a, int cluster, bool prune_
             cudaEventRecord(s.ev_fork, stream);
             cudaStreamWaitEvent(s.aux, s.ev_fork, 0);
             robot_window_kernel<<<(a.W + 127) / 128, 128, 0, s.aux>>>(a, s.robot_regs, slots, t0, t1);
-            cudaEventRecord(s.ev_join, s.aux);
             ++*launches;
+            if (a.sp.robot_on) { sensor_window_kernel<<<a.W, 32, 0, s.aux>>>(a, slots, t0, t1); ++*launches; }
+            cudaEventRecord(s.ev_join, s.aux);
         }
         if (cont) cur = s.cur;
         if (reorder && !cont) {

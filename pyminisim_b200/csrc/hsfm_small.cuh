@@ -16,6 +16,7 @@
 #pragma once
 #include <type_traits>
 #include "pms_common.cuh"
+#include "sensor_fires.cuh"
 
 namespace pms {
 
@@ -291,10 +292,10 @@ template <typename ST> struct OwnerView {
 
 // One owner step for pedestrian i of world w: O(1) dynamics + explicit Euler (_hsfm.py:86-110,290-294), waypoint
 // tracker on the new pose (:301-304), state write-back to shared memory, collision list + detector predicate.
-template <typename ST, typename Publish>
+template <typename ST, bool SENS = false, typename Publish>
 __device__ __forceinline__ SenseOut owner_update(const HsfmArgs &a, const OwnerView<ST> &ow, int i, size_t g, int w, int t,
                                                  ST fx, ST fy, const RobotSlot &rb, bool has_robot, bool last,
-                                                 int &first_bad, Publish &&publish)
+                                                 int &first_bad, Publish &&publish, int det_slot = -1)
 {
     using ST2 = typename Vec2<ST>::type;
     const PedConsts<ST> &kc = kc_of(a, ST{});
@@ -374,15 +375,21 @@ __device__ __forceinline__ SenseOut owner_update(const HsfmArgs &a, const OwnerV
     publish(x, y, vx, vy);
     if (!first_bad && !m_finite(x + y + vx + vy + th + om)) first_bad = (int)(a.steps_done + t + 1);
     // ---- collision list + detector on the new state ----
+    // det_slot >= 0: the detector fires after this step (sensor plan) -- its reading goes to record det_slot of the launch
+    const bool record_vals = SENS && det_slot >= 0 && a.sp.det_vals != nullptr;
+    const bool want = last || record_vals;
     if (has_robot) {
         if constexpr (sizeof(ST) == 4) {
-            if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, last);
-            else so = sense_ped<ST>(a, rb, x, y, last);
+            if (comp) so = sense_ped<double>(a, rb, (double)x + (double)lo.x, (double)y + (double)lo.y, want);
+            else so = sense_ped<ST>(a, rb, x, y, want);
         } else {
-            so = sense_ped<ST>(a, rb, x, y, last);
+            so = sense_ped<ST>(a, rb, x, y, want);
         }
     }
     if (last && has_robot && a.det_enabled) a.det_vals[g] = make_double2(so.v0, so.v1);
+    if constexpr (SENS) {
+        if (record_vals && has_robot) a.sp.det_vals[(size_t)det_slot * a.W * a.N + g] = make_double2(so.v0, so.v1);
+    }
     return so;
 }
 
@@ -426,7 +433,8 @@ __device__ __forceinline__ void pair_far2(const PairK<float> &k, float2 dx, floa
 // One chunk of simulation steps [t_begin, t_end) for the wpc worlds of `group`.
 // Synchronisation: the warps of one world meet twice per step at that world's named barrier; the robot
 // warp fills the robot ring ROBOT_BLOCK steps ahead and everybody meets at CTA barrier 0 once per block.
-template <typename PT, typename ST, bool SPLIT, int S>
+// SENS: the instantiation that serves a sensor plan (pms_sensor_schedule); its code is compiled out of the default kernels
+template <typename PT, typename ST, bool SPLIT, int S, bool SENS>
 __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, const int t_begin, const int t_end)
 {
     using ST2 = typename Vec2<ST>::type;
@@ -516,10 +524,24 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
         const bool robot_lane = world_ok && has_robot;
         int filled = t_begin;                  // ring holds steps < filled
         auto fill = [&](int upto) {
-            if (!robot_lane) return;
-            for (; filled < upto; ++filled) {
-                robot_step(a, w, filled, rr);
-                ring[(filled - t_begin) & (ROBOT_RING - 1)] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
+            const int from = filled;
+            for (; filled < upto; ++filled) {       // `filled` advances on every lane: the sensor pass below is warp-uniform
+                if (robot_lane) {
+                    robot_step(a, w, filled, rr);
+                    ring[(filled - t_begin) & (ROBOT_RING - 1)] = RobotSlot{rr.x, rr.y, rr.th, rr.vx, rr.vy};
+                }
+            }
+            // lidar / omni readings of the firing steps just produced (sensor plan): lane wl stepped the robot of local world
+            // wl, the whole warp reads the sensors of one world after the other
+            if (SENS && a.sp.robot_on && has_robot) {
+                __syncwarp();
+                const int lane_ = tid & 31;
+                for (int wq = 0; wq < a.wpc && group * a.wpc + wq < a.W; ++wq) {
+                    const RobotSlot *rq = reinterpret_cast<const RobotSlot *>(smem_raw + (size_t)wq * L::bytes(Np, S) + L::off_robot(Np, S));
+                    for (int st = from; st < upto; ++st)
+                        sensor_fires_block(a, group * a.wpc + wq, st, 1, rq + ((st - t_begin) & (ROBOT_RING - 1)), lane_);
+                }
+                __syncwarp();
             }
         };
         if (robot_lane) robot_load(a, w, rr);
@@ -649,24 +671,35 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
         if (owner_warp) {
             SenseOut so{false, false, 0.0, 0.0};
             const bool last = (t == a.n_steps - 1);   // last step of the launch
+            int dslot = -1, cslot = -1;               // sensor plan: records of the detector / collision list after this step
+            if constexpr (SENS) {
+                if (a.sp.ped_on) {
+                    if (a.sp.fire[SENSOR_DETECTOR]) dslot = a.sp.fire[SENSOR_DETECTOR][t];
+                    if (a.sp.fire[SENSOR_COLLISIONS]) cslot = a.sp.fire[SENSOR_COLLISIONS][t];
+                }
+            }
             if (owner) {
                 if (S > 1) {
                     fx = 0; fy = 0;
 #pragma unroll
                     for (int q = 0; q < S; ++q) { fx += fxp[q * Np + i]; fy += fyp[q * Np + i]; }
                 }
-                so = owner_update<ST>(a, ow, i, g, w, t, (ST)fx, (ST)fy, rb, has_robot, last, first_bad, publish);
+                so = owner_update<ST, SENS>(a, ow, i, g, w, t, (ST)fx, (ST)fy, rb, has_robot, last, first_bad, publish, dslot);
             }
             if (has_robot) {   // owner warps are whole warps: ballots are safe
                 const unsigned dm = __ballot_sync(0xffffffffu, so.det);
                 const unsigned cm = __ballot_sync(0xffffffffu, so.coll);
                 det_acc += __popc(dm);
                 coll_acc += __popc(cm);
-                if (last && lane == 0) {
-                    const int words = (N + 31) >> 5;
-                    if ((i >> 5) < words) {
+                const int words = (N + 31) >> 5;
+                if (lane == 0 && (i >> 5) < words) {
+                    if (last) {
                         a.det_mask[(size_t)w * words + (i >> 5)] = dm;
                         a.coll_mask[(size_t)w * words + (i >> 5)] = cm;
+                    }
+                    if constexpr (SENS) {
+                        if (dslot >= 0) a.sp.det_mask[((size_t)dslot * a.W + w) * words + (i >> 5)] = dm;
+                        if (cslot >= 0) a.sp.coll_mask[((size_t)cslot * a.W + w) * words + (i >> 5)] = cm;
                     }
                 }
             }
@@ -702,11 +735,11 @@ __device__ __forceinline__ void small_chunk(const HsfmArgs &a, const int group, 
 // chunk of its group (already held by a running CTA, so the wait cannot deadlock).  With thousands of
 // equal-length worlds this removes the partial last wave of a static grid (e.g. 1024 CTAs on 296 slots
 // = 3.46 waves run as 4) at the price of one state round trip through HBM per chunk.
-template <typename PT, typename ST, bool SPLIT, int S>
+template <typename PT, typename ST, bool SPLIT, int S, bool SENS>
 __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
 {
     if (a.n_chunks <= 1) {
-        small_chunk<PT, ST, SPLIT, S>(a, blockIdx.x, 0, a.n_steps);
+        small_chunk<PT, ST, SPLIT, S, SENS>(a, blockIdx.x, 0, a.n_steps);
         return;
     }
     __shared__ int s_item;
@@ -731,7 +764,7 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
         }
         const int t_begin = chunk * a.chunk_steps;
         const int t_end = min(a.n_steps, t_begin + a.chunk_steps);
-        small_chunk<PT, ST, SPLIT, S>(a, group, t_begin, t_end);
+        small_chunk<PT, ST, SPLIT, S, SENS>(a, group, t_begin, t_end);
         __threadfence();
         cta_barrier();
         if (threadIdx.x == 0)
@@ -740,15 +773,15 @@ __device__ __forceinline__ void hsfm_small_body(const HsfmArgs &a)
 }
 
 // Two register budgets: <=256 compute threads/CTA (several CTAs per SM) and big single-world CTAs.
-template <typename PT, typename ST, bool SPLIT, int S>
+template <typename PT, typename ST, bool SPLIT, int S, bool SENS = false>
 __global__ void __launch_bounds__(288, 2) hsfm_small_kernel(const __grid_constant__ HsfmArgs a)
 {
-    hsfm_small_body<PT, ST, SPLIT, S>(a);
+    hsfm_small_body<PT, ST, SPLIT, S, SENS>(a);
 }
-template <typename PT, typename ST, bool SPLIT, int S>
+template <typename PT, typename ST, bool SPLIT, int S, bool SENS = false>
 __global__ void __launch_bounds__(1024, 1) hsfm_small_kernel_big(const __grid_constant__ HsfmArgs a)
 {
-    hsfm_small_body<PT, ST, SPLIT, S>(a);
+    hsfm_small_body<PT, ST, SPLIT, S, SENS>(a);
 }
 
 } // namespace pms

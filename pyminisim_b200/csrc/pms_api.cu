@@ -44,23 +44,26 @@ template <typename T> cudaError_t dalloc(T **p, size_t n)
 }
 
 // ---- marshalling kernels: host layout (W,N,3) fp64 <-> native SoA --------------------------------
-template <typename ST>
-__global__ void pack_state_kernel(size_t n, const double *poses, const double *vels, HsfmArgs a, bool keep_lo)
+// IO = element type of the caller's (W,N,3) arrays: double (the reference's dtype) or float (half the bytes)
+template <typename ST, typename IO>
+__global__ void pack_state_kernel(size_t n, const IO *poses, const IO *vels, HsfmArgs a, bool keep_lo)
 {
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= n) return;
     using ST2 = typename Vec2<ST>::type;
-    store_pv(a, g, (ST)poses[3 * g], (ST)poses[3 * g + 1], (ST)vels[3 * g], (ST)vels[3 * g + 1]);
-    ST2 t; t.x = (ST)poses[3 * g + 2]; t.y = (ST)vels[3 * g + 2];
+    const double px = (double)poses[3 * g], py = (double)poses[3 * g + 1], pt = (double)poses[3 * g + 2];
+    const double qx = vels ? (double)vels[3 * g] : 0.0, qy = vels ? (double)vels[3 * g + 1] : 0.0, qt = vels ? (double)vels[3 * g + 2] : 0.0;
+    store_pv(a, g, (ST)px, (ST)py, (ST)qx, (ST)qy);
+    ST2 t; t.x = (ST)pt; t.y = (ST)qt;
     reinterpret_cast<ST2 *>(a.th)[g] = t;
     if constexpr (sizeof(ST) == 4) {       // low parts: zero for a plain fp32 state (keep_lo false), else the fp32 rounding residue
         auto lo = [&](double v) { return keep_lo ? (float)(v - (double)(float)v) : 0.0f; };
-        reinterpret_cast<float4 *>(a.pos_lo)[g] = make_float4(lo(poses[3 * g]), lo(poses[3 * g + 1]), lo(vels[3 * g]), lo(vels[3 * g + 1]));
-        reinterpret_cast<float2 *>(a.th_lo)[g] = make_float2(lo(poses[3 * g + 2]), lo(vels[3 * g + 2]));
+        reinterpret_cast<float4 *>(a.pos_lo)[g] = make_float4(lo(px), lo(py), lo(qx), lo(qy));
+        reinterpret_cast<float2 *>(a.th_lo)[g] = make_float2(lo(pt), lo(qt));
     }
 }
-template <typename ST>
-__global__ void unpack_state_kernel(size_t n, double *poses, double *vels, HsfmArgs a)
+template <typename ST, typename IO>
+__global__ void unpack_state_kernel(size_t n, IO *poses, IO *vels, HsfmArgs a)
 {
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= n) return;
@@ -68,14 +71,20 @@ __global__ void unpack_state_kernel(size_t n, double *poses, double *vels, HsfmA
     ST x, y, vx, vy;
     load_pv(a, g, x, y, vx, vy);
     const ST2 t = reinterpret_cast<const ST2 *>(a.th)[g];
-    poses[3 * g] = (double)x; poses[3 * g + 1] = (double)y; poses[3 * g + 2] = (double)t.x;
-    vels[3 * g] = (double)vx; vels[3 * g + 1] = (double)vy; vels[3 * g + 2] = (double)t.y;
+    double px = (double)x, py = (double)y, pt = (double)t.x, qx = (double)vx, qy = (double)vy, qt = (double)t.y;
     if constexpr (sizeof(ST) == 4) {       // hi + lo (the low parts are zero unless the compensated kernel ran)
         const float4 pl = reinterpret_cast<const float4 *>(a.pos_lo)[g];
         const float2 tl = reinterpret_cast<const float2 *>(a.th_lo)[g];
-        poses[3 * g] += (double)pl.x; poses[3 * g + 1] += (double)pl.y; poses[3 * g + 2] += (double)tl.x;
-        vels[3 * g] += (double)pl.z; vels[3 * g + 1] += (double)pl.w; vels[3 * g + 2] += (double)tl.y;
+        px += (double)pl.x; py += (double)pl.y; pt += (double)tl.x; qx += (double)pl.z; qy += (double)pl.w; qt += (double)tl.y;
     }
+    if (poses) { poses[3 * g] = (IO)px; poses[3 * g + 1] = (IO)py; poses[3 * g + 2] = (IO)pt; }
+    if (vels) { vels[3 * g] = (IO)qx; vels[3 * g + 1] = (IO)qy; vels[3 * g + 2] = (IO)qt; }
+}
+template <typename IO>
+__global__ void convert_vals_kernel(size_t n, const double2 *src, IO *dst)
+{
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g < n) { dst[2 * g] = (IO)src[g].x; dst[2 * g + 1] = (IO)src[g].y; }
 }
 template <typename ST>
 __global__ void convert_array_kernel(size_t n, const double *src, ST *dst)
@@ -193,6 +202,29 @@ struct pms_sim {
     bool waypoints_set = false;
     // large-crowd path scratch
     LargeScratch large{};
+    // sensors inside a fused launch (pms_sensor_schedule): scheduler state, fire tables and the records of the last launch
+    struct Sched {
+        bool enabled[SENSOR_KINDS] = {false, false, false, false};
+        double period[SENSOR_KINDS] = {0, 0, 0, 0};
+        int flags[SENSOR_KINDS] = {0, 0, 0, 0};
+        double hold_host[SENSOR_KINDS] = {0, 0, 0, 0};   // host mirror of hold_dev (same fp64 recurrence): sizes the records
+        double snap_hold[SENSOR_KINDS] = {0, 0, 0, 0};
+        int n_fires[SENSOR_KINDS] = {0, 0, 0, 0};         // readings of the last launch (host mirror)
+        double *hold_dev = nullptr;                       // (SENSOR_KINDS)
+        int *count_dev = nullptr;                         // (SENSOR_KINDS)
+        int *tables = nullptr;                            // fire[kind][t] | steps[kind][slot], 2 * SENSOR_KINDS * table_cap ints
+        int table_cap = 0;
+        // records
+        uint32_t *det_mask = nullptr, *coll_mask = nullptr; size_t det_mask_cap = 0, coll_mask_cap = 0;   // capacities in records
+        double2 *det_vals = nullptr; size_t det_vals_cap = 0;
+        int32_t *lidar_hit = nullptr; double2 *lidar_pts = nullptr; size_t lidar_cap = 0;
+        double *omni = nullptr; size_t omni_cap = 0;
+        // lidar geometry
+        int lidar_beams = 0, lidar_samples = 0;
+        double lidar_res = 0.0, lidar_max = 0.0;
+        double *lidar_dirs = nullptr;
+        bool any() const { return enabled[0] || enabled[1] || enabled[2] || enabled[3]; }
+    } sched;
     // ORCA
     OrcaState orca{};
 };
@@ -222,6 +254,37 @@ template <typename F> int by_state(pms_sim *h, F &&f)
     return f(double{});
 }
 
+// state of all pedestrians from / to (W,N,3) DEVICE arrays of doubles or floats, on the handle's stream
+int state_from_device(pms_sim *h, const void *poses, const void *vels, bool f32)
+{
+    const size_t n = (size_t)h->W * h->N;
+    const unsigned nb_ = (unsigned)((n + 255) / 256);
+    if (h->precision == PMS_FP32) {
+        if (f32) pack_state_kernel<float, float><<<nb_, 256, 0, h->stream>>>(n, (const float *)poses, (const float *)vels, h->a, h->compensated);
+        else pack_state_kernel<float, double><<<nb_, 256, 0, h->stream>>>(n, (const double *)poses, (const double *)vels, h->a, h->compensated);
+    } else {
+        if (f32) pack_state_kernel<double, float><<<nb_, 256, 0, h->stream>>>(n, (const float *)poses, (const float *)vels, h->a, false);
+        else pack_state_kernel<double, double><<<nb_, 256, 0, h->stream>>>(n, (const double *)poses, (const double *)vels, h->a, false);
+    }
+    CK(cudaGetLastError());
+    h->large.sorted_valid = false;            // the large-crowd kernel's sorted working copy no longer mirrors the state
+    return 0;
+}
+int state_to_device(pms_sim *h, void *poses, void *vels, bool f32)
+{
+    const size_t n = (size_t)h->W * h->N;
+    const unsigned nb_ = (unsigned)((n + 255) / 256);
+    if (h->precision == PMS_FP32) {
+        if (f32) unpack_state_kernel<float, float><<<nb_, 256, 0, h->stream>>>(n, (float *)poses, (float *)vels, h->a);
+        else unpack_state_kernel<float, double><<<nb_, 256, 0, h->stream>>>(n, (double *)poses, (double *)vels, h->a);
+    } else {
+        if (f32) unpack_state_kernel<double, float><<<nb_, 256, 0, h->stream>>>(n, (float *)poses, (float *)vels, h->a);
+        else unpack_state_kernel<double, double><<<nb_, 256, 0, h->stream>>>(n, (double *)poses, (double *)vels, h->a);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // ---- launch of the small-world fused kernel ----
 template <typename PT, typename ST, bool SPLIT, int S>
 int launch_small_t(pms_sim *h, int wpc, bool big)
@@ -231,7 +294,9 @@ int launch_small_t(pms_sim *h, int wpc, bool big)
     const int groups = (h->W + wpc - 1) / wpc;
     int blocks = groups;
     h->a.wpc = wpc;
-    auto kern = big ? hsfm_small_kernel_big<PT, ST, SPLIT, S> : hsfm_small_kernel<PT, ST, SPLIT, S>;
+    const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation
+    auto kern = sens ? (big ? hsfm_small_kernel_big<PT, ST, SPLIT, S, true> : hsfm_small_kernel<PT, ST, SPLIT, S, true>)
+                     : (big ? hsfm_small_kernel_big<PT, ST, SPLIT, S> : hsfm_small_kernel<PT, ST, SPLIT, S>);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // dynamic (chunk, group) scheduling when a static grid would leave a partial last wave
     int occ = 0;
@@ -314,7 +379,8 @@ int launch_warp(pms_sim *h)
     if (wpc > WARP_MAX_WPC) wpc = WARP_MAX_WPC;
     if (wpc > h->W) wpc = h->W;
     // register budget of the instantiation (WarpCfg in hsfm_warp.cuh): j_split 0 = 128 registers, 1 = 96, 2 = 80, 3 = 80 (256 threads)
-    const int T = h->Np / 32, minb = h->tune_S >= 1 && h->tune_S <= 3 ? h->tune_S : 0;   // 4..7 select / exclude hsfm_duo
+    const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation (register budget 0)
+    const int T = h->Np / 32, minb = !sens && h->tune_S >= 1 && h->tune_S <= 3 ? h->tune_S : 0;   // 4..7 select / exclude hsfm_duo
     if ((minb == 1 || minb == 2) && wpc > 4) wpc = 4;
     const bool split = h->precision == PMS_MIXED;
     const bool comp = h->precision == PMS_FP32 && h->compensated;
@@ -323,7 +389,7 @@ int launch_warp(pms_sim *h)
     int blocks = groups, occ = 0;
     size_t smem = 0;
     h->a.wpc = wpc;
-    CK(warp_kernel_prepare(split, comp, T, minb, wpc, &occ, &smem));
+    CK(warp_kernel_prepare(split, comp, sens, T, minb, wpc, &occ, &smem));
     const int slots = occ * h->sm_count;
     h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
     int want = h->tune_chunks;
@@ -344,7 +410,7 @@ int launch_warp(pms_sim *h)
         const long long total = (long long)groups * h->a.n_chunks;
         blocks = (int)(total < slots ? total : slots);
     }
-    CK(warp_kernel_launch(split, comp, T, minb, h->a, blocks, threads, smem, h->stream));
+    CK(warp_kernel_launch(split, comp, sens, T, minb, h->a, blocks, threads, smem, h->stream));
     if (h->precision == PMS_FP32 && !comp) {        // plain fp32 state: the low parts a set_state left are gone
         const size_t n = (size_t)h->W * h->N;
         CK(cudaMemsetAsync(h->a.pos_lo, 0, n * 16, h->stream));
@@ -391,8 +457,9 @@ int launch_duo(pms_sim *h)
     size_t smem = 0;
     h->a.wpc = 1;
     h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
-    CK(duo_kernel_prepare(comp, T, &occ, &smem));
-    CK(duo_kernel_launch(comp, T, h->a, h->W, smem, h->stream));
+    const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation
+    CK(duo_kernel_prepare(comp, sens, T, &occ, &smem));
+    CK(duo_kernel_launch(comp, sens, T, h->a, h->W, smem, h->stream));
     if (!comp) {        // plain fp32 state: the low parts a set_state left are gone
         const size_t n = (size_t)h->W * h->N;
         CK(cudaMemsetAsync(h->a.pos_lo, 0, n * 16, h->stream));
@@ -434,6 +501,106 @@ int launch_large(pms_sim *h)
     h->info.n_chunks = 1;
     h->info.blocks_per_sm = 0;
     h->info.kernel_launches += launches;
+    return 0;
+}
+
+// np.linspace(0, 2*pi, n_beams) -> cos, sin on the host with the C library (sensors/_lidar.py:111,113)
+void lidar_directions(int n_beams, std::vector<double> &dirs)
+{
+    dirs.resize((size_t)n_beams * 2);
+    for (int k = 0; k < n_beams; ++k) {
+        double ang;
+        if (n_beams == 1) ang = 0.0;
+        else if (k == n_beams - 1) ang = 2.0 * PMS_PI;
+        else ang = (double)k * ((2.0 * PMS_PI - 0.0) / (double)(n_beams - 1)) + 0.0;
+        dirs[2 * k] = std::cos(ang); dirs[2 * k + 1] = std::sin(ang);
+    }
+}
+
+template <typename T> int grow(T **p, size_t *cap, size_t need_records, size_t per_record)
+{
+    if (need_records <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CK(cudaMalloc((void **)p, (need_records * per_record ? need_records * per_record : 1) * sizeof(T)));
+    *cap = need_records;
+    return 0;
+}
+
+// Sensors inside the launch that follows (pms_sensor_schedule): replay the hold-time scheduler for its n_steps on the device
+// (sched_kernel) and on the host (the mirror sizes the records), and fill the SensorPlan of the kernel argument block.
+int prepare_sensor_plan(pms_sim *h, int n_steps, bool zero_masks)
+{
+    pms_sim::Sched &sc = h->sched;
+    HsfmArgs &a = h->a;
+    a.sp = SensorPlan{};
+    if (!sc.any()) return 0;
+    if (sc.enabled[SENSOR_LIDAR] && sc.lidar_beams <= 0) return fail(PMS_ERR_STATE, "lidar is scheduled but pms_lidar_config was not called");
+    if (!sc.hold_dev) {
+        CK(dalloc(&sc.hold_dev, (size_t)SENSOR_KINDS));
+        CK(dalloc(&sc.count_dev, (size_t)SENSOR_KINDS));
+        CK(cudaMemcpyAsync(sc.hold_dev, sc.hold_host, sizeof(double) * SENSOR_KINDS, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));      // hold_host is a member, but keep the source stable for the copy anyway
+    }
+    if (n_steps > sc.table_cap) {
+        if (sc.tables) cudaFree(sc.tables);
+        sc.tables = nullptr; sc.table_cap = 0;
+        const int cap = (n_steps + 255) & ~255;
+        CK(cudaMalloc((void **)&sc.tables, sizeof(int) * 2 * SENSOR_KINDS * (size_t)cap));
+        sc.table_cap = cap;
+    }
+    // host mirror of the recurrence (core/_simulation.py:177-180): IEEE fp64 additions, identical on both sides
+    SchedArgs sa{};
+    sa.n_steps = n_steps; sa.dt = a.dt; sa.hold = sc.hold_dev; sa.count = sc.count_dev;
+    for (int k = 0; k < SENSOR_KINDS; ++k) {
+        sa.enabled[k] = sc.enabled[k] ? 1 : 0; sa.period[k] = sc.period[k];
+        sa.fire[k] = sc.tables + (size_t)k * sc.table_cap;
+        sa.steps[k] = sc.tables + (size_t)(SENSOR_KINDS + k) * sc.table_cap;
+        sc.n_fires[k] = 0;
+        if (!sc.enabled[k]) continue;
+        volatile double hold = sc.hold_host[k];
+        int n = 0;
+        for (int t = 0; t < n_steps; ++t) {
+            hold = hold + a.dt;
+            if (hold >= sc.period[k]) { ++n; hold = 0.0; }
+        }
+        sc.hold_host[k] = hold; sc.n_fires[k] = n;
+    }
+    const size_t W = h->W, N = h->N, words = h->words;
+    if (sc.enabled[SENSOR_DETECTOR]) {
+        if (grow(&sc.det_mask, &sc.det_mask_cap, (size_t)sc.n_fires[SENSOR_DETECTOR], W * words)) return PMS_ERR_CUDA;
+        if ((sc.flags[SENSOR_DETECTOR] & PMS_SENSOR_VALUES) && grow(&sc.det_vals, &sc.det_vals_cap, (size_t)sc.n_fires[SENSOR_DETECTOR], W * N)) return PMS_ERR_CUDA;
+    }
+    if (sc.enabled[SENSOR_COLLISIONS] && grow(&sc.coll_mask, &sc.coll_mask_cap, (size_t)sc.n_fires[SENSOR_COLLISIONS], W * words)) return PMS_ERR_CUDA;
+    if (sc.enabled[SENSOR_LIDAR]) {
+        size_t cap2 = sc.lidar_cap;
+        if (grow(&sc.lidar_hit, &sc.lidar_cap, (size_t)sc.n_fires[SENSOR_LIDAR], W * sc.lidar_beams)) return PMS_ERR_CUDA;
+        if (grow(&sc.lidar_pts, &cap2, (size_t)sc.n_fires[SENSOR_LIDAR], W * sc.lidar_beams)) return PMS_ERR_CUDA;
+    }
+    if (sc.enabled[SENSOR_OMNI] && grow(&sc.omni, &sc.omni_cap, (size_t)sc.n_fires[SENSOR_OMNI], W)) return PMS_ERR_CUDA;
+    sched_kernel<<<1, 32, 0, h->stream>>>(sa);
+    CK(cudaGetLastError());
+    h->info.kernel_launches++;
+    SensorPlan &sp = a.sp;
+    const bool has_robot = a.robot_model != ROBOT_NONE;
+    sp.on = 1;
+    sp.ped_on = (sc.enabled[SENSOR_DETECTOR] || sc.enabled[SENSOR_COLLISIONS]) ? 1 : 0;
+    sp.robot_on = ((sc.enabled[SENSOR_LIDAR] || sc.enabled[SENSOR_OMNI]) && has_robot) ? 1 : 0;
+    for (int k = 0; k < SENSOR_KINDS; ++k) sp.fire[k] = sc.enabled[k] ? sa.fire[k] : nullptr;
+    sp.det_mask = sc.det_mask; sp.det_vals = (sc.flags[SENSOR_DETECTOR] & PMS_SENSOR_VALUES) ? sc.det_vals : nullptr;
+    sp.coll_mask = sc.coll_mask;
+    sp.lidar_beams = sc.lidar_beams; sp.lidar_samples = sc.lidar_samples; sp.lidar_res = sc.lidar_res; sp.lidar_dirs = sc.lidar_dirs;
+    sp.lidar_hit = sc.lidar_hit; sp.lidar_pts = sc.lidar_pts; sp.lidar_noise = h->lidar_noise;
+    sp.omni_dist = sc.omni; sp.omni_noise = h->omni_noise;
+    // no robot: the step kernels skip the sensor pass -- the records read as empty; sorted large-crowd copy: bits are OR-ed in
+    if (!has_robot || zero_masks) {
+        if (sc.enabled[SENSOR_DETECTOR] && sc.n_fires[SENSOR_DETECTOR])
+            CK(cudaMemsetAsync(sc.det_mask, 0, sizeof(uint32_t) * sc.n_fires[SENSOR_DETECTOR] * W * words, h->stream));
+        if (sc.enabled[SENSOR_COLLISIONS] && sc.n_fires[SENSOR_COLLISIONS])
+            CK(cudaMemsetAsync(sc.coll_mask, 0, sizeof(uint32_t) * sc.n_fires[SENSOR_COLLISIONS] * W * words, h->stream));
+        if (!has_robot && sp.det_vals && sc.n_fires[SENSOR_DETECTOR])
+            CK(cudaMemsetAsync(sc.det_vals, 0, sizeof(double2) * sc.n_fires[SENSOR_DETECTOR] * W * N, h->stream));
+    }
     return 0;
 }
 
@@ -572,6 +739,11 @@ int pms_destroy(pms_sim *h)
     for (void *p : h->snap_dst) if (p) cudaFree(p);
     if (h->tick_dev) cudaFree(h->tick_dev);
     if (h->tick_host) cudaFreeHost(h->tick_host);
+    {
+        pms_sim::Sched &sc = h->sched;
+        void *sp_[] = {sc.hold_dev, sc.count_dev, sc.tables, sc.det_mask, sc.coll_mask, sc.det_vals, sc.lidar_hit, sc.lidar_pts, sc.omni, sc.lidar_dirs};
+        for (void *p : sp_) if (p) cudaFree(p);
+    }
     large_free(h->large);
     orca_free(h->orca);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -600,35 +772,63 @@ int pms_set_async_io(pms_sim *h, int enabled)
     return PMS_OK;
 }
 
-int pms_set_ped_state(pms_sim *h, const double *poses, const double *vels)
+// host (W,N,3) arrays -> staging -> native SoA; esz = bytes of one host element (8: double, 4: float)
+static int set_ped_state_host(pms_sim *h, const void *poses, const void *vels, size_t esz)
 {
-    HCHECK(h);
     if (!poses) return fail(PMS_ERR_INVALID, "poses is NULL");
     const size_t n = (size_t)h->W * h->N;
     if (ensure_stage(h, n * 6)) return PMS_ERR_CUDA;
-    CK(cudaMemcpyAsync(h->stage, poses, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (vels) CK(cudaMemcpyAsync(h->stage + n * 3, vels, n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    else CK(cudaMemsetAsync(h->stage + n * 3, 0, n * 3 * sizeof(double), h->stream));
-    if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a, h->compensated);
-    else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a, false);
-    CK(cudaGetLastError());
-    h->large.sorted_valid = false;            // the large-crowd kernel's sorted working copy no longer mirrors the state
+    unsigned char *st = reinterpret_cast<unsigned char *>(h->stage);
+    CK(cudaMemcpyAsync(st, poses, n * 3 * esz, cudaMemcpyHostToDevice, h->stream));
+    if (vels) CK(cudaMemcpyAsync(st + n * 3 * esz, vels, n * 3 * esz, cudaMemcpyHostToDevice, h->stream));
+    int rc = state_from_device(h, st, vels ? st + n * 3 * esz : nullptr, esz == 4);
+    if (rc) return rc;
+    IO_DONE(h);
+    return PMS_OK;
+}
+static int get_ped_state_host(pms_sim *h, void *poses, void *vels, size_t esz)
+{
+    const size_t n = (size_t)h->W * h->N;
+    if (ensure_stage(h, n * 6)) return PMS_ERR_CUDA;
+    unsigned char *st = reinterpret_cast<unsigned char *>(h->stage);
+    int rc = state_to_device(h, poses ? st : nullptr, vels ? st + n * 3 * esz : nullptr, esz == 4);
+    if (rc) return rc;
+    if (poses) CK(cudaMemcpyAsync(poses, st, n * 3 * esz, cudaMemcpyDeviceToHost, h->stream));
+    if (vels) CK(cudaMemcpyAsync(vels, st + n * 3 * esz, n * 3 * esz, cudaMemcpyDeviceToHost, h->stream));
     IO_DONE(h);
     return PMS_OK;
 }
 
+int pms_set_ped_state(pms_sim *h, const double *poses, const double *vels)
+{
+    HCHECK(h);
+    return set_ped_state_host(h, poses, vels, 8);
+}
 int pms_get_ped_state(pms_sim *h, double *poses, double *vels)
 {
     HCHECK(h);
-    const size_t n = (size_t)h->W * h->N;
-    if (ensure_stage(h, n * 6)) return PMS_ERR_CUDA;
-    if (h->precision == PMS_FP32) unpack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
-    else unpack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, h->a);
-    CK(cudaGetLastError());
-    if (poses) CK(cudaMemcpyAsync(poses, h->stage, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (vels) CK(cudaMemcpyAsync(vels, h->stage + n * 3, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    IO_DONE(h);
-    return PMS_OK;
+    return get_ped_state_host(h, poses, vels, 8);
+}
+int pms_set_ped_state_f32(pms_sim *h, const float *poses, const float *vels)
+{
+    HCHECK(h);
+    return set_ped_state_host(h, poses, vels, 4);
+}
+int pms_get_ped_state_f32(pms_sim *h, float *poses, float *vels)
+{
+    HCHECK(h);
+    return get_ped_state_host(h, poses, vels, 4);
+}
+int pms_set_ped_state_device(pms_sim *h, const void *poses, const void *vels, int is_f32)
+{
+    HCHECK(h);
+    if (!poses) return fail(PMS_ERR_INVALID, "poses is NULL");
+    return state_from_device(h, poses, vels, is_f32 != 0) ? PMS_ERR_CUDA : PMS_OK;
+}
+int pms_get_ped_state_device(pms_sim *h, void *poses, void *vels, int is_f32)
+{
+    HCHECK(h);
+    return state_to_device(h, poses, vels, is_f32 != 0) ? PMS_ERR_CUDA : PMS_OK;
 }
 
 static int upload_converted(pms_sim *h, const double *src, size_t n, void *dst)
@@ -933,9 +1133,7 @@ int pms_sense_tick(pms_sim *h, const double *poses, const double *robot_pose, do
     CK(cudaMemcpyAsync(h->stage, st, n * 24, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->stage + n * 3, 0, n * 24, h->stream));
     CK(cudaMemcpyAsync(a.robot_pose, st + n * 3, (size_t)W * 24, cudaMemcpyHostToDevice, h->stream));
-    if (h->precision == PMS_FP32) pack_state_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, a, h->compensated);
-    else pack_state_kernel<double><<<nblk(n), 256, 0, h->stream>>>(n, h->stage, h->stage + n * 3, a, false);
-    h->large.sorted_valid = false;
+    if (state_from_device(h, h->stage, h->stage + n * 3, false)) return PMS_ERR_CUDA;
     int rc = clear_sensor_outputs(h);
     if (rc) return rc;
     fill_consts(a);
@@ -1005,6 +1203,7 @@ int pms_hsfm_step_async(pms_sim *h, double dt, int n_steps)
     const bool large_path = h->force_large || (!warp_ok && (h->Np + 32 > 1024 || mid_fp32));
     // the large-crowd kernel sets mask bits with atomicOr when it works on the sorted copy: start from zero
     if ((h->a.robot_model == ROBOT_NONE || large_path) && (rc = clear_sensor_outputs(h))) return rc;
+    if ((rc = prepare_sensor_plan(h, n_steps, large_path))) return rc;
     if (large_path) rc = launch_large(h);
     else if (warp_ok && duo_eligible(h) && duo_preferred(h)) rc = launch_duo(h);
     else if (warp_ok) rc = launch_warp(h);
@@ -1153,6 +1352,55 @@ int pms_get_collisions(pms_sim *h, uint32_t *mask)
     return PMS_OK;
 }
 
+int pms_get_detector_f32(pms_sim *h, uint32_t *mask, float *values)
+{
+    HCHECK(h);
+    if (h->det_noise.enabled && h->a.det_enabled) return fail(PMS_ERR_UNSUPPORTED, "pms_get_detector_f32 returns the exact reading: use pms_get_detector with the device noise");
+    const size_t n = (size_t)h->W * h->N;
+    if (mask) CK(cudaMemcpyAsync(mask, h->a.det_mask, sizeof(uint32_t) * h->W * h->words, cudaMemcpyDeviceToHost, h->stream));
+    if (values) {
+        if (ensure_stage(h, n)) return PMS_ERR_CUDA;
+        convert_vals_kernel<float><<<nblk(n), 256, 0, h->stream>>>(n, h->a.det_vals, reinterpret_cast<float *>(h->stage));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(values, h->stage, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    IO_DONE(h);
+    return PMS_OK;
+}
+
+int pms_device_buffer(pms_sim *h, int which, void **ptr, uint64_t *bytes)
+{
+    HCHECK(h);
+    if (!ptr) return fail(PMS_ERR_INVALID, "ptr is NULL");
+    const HsfmArgs &a = h->a;
+    const pms_sim::Sched &sc = h->sched;
+    const uint64_t W = h->W, N = h->N, words = h->words, nm = W * words, n = W * N;
+    void *p = nullptr;
+    uint64_t b = 0;
+    switch (which) {
+    case PMS_BUF_DET_MASK: p = a.det_mask; b = nm * 4; break;
+    case PMS_BUF_COLL_MASK: p = a.coll_mask; b = nm * 4; break;
+    case PMS_BUF_DET_VALUES: p = a.det_vals; b = n * 16; break;
+    case PMS_BUF_ROBOT_POSE: p = a.robot_pose; b = W * 24; break;
+    case PMS_BUF_ROBOT_VELOCITY: p = a.robot_vel; b = W * 24; break;
+    case PMS_BUF_DETECTIONS: p = a.det_count; b = W * 8; break;
+    case PMS_BUF_COLLISIONS: p = a.coll_count; b = W * 8; break;
+    case PMS_BUF_FIRST_NONFINITE: p = a.nonfinite; b = W * 4; break;
+    case PMS_BUF_WAYPOINT_INDEX: p = a.wp_index; b = n * 4; break;
+    case PMS_BUF_REC_DET_MASK: p = sc.det_mask; b = (uint64_t)sc.n_fires[SENSOR_DETECTOR] * nm * 4; break;
+    case PMS_BUF_REC_DET_VALUES: p = (sc.flags[SENSOR_DETECTOR] & PMS_SENSOR_VALUES) ? sc.det_vals : nullptr; b = (uint64_t)sc.n_fires[SENSOR_DETECTOR] * n * 16; break;
+    case PMS_BUF_REC_COLL_MASK: p = sc.coll_mask; b = (uint64_t)sc.n_fires[SENSOR_COLLISIONS] * nm * 4; break;
+    case PMS_BUF_REC_LIDAR_HIT: p = sc.lidar_hit; b = (uint64_t)sc.n_fires[SENSOR_LIDAR] * W * sc.lidar_beams * 4; break;
+    case PMS_BUF_REC_LIDAR_POINTS: p = sc.lidar_pts; b = (uint64_t)sc.n_fires[SENSOR_LIDAR] * W * sc.lidar_beams * 16; break;
+    case PMS_BUF_REC_OMNI: p = sc.omni; b = (uint64_t)sc.n_fires[SENSOR_OMNI] * W * 8; break;
+    default: return fail(PMS_ERR_INVALID, "unknown buffer");
+    }
+    if (!p) b = 0;
+    *ptr = p;
+    if (bytes) *bytes = b;
+    return PMS_OK;
+}
+
 int pms_get_stats(pms_sim *h, int64_t *detections, int64_t *collisions, int32_t *first_nonfinite_step)
 {
     HCHECK(h);
@@ -1205,6 +1453,7 @@ int pms_snapshot_save(pms_sim *h)
     CK(cudaStreamSynchronize(h->stream));
     h->snap_src = r;
     h->snap_steps = h->a.steps_done;
+    for (int k = 0; k < SENSOR_KINDS; ++k) h->sched.snap_hold[k] = h->sched.hold_host[k];
     h->has_snapshot = true;
     return PMS_OK;
 }
@@ -1218,6 +1467,9 @@ int pms_snapshot_restore(pms_sim *h)
     CK(cudaMemsetAsync(h->a.ev_count, 0, sizeof(int), h->stream));
     h->a.steps_done = h->snap_steps;
     h->large.sorted_valid = false;
+    for (int k = 0; k < SENSOR_KINDS; ++k) h->sched.hold_host[k] = h->sched.snap_hold[k];
+    if (h->sched.hold_dev)      // snap_hold is a member of the handle: stable until the copy has run
+        CK(cudaMemcpyAsync(h->sched.hold_dev, h->sched.snap_hold, sizeof(double) * SENSOR_KINDS, cudaMemcpyHostToDevice, h->stream));
     return PMS_OK;
 }
 
@@ -1230,14 +1482,8 @@ int pms_lidar_scan(pms_sim *h, int n_beams, double max_dist, double resolution, 
     if (h->a.robot_model == ROBOT_NONE) return fail(PMS_ERR_STATE, "no robot configured");
     const size_t nb = (size_t)h->W * n_beams;
     // np.linspace(0, 2*pi, n_beams) and np.arange(0, max_dist, resolution): _lidar.py:111-112
-    std::vector<double> dirs((size_t)n_beams * 2);
-    for (int k = 0; k < n_beams; ++k) {
-        double ang;
-        if (n_beams == 1) ang = 0.0;
-        else if (k == n_beams - 1) ang = 2.0 * PMS_PI;
-        else ang = (double)k * ((2.0 * PMS_PI - 0.0) / (double)(n_beams - 1)) + 0.0;
-        dirs[2 * k] = std::cos(ang); dirs[2 * k + 1] = std::sin(ang);
-    }
+    std::vector<double> dirs;
+    lidar_directions(n_beams, dirs);
     const int n_samples = (int)std::ceil((max_dist - 0.0) / resolution);
     // stage layout: dirs | points(double2) | hit(int)
     const size_t need = (size_t)n_beams * 2 + nb * 2 + (nb + 1) / 2 + 2;
@@ -1276,6 +1522,132 @@ int pms_omni_scan(pms_sim *h, double *min_dist)
     }
     if (min_dist) CK(cudaMemcpyAsync(min_dist, h->stage, sizeof(double) * h->W, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+// ---- sensors inside a fused launch ----
+int pms_lidar_config(pms_sim *h, int n_beams, double max_dist, double resolution)
+{
+    HCHECK(h);
+    if (n_beams <= 0) return fail(PMS_ERR_INVALID, "n_beams must be > 0");                          // _lidar.py:15
+    if (!(max_dist > resolution && resolution > 0.0)) return fail(PMS_ERR_INVALID, "need max_dist > resolution > 0"); // :16
+    pms_sim::Sched &sc = h->sched;
+    std::vector<double> dirs;
+    lidar_directions(n_beams, dirs);
+    CK(cudaStreamSynchronize(h->stream));
+    if (sc.lidar_dirs) cudaFree(sc.lidar_dirs);
+    sc.lidar_dirs = nullptr;
+    CK(cudaMalloc((void **)&sc.lidar_dirs, dirs.size() * sizeof(double)));
+    CK(cudaMemcpy(sc.lidar_dirs, dirs.data(), dirs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_beams != sc.lidar_beams) {          // records are sized per beam count
+        if (sc.lidar_hit) cudaFree(sc.lidar_hit);
+        if (sc.lidar_pts) cudaFree(sc.lidar_pts);
+        sc.lidar_hit = nullptr; sc.lidar_pts = nullptr; sc.lidar_cap = 0;
+    }
+    sc.lidar_beams = n_beams; sc.lidar_max = max_dist; sc.lidar_res = resolution;
+    sc.lidar_samples = (int)std::ceil((max_dist - 0.0) / resolution);     // np.arange(0, max_dist, resolution), _lidar.py:112
+    sc.n_fires[SENSOR_LIDAR] = 0;
+    return PMS_OK;
+}
+
+int pms_sensor_schedule(pms_sim *h, int kind, int enabled, double period, double hold_time, int flags)
+{
+    HCHECK(h);
+    if (kind < 0 || kind >= SENSOR_KINDS) return fail(PMS_ERR_INVALID, "unknown sensor kind");
+    if (enabled && !(period >= 0.0)) return fail(PMS_ERR_INVALID, "period must be >= 0");
+    if (enabled && !(hold_time >= 0.0)) return fail(PMS_ERR_INVALID, "hold_time must be >= 0");
+    pms_sim::Sched &sc = h->sched;
+    sc.enabled[kind] = enabled != 0; sc.period[kind] = period; sc.flags[kind] = flags;
+    sc.hold_host[kind] = enabled ? hold_time : 0.0;
+    sc.n_fires[kind] = 0;
+    if (sc.hold_dev) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(sc.hold_dev + kind, &sc.hold_host[kind], sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return PMS_OK;
+}
+
+int pms_get_sensor_fires(pms_sim *h, int kind, int32_t *steps, int cap, int *n_fires, double *hold_time)
+{
+    HCHECK(h);
+    if (kind < 0 || kind >= SENSOR_KINDS) return fail(PMS_ERR_INVALID, "unknown sensor kind");
+    pms_sim::Sched &sc = h->sched;
+    if (!sc.enabled[kind]) return fail(PMS_ERR_STATE, "sensor kind is not scheduled");
+    int n_dev = 0;
+    double hold_dev = sc.hold_host[kind];
+    if (sc.hold_dev) {
+        CK(cudaMemcpyAsync(&n_dev, sc.count_dev + kind, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&hold_dev, sc.hold_dev + kind, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        // the device scheduler is authoritative; the host mirror sized the records and must agree bit for bit
+        if (n_dev != sc.n_fires[kind] || hold_dev != sc.hold_host[kind])
+            return fail(PMS_ERR_STATE, "device scheduler and host mirror disagree");
+    }
+    const int n = sc.n_fires[kind];
+    if (n_fires) *n_fires = n;
+    if (hold_time) *hold_time = hold_dev;
+    if (steps && n > 0) {
+        if (cap < n) return fail(PMS_ERR_INVALID, "steps buffer too small");
+        CK(cudaMemcpyAsync(steps, sc.tables + (size_t)(SENSOR_KINDS + kind) * sc.table_cap, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return PMS_OK;
+}
+
+static int record_range(pms_sim *h, int kind, int first, int count)
+{
+    if (!h->sched.enabled[kind]) return fail(PMS_ERR_STATE, "sensor kind is not scheduled");
+    if (first < 0 || count < 0 || first + count > h->sched.n_fires[kind]) return fail(PMS_ERR_INVALID, "record range outside the readings of the last launch");
+    return 0;
+}
+
+int pms_get_detector_records(pms_sim *h, int first, int count, uint32_t *mask, double *values)
+{
+    HCHECK(h);
+    int rc = record_range(h, SENSOR_DETECTOR, first, count);
+    if (rc) return rc;
+    const size_t per_m = (size_t)h->W * h->words, per_v = (size_t)h->W * h->N;
+    if (values && !(h->sched.flags[SENSOR_DETECTOR] & PMS_SENSOR_VALUES)) return fail(PMS_ERR_STATE, "detector records were scheduled without PMS_SENSOR_VALUES");
+    if (count == 0) return PMS_OK;
+    if (mask) CK(cudaMemcpyAsync(mask, h->sched.det_mask + first * per_m, sizeof(uint32_t) * count * per_m, cudaMemcpyDeviceToHost, h->stream));
+    if (values) CK(cudaMemcpyAsync(values, h->sched.det_vals + first * per_v, sizeof(double2) * count * per_v, cudaMemcpyDeviceToHost, h->stream));
+    IO_DONE(h);
+    return PMS_OK;
+}
+
+int pms_get_collision_records(pms_sim *h, int first, int count, uint32_t *mask)
+{
+    HCHECK(h);
+    int rc = record_range(h, SENSOR_COLLISIONS, first, count);
+    if (rc) return rc;
+    const size_t per_m = (size_t)h->W * h->words;
+    if (mask && count) CK(cudaMemcpyAsync(mask, h->sched.coll_mask + first * per_m, sizeof(uint32_t) * count * per_m, cudaMemcpyDeviceToHost, h->stream));
+    IO_DONE(h);
+    return PMS_OK;
+}
+
+int pms_get_lidar_records(pms_sim *h, int first, int count, int32_t *hit_index, double *points)
+{
+    HCHECK(h);
+    int rc = record_range(h, SENSOR_LIDAR, first, count);
+    if (rc) return rc;
+    if (h->a.robot_model == ROBOT_NONE) return fail(PMS_ERR_STATE, "no robot configured");
+    const size_t per = (size_t)h->W * h->sched.lidar_beams;
+    if (count == 0) return PMS_OK;
+    if (hit_index) CK(cudaMemcpyAsync(hit_index, h->sched.lidar_hit + first * per, sizeof(int32_t) * count * per, cudaMemcpyDeviceToHost, h->stream));
+    if (points) CK(cudaMemcpyAsync(points, h->sched.lidar_pts + first * per, sizeof(double2) * count * per, cudaMemcpyDeviceToHost, h->stream));
+    IO_DONE(h);
+    return PMS_OK;
+}
+
+int pms_get_omni_records(pms_sim *h, int first, int count, double *min_dist)
+{
+    HCHECK(h);
+    int rc = record_range(h, SENSOR_OMNI, first, count);
+    if (rc) return rc;
+    if (h->a.robot_model == ROBOT_NONE) return fail(PMS_ERR_STATE, "no robot configured");
+    if (min_dist && count) CK(cudaMemcpyAsync(min_dist, h->sched.omni + (size_t)first * h->W, sizeof(double) * count * h->W, cudaMemcpyDeviceToHost, h->stream));
+    IO_DONE(h);
     return PMS_OK;
 }
 

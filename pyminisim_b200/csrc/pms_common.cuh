@@ -23,6 +23,49 @@ template <typename T> struct PedConsts {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Sensors inside a fused launch.  The reference's hold-time scheduler (Simulation._update_sensors_state,
+// core/_simulation.py:162-185: hold += dt; fire and reset when hold >= period) does not depend on the state, so
+// sched_kernel (sensor_fires.cuh) replays it in fp64 for the n_steps of the launch before the step kernel runs and leaves,
+// per sensor kind, fire[t] = slot of the reading taken after launch step t, or -1.  The step kernels write the readings of a
+// firing step to record s of the kind's ring; the collision list (not a sensor in the reference: WorldState carries
+// it every step, core/_simulation.py:141-143) is the pseudo-kind SENSOR_COLLISIONS.
+// ---------------------------------------------------------------------------------------------
+enum { SENSOR_DETECTOR = 0, SENSOR_LIDAR = 1, SENSOR_OMNI = 2, SENSOR_COLLISIONS = 3, SENSOR_KINDS = 4 };
+
+struct LidarNoise {          // LidarSensorNoise (sensors/_lidar.py:52-87); l** = Cholesky factor of point_cov
+    double drop_prob, mean_x, mean_y, l00, l10, l11;
+    unsigned long long seed;
+    int enabled;
+};
+struct OmniNoise {           // OmniObstacleDetectorNoise (sensors/_omni_obstacle_detector.py:25-37,64-69)
+    double p_miss, mu, sigma;
+    unsigned long long seed;
+    int enabled;
+};
+
+struct SensorPlan {
+    int on;                          // any kind scheduled for this launch
+    int ped_on;                      // detector or collision-list records (written by the pedestrian warps)
+    int robot_on;                    // lidar or omni records (written by the warp that integrates the robot)
+    const int *fire[SENSOR_KINDS];   // (n_steps) record slot per launch step, -1 = no reading; NULL = kind not scheduled
+    // detector records: mask (F, W, words); values (F, W, N) or NULL (masks only)
+    uint32_t *det_mask;
+    double2 *det_vals;
+    // collision-list records (F, W, words)
+    uint32_t *coll_mask;
+    // lidar records: first occupied sample index or -1 (F, W, B); absolute sample point (F, W, B)
+    int lidar_beams, lidar_samples;
+    double lidar_res;
+    const double *lidar_dirs;        // (B, 2) cos, sin of the beam angles, computed on the host with the C library
+    int32_t *lidar_hit;
+    double2 *lidar_pts;
+    LidarNoise lidar_noise;
+    // omni records (F, W)
+    double *omni_dist;
+    OmniNoise omni_noise;
+};
+
+// ---------------------------------------------------------------------------------------------
 // Kernel argument block (passed by value as a __grid_constant__).
 // ---------------------------------------------------------------------------------------------
 struct HsfmArgs {
@@ -88,6 +131,7 @@ struct HsfmArgs {
     // fp32 pre-filter of the collision list / detector: squared radii 1e-5 inside and outside the exact thresholds and
     // cos(fov/2); only pedestrians between the two (or detected on the last step) reach the fp64 predicate
     float sn_coll_lo2, sn_coll_hi2, sn_det_lo2, sn_det_hi2, sn_any_hi2, sn_chf;
+    SensorPlan sp;                   // sensors inside the launch (all zero = off)
 };
 
 template <typename T> __host__ __device__ inline void fill_pair(PairK<T> &k, const HsfmArgs &a, double radius_j)

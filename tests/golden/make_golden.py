@@ -309,8 +309,68 @@ def gen_replay():
     np.savez(os.path.join(HERE, "replay.npz"), **res)
 
 
+def gen_episode():
+    """A 260-step Simulation with every sensor at once (the reference's own scheduler decides who fires when): HSFM crowd of 8,
+    unicycle robot with a control sequence driving past obstacles (some moves vetoed by the map), PedestrianDetector
+    (period 0), 10 Hz LidarSensor (fires every 11 steps), OmniObstacleDetector (period 0); CirclesWorld and AABBWorld."""
+    sc = make_crowd(1, 8, side=5.0, first_world=77)
+    circles = np.array([[1.6, 0.9, 0.5], [-2.5, 1.5, 0.7], [0.5, -2.2, 0.6], [3.5, -1.0, 0.4], [-0.5, 3.2, 0.8]])
+    boxes = [(2.8, 0.6, 1.2, 1.0), (-1.5, -3.5, 0.8, 1.5), (0.4, 2.6, 0.6, 0.6), (-3.0, 1.0, 1.5, 0.3)]
+    K = 260
+    ctr = np.stack([np.array([0.9 + 0.3 * np.sin(0.03 * k), 0.8 * np.cos(0.021 * k)]) for k in range(K)])
+    res = {"init_poses": sc.poses[0], "table": sc.table[0], "controls": ctr, "circles": circles, "boxes": np.array(boxes),
+           "robot_pose0": np.array([-1.0, 0.2, 0.3])}
+    for name, world in (("circles", CirclesWorld(circles=circles)), ("aabb", AABBWorld([AABBObject(box=b) for b in boxes]))):
+        n = 8
+        tracker = FixedWaypointTracker(initial_positions=sc.table[0][:, 0, :].copy(), waypoints=sc.table[0][:, 1:, :].copy(), loop=True)
+        model = HeadedSocialForceModelPolicy(waypoint_tracker=tracker, n_pedestrians=n, initial_poses=sc.poses[0].copy(),
+                                             pedestrian_linear_velocity_magnitude=1.5)
+        rm = UnicycleRobotModel(initial_pose=res["robot_pose0"].copy(), initial_control=np.array([0.0, 0.0]))
+        lidar_cfg = LidarSensorConfig(n_beams=37, max_dist=5.0, resolution=0.03)
+        sensors = [PedestrianDetector(config=PedestrianDetectorConfig(max_dist=4.0, fov=np.deg2rad(200.0), return_type="relative")),
+                   LidarSensor(config=lidar_cfg), OmniObstacleDetector()]
+        sim = Simulation(world_map=world, robot_model=rm, pedestrians_model=model, sensors=sensors, sim_dt=0.01, rt_factor=None)
+        fired, pts_all, cnt, omni, dmask, dvals, cmask, rpose, rwc, pposes, hits_all = [], [], [], [], [], [], [], [], [], [], []
+        prev_lidar = sim.current_state.sensors["lidar"].reading
+        for k in range(K):
+            st = sim.step(ctr[k])
+            rd = st.sensors["lidar"].reading
+            if rd is not prev_lidar:            # a new reading object = the scheduler fired (core/_simulation.py:178-180)
+                assert st.sensors["lidar"].hold_time == 0.0
+                fired.append(k)
+                pts = rd.points.reshape(-1, 2)
+                pad = np.zeros((lidar_cfg.n_beams, 2)); pad[:len(pts)] = pts
+                pts_all.append(pad); cnt.append(len(pts))
+                prev_lidar = rd
+                # index of the first occupied sample per beam (-1: no hit or the beam starts inside an obstacle): the reference
+                # does not return it, so it is re-derived here with the reference's own is_occupied on the very sample
+                # points get_reading builds (sensors/_lidar.py:111-119)
+                center = st.world.robot.pose[:2]
+                angles = np.linspace(0., 2 * np.pi, lidar_cfg.n_beams)
+                distances = np.arange(0., lidar_cfg.max_dist, lidar_cfg.resolution)
+                cp = np.array([center + np.stack((distances * np.cos(a), distances * np.sin(a)), axis=1) for a in angles])
+                occ = world.is_occupied(cp.reshape((-1, 2))).reshape((lidar_cfg.n_beams, -1))
+                hit = np.array([int(np.argmax(b)) if (b.any() and not b[0]) else -1 for b in occ], dtype=np.int32)
+                assert np.array_equal(cp[hit >= 0, hit[hit >= 0]], pts)
+                hits_all.append(hit)
+            omni.append(st.sensors["omni_obstacle_detector"].reading.min_obstacle_dist)
+            m, v = _det_arrays(st.sensors["pedestrian_detector"].reading, n)
+            dmask.append(m); dvals.append(v)
+            cmask.append(_mask(st.world.robot_to_pedestrians_collisions, n))
+            rpose.append(st.world.robot.pose); rwc.append(int(st.world.robot_to_world_collision))
+            pposes.append(_ped_arrays(st.world.pedestrians)[0])
+        res.update({f"{name}_lidar_steps": np.array(fired), f"{name}_lidar_points": np.array(pts_all), f"{name}_lidar_count": np.array(cnt), f"{name}_lidar_hit": np.array(hits_all),
+                    f"{name}_lidar_hold": np.array(sim.current_state.sensors["lidar"].hold_time),
+                    f"{name}_omni": np.array(omni), f"{name}_det_mask": np.array(dmask), f"{name}_det_vals": np.array(dvals),
+                    f"{name}_coll_mask": np.array(cmask), f"{name}_robot_pose": np.array(rpose), f"{name}_robot_world_collision": np.array(rwc),
+                    f"{name}_ped_poses_last": pposes[-1]})
+        print("episode", name, "lidar fires", fired[:4], "...", len(fired), "vetoed robot steps", int(np.sum(rwc)),
+              "detections", int(sum(np.count_nonzero(m) for m in dmask)), "lidar points", int(np.sum(cnt)))
+    np.savez_compressed(os.path.join(HERE, "episode.npz"), **res)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random", "replay"]
+    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random", "replay", "episode"]
     if "pair" in which:
         gen_pair_forces()
     if "kat2" in which:
@@ -325,4 +385,6 @@ if __name__ == "__main__":
         gen_random_tracker()
     if "replay" in which:
         gen_replay()
+    if "episode" in which:
+        gen_episode()
     print("golden fixtures written to", HERE)
