@@ -326,28 +326,9 @@ def main():
     # Every step: H2D of the step's initial state from pinned memory, the fused launch, D2H of the final state, the
     # detector reading, the collision list and the episode statistics.  Two handles alternate in asynchronous-I/O mode
     # (BatchedSimulation.set_async_io): the copies of one step overlap the kernel of the other, each step still pays
-    # for its own transfers.  `e2e_serial` is the same loop with one handle and blocking calls.
-    def e2e_step():
-        sim.snapshot_restore()                 # robot / tracker / statistics back to t = 0 (device-side)
-        sim.set_state(h_poses, h_vels)          # H2D from pinned memory
-        sim.step(0.01, K)
-        sim.get_state(o_poses, o_vels)          # D2H
-        mask, vals = sim.get_detector()
-        coll = sim.get_collisions()
-        stats = sim.get_stats()
-        return mask, vals, coll, stats
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        mask, vals, coll, stats = e2e_step()
-    torch.cuda.synchronize()
-    e2e_serial_s = time.perf_counter() - t0
-    e2e_serial = updates_total / max_over_ranks(e2e_serial_s, device="cuda")
-    h2d = h_poses.nbytes + h_vels.nbytes
-    d2h = o_poses.nbytes + o_vels.nbytes + mask.nbytes + vals.nbytes + coll.nbytes + sum(s.nbytes for s in stats)
-
+    # for its own transfers.  `value_serial_one_handle` is the same loop with one handle and blocking calls.
+    # io dtype: the float32 host interface (pms_set/get_ped_state_f32, pms_get_detector_f32: the bytes the FP32 kernels
+    # consume) is the headline; the reference's float64 arrays are timed next to it.
     sim2 = BatchedSimulation(W, N, precision=args.precision, device=local_rank)
     if args.j_split or args.wpc or args.chunks or args.cluster:
         sim2.set_tuning(args.j_split, args.wpc, args.chunks, args.cluster)
@@ -355,46 +336,66 @@ def main():
     sim2.set_robot(capi.ROBOT_UNICYCLE, sc.robot_pose, control=sc.robot_control)
     sim2.set_detector(5.0, np.deg2rad(120.0), capi.DET_POLAR)
     sim2.snapshot_save()
-    pipe = []
-    for s_ in (sim, sim2):
-        s_.set_async_io(True)
-        pipe.append((s_, dict(poses=capi.pinned_array((W, N, 3)), vels=capi.pinned_array((W, N, 3)),
-                              mask=capi.pinned_array((W, sim.words), np.uint32), vals=capi.pinned_array((W, N, 2)),
-                              coll=capi.pinned_array((W, sim.words), np.uint32), det=capi.pinned_array((W,), np.int64),
-                              col=capi.pinned_array((W,), np.int64), nf=capi.pinned_array((W,), np.int32))))
 
-    def submit(k):
-        s_, b_ = pipe[k & 1]
-        s_.snapshot_restore()
-        s_.set_state(h_poses, h_vels)
-        s_.step_async(0.01, K)
-        s_.get_state(b_["poses"], b_["vels"])
-        s_.get_detector(b_["mask"], b_["vals"])
-        s_.get_collisions(b_["coll"])
-        s_.get_stats((b_["det"], b_["col"], b_["nf"]))
+    def run_e2e(io_dtype):
+        f32 = io_dtype == np.float32
+        in_p = capi.pinned_array((W, N, 3), io_dtype); in_p[:] = sc.poses
+        in_v = capi.pinned_array((W, N, 3), io_dtype); in_v[:] = sc.vels
+        bufs = [dict(poses=capi.pinned_array((W, N, 3), io_dtype), vels=capi.pinned_array((W, N, 3), io_dtype),
+                     mask=capi.pinned_array((W, sim.words), np.uint32), vals=capi.pinned_array((W, N, 2), io_dtype),
+                     coll=capi.pinned_array((W, sim.words), np.uint32), det=capi.pinned_array((W,), np.int64),
+                     col=capi.pinned_array((W,), np.int64), nf=capi.pinned_array((W,), np.int32)) for _ in range(3)]
 
-    def finish(k):
-        pipe[k & 1][0].sync()                  # the step's results are in its pinned buffers now
+        def submit(s_, b_):
+            s_.snapshot_restore()                  # robot / tracker / statistics back to t = 0 (device-side)
+            s_.set_state(in_p, in_v)                # H2D from pinned memory
+            s_.step_async(0.01, K)
+            s_.get_state(b_["poses"], b_["vels"])   # D2H
+            (s_.get_detector_f32 if f32 else s_.get_detector)(b_["mask"], b_["vals"])
+            s_.get_collisions(b_["coll"])
+            s_.get_stats((b_["det"], b_["col"], b_["nf"]))
 
-    def pipelined(n):
-        submit(0)
-        for k in range(1, n):
-            submit(k)
-            finish(k - 1)
-        finish(n - 1)
-    pipelined(2)
-    barrier()
-    t0 = time.perf_counter()
-    pipelined(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None      # sampled over the device-resident and both end-to-end timed regions
-    e2e_value = updates_total / max_over_ranks(e2e_s, device="cuda")
-    last_buf = pipe[(args.steps - 1) & 1][1]
-    e2e_matches = bool(np.array_equal(last_buf["poses"], o_poses) and np.array_equal(last_buf["mask"], mask)
-                       and np.array_equal(last_buf["det"], stats[0]))
-    for s_, _ in pipe:
-        s_.set_async_io(False)
+        # one handle, blocking calls
+        ser = bufs[2]
+        for _ in range(2):
+            submit(sim, ser)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            submit(sim, ser)
+        torch.cuda.synchronize()
+        serial = updates_total / max_over_ranks(time.perf_counter() - t0, device="cuda")
+        # two handles, asynchronous I/O
+        pipe = [(sim, bufs[0]), (sim2, bufs[1])]
+        for s_, _ in pipe:
+            s_.set_async_io(True)
+
+        def pipelined(n):
+            submit(*pipe[0])
+            for k in range(1, n):
+                submit(*pipe[k & 1])
+                pipe[(k - 1) & 1][0].sync()        # the step's results are in its pinned buffers now
+            pipe[(n - 1) & 1][0].sync()
+        pipelined(2)
+        barrier()
+        t0 = time.perf_counter()
+        pipelined(args.steps)
+        torch.cuda.synchronize()
+        piped = updates_total / max_over_ranks(time.perf_counter() - t0, device="cuda")
+        for s_, _ in pipe:
+            s_.set_async_io(False)
+        last = pipe[(args.steps - 1) & 1][1]
+        same = bool(np.array_equal(last["poses"], ser["poses"]) and np.array_equal(last["mask"], ser["mask"])
+                    and np.array_equal(last["det"], ser["det"]))
+        h2d_ = in_p.nbytes + in_v.nbytes
+        d2h_ = sum(ser[k].nbytes for k in ("poses", "vels", "mask", "vals", "coll", "det", "col", "nf"))
+        return piped, serial, h2d_, d2h_, same, ser
+
+    e2e64 = run_e2e(np.float64)
+    e2e_value, e2e_serial, h2d, d2h, e2e_matches, ser = run_e2e(np.float32)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over the device-resident and the end-to-end timed regions
+    stats = (ser["det"], ser["col"], ser["nf"])
+    o_vels = ser["vels"]
     sim2.close()
 
     # ---- episode statistics: the only collective (NCCL all-reduce of a few numbers) ----
@@ -447,9 +448,12 @@ def main():
             "scaling": args.scaling, "vs_baseline": None, "dtype": {"fp32": "f32", "fp32_plain": "f32", "mixed": "f32/f64", "fp64": "f64"}[args.precision],
             "data": "synthetic", "config": config_dict(args, world_size),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "io_dtype": "float32 host arrays (pms_set/get_ped_state_f32, pms_get_detector_f32)",
                     "how": "two handles alternate in asynchronous-I/O mode: the copies of one step overlap the kernel of the "
                            "other; every step pays its own H2D and D2H", "value_serial_one_handle": e2e_serial,
-                    "pipelined_results_equal_serial": e2e_matches},
+                    "pipelined_results_equal_serial": e2e_matches,
+                    "float64_io": {"value": e2e64[0], "value_serial_one_handle": e2e64[1], "h2d_bytes_per_step": int(e2e64[2]),
+                                   "d2h_bytes_per_step": int(e2e64[3]), "pipelined_results_equal_serial": e2e64[4]}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / peak,
