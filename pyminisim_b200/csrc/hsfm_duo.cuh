@@ -53,29 +53,6 @@ template <int T> struct DuoSmem {
     static constexpr size_t BYTES = (ROBOT + DUO_RING * sizeof(WarpRobotSlot) + sizeof(RobotRegs) + 15) & ~size_t(15);
 };
 
-// sin / cos for |a| < 1e5 without the slow-path branch of fast_sincos (same arithmetic)
-__device__ __forceinline__ void fast_sincos_small(float a, float &sn, float &cs)
-{
-    const float t = fmaf(a, 0.636619747f, 12582912.f);
-    const int q = __float_as_int(t);
-    const float k = t - 12582912.f;
-    float r = fmaf(k, -1.57079625f, a);
-    r = fmaf(k, -7.54978942e-8f, r);
-    r = fmaf(k, -5.39030295e-15f, r);
-    const float r2 = r * r;
-    float ps = fmaf(r2, -1.95152956e-4f, 8.33270326e-3f);
-    ps = fmaf(r2, ps, -0.166666627f);
-    const float s0 = fmaf(r2 * r, ps, r);
-    float pc = fmaf(r2, 2.44331571e-5f, -1.38878601e-3f);
-    pc = fmaf(r2, pc, 4.16667275e-2f);
-    pc = fmaf(r2, pc, -0.49999997f);
-    const float c0 = fmaf(r2, pc, 1.0f);
-    const bool odd = q & 1;
-    const float s1 = odd ? c0 : s0, c1 = odd ? s0 : c0;
-    sn = __int_as_float(__float_as_int(s1) ^ ((q & 2) << 30));
-    cs = __int_as_float(__float_as_int(c1) ^ (((q + 1) & 2) << 30));
-}
-
 // warp_sense without its early-out vote: in this kernel the sensor pass is a side duty of a pair warp and what counts is the
 // length of its dependent chain (vote -> branch -> vote -> branch costs more than the 12 arithmetic instructions it skips)
 __device__ __forceinline__ void duo_sense(const HsfmArgs &a, const WarpRobotSlot &rb, float qx, float qy, float px, float py,
