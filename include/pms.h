@@ -264,6 +264,21 @@ int pms_get_collision_records(pms_sim *h, int first, int count, uint32_t *mask /
 int pms_get_lidar_records(pms_sim *h, int first, int count, int32_t *hit_index /*(count,W,n_beams)*/, double *points /*(count,W,n_beams,2) or NULL*/);
 int pms_get_omni_records(pms_sim *h, int first, int count, double *min_dist /*(count,W)*/);
 
+/* ---- recorded trajectories: ReplayPedestriansPolicy (pedestrians/_replay.py:19-59) as a batched gather ----
+ * The frames (T,W,N,3) are uploaded once and stay in HBM.  pms_replay_step plays n_steps of them in ONE launch: per step
+ * the robot model steps (pms_set_robot; device models or the external pose), the frame counter advances by the rule of
+ * _replay.py:46-52 (next frame; at the last frame: back to 0 when loop, else stay), and the collision list + pedestrian
+ * detector are evaluated on the frame's poses (exact fp64 predicates) -- with the records of pms_sensor_schedule when kinds
+ * are scheduled.  The frame shown becomes the pedestrian state (pms_get_ped_state).  pms_replay_frame jumps
+ * (reset_to_state, _replay.py:57-59: set_frame >= 0) or queries (-1).  pms_replay_tick = one tick of the drop-in class in
+ * one call and one synchronisation: external robot pose in (NULL = no robot), collision list + detector reading out. */
+int pms_set_replay(pms_sim *h, const double *poses /*(T,W,N,3)*/, const double *vels /*(T,W,N,3)*/, int n_frames, int loop);
+int pms_replay_step(pms_sim *h, double dt, int n_steps);
+int pms_replay_frame(pms_sim *h, int set_frame, int *frame_out /*or NULL*/);
+int pms_replay_tick(pms_sim *h, int n_steps, const double *robot_pose /*(W,3) or NULL*/, double robot_radius,
+                    uint32_t *coll_mask /*(W,ceil(N/32)) or NULL*/, uint32_t *det_mask /*or NULL*/, double *det_vals /*(W,N,2) or NULL*/,
+                    int32_t *frame_out /*or NULL*/);
+
 /* ---- ORCA (pedestrians/_orca.py:95-127 around rvo2.doStep) ---- */
 int pms_orca_create(int device, int n_worlds, int n_agents, const pms_orca_params *params, pms_sim **out);
 int pms_orca_set_agents(pms_sim *h, const double *positions /*(W,N,2)*/, const double *velocities /*(W,N,2)*/,
@@ -286,7 +301,7 @@ int pms_orca_get_agents(pms_sim *h, double *poses /*(W,N,3)*/, double *velocitie
 /* ---- launch introspection (bench / tests) ---- */
 typedef struct {
     int kernel;            /* 0 = directed-pair small-world kernel, 1 = large-crowd kernel, 2 = ORCA, 3 = warp-per-world kernel,
-                              4 = pair-warp / owner-warp kernel (under-filled batches, N <= 64) */
+                              4 = pair-warp / owner-warp kernel (under-filled batches, N <= 64), 5 = replay kernel */
     int threads_per_block, blocks, worlds_per_block, j_split; /* large kernel: j_split = cluster size */
     int smem_bytes;
     int n_chunks;          /* > 1: persistent CTAs pull (chunk, world-group) items dynamically */

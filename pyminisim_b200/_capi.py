@@ -103,6 +103,10 @@ PROTOTYPES = {
     "pms_reset_stats": (C.c_int, [_h]),
     "pms_lidar_scan": (C.c_int, [_h, C.c_int, C.c_double, C.c_double, _ip, _dp]),
     "pms_omni_scan": (C.c_int, [_h, _dp]),
+    "pms_set_replay": (C.c_int, [_h, _dp, _dp, C.c_int, C.c_int]),
+    "pms_replay_step": (C.c_int, [_h, C.c_double, C.c_int]),
+    "pms_replay_frame": (C.c_int, [_h, C.c_int, C.POINTER(C.c_int)]),
+    "pms_replay_tick": (C.c_int, [_h, C.c_int, _dp, C.c_double, _up, _up, _dp, _ip]),
     "pms_lidar_config": (C.c_int, [_h, C.c_int, C.c_double, C.c_double]),
     "pms_sensor_schedule": (C.c_int, [_h, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]),
     "pms_get_sensor_fires": (C.c_int, [_h, C.c_int, _ip, C.c_int, C.POINTER(C.c_int), _dp]),

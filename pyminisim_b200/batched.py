@@ -354,6 +354,37 @@ class BatchedSimulation:
         check(self._lib.pms_omni_scan(self._h, dptr(out)))
         return out
 
+    # ---- recorded trajectories (ReplayPedestriansPolicy, pedestrians/_replay.py) as a batched gather -----------------------
+    def set_replay(self, poses, velocities, loop: bool = False):
+        """Frames (T, W, N, 3) -- or (T, N, 3), shared by every world -- uploaded once; frame 0 becomes the state."""
+        poses, velocities = np.asarray(poses, dtype=np.float64), np.asarray(velocities, dtype=np.float64)
+        if poses.ndim == 3:
+            poses = np.broadcast_to(poses[:, None], (poses.shape[0], self.W, self.N, 3))
+            velocities = np.broadcast_to(velocities[:, None], (velocities.shape[0], self.W, self.N, 3))
+        T = poses.shape[0]
+        check(self._lib.pms_set_replay(self._h, dptr(f64(poses, (T, self.W, self.N, 3))), dptr(f64(velocities, (T, self.W, self.N, 3))),
+                                       T, int(bool(loop))))
+
+    def replay_step(self, dt: float = 0.01, n_steps: int = 1):
+        """n_steps frames under the robot model and the sensors in one launch (``pms_replay_step``)."""
+        check(self._lib.pms_replay_step(self._h, float(dt), int(n_steps)))
+
+    def replay_frame(self, set_frame: int = -1) -> int:
+        f = C.c_int(0)
+        check(self._lib.pms_replay_frame(self._h, int(set_frame), C.byref(f)))
+        return f.value
+
+    def replay_tick(self, robot_pose=None, robot_radius: float = 0.35, n_steps: int = 1):
+        """One tick of the drop-in replay policy: (collision mask, detector mask, detector values, frame)."""
+        coll = np.empty((self.W, self.words), dtype=np.uint32)
+        det = np.empty((self.W, self.words), dtype=np.uint32)
+        vals = np.empty((self.W, self.N, 2))
+        frame = np.zeros(1, dtype=np.int32)
+        rp = None if robot_pose is None else f64(robot_pose, (self.W, 3))
+        self.robot_model = capi.ROBOT_NONE if rp is None else capi.ROBOT_EXTERNAL
+        check(self._lib.pms_replay_tick(self._h, int(n_steps), dptr(rp), float(robot_radius), uptr(coll), uptr(det), dptr(vals), iptr(frame)))
+        return coll, det, vals, int(frame[0])
+
     # ---- sensors inside a fused launch (the reference's hold-time scheduler on the device) -----------
     def set_lidar(self, n_beams: int = 100, max_dist: float = 8.0, resolution: float = 0.01):
         """LidarSensorConfig (sensors/_lidar.py:8-23) of the lidar readings taken inside fused launches."""

@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpms_b200.so")
-SOURCES = ["pms_api.cu", "hsfm_warp.cu", "hsfm_duo.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
-HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_warp.cuh", "hsfm_warp_api.cuh", "hsfm_duo.cuh", "hsfm_duo_api.cuh", "hsfm_large.cuh", "sensors.cuh", "orca.cuh"]
+SOURCES = ["pms_api.cu", "hsfm_warp.cu", "hsfm_duo.cu", "replay.cu", "orca.cu"]   # orca.cu is compiled with -fmad=false (RVO2 rounds every op)
+HEADERS = ["pms_common.cuh", "hsfm_small.cuh", "hsfm_warp.cuh", "hsfm_warp_api.cuh", "hsfm_duo.cuh", "hsfm_duo_api.cuh", "hsfm_large.cuh", "sensors.cuh", "sensor_fires.cuh", "replay_api.cuh", "orca.cuh"]
 
 
 def nvcc_path() -> str:

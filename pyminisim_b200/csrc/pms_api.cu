@@ -14,6 +14,7 @@
 #include "hsfm_duo_api.cuh"
 #include "hsfm_large.cuh"
 #include "sensors.cuh"
+#include "replay_api.cuh"
 #include "orca.cuh"
 
 using namespace pms;
@@ -225,6 +226,9 @@ struct pms_sim {
         double *lidar_dirs = nullptr;
         bool any() const { return enabled[0] || enabled[1] || enabled[2] || enabled[3]; }
     } sched;
+    // recorded trajectories (pms_set_replay): frames resident in HBM, frame counter (the same for every world)
+    double *replay_poses = nullptr, *replay_vels = nullptr;
+    int replay_frames = 0, replay_loop = 0, replay_frame = 0, snap_replay_frame = 0;
     // ORCA
     OrcaState orca{};
 };
@@ -739,6 +743,8 @@ int pms_destroy(pms_sim *h)
     for (void *p : h->snap_dst) if (p) cudaFree(p);
     if (h->tick_dev) cudaFree(h->tick_dev);
     if (h->tick_host) cudaFreeHost(h->tick_host);
+    if (h->replay_poses) cudaFree(h->replay_poses);
+    if (h->replay_vels) cudaFree(h->replay_vels);
     {
         pms_sim::Sched &sc = h->sched;
         void *sp_[] = {sc.hold_dev, sc.count_dev, sc.tables, sc.det_mask, sc.coll_mask, sc.det_vals, sc.lidar_hit, sc.lidar_pts, sc.omni, sc.lidar_dirs};
@@ -1454,6 +1460,7 @@ int pms_snapshot_save(pms_sim *h)
     h->snap_src = r;
     h->snap_steps = h->a.steps_done;
     for (int k = 0; k < SENSOR_KINDS; ++k) h->sched.snap_hold[k] = h->sched.hold_host[k];
+    h->snap_replay_frame = h->replay_frame;
     h->has_snapshot = true;
     return PMS_OK;
 }
@@ -1468,6 +1475,7 @@ int pms_snapshot_restore(pms_sim *h)
     h->a.steps_done = h->snap_steps;
     h->large.sorted_valid = false;
     for (int k = 0; k < SENSOR_KINDS; ++k) h->sched.hold_host[k] = h->sched.snap_hold[k];
+    h->replay_frame = h->snap_replay_frame;
     if (h->sched.hold_dev)      // snap_hold is a member of the handle: stable until the copy has run
         CK(cudaMemcpyAsync(h->sched.hold_dev, h->sched.snap_hold, sizeof(double) * SENSOR_KINDS, cudaMemcpyHostToDevice, h->stream));
     return PMS_OK;
@@ -1522,6 +1530,116 @@ int pms_omni_scan(pms_sim *h, double *min_dist)
     }
     if (min_dist) CK(cudaMemcpyAsync(min_dist, h->stage, sizeof(double) * h->W, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+// ---- recorded trajectories: ReplayPedestriansPolicy as a batched gather ----
+int pms_set_replay(pms_sim *h, const double *poses, const double *vels, int n_frames, int loop)
+{
+    HCHECK(h);
+    if (!poses || !vels || n_frames < 1) return fail(PMS_ERR_INVALID, "poses / vels NULL or n_frames < 1");
+    const size_t per = (size_t)h->W * h->N * 3, total = per * n_frames;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->replay_poses) cudaFree(h->replay_poses);
+    if (h->replay_vels) cudaFree(h->replay_vels);
+    h->replay_poses = h->replay_vels = nullptr; h->replay_frames = 0;
+    CK(cudaMalloc((void **)&h->replay_poses, total * sizeof(double)));
+    CK(cudaMalloc((void **)&h->replay_vels, total * sizeof(double)));
+    CK(cudaMemcpy(h->replay_poses, poses, total * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->replay_vels, vels, total * sizeof(double), cudaMemcpyHostToDevice));
+    h->replay_frames = n_frames; h->replay_loop = loop ? 1 : 0; h->replay_frame = 0;
+    if (state_from_device(h, h->replay_poses, h->replay_vels, false)) return PMS_ERR_CUDA;     // frame 0 is the state (_replay.py:36-38)
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+static int replay_step_async(pms_sim *h, double dt, int n_steps)
+{
+    if (!h->replay_frames) return fail(PMS_ERR_STATE, "no recorded trajectories: call pms_set_replay first");
+    if (n_steps < 0) return fail(PMS_ERR_INVALID, "n_steps < 0");
+    if (n_steps == 0) return PMS_OK;
+    h->a.dt = dt; h->a.n_steps = n_steps;
+    fill_consts(h->a);
+    int rc;
+    if (h->a.robot_model == ROBOT_NONE && (rc = clear_sensor_outputs(h))) return rc;
+    if ((rc = prepare_sensor_plan(h, n_steps, false))) return rc;
+    const ReplayArgs ra{h->replay_poses, h->replay_frames, h->replay_loop, h->replay_frame};
+    CK(replay_launch(h->a, ra, h->a.sp.on != 0, h->stream));
+    h->info.kernel = 5; h->info.threads_per_block = 128; h->info.blocks = (h->W + 3) / 4; h->info.worlds_per_block = 4;
+    h->info.j_split = 0; h->info.smem_bytes = 0; h->info.n_chunks = 1; h->info.blocks_per_sm = 0;
+    h->info.kernel_launches++;
+    h->replay_frame = replay_advance(h->replay_frame, h->replay_frames, h->replay_loop, n_steps);
+    const size_t per = (size_t)h->W * h->N * 3;
+    if (state_from_device(h, h->replay_poses + per * h->replay_frame, h->replay_vels + per * h->replay_frame, false)) return PMS_ERR_CUDA;
+    h->a.steps_done += n_steps;
+    return PMS_OK;
+}
+
+int pms_replay_step(pms_sim *h, double dt, int n_steps)
+{
+    HCHECK(h);
+    int rc = replay_step_async(h, dt, n_steps);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return PMS_OK;
+}
+
+int pms_replay_frame(pms_sim *h, int set_frame, int *frame_out)
+{
+    HCHECK(h);
+    if (!h->replay_frames) return fail(PMS_ERR_STATE, "no recorded trajectories: call pms_set_replay first");
+    if (set_frame >= 0) {
+        if (set_frame >= h->replay_frames) return fail(PMS_ERR_INVALID, "frame out of range");
+        h->replay_frame = set_frame;
+        const size_t per = (size_t)h->W * h->N * 3;
+        if (state_from_device(h, h->replay_poses + per * set_frame, h->replay_vels + per * set_frame, false)) return PMS_ERR_CUDA;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (frame_out) *frame_out = h->replay_frame;
+    return PMS_OK;
+}
+
+int pms_replay_tick(pms_sim *h, int n_steps, const double *robot_pose, double robot_radius, uint32_t *coll_mask, uint32_t *det_mask,
+                    double *det_vals, int32_t *frame_out)
+{
+    HCHECK(h);
+    if (n_steps < 1) return fail(PMS_ERR_INVALID, "n_steps < 1");
+    HsfmArgs &a = h->a;
+    const int W = h->W;
+    const size_t n = (size_t)W * h->N, nm = (size_t)W * h->words;
+    const size_t o_coll = n * 16, o_det = o_coll + nm * 4, total = o_det + nm * 4;
+    const size_t need = total > (size_t)W * 96 ? total : (size_t)W * 96;
+    if (need > h->tick_bytes) {
+        if (h->tick_dev) cudaFree(h->tick_dev);
+        if (h->tick_host) cudaFreeHost(h->tick_host);
+        h->tick_dev = h->tick_host = nullptr; h->tick_bytes = 0;
+        CK(cudaMalloc((void **)&h->tick_dev, need));
+        CK(cudaMallocHost((void **)&h->tick_host, need));
+        h->tick_bytes = need;
+    }
+    if (!robot_pose) {
+        a.robot_model = PMS_ROBOT_NONE;
+    } else {
+        if (!(robot_radius > 0.0)) return fail(PMS_ERR_INVALID, "robot radius must be > 0");
+        a.robot_model = PMS_ROBOT_EXTERNAL; a.robot_radius = robot_radius;
+        double *st = reinterpret_cast<double *>(h->tick_host);       // the previous tick was synchronised: the block is free
+        std::memset(st, 0, sizeof(double) * W * 11 + sizeof(int) * W);
+        std::memcpy(st, robot_pose, sizeof(double) * W * 3);
+        CK(cudaMemcpyAsync(h->robot_block, st, sizeof(double) * W * 11 + sizeof(int) * W, cudaMemcpyHostToDevice, h->stream));
+    }
+    int rc = replay_step_async(h, a.dt > 0.0 ? a.dt : 0.01, n_steps);
+    if (rc) return rc;
+    unsigned char *d = h->tick_dev;
+    CK(cudaMemcpyAsync(d, a.det_vals, n * 16, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + o_coll, a.coll_mask, nm * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + o_det, a.det_mask, nm * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tick_host, d, total, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const unsigned char *q = h->tick_host;
+    if (det_vals) std::memcpy(det_vals, q, n * 16);
+    if (coll_mask) std::memcpy(coll_mask, q + o_coll, nm * 4);
+    if (det_mask) std::memcpy(det_mask, q + o_det, nm * 4);
+    if (frame_out) *frame_out = h->replay_frame;
     return PMS_OK;
 }
 

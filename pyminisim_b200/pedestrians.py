@@ -543,6 +543,13 @@ class ReplayPedestriansPolicy(AbstractPedestriansModel):
         self._max_step, self._n = poses.shape[0] - 1, poses.shape[1]
         self._current_step = 0
         self._state = self._frame(0)
+        # Under this package's Simulation (which sets _collision_radius and the detector configuration) the recorded frames
+        # live on the device: a tick uploads the robot pose only and one launch returns the collision list and the detector
+        # reading of the frame (pms_replay_tick) instead of a pose upload + sense pass per tick.
+        self._collision_radius = None
+        self._det_cfg = None
+        self._sim = None
+        self._fused = None
 
     def _frame(self, step: int) -> ReplayPedestriansState:
         return ReplayPedestriansState(step, {i: (self._poses[step, i], self._velocities[step, i]) for i in range(self._n)})
@@ -551,15 +558,53 @@ class ReplayPedestriansPolicy(AbstractPedestriansModel):
     def state(self) -> ReplayPedestriansState:
         return self._state
 
+    def configure_fused_detector(self, max_dist: float, fov: float, code: int):
+        self._det_cfg = (float(max_dist), float(fov), int(code))
+        if self._sim is not None:
+            self._sim.set_detector(*self._det_cfg, enabled=True)
+
+    def fused_collisions(self, robot_pose: np.ndarray, radius: float):
+        f = self._fused
+        if f is None or f[1] != radius or not np.array_equal(f[0], robot_pose):
+            return None
+        return list(f[2])
+
+    def _device(self):
+        if self._sim is None:
+            self._sim = BatchedSimulation(1, self._n, precision="fp64")
+            self._sim.set_replay(self._poses, self._velocities, self._loop)
+            self._sim.replay_frame(self._current_step)
+            if self._det_cfg is not None:
+                self._sim.set_detector(*self._det_cfg, enabled=True)
+        return self._sim
+
     def step(self, dt: float = None, robot_pose: Optional[np.ndarray] = None, robot_velocity: Optional[np.ndarray] = None):
+        self._fused = None
+        fused = robot_pose is not None and self._collision_radius is not None      # running under this package's Simulation
+        if fused:
+            rp = np.asarray(robot_pose, dtype=np.float64)
+            coll, det, vals, frame = self._device().replay_tick(rp[None], self._collision_radius)
         if self._current_step == self._max_step:        # _replay.py:46-52: stay on the last frame unless looping
             if not self._loop:
+                if fused:
+                    self._attach(rp, coll, det, vals, frame)
                 return
             self._current_step = 0
         else:
             self._current_step += 1
         self._state = self._frame(self._current_step)
+        if fused:
+            self._attach(rp, coll, det, vals, frame)
+
+    def _attach(self, rp, coll, det, vals, frame):
+        assert frame == self._current_step, (frame, self._current_step)            # device and host follow the same rule
+        self._fused = (rp.copy(), self._collision_radius, _mask_ids(coll[0], self._n))
+        if self._det_cfg is not None:
+            self._state._fused_sense = (self._fused[0], self._det_cfg, _mask_ids(det[0], self._n), vals[0].copy())
 
     def reset_to_state(self, state: ReplayPedestriansState):
         self._state = state
         self._current_step = state.current_step
+        self._fused = None
+        if self._sim is not None:
+            self._sim.replay_frame(self._current_step)
