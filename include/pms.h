@@ -296,6 +296,10 @@ int pms_orca_set_waypoints_current(pms_sim *h, const double *current /*(W,N,2)*/
  * preferred velocities and _update_preferred_velocities (:118-127) follows after it.  Default 1 (constructor semantics, :86). */
 int pms_orca_set_pref_refresh(pms_sim *h, int enabled);
 int pms_orca_step(pms_sim *h, int n_steps);
+int pms_orca_step_async(pms_sim *h, int n_steps);          /* no host synchronisation; pair with pms_sync */
+/* device-side snapshot of the agents (positions, velocities, preferred velocities, waypoint indices): checkpoint / resume */
+int pms_orca_snapshot_save(pms_sim *h);
+int pms_orca_snapshot_restore(pms_sim *h);
 int pms_orca_get_agents(pms_sim *h, double *poses /*(W,N,3)*/, double *velocities /*(W,N,3)*/);
 
 /* ---- launch introspection (bench / tests) ---- */

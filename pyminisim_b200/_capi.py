@@ -120,6 +120,9 @@ PROTOTYPES = {
     "pms_orca_set_waypoints_current": (C.c_int, [_h, _dp]),
     "pms_orca_set_pref_refresh": (C.c_int, [_h, C.c_int]),
     "pms_orca_step": (C.c_int, [_h, C.c_int]),
+    "pms_orca_step_async": (C.c_int, [_h, C.c_int]),
+    "pms_orca_snapshot_save": (C.c_int, [_h]),
+    "pms_orca_snapshot_restore": (C.c_int, [_h]),
     "pms_orca_get_agents": (C.c_int, [_h, _dp, _dp]),
     "pms_get_launch_info": (C.c_int, [_h, C.POINTER(LaunchInfoC)]),
     "pms_set_tuning": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -521,6 +521,22 @@ class BatchedOrca:
     def step(self, n_steps: int = 1):
         check(self._lib.pms_orca_step(self._h, int(n_steps)))
 
+    def step_async(self, n_steps: int = 1):
+        check(self._lib.pms_orca_step_async(self._h, int(n_steps)))
+
+    def sync(self):
+        check(self._lib.pms_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.pms_stream(self._h) or 0)
+
+    def snapshot_save(self):
+        check(self._lib.pms_orca_snapshot_save(self._h))
+
+    def snapshot_restore(self):
+        check(self._lib.pms_orca_snapshot_restore(self._h))
+
     def get_agents(self) -> Tuple[np.ndarray, np.ndarray]:
         poses = np.empty((self.W, self.N, 3))
         vels = np.empty((self.W, self.N, 3))

@@ -1918,7 +1918,7 @@ int pms_orca_set_pref_refresh(pms_sim *h, int enabled)
     return PMS_OK;
 }
 
-int pms_orca_step(pms_sim *h, int n_steps)
+int pms_orca_step_async(pms_sim *h, int n_steps)
 {
     OCHECK(h);
     if (n_steps < 0) return fail(PMS_ERR_INVALID, "n_steps < 0");
@@ -1929,7 +1929,47 @@ int pms_orca_step(pms_sim *h, int n_steps)
     if (orca_step(h->orca, n_steps, h->stream, &launches)) return fail(PMS_ERR_CUDA, std::string("orca launch: ") + cudaGetErrorString(cudaGetLastError()));
     h->info.kernel = 2;
     h->info.kernel_launches += launches;
+    return PMS_OK;
+}
+
+int pms_orca_step(pms_sim *h, int n_steps)
+{
+    int rc = pms_orca_step_async(h, n_steps);
+    if (rc) return rc;
+    return pms_sync(h);
+}
+
+// device-side snapshot of the ORCA agents (positions, velocities, preferred velocities, tracker position)
+static void orca_snapshot_regions(pms_sim *h, std::vector<std::pair<void *, size_t>> &r)
+{
+    const OrcaState &o = h->orca;
+    const size_t n = (size_t)h->W * h->N;
+    r = {{o.pos, n * sizeof(float2)}, {o.vel, n * sizeof(float2)}, {o.pref, n * sizeof(float2)}, {o.cur_wp, n * sizeof(double2)},
+         {o.wp_index, n * sizeof(int)}, {o.heading, n * sizeof(double)}};
+}
+int pms_orca_snapshot_save(pms_sim *h)
+{
+    OCHECK(h);
+    if (!h->orca.agents_set) return fail(PMS_ERR_STATE, "agents are not set");
+    std::vector<std::pair<void *, size_t>> r;
+    orca_snapshot_regions(h, r);
+    for (void *p : h->snap_dst) if (p) cudaFree(p);
+    h->snap_dst.assign(r.size(), nullptr);
+    for (size_t k = 0; k < r.size(); ++k) {
+        CK(cudaMalloc(&h->snap_dst[k], r[k].second ? r[k].second : 1));
+        CK(cudaMemcpyAsync(h->snap_dst[k], r[k].first, r[k].second, cudaMemcpyDeviceToDevice, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
+    h->snap_src = r;
+    h->has_snapshot = true;
+    return PMS_OK;
+}
+int pms_orca_snapshot_restore(pms_sim *h)
+{
+    OCHECK(h);
+    if (!h->has_snapshot) return fail(PMS_ERR_STATE, "no snapshot saved");
+    for (size_t k = 0; k < h->snap_src.size(); ++k)
+        CK(cudaMemcpyAsync(h->snap_src[k].first, h->snap_dst[k], h->snap_src[k].second, cudaMemcpyDeviceToDevice, h->stream));
     return PMS_OK;
 }
 

@@ -74,3 +74,20 @@ def test_orca_error_paths():
         c.set_agents(np.zeros((1, 4, 2)), np.full((1, 4, 2), 5.0), max_speeds=np.ones((1, 4)))
     with pytest.raises(PmsError):
         BatchedOrca(0.01, 1, 4, ORCAParams(max_neighbors=99))
+
+
+def test_orca_async_step_and_snapshot():
+    """pms_orca_step_async + pms_sync == pms_orca_step; a snapshot restores positions, velocities and tracker position bit for bit"""
+    sc = make_crowd(6, 32, side=8.0)
+    _, a = _pair(sc)
+    _, b = _pair(sc)
+    a.step(40); b.step_async(25); b.step_async(15); b.sync()
+    pa, va = a.get_agents(); pb, vb = b.get_agents()
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+    b.snapshot_save()
+    b.step(60)
+    b.snapshot_restore()
+    b.step(10); a.step(10)
+    pa, va = a.get_agents(); pb, vb = b.get_agents()
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+    a.close(); b.close()
