@@ -127,10 +127,16 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
     const int wl = threadIdx.x / Np, i = threadIdx.x - wl * Np;
     const int w = blockIdx.x * a.wpc + wl;
     const bool valid = w < a.W && i < N;
-    // per world: positions as two arrays sx | sy (four candidates per LDS.128, packed-FP32 differences), velocities float2
-    float *sx = reinterpret_cast<float *>(smem_raw) + (size_t)wl * 4 * Np;
-    float *sy = sx + Np;
-    float2 *svel = reinterpret_cast<float2 *>(sx + 2 * Np);
+    // per world: positions as two arrays sx | sy (four candidates per LDS.128, packed-FP32 differences), velocities float2 --
+    // TWO copies by step parity: step s reads copy s & 1 and publishes the new state to the other one, so ONE barrier per
+    // step is enough (a thread that runs ahead writes the copy nobody reads in this step).  Worlds are independent: the
+    // barrier is the WORLD's (named barrier 1 + local world, or __syncwarp for a one-warp world), not the CTA's -- an agent with
+    // many neighbours (the LP is divergent work) holds up its own world only.
+    float *sbase = reinterpret_cast<float *>(smem_raw) + (size_t)wl * 8 * Np;
+    auto world_sync = [&]() {
+        if (Np == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" :: "r"(wl + 1), "r"(Np) : "memory");
+    };
     const size_t g = (size_t)(valid ? w : 0) * N + (valid ? i : 0);
 
     V2 p = mk(0.f, 0.f), v = p, pref = p;
@@ -147,9 +153,11 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
     const float inv_th = 1.0f / a.time_horizon;
     const float R = a.radius + a.radius, R2 = R * R;
 
+    { sbase[i] = p.x; sbase[Np + i] = p.y; reinterpret_cast<float2 *>(sbase + 2 * Np)[i] = make_float2(v.x, v.y); }
+    world_sync();
     for (int step = 0; step < a.n_steps; ++step) {
-        if (i < Np) { sx[i] = p.x; sy[i] = p.y; svel[i] = make_float2(v.x, v.y); }
-        __syncthreads();
+        const float *sx = sbase + (step & 1) * 4 * Np, *sy = sx + Np;
+        const float2 *svel = reinterpret_cast<const float2 *>(sx + 2 * Np);
         V2 newv = v;
         if (valid) {
             // ---- neighbours: nearest kmax within neighbor_dist, insertion-sorted by squared distance ----
@@ -223,7 +231,6 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
             const int failed = lp_plane(hp, cnt, vmax, pref, false, newv);
             if (failed < cnt) lp_relax(hp, cnt, failed, vmax, newv);
         }
-        __syncthreads();   // every agent has read the old state
         if (valid) {
             v = newv;
             p = mk(p.x + v.x * a.time_step, p.y + v.y * a.time_step);
@@ -243,6 +250,11 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
             if (nr <= a.goal_threshold) pref = mk(0.f, 0.f);
             else pref = mk((float)(dx / nr * pspeed), (float)(dy / nr * pspeed));
         }
+        {   // publish the new state in the other copy; one barrier per step
+            float *nx_ = sbase + ((step + 1) & 1) * 4 * Np;
+            nx_[i] = p.x; nx_[Np + i] = p.y; reinterpret_cast<float2 *>(nx_ + 2 * Np)[i] = make_float2(v.x, v.y);
+        }
+        world_sync();
     }
     if (valid) {
         if (a.n_steps > 0) head = atan2((double)v.y, (double)v.x);
@@ -401,7 +413,7 @@ int orca_step(OrcaState &s, int n_steps, cudaStream_t stream, long long *launche
     OrcaArgs a = make_args(s, n_steps);
     const int threads = a.wpc * s.Np;
     const int blocks = (s.W + a.wpc - 1) / a.wpc;
-    const size_t smem = (size_t)a.wpc * 2 * s.Np * sizeof(float2);
+    const size_t smem = (size_t)a.wpc * 2 * 2 * s.Np * sizeof(float2);    // two copies (step parity) of sx | sy | svel per world
     orca_kernel<<<blocks, threads, smem, stream>>>(a);
     ++*launches;
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
