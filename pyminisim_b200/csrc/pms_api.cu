@@ -218,7 +218,7 @@ struct pms_sim {
         // records
         uint32_t *det_mask = nullptr, *coll_mask = nullptr; size_t det_mask_cap = 0, coll_mask_cap = 0;   // capacities in records
         double2 *det_vals = nullptr; size_t det_vals_cap = 0;
-        int32_t *lidar_hit = nullptr; double2 *lidar_pts = nullptr; size_t lidar_cap = 0;
+        int32_t *lidar_hit = nullptr; double2 *lidar_pts = nullptr; size_t lidar_cap = 0, lidar_pts_cap = 0;
         double *omni = nullptr; size_t omni_cap = 0;
         // lidar geometry
         int lidar_beams = 0, lidar_samples = 0;
@@ -554,13 +554,15 @@ int prepare_sensor_plan(pms_sim *h, int n_steps, bool zero_masks)
         sc.table_cap = cap;
     }
     // host mirror of the recurrence (core/_simulation.py:177-180): IEEE fp64 additions, identical on both sides
+    double new_hold[SENSOR_KINDS];
+    int new_fires[SENSOR_KINDS];
     SchedArgs sa{};
     sa.n_steps = n_steps; sa.dt = a.dt; sa.hold = sc.hold_dev; sa.count = sc.count_dev;
     for (int k = 0; k < SENSOR_KINDS; ++k) {
         sa.enabled[k] = sc.enabled[k] ? 1 : 0; sa.period[k] = sc.period[k];
         sa.fire[k] = sc.tables + (size_t)k * sc.table_cap;
         sa.steps[k] = sc.tables + (size_t)(SENSOR_KINDS + k) * sc.table_cap;
-        sc.n_fires[k] = 0;
+        new_hold[k] = sc.hold_host[k]; new_fires[k] = 0;
         if (!sc.enabled[k]) continue;
         volatile double hold = sc.hold_host[k];
         int n = 0;
@@ -568,22 +570,25 @@ int prepare_sensor_plan(pms_sim *h, int n_steps, bool zero_masks)
             hold = hold + a.dt;
             if (hold >= sc.period[k]) { ++n; hold = 0.0; }
         }
-        sc.hold_host[k] = hold; sc.n_fires[k] = n;
+        new_hold[k] = hold; new_fires[k] = n;
     }
+    // the mirror is committed only once the device scheduler has been launched: a failed allocation below leaves both sides as they were
+    auto commit = [&]() { for (int k = 0; k < SENSOR_KINDS; ++k) { sc.hold_host[k] = new_hold[k]; sc.n_fires[k] = new_fires[k]; } };
+    const int *nf = new_fires;
     const size_t W = h->W, N = h->N, words = h->words;
     if (sc.enabled[SENSOR_DETECTOR]) {
-        if (grow(&sc.det_mask, &sc.det_mask_cap, (size_t)sc.n_fires[SENSOR_DETECTOR], W * words)) return PMS_ERR_CUDA;
-        if ((sc.flags[SENSOR_DETECTOR] & PMS_SENSOR_VALUES) && grow(&sc.det_vals, &sc.det_vals_cap, (size_t)sc.n_fires[SENSOR_DETECTOR], W * N)) return PMS_ERR_CUDA;
+        if (grow(&sc.det_mask, &sc.det_mask_cap, (size_t)nf[SENSOR_DETECTOR], W * words)) return PMS_ERR_CUDA;
+        if ((sc.flags[SENSOR_DETECTOR] & PMS_SENSOR_VALUES) && grow(&sc.det_vals, &sc.det_vals_cap, (size_t)nf[SENSOR_DETECTOR], W * N)) return PMS_ERR_CUDA;
     }
-    if (sc.enabled[SENSOR_COLLISIONS] && grow(&sc.coll_mask, &sc.coll_mask_cap, (size_t)sc.n_fires[SENSOR_COLLISIONS], W * words)) return PMS_ERR_CUDA;
+    if (sc.enabled[SENSOR_COLLISIONS] && grow(&sc.coll_mask, &sc.coll_mask_cap, (size_t)nf[SENSOR_COLLISIONS], W * words)) return PMS_ERR_CUDA;
     if (sc.enabled[SENSOR_LIDAR]) {
-        size_t cap2 = sc.lidar_cap;
-        if (grow(&sc.lidar_hit, &sc.lidar_cap, (size_t)sc.n_fires[SENSOR_LIDAR], W * sc.lidar_beams)) return PMS_ERR_CUDA;
-        if (grow(&sc.lidar_pts, &cap2, (size_t)sc.n_fires[SENSOR_LIDAR], W * sc.lidar_beams)) return PMS_ERR_CUDA;
+        if (grow(&sc.lidar_hit, &sc.lidar_cap, (size_t)nf[SENSOR_LIDAR], W * sc.lidar_beams)) return PMS_ERR_CUDA;
+        if (grow(&sc.lidar_pts, &sc.lidar_pts_cap, (size_t)nf[SENSOR_LIDAR], W * sc.lidar_beams)) return PMS_ERR_CUDA;
     }
-    if (sc.enabled[SENSOR_OMNI] && grow(&sc.omni, &sc.omni_cap, (size_t)sc.n_fires[SENSOR_OMNI], W)) return PMS_ERR_CUDA;
+    if (sc.enabled[SENSOR_OMNI] && grow(&sc.omni, &sc.omni_cap, (size_t)nf[SENSOR_OMNI], W)) return PMS_ERR_CUDA;
     sched_kernel<<<1, 32, 0, h->stream>>>(sa);
     CK(cudaGetLastError());
+    commit();
     h->info.kernel_launches++;
     SensorPlan &sp = a.sp;
     const bool has_robot = a.robot_model != ROBOT_NONE;
@@ -1660,7 +1665,7 @@ int pms_lidar_config(pms_sim *h, int n_beams, double max_dist, double resolution
     if (n_beams != sc.lidar_beams) {          // records are sized per beam count
         if (sc.lidar_hit) cudaFree(sc.lidar_hit);
         if (sc.lidar_pts) cudaFree(sc.lidar_pts);
-        sc.lidar_hit = nullptr; sc.lidar_pts = nullptr; sc.lidar_cap = 0;
+        sc.lidar_hit = nullptr; sc.lidar_pts = nullptr; sc.lidar_cap = 0; sc.lidar_pts_cap = 0;
     }
     sc.lidar_beams = n_beams; sc.lidar_max = max_dist; sc.lidar_res = resolution;
     sc.lidar_samples = (int)std::ceil((max_dist - 0.0) / resolution);     // np.arange(0, max_dist, resolution), _lidar.py:112
