@@ -40,7 +40,7 @@ constexpr int DUO_RING = 2 * WARP_ROBOT_BLOCK;      // robot slots: the block in
 
 template <int T> struct DuoSmem {
     static constexpr int Np = 32 * T;
-    static constexpr int NU = 2 * T;                                    // pair warps = units of the pair scheme
+    static constexpr int NU = 2 * T;                                    // units of the pair scheme (partial-force slots); duo_pair_warps(T) warps evaluate them
     // one FRAME per step parity holds what is double-buffered; every access is frame base + constant
     static constexpr size_t PV = 0;                                     // packed pair view [x | y][2 Np] float2
     static constexpr size_t XL = PV + 2 * 2 * Np * sizeof(float2);      // [xl | yl][Np] low parts of the position
@@ -130,14 +130,138 @@ __device__ __forceinline__ bool duo_unit(const HsfmArgs &a, const float2 *pl, in
     return __any_sync(0xffffffffu, d2min < rij2);
 }
 
+// The two units of a one-tile world (rotations 16..23 and 24..31 of the diagonal tile) side by side in ONE warp: two independent
+// chains, iteration by iteration; the lane's row force is the sum of the two units' (the value the owner used to add up).
+template <int NIT>
+__device__ __forceinline__ bool duo_unit_pair_t1(const HsfmArgs &a, const float2 *pl, int lane, float *fpart)
+{
+    constexpr int Np = 32, K0a = 16, K0b = 16 + 2 * NIT;
+    const float ncexp = -a.kpp_f.cexp, rc = a.warp_rc;
+    const float2 ncexp2 = make_float2(ncexp, ncexp), rc2 = make_float2(rc, rc);
+    const float mx = pl[0].x, my = pl[2 * Np].x;
+    const float2 nmx = make_float2(-mx, -mx), nmy = make_float2(-my, -my);
+    const float2 z = make_float2(0.f, 0.f);
+    float2 fxa = z, fya = z, rxa = z, rya = z, fxb = z, fyb = z, rxb = z, ryb = z;
+    float d2min = CUDART_INF_F;
+    auto iter = [&](int off, bool first, float2 &fx, float2 &fy, float2 &rx, float2 &ry) {
+        float2 dx = __fadd2_rn(pl[off], nmx);
+        const float2 dy = __fadd2_rn(pl[2 * Np + off], nmy);
+        if (first) dx.x = lane >= 16 ? 1e18f : dx.x;                               // pedestrians l and l + 16 meet twice
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        float2 inv; inv.x = fast_rsqrt(d2.x); inv.y = fast_rsqrt(d2.y);
+        const float2 arg = __ffma2_rn(d2, __fmul2_rn(inv, ncexp2), rc2);          // (r_ij - d) * log2(e) / B
+        float2 e; e.x = fast_ex2(arg.x); e.y = fast_ex2(arg.y);
+        const float2 c = __fmul2_rn(e, inv);                                       // e / d
+        fx = __ffma2_rn(c, dx, fx); fy = __ffma2_rn(c, dy, fy);
+        rx = __ffma2_rn(c, dx, rx); ry = __ffma2_rn(c, dy, ry);
+        d2min = fminf(d2min, fminf(d2.x, d2.y));
+    };
+    auto travel = [&](float2 &rx, float2 &ry) {                                     // partners advance two lanes
+        const int src = (lane + 2) & 31;
+        rx.x = __shfl_sync(0xffffffffu, rx.x, src); rx.y = __shfl_sync(0xffffffffu, rx.y, src);
+        ry.x = __shfl_sync(0xffffffffu, ry.x, src); ry.y = __shfl_sync(0xffffffffu, ry.y, src);
+    };
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        iter(K0a + 2 * it, it == 0, fxa, fya, rxa, rya);
+        iter(K0b + 2 * it, false, fxb, fyb, rxb, ryb);
+        if (it != NIT - 1) { travel(rxa, rya); travel(rxb, ryb); }
+    }
+    const float A_ = a.warp_A;
+    auto deliver = [&](int K0, float2 fx, float2 fy, float2 rx, float2 ry, float &ox, float &oy) {   // duo_unit's hand-over, diagonal unit
+        const int kx = K0 + 2 * (NIT - 1);
+        const int below = (lane + 31) & 31;
+        float sx = rx.x + __shfl_sync(0xffffffffu, rx.y, below);
+        float sy = ry.x + __shfl_sync(0xffffffffu, ry.y, below);
+        const int src = (lane - kx) & 31;
+        sx = __shfl_sync(0xffffffffu, sx, src);
+        sy = __shfl_sync(0xffffffffu, sy, src);
+        const float fxr = -A_ * (fx.x + fx.y), fyr = -A_ * (fy.x + fy.y);
+        ox = fmaf(A_, sx, fxr); oy = fmaf(A_, sy, fyr);
+    };
+    float ax, ay, bx, by;
+    deliver(K0a, fxa, fya, rxa, rya, ax, ay);
+    deliver(K0b, fxb, fyb, rxb, ryb, bx, by);
+    fpart[lane] = ax + bx; fpart[32 + lane] = ay + by;                             // = the sum the owner formed of the two units
+    const float rij2 = a.kpp_f.rij * a.kpp_f.rij;
+    return __any_sync(0xffffffffu, d2min < rij2);
+}
+
+// Two units of a two-tile world side by side in one warp: unit 1 = row tile A1 x partner tile B1 from rotation K1, unit 2 = A2 x B2
+// from K2, NIT packed iterations each, separate accumulators (each unit's partial forces are bit-identical to duo_unit's), the
+// iterations of the two chains alternating.  fp1 / fp2: the units' partial-force slots (layout of duo_unit).
+template <int T, int A1, int B1, int K1, int A2, int B2, int K2, int NIT>
+__device__ __forceinline__ bool duo_two_units(const HsfmArgs &a, const float2 *pl, int lane, float *fp1, float *fp2)
+{
+    constexpr int Np = 32 * T;
+    const float ncexp = -a.kpp_f.cexp, rc = a.warp_rc;
+    const float2 ncexp2 = make_float2(ncexp, ncexp), rc2 = make_float2(rc, rc);
+    const float2 z = make_float2(0.f, 0.f);
+    const float mx1 = pl[64 * A1].x, my1 = pl[2 * Np + 64 * A1].x, mx2 = pl[64 * A2].x, my2 = pl[2 * Np + 64 * A2].x;
+    const float2 nmx1 = make_float2(-mx1, -mx1), nmy1 = make_float2(-my1, -my1), nmx2 = make_float2(-mx2, -mx2), nmy2 = make_float2(-my2, -my2);
+    float2 fx1 = z, fy1 = z, rx1 = z, ry1 = z, fx2 = z, fy2 = z, rx2 = z, ry2 = z;
+    float d2min = CUDART_INF_F;
+    auto iter = [&](int off, bool mask16, float2 nmx, float2 nmy, float2 &fx, float2 &fy, float2 &rx, float2 &ry) {
+        float2 dx = __fadd2_rn(pl[off], nmx);
+        const float2 dy = __fadd2_rn(pl[2 * Np + off], nmy);
+        if (mask16) dx.x = lane >= 16 ? 1e18f : dx.x;                              // pedestrians l and l + 16 meet twice
+        const float2 d2 = __ffma2_rn(dx, dx, __fmul2_rn(dy, dy));
+        float2 inv; inv.x = fast_rsqrt(d2.x); inv.y = fast_rsqrt(d2.y);
+        const float2 arg = __ffma2_rn(d2, __fmul2_rn(inv, ncexp2), rc2);          // (r_ij - d) * log2(e) / B
+        float2 e; e.x = fast_ex2(arg.x); e.y = fast_ex2(arg.y);
+        const float2 c = __fmul2_rn(e, inv);                                       // e / d
+        fx = __ffma2_rn(c, dx, fx); fy = __ffma2_rn(c, dy, fy);
+        rx = __ffma2_rn(c, dx, rx); ry = __ffma2_rn(c, dy, ry);
+        d2min = fminf(d2min, fminf(d2.x, d2.y));
+    };
+    auto travel = [&](float2 &rx, float2 &ry) {                                     // partners advance two lanes
+        const int src = (lane + 2) & 31;
+        rx.x = __shfl_sync(0xffffffffu, rx.x, src); rx.y = __shfl_sync(0xffffffffu, rx.y, src);
+        ry.x = __shfl_sync(0xffffffffu, ry.x, src); ry.y = __shfl_sync(0xffffffffu, ry.y, src);
+    };
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        iter(64 * B1 + K1 + 2 * it, A1 == B1 && K1 == 16 && it == 0, nmx1, nmy1, fx1, fy1, rx1, ry1);
+        iter(64 * B2 + K2 + 2 * it, A2 == B2 && K2 == 16 && it == 0, nmx2, nmy2, fx2, fy2, rx2, ry2);
+        if (it != NIT - 1) { travel(rx1, ry1); travel(rx2, ry2); }
+    }
+    const float A_ = a.warp_A;
+    auto deliver = [&](int K0, bool diag, float2 fx, float2 fy, float2 rx, float2 ry, float *fpart) {   // duo_unit's hand-over
+        const int kx = K0 + 2 * (NIT - 1);
+        const int below = (lane + 31) & 31;
+        float sx = rx.x + __shfl_sync(0xffffffffu, rx.y, below);
+        float sy = ry.x + __shfl_sync(0xffffffffu, ry.y, below);
+        const int src = (lane - kx) & 31;
+        sx = __shfl_sync(0xffffffffu, sx, src);
+        sy = __shfl_sync(0xffffffffu, sy, src);
+        const float fxr = -A_ * (fx.x + fx.y), fyr = -A_ * (fy.x + fy.y);
+        if (diag) {
+            fpart[lane] = fmaf(A_, sx, fxr); fpart[32 + lane] = fmaf(A_, sy, fyr);
+        } else {
+            fpart[lane] = fxr; fpart[32 + lane] = fyr;
+            fpart[64 + lane] = A_ * sx; fpart[96 + lane] = A_ * sy;
+        }
+    };
+    deliver(K1, A1 == B1, fx1, fy1, rx1, ry1, fp1);
+    deliver(K2, A2 == B2, fx2, fy2, rx2, ry2, fp2);
+    const float rij2 = a.kpp_f.rij * a.kpp_f.rij;
+    return __any_sync(0xffffffffu, d2min < rij2);
+}
+
 // unit u of the world: T = 1: u0 = rotations 16..23, u1 = 24..31 of the one (diagonal) tile; T = 2: u0 = tile 0 diagonal,
 // u1 / u2 = row tile 0 x partner tile 1 rotations 0..15 / 16..31, u3 = tile 1 diagonal
-template <int T>
+template <int T, int UPW>
 __device__ __forceinline__ bool duo_far(const HsfmArgs &a, const float2 *pl, int u, int lane, float *fpart)
 {
     if constexpr (T == 1) {
+        if constexpr (UPW == 2) return duo_unit_pair_t1<4>(a, pl, lane, fpart);
         if (u == 0) return duo_unit<1, 0, 0, 16, 4>(a, pl, lane, fpart);
         return duo_unit<1, 0, 0, 24, 4>(a, pl, lane, fpart);
+    } else if constexpr (UPW == 2) {
+        // pair warp 0: units 0 + 1 (both row tile 0: diagonal, and tile 1 from rotation 0); pair warp 1: units 2 + 3 (row tile 0 and
+        // row tile 1 against the same partners: tile 1, rotations 16..31).  `fpart` = slot of the warp's first unit, the second follows.
+        if (u == 0) return duo_two_units<2, 0, 0, 16, 0, 1, 0, 8>(a, pl, lane, fpart, fpart + 128);
+        return duo_two_units<2, 0, 1, 16, 1, 1, 16, 8>(a, pl, lane, fpart, fpart + 128);
     } else {
         if (u == 0) return duo_unit<2, 0, 0, 16, 8>(a, pl, lane, fpart);
         if (u == 1) return duo_unit<2, 0, 1, 0, 8>(a, pl, lane, fpart);
@@ -160,21 +284,21 @@ __device__ __forceinline__ void duo_contact(const HsfmArgs &a, const float2 *pl,
     }
 }
 
-// SENS: the instantiation that serves a sensor plan (see warp_robot_block in hsfm_warp.cuh)
-template <int T, bool COMP, bool SENS>
-__global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(const __grid_constant__ HsfmArgs a)
+// SENS: the instantiation that serves a sensor plan (see warp_robot_block in hsfm_warp.cuh); UPW: units per pair warp
+template <int T, bool COMP, bool SENS, int UPW>
+__global__ void __launch_bounds__(duo_threads(T, UPW), duo_min_blocks(T, UPW)) hsfm_duo_kernel(const __grid_constant__ HsfmArgs a)
 {
     using L = DuoSmem<T>;
     constexpr int Np = 32 * T;
-    constexpr int NU = 2 * T;                        // pair warps
-    constexpr int WPW = 3 * T + 1;                   // warps of the world (= of the CTA): 2T pair, T owner, 1 service
+    constexpr int NU = duo_pair_warps(T, UPW);       // pair warps (DuoSmem::NU = 2T units, UPW per pair warp)
+    constexpr int WPW = NU + T + 1;                  // warps of the world (= of the CTA): NU pair, T owner, 1 service
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int N = a.N;
     const int tid = threadIdx.x, lane = tid & 31;
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform (see hsfm_warp.cuh)
     const int w = blockIdx.x;
-    const bool is_pair = wid < NU, is_service = wid == 3 * T;
+    const bool is_pair = wid < NU, is_service = wid == NU + T;
     const bool has_robot = a.robot_model != ROBOT_NONE;
     const int t_begin = 0, t_end = a.n_steps;
 
@@ -215,7 +339,7 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
 #endif
     auto contact_flag = [&](int b) {
         const int4 f = *reinterpret_cast<const int4 *>(frame(b) + L::FLAGS);
-        return T == 1 ? (f.x | f.y) : ((f.x | f.y) | (f.z | f.w));
+        return NU == 1 ? f.x : (NU == 2 ? (f.x | f.y) : ((f.x | f.y) | (f.z | f.w)));
     };
 
     if (is_service) {
@@ -318,7 +442,7 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
         const int u = wid;
         world_sync();                                                   // #1: r_t0 published by the owners
         {
-            const bool touch = duo_far<T>(a, pvb(0) + lane, u, lane, fpb(0, u));
+            const bool touch = duo_far<T, UPW>(a, pvb(0) + lane, u, lane, fpb(0, UPW * u));
             if (lane == 0) flb(0)[u] = touch ? 1 : 0;
         }
         world_sync();                                                   // #2: F(r_t0), r_{t0+1}
@@ -331,7 +455,7 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
             }
             // ---- pair forces of step t + 1 on r_{t+1} ----
             if (t + 1 < t_end) {
-                const bool touch = duo_far<T>(a, pvb(nb) + lane, u, lane, fpb(nb, u));
+                const bool touch = duo_far<T, UPW>(a, pvb(nb) + lane, u, lane, fpb(nb, UPW * u));
                 if (lane == 0) flb(nb)[u] = touch ? 1 : 0;
             }
             world_sync();
@@ -446,7 +570,9 @@ __global__ void __launch_bounds__(96 * T + 32, T == 1 ? 7 : 4) hsfm_duo_kernel(c
             }
             // ---- early block: forces, new heading, robot far field, one vote for the rare cases ----
             float fx, fy;
-            if constexpr (T == 1) {
+            if constexpr (T == 1 && NU == 1) {
+                fx = fpb(b, 0)[lane]; fy = fpb(b, 0)[32 + lane];            // the pair warp added its two units up
+            } else if constexpr (T == 1) {
                 fx = fpb(b, 0)[lane] + fpb(b, 1)[lane]; fy = fpb(b, 0)[32 + lane] + fpb(b, 1)[32 + lane];
             } else {
                 if (tile == 0) {

@@ -444,36 +444,51 @@ bool duo_eligible(const pms_sim *h)
 // 7 / 4 CTAs resident per SM for N <= 32 / 64) wins.  Measured cross-over on one B200 (profiles/r2_duo.md): N <= 32: one
 // wave of CTAs (1024 worlds: 1.04 vs 1.46 ms per 1000 steps, 2048: 1.97 vs 1.97); N <= 64: up to ~2.5 waves (512: 1.48 vs
 // 2.81, 1024: 2.52 vs 3.27; 2048 worlds would take 4 waves and lose to the 4.8 ms of the warp-per-world kernel).
+// units of the pair scheme per pair warp (hsfm_duo_api.cuh): one tile: 2; two tiles: 2 when that -- 5 instead of 4 worlds per
+// SM -- lets the batch fit one wave of CTAs it would not fit with one unit per warp, and the SMs would hold 3 worlds or more anyway
+int duo_upw(const pms_sim *h)
+{
+    if (h->Np <= 32) return 2;
+    if (h->tune_S == 4 && (h->tune_wpc == 1 || h->tune_wpc == 2)) return h->tune_wpc;     // forced (tests, A/B runs)
+    const long long w4 = 4LL * h->sm_count, w5 = 5LL * h->sm_count;
+    return (h->W > 2 * w4 / 3 && h->W <= w5) ? 2 : 1;
+}
+
 bool duo_preferred(const pms_sim *h)
 {
     if (h->tune_S == 5) return false;                      // forced: warp-per-world kernel
     if (h->tune_S == 4) return true;                       // forced: pair-warp / owner-warp kernel
     if (h->tune_S != 0 || h->tune_wpc > 0 || h->tune_chunks > 0) return false;   // explicit launch knobs of the other kernels
-    const long long wave = (long long)(h->Np <= 32 ? 7 : 4) * h->sm_count;
-    return h->Np <= 32 ? h->W <= wave : 2LL * h->W <= 5 * wave;
+    int occ = h->Np <= 32 ? 9 : 4;                         // resident CTAs (= worlds) per SM of the instantiation
+    size_t smem = 0;
+    if (duo_kernel_prepare(h->compensated, false, h->Np / 32, h->Np <= 32 ? 2 : 1, &occ, &smem) != cudaSuccess || occ < 1) return false;
+    const long long wave = (long long)occ * h->sm_count;
+    // measured cross-overs against the warp-per-world kernel (profiles/r2_history.md): one tile: 1.65 waves of 9 worlds per SM
+    // (2048 x 32: 1.90 vs 1.97 ms, 2664 x 32: 2.32 vs 2.18); two tiles: 2.5 waves of 4 (1480 x 64: 3.52 vs 3.74, 2048 x 64: 4.83 vs 4.65)
+    return h->Np <= 32 ? 20LL * h->W <= 33 * wave : 2LL * h->W <= 5 * wave;
 }
 
 int launch_duo(pms_sim *h)
 {
-    const int T = h->Np / 32;
+    const int T = h->Np / 32, upw = duo_upw(h);
     const bool comp = h->compensated;
     int occ = 0;
     size_t smem = 0;
     h->a.wpc = 1;
     h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
     const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation
-    CK(duo_kernel_prepare(comp, sens, T, &occ, &smem));
-    CK(duo_kernel_launch(comp, sens, T, h->a, h->W, smem, h->stream));
+    CK(duo_kernel_prepare(comp, sens, T, upw, &occ, &smem));
+    CK(duo_kernel_launch(comp, sens, T, upw, h->a, h->W, smem, h->stream));
     if (!comp) {        // plain fp32 state: the low parts a set_state left are gone
         const size_t n = (size_t)h->W * h->N;
         CK(cudaMemsetAsync(h->a.pos_lo, 0, n * 16, h->stream));
         CK(cudaMemsetAsync(h->a.th_lo, 0, n * 8, h->stream));
     }
     h->info.kernel = 4;
-    h->info.threads_per_block = 96 * T + 32;
+    h->info.threads_per_block = duo_threads(T, upw);
     h->info.blocks = h->W;
     h->info.worlds_per_block = 1;
-    h->info.j_split = 0;
+    h->info.j_split = upw;
     h->info.smem_bytes = (int)smem;
     h->info.n_chunks = 1;
     h->info.blocks_per_sm = occ;

@@ -107,16 +107,19 @@ def test_contact_pass_is_exercised_one_step():
 
 @pytest.mark.parametrize("precision", ["fp32", "mixed"])
 def test_warp_kernel_tuning_is_bit_identical(precision):
-    """Worlds per CTA and the dynamic (chunk, group) scheduler only move work around."""
+    """Worlds per CTA and the dynamic (chunk, group) scheduler only move work around.  (Pair-warp / owner-warp kernel:
+    worlds_per_block 1 / 2 force one / two units of the pair scheme per pair warp -- bit-identical too.)"""
     sc = make_bench_crowd(37, 64)
     outs = []
-    for wpc, chunks in ((0, 1), (1, 1), (3, 1), (8, 4), (5, 3)):
+    for wpc, chunks in ((0, 1), (1, 1), (2, 1), (3, 1), (8, 4), (5, 3)):
         sim = make_cuda(sc, precision)
         sim.set_tuning(FORCE["j_split"], wpc, chunks)
         sim.step(0.01, 130)
         info = sim.launch_info()
         # (the pair-warp / owner-warp kernel runs one world per CTA on a static grid: wpc / chunks do not apply)
         assert info["kernel"] == expected_kernel(sim) and info["n_chunks"] == (chunks if info["kernel"] == KERNEL_WARP else 1)
+        if info["kernel"] == KERNEL_DUO:
+            assert info["j_split"] == (2 if wpc == 2 else 1)                  # units per pair warp
         outs.append(sim.get_state() + sim.get_detector() + (sim.get_collisions(),) + sim.get_stats() + sim.get_robot())
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
