@@ -81,7 +81,10 @@ __device__ __forceinline__ void robot_store(const HsfmArgs &a, int w, const Robo
 }
 
 // One robot step `s` of world w (robot/_unicycle.py:53-69,27-33; robot/_bicycle.py:71-95,30-32).
-static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, RobotRegs &r)
+// WARP: executed by a whole warp with a warp-uniform `r` -- the scalar arithmetic is the same on every lane, the map veto
+// spreads the obstacles over the lanes (map_is_collision_warp); else by one lane.
+template <bool WARP>
+__device__ __forceinline__ void robot_step_impl(const HsfmArgs &a, int w, int s, RobotRegs &r, int lane)
 {
     if (a.robot_model != ROBOT_UNICYCLE && a.robot_model != ROBOT_BICYCLE) return;
     double u0 = r.c0, u1 = r.c1;
@@ -97,7 +100,9 @@ static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, 
         const double ny = r.y + u0 * r.sn * a.dt;
         double nth = r.th + u1 * a.dt;
         nth = py_mod(nth + PMS_PI, PMS_TWO_PI) - PMS_PI;
-        if (map_is_collision(a.map_kind, a.map_count, map, nx, ny, a.robot_radius)) {
+        const bool blocked = WARP ? map_is_collision_warp(a.map_kind, a.map_count, map, nx, ny, a.robot_radius, lane)
+                                  : map_is_collision(a.map_kind, a.map_count, map, nx, ny, a.robot_radius);
+        if (blocked) {
             r.world_collision = 1;            // move rejected: pose AND control stay (robot/_unicycle.py:64-65)
         } else {
             r.world_collision = 0;
@@ -117,7 +122,9 @@ static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, 
         const double d = a.wheel_base / 2.0;
         sincos(nth, &sn, &cs_);
         const double xc = xr + d * cs_, yc = yr + d * sn;
-        if (map_is_collision(a.map_kind, a.map_count, map, xc, yc, a.robot_radius)) {
+        const bool blocked = WARP ? map_is_collision_warp(a.map_kind, a.map_count, map, xc, yc, a.robot_radius, lane)
+                                  : map_is_collision(a.map_kind, a.map_count, map, xc, yc, a.robot_radius);
+        if (blocked) {
             r.world_collision = 1;
         } else {
             r.world_collision = 0;
@@ -128,6 +135,8 @@ static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, 
         r.vx = 0.0; r.vy = 0.0; r.vw = 0.0;   // BicycleRobotModelState.velocity is always zero
     }
 }
+static __device__ __noinline__ void robot_step(const HsfmArgs &a, int w, int s, RobotRegs &r) { robot_step_impl<false>(a, w, s, r, 0); }
+static __device__ __noinline__ void robot_step_warp(const HsfmArgs &a, int w, int s, RobotRegs &r, int lane) { robot_step_impl<true>(a, w, s, r, lane); }
 
 // ---- per-pedestrian O(1) dynamics (pedestrians/_hsfm.py:69-71,86-110,146-158,290-294) ----------
 // Advances one pedestrian by dt given the social force (fx,fy).  c,s = cos/sin(theta) cached from the

@@ -430,8 +430,63 @@ __device__ __forceinline__ double map_closest(int kind, int count, const double 
 __device__ __forceinline__ bool map_is_collision(int kind, int count, const double *m, double x, double y, double radius)
 {
     if (kind == MAP_EMPTY || count == 0) return false;
+    if (kind == MAP_CIRCLES) {          // is_occupied and closest-distance share |p - c| - r: one pass, the same values
+        bool occ = false;
+        double best = CUDART_INF;
+        for (int c = 0; c < count; ++c) {
+            const double dx = x - m[3 * c], dy = y - m[3 * c + 1];
+            const double d = sqrt(dx * dx + dy * dy) - m[3 * c + 2];
+            occ = occ || d <= 0.0;
+            if (d < best || d != d) best = d;
+        }
+        return occ || (best - radius + 0.05 <= 0.0);
+    }
     const bool occ = map_occupied(kind, count, m, x, y);
     const double dist = map_closest(kind, count, m, x, y) - radius + 0.05;
+    return occ || (dist <= 0.0);
+}
+
+// ---- the same predicates evaluated by a whole warp: obstacle c on lane c & 31, results reduced with shuffles ----
+// (the per-obstacle arithmetic is that of map_closest / map_is_collision; the reduction -- min, any, NaN wins -- returns what
+// the sequential loops return)
+__device__ __forceinline__ double map_closest_warp(int kind, int count, const double *m, double x, double y, int lane, bool *occupied = nullptr)
+{
+    double best = CUDART_INF;
+    bool nan_seen = false, occ = false;
+    if (kind == MAP_CIRCLES) {
+        for (int c = lane; c < count; c += 32) {
+            const double dx = x - m[3 * c], dy = y - m[3 * c + 1];
+            const double d = sqrt(dx * dx + dy * dy) - m[3 * c + 2];
+            occ = occ || d <= 0.0;
+            nan_seen = nan_seen || d != d;
+            if (d < best) best = d;
+        }
+    } else if (kind == MAP_AABB) {
+        for (int c = lane; c < count; c += 32) {
+            const double tlx = m[4 * c], tly = m[4 * c + 1], bw = m[4 * c + 2], bh = m[4 * c + 3];
+            occ = occ || (x <= tlx && x >= (tlx - bh) && y >= tly && y <= (tly + bw));
+            double d;
+            d = seg_dist(x, y, tlx, tly, tlx, tly + bw);            nan_seen = nan_seen || d != d; if (d < best) best = d;
+            d = seg_dist(x, y, tlx - bh, tly, tlx - bh, tly + bw);  nan_seen = nan_seen || d != d; if (d < best) best = d;
+            d = seg_dist(x, y, tlx, tly, tlx - bh, tly);            nan_seen = nan_seen || d != d; if (d < best) best = d;
+            d = seg_dist(x, y, tlx, tly + bw, tlx - bh, tly + bw);  nan_seen = nan_seen || d != d; if (d < best) best = d;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        if (other < best) best = other;
+    }
+    if (occupied) *occupied = __any_sync(0xffffffffu, occ);
+    // the sequential rule `if (d < best || d != d) best = d` keeps a NaN once one was seen (nothing compares below it): any NaN => NaN
+    if (__any_sync(0xffffffffu, nan_seen)) best = CUDART_NAN;
+    return best;
+}
+__device__ __forceinline__ bool map_is_collision_warp(int kind, int count, const double *m, double x, double y, double radius, int lane)
+{
+    if (kind == MAP_EMPTY || count == 0) return false;
+    bool occ = false;
+    const double dist = map_closest_warp(kind, count, m, x, y, lane, &occ) - radius + 0.05;
     return occ || (dist <= 0.0);
 }
 

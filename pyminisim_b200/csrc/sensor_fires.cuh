@@ -53,32 +53,40 @@ struct LidarGeom {
 
 // Exactly the reference's sample point and occupancy predicate (no FMA contraction):
 // sensors/_lidar.py:113-115, world_map/_circles_world.py:47-50, _aabb_world.py:145-152.
-__device__ __forceinline__ bool lidar_sample_occupied(const LidarGeom &a, double cx, double cy, double ca, double sa, int k,
-                                                      double &px, double &py)
+__device__ __forceinline__ void lidar_sample_point(const LidarGeom &a, double cx, double cy, double ca, double sa, int k, double &px, double &py)
 {
-    const double *m = a.map;
     const double dist = __dmul_rn((double)k, a.resolution);
     px = __dadd_rn(cx, __dmul_rn(dist, ca));
     py = __dadd_rn(cy, __dmul_rn(dist, sa));
+}
+// the predicate of ONE obstacle c on the sample point (the map's predicate is the OR over its obstacles)
+__device__ __forceinline__ bool lidar_point_in_obstacle(const LidarGeom &a, int c, double px, double py)
+{
+    const double *m = a.map;
     if (a.map_kind == MAP_CIRCLES) {
-        for (int c = 0; c < a.map_count; ++c) {
-            const double dx = __dsub_rn(px, m[3 * c]), dy = __dsub_rn(py, m[3 * c + 1]);
-            const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-            if (__dsub_rn(d, m[3 * c + 2]) <= 0.0) return true;
-        }
-    } else if (a.map_kind == MAP_AABB) {
-        for (int c = 0; c < a.map_count; ++c) {
-            const double tlx = m[4 * c], tly = m[4 * c + 1], bw = m[4 * c + 2], bh = m[4 * c + 3];
-            if (px <= tlx && px >= __dsub_rn(tlx, bh) && py >= tly && py <= __dadd_rn(tly, bw)) return true;
-        }
+        const double dx = __dsub_rn(px, m[3 * c]), dy = __dsub_rn(py, m[3 * c + 1]);
+        const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        return __dsub_rn(d, m[3 * c + 2]) <= 0.0;
     }
+    const double tlx = m[4 * c], tly = m[4 * c + 1], bw = m[4 * c + 2], bh = m[4 * c + 3];
+    return px <= tlx && px >= __dsub_rn(tlx, bh) && py >= tly && py <= __dadd_rn(tly, bw);
+}
+__device__ __forceinline__ bool lidar_sample_occupied(const LidarGeom &a, double cx, double cy, double ca, double sa, int k,
+                                                      double &px, double &py)
+{
+    lidar_sample_point(a, cx, cy, ca, sa, k, px, py);
+    if (a.map_kind != MAP_CIRCLES && a.map_kind != MAP_AABB) return false;
+    for (int c = 0; c < a.map_count; ++c)
+        if (lidar_point_in_obstacle(a, c, px, py)) return true;
     return false;
 }
 
-// The reference marches n_samples points per beam through is_occupied; we obtain the same first-occupied sample index by
-// bracketing it analytically (ray/circle, ray/box entry distance) and then testing the reference's exact sampled predicate
-// in a window of a few samples around the entry -- O(C) per beam instead of O(C * n_samples).  Returns the index of the
-// first occupied sample (point in bx, by) or -1: no hit, or the beam starts inside an obstacle (skipped, _lidar.py:118).
+// The reference marches n_samples points per beam through is_occupied and takes the first occupied one.  The map's predicate
+// is the OR over its obstacles, so that sample is the minimum over the obstacles of "first sample inside obstacle c": per
+// obstacle the kernel brackets the entry analytically (ray / circle, ray / box; a generous window, not a decision) and
+// evaluates the reference's exact sampled predicate OF THAT OBSTACLE on the few samples of the window -- O(C) per beam instead
+// of O(C * n_samples), and O(1) predicates per window sample instead of O(C).  Returns the index of the first occupied sample
+// (point in bx, by) or -1: no hit, or the beam starts inside an obstacle (skipped, _lidar.py:118).
 static __device__ __noinline__ int lidar_beam(const LidarGeom &a, double cx, double cy, double ca, double sa, double &bx, double &by)
 {
     int best = a.n_samples;
@@ -86,10 +94,49 @@ static __device__ __noinline__ int lidar_beam(const LidarGeom &a, double cx, dou
     bx = 0.0; by = 0.0;
     if (a.map_kind != MAP_EMPTY && a.map_count > 0 && a.n_samples > 0) {
         const double *m = a.map;
-        if (lidar_sample_occupied(a, cx, cy, ca, sa, 0, px, py)) {
-            best = -1;
+        const double res = a.resolution;
+        // The windows are bracketed in fp32 (single MUFU sqrt / rcp, conservative slack well above the fp32 error of map-sized
+        // coordinates) -- only the sampled predicate itself is fp64.  Very fine resolutions keep the fp64 brackets.
+        const bool f32_windows = res >= 1e-3;
+        const float caf = (float)ca, saf = (float)sa, resf = (float)res;
+        bool start_inside = false;                                      // sample 0 = the robot position itself (_lidar.py:118)
+        if (f32_windows && a.map_kind == MAP_CIRCLES) {
+            for (int c = 0; c < a.map_count; ++c) {
+                const float ox = (float)(m[3 * c] - cx), oy = (float)(m[3 * c + 1] - cy), r = (float)m[3 * c + 2];
+                const float o2 = fmaf(ox, ox, oy * oy), rs = r + 1e-3f + 1e-6f * o2;
+                if (o2 <= rs * rs && lidar_point_in_obstacle(a, c, cx, cy)) start_inside = true;     // exact test only near / inside
+            }
         } else {
-            const double res = a.resolution;
+            start_inside = lidar_sample_occupied(a, cx, cy, ca, sa, 0, px, py);
+        }
+        if (start_inside) {
+            best = -1;
+        } else if (f32_windows && a.map_kind == MAP_CIRCLES) {
+            // fp32 error of the bracket for map-sized coordinates ~1e-5 m; the padded radius moves the window start at least
+            // 1e-3 m in front of the true entry, floor() - 1 covers the rounding of the division: 2-3 exact samples per hit
+            const float padf = 1e-3f, inv_res = 1.0f / resf;
+            for (int c = 0; c < a.map_count && best != 1; ++c) {
+                const float ox = (float)(m[3 * c] - cx), oy = (float)(m[3 * c + 1] - cy), rp = (float)m[3 * c + 2] + padf;
+                const float o2 = fmaf(ox, ox, oy * oy);
+                const float tca = fmaf(ox, caf, oy * saf);
+                const float d2 = fmaxf(o2 - tca * tca, 0.0f);
+                const float rr = fmaf(rp, rp, 1e-3f + 1e-6f * o2);      // generous: window, not decision
+                if (d2 > rr) continue;
+                const float thc = sqrtf(rr - d2);
+                const float t_in = tca - thc, t_out = tca + thc;
+                if (t_out < 0.0f) continue;
+                const float k0f = floorf(t_in * inv_res) - 1.0f, k1f = ceilf(t_out * inv_res) + 1.0f;
+                const int k0 = k0f < 1.0f ? 1 : (k0f > 2.0e9f ? a.n_samples : (int)k0f);
+                const int k1 = k1f > (float)(best - 1) ? best - 1 : (int)k1f;
+                for (int q = k0; q <= k1; ++q) {
+                    lidar_sample_point(a, cx, cy, ca, sa, q, px, py);
+                    if (lidar_point_in_obstacle(a, c, px, py)) {            // every sample inside obstacle c lies in its window
+                        best = q; bx = px; by = py;
+                        break;
+                    }
+                }
+            }
+        } else {
             for (int c = 0; c < a.map_count && best != 1; ++c) {
                 double t_in, t_out;
                 if (a.map_kind == MAP_CIRCLES) {
@@ -122,7 +169,8 @@ static __device__ __noinline__ int lidar_beam(const LidarGeom &a, double cx, dou
                 int k0 = k0d < 1.0 ? 1 : (k0d > 2.0e9 ? a.n_samples : (int)k0d);
                 int k1 = k1d > (double)(best - 1) ? best - 1 : (int)k1d;
                 for (int q = k0; q <= k1; ++q) {
-                    if (lidar_sample_occupied(a, cx, cy, ca, sa, q, px, py)) {
+                    lidar_sample_point(a, cx, cy, ca, sa, q, px, py);
+                    if (lidar_point_in_obstacle(a, c, px, py)) {            // every sample inside obstacle c lies in its window
                         best = q; bx = px; by = py;
                         break;
                     }
@@ -154,46 +202,48 @@ __device__ __forceinline__ double omni_noise_apply(const OmniNoise &nz, int w, l
     return d + (nz.mu + nz.sigma * noise_normal2(b.y, b.z).x);
 }
 
-// The lidar / omni reading of world w taken after launch step t with the robot at (x, y): one warp, beams strided over the
-// lanes.  Rare (every 11th step with the reference's defaults) and out of line.
-static __device__ __noinline__ void sensor_fire_robot(const HsfmArgs &a, int w, int t, double x, double y, int lane)
+// The lidar reading of world w taken after launch step t with the robot at (x, y), into record `slot`: one warp, beams strided
+// over the lanes.  Rare (every 11th step with the reference's defaults) and out of line.
+static __device__ __noinline__ void lidar_fire(const HsfmArgs &a, int w, int t, int slot, double x, double y, int lane)
 {
     const SensorPlan &sp = a.sp;
     const double *map = a.map_data ? a.map_data + (size_t)w * a.map_stride : nullptr;
     const long long step = a.steps_done + t + 1;
-    if (sp.fire[SENSOR_LIDAR]) {
-        const int slot = sp.fire[SENSOR_LIDAR][t];
-        if (slot >= 0) {
-            const LidarGeom lg{sp.lidar_samples, sp.lidar_res, a.map_kind, a.map_count, map};
-            const size_t base = ((size_t)slot * a.W + w) * sp.lidar_beams;
-            for (int k = lane; k < sp.lidar_beams; k += 32) {
-                double bx, by;
-                int hit = lidar_beam(lg, x, y, sp.lidar_dirs[2 * k], sp.lidar_dirs[2 * k + 1], bx, by);
-                if (sp.lidar_noise.enabled) lidar_noise_apply(sp.lidar_noise, (size_t)w * sp.lidar_beams + k, step, hit, bx, by);
-                sp.lidar_hit[base + k] = hit;
-                sp.lidar_pts[base + k] = make_double2(bx, by);
-            }
-        }
-    }
-    if (sp.fire[SENSOR_OMNI] && lane == 0) {
-        const int slot = sp.fire[SENSOR_OMNI][t];
-        if (slot >= 0) {
-            double d = map_closest(a.map_kind, a.map_count, map, x, y);
-            if (sp.omni_noise.enabled) d = omni_noise_apply(sp.omni_noise, w, step, d);
-            sp.omni_dist[(size_t)slot * a.W + w] = d;
-        }
+    const LidarGeom lg{sp.lidar_samples, sp.lidar_res, a.map_kind, a.map_count, map};
+    const size_t base = ((size_t)slot * a.W + w) * sp.lidar_beams;
+    for (int k = lane; k < sp.lidar_beams; k += 32) {
+        double bx, by;
+        int hit = lidar_beam(lg, x, y, sp.lidar_dirs[2 * k], sp.lidar_dirs[2 * k + 1], bx, by);
+        if (sp.lidar_noise.enabled) lidar_noise_apply(sp.lidar_noise, (size_t)w * sp.lidar_beams + k, step, hit, bx, by);
+        sp.lidar_hit[base + k] = hit;
+        sp.lidar_pts[base + k] = make_double2(bx, by);
     }
 }
 
-// Readings of the firing steps among launch steps s0 .. s0 + n - 1 whose robot poses are ring[0 .. n-1] (any slot type with
-// fp64 members x, y).  Called by a whole warp.
+// Readings of the firing steps among launch steps s0 .. s0 + n - 1 (n <= 32) whose robot poses are ring[0 .. n-1] (any slot
+// type with fp64 members x, y).  Called by a whole warp.  Omni: lane k takes the reading of step s0 + k (the obstacle loop runs
+// once for the whole block); lidar: one warp per firing step, beams over the lanes.
 template <typename Slot>
 static __device__ __noinline__ void sensor_fires_block(const HsfmArgs &a, int w, int s0, int n, const Slot *ring, int lane)
 {
-    const int *fl = a.sp.fire[SENSOR_LIDAR], *fo = a.sp.fire[SENSOR_OMNI];
-    for (int k = 0; k < n; ++k) {
-        const bool fire = (fl && fl[s0 + k] >= 0) || (fo && fo[s0 + k] >= 0);   // warp-uniform
-        if (fire) sensor_fire_robot(a, w, s0 + k, ring[k].x, ring[k].y, lane);
+    const SensorPlan &sp = a.sp;
+    if (sp.fire[SENSOR_OMNI]) {
+        const int slot = lane < n ? sp.fire[SENSOR_OMNI][s0 + lane] : -1;
+        if (slot >= 0) {
+            const double *map = a.map_data ? a.map_data + (size_t)w * a.map_stride : nullptr;
+            double d = map_closest(a.map_kind, a.map_count, map, ring[lane].x, ring[lane].y);
+            if (sp.omni_noise.enabled) d = omni_noise_apply(sp.omni_noise, w, a.steps_done + s0 + lane + 1, d);
+            sp.omni_dist[(size_t)slot * a.W + w] = d;
+        }
+    }
+    if (sp.fire[SENSOR_LIDAR]) {
+        const int slot = lane < n ? sp.fire[SENSOR_LIDAR][s0 + lane] : -1;
+        unsigned fires = __ballot_sync(0xffffffffu, slot >= 0);
+        while (fires) {                                                 // warp-uniform
+            const int k = __ffs(fires) - 1;
+            fires &= fires - 1;
+            lidar_fire(a, w, s0 + k, __shfl_sync(0xffffffffu, slot, k), ring[k].x, ring[k].y, lane);
+        }
     }
 }
 

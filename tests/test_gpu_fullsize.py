@@ -122,3 +122,55 @@ def test_c5_full_size_world_independence():
     for w in (0, 1000, 2047):
         p1, v1 = run(slice(w, w + 1))
         assert np.array_equal(p1[0], pa[w]) and np.array_equal(v1[0], va[w])
+
+
+def test_c4_full_size_sensor_plan_records_are_consistent():
+    """C4 with the reference's sensors scheduled inside the ONE launch of 1000 steps (10 Hz lidar, omni, detector masks and
+    collision list every step): size-independent properties of the records -- the lidar fires after steps 10, 21, 32, ...
+    (core/_simulation.py:177-180), the records' population counts add up to the episode counters the kernel keeps
+    independently, the last record equals the readings of the final state, a world inside the batch has the records of the
+    same world run alone, and the plan does not change the trajectory."""
+    from pyminisim_b200 import _capi as capi
+    W, N, K = 4096, 64, 1000
+    sc = make_bench_crowd(W, N)
+    rng = np.random.default_rng(5)
+    circles = np.concatenate([rng.uniform(-25, 25, (W, 8, 2)), rng.uniform(0.3, 1.5, (W, 8, 1))], axis=2)
+
+    def make(worlds=None, plan=True):
+        sim = make_cuda(sc, "fp32", worlds=worlds)
+        sim.set_map(capi.MAP_CIRCLES, circles if worlds is None else circles[worlds])
+        if plan:
+            sim.set_lidar(100, 8.0, 0.01)
+            sim.schedule_sensor(capi.SENSOR_LIDAR, 0.1)
+            sim.schedule_sensor(capi.SENSOR_OMNI, 0.0)
+            sim.schedule_sensor(capi.SENSOR_DETECTOR, 0.0)
+            sim.schedule_sensor(capi.SENSOR_COLLISIONS, 0.0)
+        return sim
+    a = make()
+    a.step(0.01, K)
+    assert a.launch_info()["kernel"] == 3
+    steps, hold = a.sensor_fires(capi.SENSOR_LIDAR)
+    assert np.array_equal(steps, np.arange(10, K, 11)) and len(steps) == 90
+    hit, pts = a.lidar_records()
+    omni = a.omni_records()
+    dm, cm = a.detector_records(), a.collision_records()
+    assert hit.shape == (90, W, 100) and omni.shape == (K, W) and dm.shape == (K, W, 2) and cm.shape == (K, W, 2)
+    det, col, nf = a.get_stats()
+    pop = lambda m: np.unpackbits(m.view(np.uint8), axis=-1).reshape(m.shape[0], m.shape[1], -1).sum(axis=(0, 2))
+    assert np.array_equal(pop(dm), det) and np.array_equal(pop(cm), col) and (nf == 0).all()
+    assert np.array_equal(dm[-1], a.get_detector()[0]) and np.array_equal(cm[-1], a.get_collisions())
+    assert np.array_equal(omni[-1], a.omni_scan())
+    assert (hit >= -1).all() and (hit < 800).all() and (hit >= 0).any()
+    sel = hit >= 0                                       # a hit point lies on its beam at hit * resolution from ... some robot position:
+    assert np.isfinite(pts[sel]).all() and (pts[~sel] == 0).all()
+    # the plan does not touch the dynamics; worlds are independent
+    b = make(plan=False)
+    b.step(0.01, K)
+    assert np.array_equal(a.get_state()[0], b.get_state()[0])
+    for w in (0, 2500):
+        one = make(worlds=slice(w, w + 1))
+        one.set_tuning(5)
+        one.step(0.01, K)
+        h1, p1 = one.lidar_records()
+        assert np.array_equal(h1[:, 0], hit[:, w]) and np.array_equal(p1[:, 0], pts[:, w])
+        assert np.array_equal(one.omni_records()[:, 0], omni[:, w]) and np.array_equal(one.detector_records()[:, 0], dm[:, w])
