@@ -145,6 +145,9 @@ int pms_set_robot(pms_sim *h, int model, const double *pose /*(W,3)*/, const dou
                   const double *control /*(W,2) or NULL*/, double radius, double wheel_base, int visible);
 /* controls for the next pms_hsfm_step call: row s drives step s; the last row is held. NULL/0 clears. */
 int pms_set_robot_controls(pms_sim *h, const double *controls /*(n_rows,W,2)*/, int n_rows);
+/* the same from a DEVICE array (n_rows,W,2) of float64 owned by the caller (e.g. a policy's output tensor): read in place by
+ * the following launches -- keep it alive and complete until they have run; NULL/0 clears */
+int pms_set_robot_controls_device(pms_sim *h, const double *controls_dev, int n_rows);
 int pms_get_robot(pms_sim *h, double *pose /*(W,3)*/, double *velocity /*(W,3)*/, int32_t *world_collision /*(W) or NULL*/);
 
 /* ---- world map: world_map/_circles_world.py, _aabb_world.py, _empty_world.py ---- */

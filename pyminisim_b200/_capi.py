@@ -81,6 +81,7 @@ PROTOTYPES = {
     "pms_get_waypoints": (C.c_int, [_h, _dp, _ip]),
     "pms_set_robot": (C.c_int, [_h, C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int]),
     "pms_set_robot_controls": (C.c_int, [_h, _dp, C.c_int]),
+    "pms_set_robot_controls_device": (C.c_int, [_h, C.c_void_p, C.c_int]),
     "pms_get_robot": (C.c_int, [_h, _dp, _dp, _ip]),
     "pms_set_map": (C.c_int, [_h, C.c_int, _dp, C.c_int, C.c_int]),
     "pms_set_accel_noise": (C.c_int, [_h, _dp]),

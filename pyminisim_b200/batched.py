@@ -210,6 +210,19 @@ class BatchedSimulation:
         c = f64(controls).reshape(-1, self.W, 2)
         check(self._lib.pms_set_robot_controls(self._h, dptr(c), c.shape[0]))
 
+    def set_robot_controls_torch(self, controls):
+        """Controls (n_rows, W, 2) as a CUDA float64 torch tensor, read in place by the launches that follow (row s drives step
+        s, the last row is held): a policy's output reaches the robot model without leaving the device.  The tensor must stay
+        alive and complete until those launches have run; ``None`` clears."""
+        if controls is None:
+            check(self._lib.pms_set_robot_controls_device(self._h, None, 0))
+            self._controls_ref = None
+            return
+        import torch
+        assert controls.is_cuda and controls.is_contiguous() and controls.dtype == torch.float64 and controls.shape[1:] == (self.W, 2)
+        self._controls_ref = controls
+        check(self._lib.pms_set_robot_controls_device(self._h, C.c_void_p(controls.data_ptr()), int(controls.shape[0])))
+
     def get_robot(self):
         pose = np.empty((self.W, 3))
         vel = np.empty((self.W, 3))

@@ -1042,6 +1042,14 @@ int pms_set_robot_controls(pms_sim *h, const double *controls, int n_rows)
     return PMS_OK;
 }
 
+int pms_set_robot_controls_device(pms_sim *h, const double *controls_dev, int n_rows)
+{
+    HCHECK(h);
+    if (!controls_dev || n_rows <= 0) { h->a.controls = nullptr; h->a.n_controls = 0; return PMS_OK; }
+    h->a.controls = controls_dev; h->a.n_controls = n_rows;      // read in place by the launches that follow: no copy, no synchronisation
+    return PMS_OK;
+}
+
 int pms_get_robot(pms_sim *h, double *pose, double *velocity, int32_t *world_collision)
 {
     HCHECK(h);

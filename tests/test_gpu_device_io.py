@@ -81,3 +81,28 @@ def test_record_buffers_alias_the_records():
     assert np.array_equal(sim.device_tensor(capi.BUF_REC_DET_VALUES, np.float64, (F, sim.W, sim.N, 2)).cpu().numpy(), dv)
     assert np.array_equal(sim.device_tensor(capi.BUF_REC_COLL_MASK, np.int32, (30, sim.W, sim.words)).cpu().numpy().view(np.uint32), cm)
     sim.close()
+
+
+def test_device_resident_rollout_loop():
+    """An RL-style loop that never leaves the GPU: controls from a CUDA tensor, state and readings as CUDA tensors / aliases;
+    equal to the host-array path bit for bit."""
+    import torch
+    from pyminisim_b200 import _capi as capi
+    sc = _scene(16, 32)
+    rng = np.random.default_rng(9)
+    ctr = np.stack([np.concatenate([rng.uniform(0.2, 1.0, (16, 1)), rng.uniform(-0.5, 0.5, (16, 1))], axis=1) for _ in range(60)])
+    host, dev = make_cuda(sc, "fp32"), make_cuda(sc, "fp32")
+    tctr = torch.from_numpy(ctr).cuda()
+    torch.cuda.synchronize()
+    for k in range(0, 60, 20):
+        host.set_robot_controls(ctr[k:k + 20]); host.step(0.01, 20)
+        dev.set_robot_controls_torch(tctr[k:k + 20]); dev.step_async(0.01, 20)
+    poses, vels = dev.get_state_torch(torch.float32)
+    det = dev.device_tensor(capi.BUF_DET_MASK, np.int32, (dev.W, dev.words))
+    rp = dev.device_tensor(capi.BUF_ROBOT_POSE, np.float64, (dev.W, 3))
+    dev.sync()
+    ph, vh = host.get_state(dtype=np.float32)
+    assert np.array_equal(poses.cpu().numpy(), ph) and np.array_equal(vels.cpu().numpy(), vh)
+    assert np.array_equal(det.cpu().numpy().view(np.uint32), host.get_detector()[0])
+    assert np.array_equal(rp.cpu().numpy(), host.get_robot()[0])
+    host.close(); dev.close()
