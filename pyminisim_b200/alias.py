@@ -12,7 +12,7 @@ The import paths SURVEY.md 8b lists are served: ``pyminisim.core`` (core/__init_
 (pedestrians/__init__.py:1-6), ``pyminisim.sensors`` (sensors/__init__.py:1-7), ``pyminisim.robot``, ``pyminisim.world_map``,
 ``pyminisim.util``.  ``pyminisim.visual`` (the pygame renderer) is outside the accelerated path: the alias serves a headless
 stand-in whose ``Renderer`` accepts the reference's calls and draws nothing, so that a script's step loop still runs.
-Names the accelerated path does not implement (ETHPedestriansRecord, SemanticDetector) raise ImportError on import.
+Names the accelerated path does not implement (SemanticDetector) raise ImportError on import.
 If the real reference is importable it is NOT replaced unless ``force=True``.
 """
 from __future__ import annotations
@@ -21,22 +21,6 @@ import importlib
 import runpy
 import sys
 import types
-
-
-def _util_module() -> types.ModuleType:
-    import numpy as np
-    m = types.ModuleType("pyminisim.util")
-
-    def wrap_angle(angle):                                   # util/_util.py:5-6
-        return (angle + np.pi) % (2 * np.pi) - np.pi
-
-    def angle_linspace(start_angle, end_angle, n):           # util/_util.py:9-15
-        diff = wrap_angle(end_angle - start_angle)
-        return wrap_angle(start_angle + np.linspace(0., diff, n))
-
-    m.wrap_angle, m.angle_linspace = wrap_angle, angle_linspace
-    m.__doc__ = "pyminisim.util of the alias: wrap_angle, angle_linspace (util/_util.py)"
-    return m
 
 
 def _visual_module() -> types.ModuleType:
@@ -98,11 +82,11 @@ def install_as_pyminisim(force: bool = False) -> types.ModuleType:
     pkg.__doc__ = "alias of pyminisim_b200 (pyminisim_b200.alias.install_as_pyminisim)"
     sys.modules["pyminisim"] = pkg
     # core first: with the alias flag up it defines its own ABCs instead of looking for the reference
-    for sub in ("core", "pedestrians", "sensors", "robot", "world_map"):
+    for sub in ("core", "pedestrians", "sensors", "robot", "world_map", "util"):
         mod = importlib.import_module(f"pyminisim_b200.{sub}")
         sys.modules[f"pyminisim.{sub}"] = mod
         setattr(pkg, sub, mod)
-    for sub, mod in (("util", _util_module()), ("visual", _visual_module())):
+    for sub, mod in (("visual", _visual_module()),):
         sys.modules[f"pyminisim.{sub}"] = mod
         setattr(pkg, sub, mod)
     return pkg

@@ -13,11 +13,13 @@ import numpy as np
 
 from . import _capi as capi
 from .batched import BatchedOrca, BatchedSimulation, HSFMParams, ORCAParams
+from .util import angle_linspace, wrap_angle
 from .core import (DEFAULT_ROBOT_RADIUS, PEDESTRIAN_RADIUS, AbstractPedestriansModel, AbstractPedestriansModelState,
                    AbstractWaypointTracker, AbstractWaypointTrackerState)
 
 __all__ = ["HSFMParams", "HeadedSocialForceModelPolicy", "RandomWaypointTracker", "FixedWaypointTracker",
-           "ORCAParams", "ORCAPedestriansModel", "HSFMState", "ORCAState", "ReplayPedestriansPolicy", "ReplayPedestriansState"]
+           "ORCAParams", "ORCAPedestriansModel", "HSFMState", "ORCAState", "ReplayPedestriansPolicy", "ReplayPedestriansState",
+           "ETHPedestriansRecord", "ETHState"]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -608,3 +610,186 @@ class ReplayPedestriansPolicy(AbstractPedestriansModel):
         self._fused = None
         if self._sim is not None:
             self._sim.replay_frame(self._current_step)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ETHPedestriansRecord (pedestrians/_eth.py): the BIWI "eth" / "hotel" recordings (2.5 Hz) played back at the simulation's
+# rate -- positions interpolated between two recorded frames, pedestrians that leave before the next frame extrapolated
+# with their recorded velocity.  The set of pedestrians changes from frame to frame (ids are the recording's).
+# The recordings are data of the reference's distribution (pedestrians/assets/obsmat_<sequence>.txt), not part of this
+# package: they are read from `obsmat_path`, $PMS_ETH_ASSETS, or an installed pyminisim's assets directory.
+# Under this package's Simulation the interpolated frames live in HBM (slots = the pedestrians present, padding parked
+# far away) and a tick is one pms_replay_tick, like ReplayPedestriansPolicy.
+# ---------------------------------------------------------------------------------------------------------
+class ETHState(AbstractPedestriansModelState):
+    def __init__(self, pedestrians: Dict[int, Tuple[np.ndarray, np.ndarray]], current_frame: int, current_sub_step: int):
+        super().__init__(pedestrians, None)
+        self._current_frame, self._current_sub_step = current_frame, current_sub_step
+
+    @property
+    def current_frame(self) -> int:
+        return self._current_frame
+
+    @property
+    def current_sub_step(self) -> int:
+        return self._current_sub_step
+
+
+def _find_obsmat(sequence: str, obsmat_path: Optional[str]) -> str:
+    import importlib.util
+    import os
+    name = f"obsmat_{sequence}.txt"
+    candidates = []
+    if obsmat_path is not None:
+        candidates.append(os.path.join(obsmat_path, name) if os.path.isdir(obsmat_path) else obsmat_path)
+    if os.environ.get("PMS_ETH_ASSETS"):
+        candidates.append(os.path.join(os.environ["PMS_ETH_ASSETS"], name))
+    try:
+        spec = importlib.util.find_spec("pyminisim")
+        for root in (spec.submodule_search_locations or []) if spec is not None else []:
+            candidates.append(os.path.join(root, "pedestrians", "assets", name))
+    except (ImportError, ValueError):
+        pass
+    for c in candidates:
+        if os.path.isfile(c):
+            return c
+    raise FileNotFoundError(f"{name} not found (looked at {candidates or 'nothing'}): pass obsmat_path= or set PMS_ETH_ASSETS "
+                            f"to the directory that holds the reference's pedestrians/assets")
+
+
+class ETHPedestriansRecord(AbstractPedestriansModel):
+    SEQUENCE_ETH = "eth"
+    SEQUENCE_HOTEL = "hotel"
+
+    _RECORD_DT = 0.4
+    _CENTER_ETH = (3.86457727, 3.82923192)
+    _CENTER_HOTEL = (-0.21777709, -3.30031001)
+    _PARKED = 1.0e18                  # device slots without a pedestrian: out of every sensor's and the collision test's reach
+
+    def __init__(self, sequence: str, dt: float, start_frame: int = 0, obsmat_path: Optional[str] = None):
+        centers = {self.SEQUENCE_ETH: self._CENTER_ETH, self.SEQUENCE_HOTEL: self._CENTER_HOTEL}
+        if sequence not in centers:                                                              # _eth.py:38-45
+            raise ValueError(f"Unknown sequence name {sequence}, available options: "
+                             f"{self.SEQUENCE_ETH} and {self.SEQUENCE_HOTEL}")
+        cx, cy = centers[sequence]
+        # obsmat columns: frame, id, x, z, y, v_x, v_z, v_y; the scene is mirrored in x about its centre (_eth.py:56-69)
+        frames: List[Dict[int, np.ndarray]] = []
+        last_frame, seen = None, set()
+        with open(_find_obsmat(sequence, obsmat_path)) as f:
+            for line in f:
+                e = line.split()
+                if not e:
+                    continue
+                frame, ped = int(float(e[0])), int(float(e[1]))
+                x, y, vx, vy = -(float(e[2]) - cx), float(e[4]) - cy, -float(e[5]), float(e[7])
+                if frame != last_frame:
+                    frames.append({})
+                    last_frame = frame
+                frames[-1][ped] = np.array([x, y, np.arctan2(vy, vx), vx, vy, 0.])
+                seen.add(ped)
+        assert start_frame < len(frames), \
+            f"start_frame must be less than number of frames in sequence which is {len(frames)}"
+        self._dt = dt
+        self._frames = frames
+        self._n_peds = len(seen)
+        self._n_frames = len(frames) - 1                        # the last recorded frame only ever serves as "next" (_eth.py:88)
+        self._steps_per_gap = int(self._RECORD_DT // dt)
+        self._blocks: Dict[int, tuple] = {}
+        self._state = ETHState(self._pedestrians_at(0, 0), start_frame, 0)       # frame 0 shown, counter at start_frame (:91)
+        self._collision_radius = None
+        self._det_cfg = None
+        self._sim = None
+        self._fused = None
+
+    @property
+    def state(self) -> ETHState:
+        return self._state
+
+    # ---- the interpolation (_eth.py:113-137), one recorded frame = steps_per_gap simulation frames -----------------
+    def _block(self, frame: int):
+        """(ids, poses (steps_per_gap, P, 3), velocities (P, 3)) of the simulation frames between recorded frames
+        `frame` and `frame + 1`."""
+        blk = self._blocks.get(frame)
+        if blk is None:
+            cur, nxt, n = self._frames[frame], self._frames[frame + 1], self._steps_per_gap
+            ids = list(cur.keys())
+            poses, vels = np.empty((n, len(ids), 3)), np.empty((len(ids), 3))
+            for k, ped in enumerate(ids):
+                a = cur[ped]
+                if ped in nxt:
+                    b = nxt[ped]
+                    poses[:, k, :2] = np.linspace(a[:2], b[:2], n)
+                    poses[:, k, 2] = angle_linspace(a[2], b[2], n)[:n]
+                    vels[k] = (a[3], a[4], wrap_angle(b[2] - a[2]) / self._RECORD_DT)
+                else:                                            # leaves before the next recorded frame: constant velocity
+                    for s in range(n):
+                        poses[s, k, :2] = a[:2] + a[3:5] * (s * self._dt)
+                    poses[:, k, 2] = a[2]
+                    vels[k] = (a[3], a[4], 0.)
+            blk = self._blocks[frame] = (ids, poses, vels)
+        return blk
+
+    def _pedestrians_at(self, frame: int, sub_step: int) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
+        ids, poses, vels = self._block(frame)
+        return {ped: (poses[sub_step, k].copy(), vels[k].copy()) for k, ped in enumerate(ids)}
+
+    # ---- device playback ---------------------------------------------------------------------------------------------
+    def configure_fused_detector(self, max_dist: float, fov: float, code: int):
+        self._det_cfg = (float(max_dist), float(fov), int(code))
+        if self._sim is not None:
+            self._sim.set_detector(*self._det_cfg, enabled=True)
+
+    def fused_collisions(self, robot_pose: np.ndarray, radius: float):
+        f = self._fused
+        if f is None or f[1] != radius or not np.array_equal(f[0], robot_pose):
+            return None
+        return list(f[2])
+
+    def _flat(self, frame: int, sub_step: int) -> int:
+        return frame * self._steps_per_gap + sub_step
+
+    def _device(self):
+        if self._sim is None:
+            n, slots = self._steps_per_gap, max(1, max(len(self._frames[f]) for f in range(self._n_frames)))
+            poses = np.zeros((self._n_frames * n, slots, 3))
+            poses[:, :, 0] = self._PARKED
+            poses[:, :, 1] = self._PARKED + 1.0e15 * np.arange(1, slots + 1)
+            vels = np.zeros_like(poses)
+            for f in range(self._n_frames):
+                ids, p, v = self._block(f)
+                poses[f * n:(f + 1) * n, :len(ids)] = p
+                vels[f * n:(f + 1) * n, :len(ids)] = v
+            self._slots = slots
+            self._sim = BatchedSimulation(1, slots, precision="fp64")
+            self._sim.set_replay(poses, vels, loop=True)        # the recording wraps to its first frame (_eth.py:101-102)
+            self._sim.replay_frame(self._flat(self._state.current_frame, self._state.current_sub_step))
+            if self._det_cfg is not None:
+                self._sim.set_detector(*self._det_cfg, enabled=True)
+        return self._sim
+
+    def step(self, dt: float = None, robot_pose: Optional[np.ndarray] = None, robot_velocity: Optional[np.ndarray] = None):
+        self._fused = None
+        sub, frame = self._state.current_sub_step + 1, self._state.current_frame                 # _eth.py:97-106
+        if sub >= self._steps_per_gap:
+            sub, frame = 0, frame + 1
+            if frame >= self._n_frames:
+                frame = 0
+        fused = robot_pose is not None and self._collision_radius is not None      # running under this package's Simulation
+        if fused:
+            rp = np.asarray(robot_pose, dtype=np.float64)
+            coll, det, vals, shown = self._device().replay_tick(rp[None], self._collision_radius)
+            assert shown == self._flat(frame, sub), (shown, frame, sub)            # device and host follow the same rule
+        self._state = ETHState(self._pedestrians_at(frame, sub), frame, sub)
+        if fused:
+            ids = self._block(frame)[0]
+            self._fused = (rp.copy(), self._collision_radius, [ids[k] for k in _mask_ids(coll[0], self._slots) if k < len(ids)])
+            if self._det_cfg is not None:
+                seen = [k for k in _mask_ids(det[0], self._slots) if k < len(ids)]
+                self._state._fused_sense = (self._fused[0], self._det_cfg, [ids[k] for k in seen],
+                                            {ids[k]: vals[0, k].copy() for k in seen})
+
+    def reset_to_state(self, state: ETHState):
+        self._state = state
+        self._fused = None
+        if self._sim is not None:
+            self._sim.replay_frame(self._flat(state.current_frame, state.current_sub_step))

@@ -309,6 +309,76 @@ def gen_replay():
     np.savez(os.path.join(HERE, "replay.npz"), **res)
 
 
+def gen_eth():
+    """ETHPedestriansRecord (pedestrians/_eth.py) on an excerpt of each recording -- the first 14 recorded frames of "eth"
+    and frames 40-53 of "hotel" -- at dt = 0.1 (4 simulation frames per recorded gap), 0.05 (8) and 0.03 (13), long
+    enough to wrap to frame 0; the policy alone (ids, poses, velocities, frame counters) and under a Simulation with a
+    unicycle robot and the detector (readings, collision list).  The reference reads its assets through
+    pkg_resources.resource_filename: the excerpt is served by patching that one lookup, the reference's code is unmodified.
+    The excerpt's lines are stored in the fixture (they are the input the accelerated class is tested on)."""
+    import tempfile
+    import pkg_resources
+    from pyminisim.pedestrians._eth import ETHPedestriansRecord
+    from pyminisim.util import angle_linspace
+    res = {}
+    real_lookup = pkg_resources.resource_filename
+    tmp = tempfile.mkdtemp()
+    for seq, first, count in (("eth", 0, 14), ("hotel", 40, 14)):
+        lines, frames_seen, last = [], -1, None
+        for line in open(real_lookup("pyminisim.pedestrians", f"assets/obsmat_{seq}.txt")):
+            fr = int(float(line.split()[0]))
+            if fr != last:
+                frames_seen += 1
+                last = fr
+            if first <= frames_seen < first + count:
+                lines.append(line)
+        with open(os.path.join(tmp, f"obsmat_{seq}.txt"), "w") as f:
+            f.writelines(lines)
+        res[f"{seq}_lines"] = np.array("".join(lines))
+    pkg_resources.resource_filename = lambda pkg, name: os.path.join(tmp, os.path.basename(name))
+    try:
+        for seq, dt, start, n_steps, robot in (("eth", 0.1, 0, 70, None), ("eth", 0.05, 3, 120, (-6.2, 2.5, 3.0, 0.0, 0.2)),
+                                               ("hotel", 0.03, 1, 200, (-1.1, 0.2, 1.5, 0.1, 0.3)), ("hotel", 0.1, 12, 30, None)):
+            tag = f"{seq}_{dt}_{start}"
+            model = ETHPedestriansRecord(seq, dt, start)
+            sim = None
+            if robot is not None:
+                rm = UnicycleRobotModel(initial_pose=np.array(robot[:3]), initial_control=np.array(robot[3:]))
+                sensors = [PedestrianDetector(config=PedestrianDetectorConfig(max_dist=6.0, fov=np.deg2rad(200.0), return_type="absolute"))]
+                sim = Simulation(world_map=EmptyWorld(), robot_model=rm, pedestrians_model=model, sensors=sensors, sim_dt=dt, rt_factor=None)
+            rows, det, coll = [], [], []        # rows: step, ped id, pose(3), velocity(3); det: step, ped id, value(2); coll: step, ped id
+            counters = []
+
+            def record(k, st):
+                for ped, pose in st.poses.items():
+                    rows.append([k, ped, *pose, *st.velocities[ped]])
+                counters.append([st.current_frame, st.current_sub_step])
+            record(0, model.state)
+            for k in range(1, n_steps + 1):
+                if sim is None:
+                    model.step(dt, None, None)
+                    record(k, model.state)
+                else:
+                    state = sim.step()
+                    record(k, state.world.pedestrians)
+                    for ped, v in state.sensors["pedestrian_detector"].reading.pedestrians.items():
+                        det.append([k, ped, *v])
+                    for ped in state.world.robot_to_pedestrians_collisions:
+                        coll.append([k, ped])
+            res.update({f"{tag}_rows": np.array(rows), f"{tag}_counters": np.array(counters),
+                        f"{tag}_det": np.array(det).reshape(-1, 4), f"{tag}_coll": np.array(coll).reshape(-1, 2)})
+    finally:
+        pkg_resources.resource_filename = real_lookup
+    # util.angle_linspace / wrap_angle known answers (util/_util.py)
+    rng = np.random.default_rng(5)
+    ang = rng.uniform(-np.pi, np.pi, (40, 2))
+    res["angle_in"] = ang
+    res["angle_linspace_7"] = np.array([angle_linspace(a, b, 7) for a, b in ang])
+    res["wrap_in"] = rng.uniform(-20, 20, 64)
+    res["wrap_out"] = wrap_angle(res["wrap_in"])
+    np.savez_compressed(os.path.join(HERE, "eth.npz"), **res)
+
+
 def gen_episode():
     """A 260-step Simulation with every sensor at once (the reference's own scheduler decides who fires when): HSFM crowd of 8,
     unicycle robot with a control sequence driving past obstacles (some moves vetoed by the map), PedestrianDetector
@@ -370,7 +440,7 @@ def gen_episode():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random", "replay", "episode"]
+    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random", "replay", "eth", "episode"]
     if "pair" in which:
         gen_pair_forces()
     if "kat2" in which:
@@ -385,6 +455,8 @@ if __name__ == "__main__":
         gen_random_tracker()
     if "replay" in which:
         gen_replay()
+    if "eth" in which:
+        gen_eth()
     if "episode" in which:
         gen_episode()
     print("golden fixtures written to", HERE)

@@ -27,17 +27,17 @@ def test_alias_serves_the_reference_import_paths():
         alias.install_as_pyminisim()
         from pyminisim.core import Simulation, SimulationState, WorldState, AbstractSensor, AbstractPedestriansModel, PEDESTRIAN_RADIUS
         from pyminisim.pedestrians import (HSFMParams, HeadedSocialForceModelPolicy, RandomWaypointTracker, FixedWaypointTracker,
-                                           ORCAParams, ORCAPedestriansModel, ReplayPedestriansPolicy)
+                                           ORCAParams, ORCAPedestriansModel, ReplayPedestriansPolicy, ETHPedestriansRecord)
         from pyminisim.sensors import (PedestrianDetectorNoise, PedestrianDetectorConfig, PedestrianDetectorReading, PedestrianDetector,
                                        OmniObstacleDetectorNoise, OmniObstacleDetectorConfig, OmniObstacleDetectorReading, OmniObstacleDetector,
                                        LidarSensorConfig, LidarSensorReading, LidarSensorNoise, LidarSensor)
         from pyminisim.robot import UnicycleRobotModel, BicycleRobotModel
         from pyminisim.world_map import CirclesWorld, EmptyWorld, AABBWorld, AABBObject
-        from pyminisim.util import wrap_angle, angle_linspace
+        from pyminisim.util import wrap_angle, angle_linspace, point_to_segment_distance, closest_point_of_segment
         from pyminisim.visual import Renderer, CircleDrawing
         import pyminisim_b200.core as c, pyminisim_b200.pedestrians as p
         assert Simulation is c.Simulation and HeadedSocialForceModelPolicy is p.HeadedSocialForceModelPolicy
-        assert abs(wrap_angle(3.5) - (3.5 - 2 * 3.141592653589793)) < 1e-15
+        assert abs(wrap_angle(3.5) - (3.5 - 2 * 3.141592653589793)) < 1e-15 and len(angle_linspace(0.0, 1.0, 4)) == 5
         r = Renderer(simulation=None, resolution=80.0, screen_size=(700, 700)); r.initialize(); r.render(); r.close()
         print("ok", c.USING_REFERENCE_ABCS)
     """)
