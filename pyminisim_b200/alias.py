@@ -12,7 +12,6 @@ The import paths SURVEY.md 8b lists are served: ``pyminisim.core`` (core/__init_
 (pedestrians/__init__.py:1-6), ``pyminisim.sensors`` (sensors/__init__.py:1-7), ``pyminisim.robot``, ``pyminisim.world_map``,
 ``pyminisim.util``.  ``pyminisim.visual`` (the pygame renderer) is outside the accelerated path: the alias serves a headless
 stand-in whose ``Renderer`` accepts the reference's calls and draws nothing, so that a script's step loop still runs.
-Names the accelerated path does not implement (SemanticDetector) raise ImportError on import.
 If the real reference is importable it is NOT replaced unless ``force=True``.
 """
 from __future__ import annotations

@@ -264,3 +264,78 @@ class OmniObstacleDetector(AbstractSensor):
             else:
                 dist = dist + np.random.normal(self._noise.distance_mu, self._noise.distance_sigma)
         return OmniObstacleDetectorReading(dist)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SemanticDetector (sensors/_semantic_object_detector.py): named AABB objects near the robot.  Host arithmetic over a
+# handful of boxes (AABBWorld.closest_semantic_objects) -- kept for drop-in completeness, not on the accelerated path.
+# ---------------------------------------------------------------------------------------------------------
+class SemanticDetectorConfig(AbstractSensorConfig):
+    def __init__(self, max_dist: float = 8., frequency: float = 10.):
+        assert max_dist > 0.
+        assert frequency > 0.
+        super().__init__()
+        self._max_dist, self._frequency = max_dist, frequency
+
+    max_dist = property(lambda self: self._max_dist)
+    frequency = property(lambda self: self._frequency)
+
+
+@dataclass
+class SemanticDetection:
+    class_name: str
+    object_name: Optional[str]
+    position: np.ndarray
+
+
+class SemanticDetectorReading(AbstractSensorReading):
+    def __init__(self, detections: Dict[int, SemanticDetection]):
+        super().__init__()
+        self._detections = detections
+
+    @property
+    def detections(self) -> Dict[int, SemanticDetection]:
+        return self._detections
+
+
+class SemanticDetectorNoise:
+    def __init__(self, position_mean: np.ndarray = np.array([0., 0.]), position_cov: np.ndarray = np.diag([0.001, 0.001]),
+                 drop_prob: float = 0.):
+        assert position_mean.shape == (2,)
+        assert position_cov.shape == (2, 2)
+        assert (position_cov >= 0.).all()
+        assert 0. <= drop_prob <= 1.
+        self._position_mean, self._position_cov, self._drop_prob = position_mean, position_cov, drop_prob
+
+    mean = property(lambda self: self._position_mean.copy())
+    cov = property(lambda self: self._position_cov.copy())
+    drop_prob = property(lambda self: self._drop_prob)
+
+    def noisify_reading(self, reading: SemanticDetectorReading) -> SemanticDetectorReading:
+        # the global numpy generator, one binomial then one multivariate normal draw per reading (:73-82); a detection
+        # survives where the binomial draw (probability 1 - drop_prob) is ZERO -- the reference's rule, reproduced
+        found = reading.detections
+        drawn = np.random.binomial(1, 1 - self._drop_prob, len(found)).astype(bool)
+        shift = np.random.multivariate_normal(self._position_mean, self._position_cov, len(found))
+        return SemanticDetectorReading({idx: SemanticDetection(d.class_name, d.object_name, d.position + shift[k])
+                                        for k, (idx, d) in enumerate(found.items()) if not drawn[k]})
+
+
+class SemanticDetector(AbstractSensor):
+    NAME = "semantic_detector"
+
+    def __init__(self, config: SemanticDetectorConfig = SemanticDetectorConfig(), noise: Optional[SemanticDetectorNoise] = None):
+        super().__init__(SemanticDetector.NAME, period=1. / config.frequency if np.isfinite(config.frequency) else 0.)
+        self._config, self._noise = config, noise
+
+    @property
+    def sensor_config(self) -> AbstractSensorConfig:
+        return self._config
+
+    def get_reading(self, world_state: WorldState, world_map: AbstractWorldMap) -> AbstractSensorReading:
+        from .world_map import AABBWorld
+        assert isinstance(world_map, AABBWorld), \
+            f"Semantic detector can work only with AABBWorld worlds, got instance of {type(world_map)}"
+        near = world_map.closest_semantic_objects(world_state.robot.pose[:2], self._config.max_dist)
+        reading = SemanticDetectorReading({idx: SemanticDetection(*v) for idx, v in near.items()})
+        return self._noise.noisify_reading(reading) if self._noise is not None else reading

@@ -167,3 +167,17 @@ class AABBWorld(_MapBase):
     @property
     def colors(self):
         return self._state.colors
+
+    def closest_semantic_objects(self, point: np.ndarray, max_distance: float) -> Dict[int, Tuple[str, Optional[str], np.ndarray]]:
+        """Objects with a class name whose nearest boundary point lies within ``max_distance`` of ``point``:
+        ``{object index: (class_name, object_name, nearest point)}`` (_aabb_world.py:166-186; first minimum on ties, like
+        ``argmin``).  A handful of boxes on the host -- the SemanticDetector is not on the accelerated path."""
+        from .util import closest_point_of_segment
+        out = {}
+        for idx, names in self._state.semantic_objects.items():
+            near = closest_point_of_segment(point, self._state.segments[4 * idx:4 * idx + 4])
+            dist = np.linalg.norm(point - near, axis=1)
+            k = int(np.argmin(dist))
+            if dist[k] <= max_distance:
+                out[idx] = names + (near[k],)
+        return out

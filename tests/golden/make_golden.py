@@ -379,6 +379,38 @@ def gen_eth():
     np.savez_compressed(os.path.join(HERE, "eth.npz"), **res)
 
 
+SEMANTIC_OBJECTS = [((3.0, 1.0, 2.0, 1.5), "table", "t1"), ((-2.0, -4.0, 1.0, 3.0), "shelf", None), ((0.5, 3.0, 0.5, 0.5), None, None),
+                    ((-4.0, 2.0, 3.0, 0.2), "door", "d7"), ((9.0, 9.0, 1.0, 1.0), "far", "f")]
+
+
+def gen_semantic():
+    """SemanticDetector (sensors/_semantic_object_detector.py) in a Simulation without pedestrians: an AABBWorld with named,
+    class-only and anonymous objects, a unicycle robot circling among them; 10 Hz readings without noise and, under
+    Simulation.seed(11), with noise (drop_prob 0.4).  Rows: step, object index, nearest point (2)."""
+    from pyminisim.sensors import SemanticDetector, SemanticDetectorConfig, SemanticDetectorNoise
+    res = {}
+    for tag, noise in (("clean", None), ("noisy", SemanticDetectorNoise(drop_prob=0.4))):
+        Simulation.seed(11)
+        world = AABBWorld([AABBObject(box, class_name=c, object_name=o) for box, c, o in SEMANTIC_OBJECTS])
+        rm = UnicycleRobotModel(initial_pose=np.array([0.0, 0.0, 0.5]), initial_control=np.array([1.5, 0.9]))
+        sim = Simulation(world_map=world, robot_model=rm, pedestrians_model=None,
+                         sensors=[SemanticDetector(SemanticDetectorConfig(max_dist=3.0, frequency=10.), noise=noise)], sim_dt=0.01, rt_factor=None)
+        rows, last = [], None
+        for k in range(1, 401):
+            st = sim.step()
+            reading = st.sensors["semantic_detector"].reading
+            if reading is not last:                      # a new reading object = the sensor fired on this step
+                last = reading
+                rows += [[k, idx, *d.position] for idx, d in reading.detections.items()]
+                rows.append([k, -1, 0., 0.])             # marks the firing step even when nothing is seen
+        res[f"{tag}_rows"] = np.array(rows)
+    # AABBWorld.closest_semantic_objects on its own: 60 query points, rows = query index, object index, nearest point
+    pts = np.random.default_rng(3).uniform(-6, 6, (60, 2))
+    res["query_points"] = pts
+    res["query_rows"] = np.array([[q, idx, *v[2]] for q, p in enumerate(pts) for idx, v in world.closest_semantic_objects(p, 2.5).items()])
+    np.savez(os.path.join(HERE, "semantic.npz"), **res)
+
+
 def gen_episode():
     """A 260-step Simulation with every sensor at once (the reference's own scheduler decides who fires when): HSFM crowd of 8,
     unicycle robot with a control sequence driving past obstacles (some moves vetoed by the map), PedestrianDetector
@@ -440,7 +472,7 @@ def gen_episode():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random", "replay", "eth", "episode"]
+    which = sys.argv[1:] or ["pair", "kat2", "crowds", "variants", "sensors", "random", "replay", "eth", "semantic", "episode"]
     if "pair" in which:
         gen_pair_forces()
     if "kat2" in which:
@@ -457,6 +489,8 @@ if __name__ == "__main__":
         gen_replay()
     if "eth" in which:
         gen_eth()
+    if "semantic" in which:
+        gen_semantic()
     if "episode" in which:
         gen_episode()
     print("golden fixtures written to", HERE)

@@ -30,7 +30,8 @@ def test_alias_serves_the_reference_import_paths():
                                            ORCAParams, ORCAPedestriansModel, ReplayPedestriansPolicy, ETHPedestriansRecord)
         from pyminisim.sensors import (PedestrianDetectorNoise, PedestrianDetectorConfig, PedestrianDetectorReading, PedestrianDetector,
                                        OmniObstacleDetectorNoise, OmniObstacleDetectorConfig, OmniObstacleDetectorReading, OmniObstacleDetector,
-                                       LidarSensorConfig, LidarSensorReading, LidarSensorNoise, LidarSensor)
+                                       LidarSensorConfig, LidarSensorReading, LidarSensorNoise, LidarSensor,
+                                       SemanticDetectorNoise, SemanticDetectorConfig, SemanticDetection, SemanticDetectorReading, SemanticDetector)
         from pyminisim.robot import UnicycleRobotModel, BicycleRobotModel
         from pyminisim.world_map import CirclesWorld, EmptyWorld, AABBWorld, AABBObject
         from pyminisim.util import wrap_angle, angle_linspace, point_to_segment_distance, closest_point_of_segment
