@@ -300,6 +300,8 @@ int pms_orca_set_waypoints_current(pms_sim *h, const double *current /*(W,N,2)*/
 int pms_orca_set_pref_refresh(pms_sim *h, int enabled);
 int pms_orca_step(pms_sim *h, int n_steps);
 int pms_orca_step_async(pms_sim *h, int n_steps);          /* no host synchronisation; pair with pms_sync */
+/* one tick of ORCAPedestriansModel.step (_orca.py:95-112): n_steps doStep and the agents' poses / velocities back in one call */
+int pms_orca_tick(pms_sim *h, int n_steps, double *poses /*(W,N,3)*/, double *velocities /*(W,N,3)*/);
 /* device-side snapshot of the agents (positions, velocities, preferred velocities, waypoint indices): checkpoint / resume */
 int pms_orca_snapshot_save(pms_sim *h);
 int pms_orca_snapshot_restore(pms_sim *h);

@@ -125,6 +125,7 @@ PROTOTYPES = {
     "pms_orca_snapshot_save": (C.c_int, [_h]),
     "pms_orca_snapshot_restore": (C.c_int, [_h]),
     "pms_orca_get_agents": (C.c_int, [_h, _dp, _dp]),
+    "pms_orca_tick": (C.c_int, [_h, C.c_int, _dp, _dp]),
     "pms_get_launch_info": (C.c_int, [_h, C.POINTER(LaunchInfoC)]),
     "pms_set_tuning": (C.c_int, [_h, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pms_measure_fp32_tflops": (C.c_double, [C.c_int]),

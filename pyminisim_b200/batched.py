@@ -537,6 +537,13 @@ class BatchedOrca:
     def step_async(self, n_steps: int = 1):
         check(self._lib.pms_orca_step_async(self._h, int(n_steps)))
 
+    def tick(self, n_steps: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        """n_steps and the agents back in one call and one synchronisation (``pms_orca_tick``): fresh (W, N, 3) arrays."""
+        poses = np.empty((self.W, self.N, 3))
+        vels = np.empty((self.W, self.N, 3))
+        check(self._lib.pms_orca_tick(self._h, int(n_steps), dptr(poses), dptr(vels)))
+        return poses, vels
+
     def sync(self):
         check(self._lib.pms_sync(self._h))
 

@@ -255,11 +255,13 @@ class _GpuSenseContext:
         self._sim = None
         self._n = -1
 
-    def run(self, ped_poses: Dict[int, np.ndarray], robot_pose: np.ndarray, robot_radius: float,
+    def run(self, ped_poses, robot_pose: np.ndarray, robot_radius: float,
             detector: Optional[Tuple[float, float, int]] = None):
+        """ped_poses: the reference's ``{id: pose}`` dict, or an (N, 3) array of pedestrians 0..N-1 (array-backed states)."""
         from . import _capi as capi
         from .batched import BatchedSimulation
-        ids = list(ped_poses.keys())
+        as_array = isinstance(ped_poses, np.ndarray)
+        ids = list(range(ped_poses.shape[0])) if as_array else list(ped_poses.keys())
         n = len(ids)
         if n == 0:
             return ids, np.zeros((0,), dtype=bool), np.zeros((0,), dtype=bool), np.zeros((0, 2))
@@ -268,7 +270,7 @@ class _GpuSenseContext:
                 self._sim.close()
             self._sim = BatchedSimulation(1, n, precision="fp64")
             self._n = n
-        poses = np.stack([ped_poses[k] for k in ids])[None]
+        poses = ped_poses[None] if as_array else np.stack([ped_poses[k] for k in ids])[None]
         if detector is None:
             self._sim.set_detector(enabled=False)
         else:
@@ -394,7 +396,9 @@ class Simulation:
                 # one pass serves the collision list and the (first) pedestrian detector: its reading travels with the
                 # state object like the fused step's does
                 cfg = self._detector_cfg
-                ids, coll, det, vals = self._sense.run(ped_state.poses, robot_state.pose, self._robot_model.radius, cfg)
+                arrays = getattr(ped_state, "_arrays", None)        # array-backed state: no dict of copies for the upload
+                ids, coll, det, vals = self._sense.run(arrays[0] if arrays is not None else ped_state.poses, robot_state.pose,
+                                                       self._robot_model.radius, cfg)
                 collisions = [k for k, c in zip(ids, coll) if c]
                 if cfg is not None and ids == list(range(len(ids))):
                     try:

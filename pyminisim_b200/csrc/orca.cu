@@ -430,4 +430,13 @@ int orca_get_agents(OrcaState &s, double *poses, double *vels, int32_t *n_constr
     return cudaStreamSynchronize(stream) == cudaSuccess ? 0 : -2;
 }
 
+// poses | velocities (6 n doubles) into a pinned host block with ONE asynchronous copy; the caller synchronises
+int orca_get_agents_async(OrcaState &s, double *pinned, cudaStream_t stream)
+{
+    const size_t n = (size_t)s.W * s.N;
+    if (ensure_stage(s, n * 6)) return -2;
+    orca_unpack_kernel<<<nb(n), 256, 0, stream>>>(n, s.pos, s.vel, s.heading, s.stage, s.stage + 3 * n);
+    return cudaMemcpyAsync(pinned, s.stage, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, stream) == cudaSuccess ? 0 : -2;
+}
+
 } // namespace pms

@@ -41,5 +41,6 @@ int orca_set_waypoints(OrcaState &s, const double *table, int n_rows, const int3
 int orca_set_current_waypoints(OrcaState &s, const double *current, cudaStream_t stream);
 int orca_step(OrcaState &s, int n_steps, cudaStream_t stream, long long *launches);
 int orca_get_agents(OrcaState &s, double *poses, double *vels, int32_t *n_constraints, cudaStream_t stream);
+int orca_get_agents_async(OrcaState &s, double *pinned /*(6 W N) host-pinned*/, cudaStream_t stream);
 
 } // namespace pms

@@ -2001,6 +2001,31 @@ int pms_orca_snapshot_restore(pms_sim *h)
     return PMS_OK;
 }
 
+// one tick of the drop-in ORCAPedestriansModel: n_steps doStep + the agents back, one launch chain, ONE pinned transfer, one
+// host synchronisation
+int pms_orca_tick(pms_sim *h, int n_steps, double *poses, double *velocities)
+{
+    OCHECK(h);
+    if (!poses || !velocities) return fail(PMS_ERR_INVALID, "null output");
+    const size_t n = (size_t)h->W * h->N, need = n * 48;
+    if (need > h->tick_bytes) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->tick_dev) cudaFree(h->tick_dev);
+        if (h->tick_host) cudaFreeHost(h->tick_host);
+        h->tick_dev = h->tick_host = nullptr; h->tick_bytes = 0;
+        CK(cudaMalloc((void **)&h->tick_dev, need));
+        CK(cudaMallocHost((void **)&h->tick_host, need));
+        h->tick_bytes = need;
+    }
+    int rc = pms_orca_step_async(h, n_steps);
+    if (rc) return rc;
+    if (orca_get_agents_async(h->orca, reinterpret_cast<double *>(h->tick_host), h->stream)) return fail(PMS_ERR_CUDA, "orca_get_agents failed");
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(poses, h->tick_host, n * 24);
+    std::memcpy(velocities, h->tick_host + n * 24, n * 24);
+    return PMS_OK;
+}
+
 int pms_orca_get_agents(pms_sim *h, double *poses, double *velocities)
 {
     OCHECK(h);

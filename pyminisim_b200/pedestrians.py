@@ -62,6 +62,7 @@ class FixedWaypointTracker(AbstractWaypointTracker):
         self._current_indices = {k: 1 for k in self._all_waypoints}
         rows = {v.shape[0] for v in self._all_waypoints.values()}
         self._stacked = (list(self._all_waypoints.keys()), np.stack(list(self._all_waypoints.values()))) if len(rows) == 1 else None
+        self._idx_cache = None
 
     # -- device hand-off helpers --
     @property
@@ -80,6 +81,7 @@ class FixedWaypointTracker(AbstractWaypointTracker):
 
     def _set_indices(self, idx):
         self._current_indices = {k: int(i) for k, i in zip(self._all_waypoints.keys(), idx)}
+        self._idx_cache = None
 
     @property
     def state(self) -> FixedWaypointTrackerState:
@@ -91,6 +93,7 @@ class FixedWaypointTracker(AbstractWaypointTracker):
     def update_waypoints(self, agents_poses):
         assert agents_poses.keys() == self._all_waypoints.keys()
         out = {}
+        self._idx_cache = None
         if self._stacked is not None:      # same rule, one distance evaluation for all pedestrians
             keys, tabs = self._stacked
             idx = np.fromiter((self._current_indices[k] for k in keys), dtype=np.int64, count=len(keys))
@@ -112,6 +115,37 @@ class FixedWaypointTracker(AbstractWaypointTracker):
                 self._current_indices[k] = nxt
                 out[k] = (tab[nxt], steady)
         return out
+
+    def update_from_array(self, positions: np.ndarray) -> np.ndarray:
+        """update_waypoints for the accelerated models, whose pedestrians are rows 0..N-1 of an array: same rule, no per-pedestrian
+        Python objects unless somebody reached a waypoint.  Returns the (N,) table indices after the hand-off."""
+        keys, tabs = self._stacked
+        idx = self._index_array()
+        reached = np.sqrt(((tabs[self._rows, idx] - positions) ** 2).sum(axis=1)) <= self._reach_distance
+        if reached.any():
+            for j in np.nonzero(reached)[0]:
+                nxt = int(idx[j]) + 1
+                if nxt >= tabs.shape[1]:
+                    nxt = 0 if self._loop else tabs.shape[1] - 1
+                idx[j] = nxt
+                self._current_indices[keys[j]] = nxt
+        return idx
+
+    def _index_array(self) -> np.ndarray:
+        # cache of the indices dict as an array (the dict stays the tracker's state: states alias it like in the reference)
+        cache = self._idx_cache
+        if cache is None or cache[0] is not self._current_indices:
+            keys = self._stacked[0]
+            self._rows = np.arange(len(keys))
+            cache = self._idx_cache = (self._current_indices, np.fromiter((self._current_indices[k] for k in keys), dtype=np.int64, count=len(keys)))
+        return cache[1]
+
+    def state_later(self):
+        """The state as of now, built when somebody asks for it: current waypoints from a copy of the indices taken now, the
+        indices dict the tracker's own (the reference's state holds that very dict, _fixed_waypoint_tracker.py:62-66)."""
+        keys, tabs = self._stacked
+        idx, live = self._index_array().copy(), self._current_indices
+        return lambda: FixedWaypointTrackerState({k: tabs[j, idx[j], :] for j, k in enumerate(keys)}, live)
 
     def reset_to_state(self, state: FixedWaypointTrackerState):
         self._current_indices = state.current_indices
@@ -241,7 +275,13 @@ class _ArrayBackedState(AbstractPedestriansModelState):
             assert poses.ndim == 2 and poses.shape[1] == 3 and velocities.shape == poses.shape
             self._arrays = (poses, velocities)
             self._dict = None
-            self._waypoints = waypoints_state
+            self._waypoints = waypoints_state        # a tracker state, or a zero-argument callable that builds it on first use
+
+    @property
+    def waypoints(self):
+        if callable(self._waypoints):
+            self._waypoints = self._waypoints()
+        return self._waypoints
 
     @property
     def _pedestrians(self):                       # what the base class (and code written against it) reads
@@ -469,6 +509,7 @@ class ORCAPedestriansModel(AbstractPedestriansModel):
         else:
             preferred_speeds = max_speeds.copy()
         self._n = poses.shape[0]
+        self._ids = list(range(self._n))
         self._tracker = waypoint_tracker
         if self._tracker.state is None:
             self._tracker.resample_all({i: poses[i] for i in range(self._n)})
@@ -495,8 +536,12 @@ class ORCAPedestriansModel(AbstractPedestriansModel):
         return self._state
 
     def step(self, dt: float = None, robot_pose: Optional[np.ndarray] = None, robot_velocity: Optional[np.ndarray] = None):
-        self._sim.step(1)
-        poses, vels = self._sim.get_agents()
+        poses, vels = self._sim.tick(1)                # doStep + the agents back: one call, one synchronisation
+        if self._device_tracker and self._tracker._stacked is not None and list(self._tracker._stacked[0]) == self._ids:
+            # host mirror of the device hand-off on the position array; the tracker state object is built on demand
+            self._tracker.update_from_array(poses[0, :, :2])
+            self._state = ORCAState((poses[0], vels[0]), self._tracker.state_later())
+            return
         if self._tracker.state is not None:
             # FixedWaypointTracker: host mirror of the device hand-off; any other tracker: THE hand-off (_orca.py:106-107),
             # followed by _update_preferred_velocities (:118-127) on the device from the new current waypoints

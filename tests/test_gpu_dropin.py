@@ -178,6 +178,41 @@ def test_orca_dropin_model():
     assert model.state.waypoints.current_indices == {i: int(o.wp_index[0, i]) for i in range(7)}
 
 
+@pytest.mark.parametrize("loop", [True, False])
+def test_orca_dropin_hand_offs_on_the_array_path(loop):
+    """Short legs, so every agent hands over several times in 500 steps: the host mirror of the device tracker (array fast path,
+    state object built on demand) against the oracle's tracker -- indices and current waypoints -- and against the dict rule."""
+    from oracle import oracle as orc
+    from pyminisim_b200.pedestrians import FixedWaypointTracker, ORCAParams, ORCAPedestriansModel
+    rng = np.random.default_rng(8)
+    n = 9
+    init = np.concatenate([rng.uniform(-3, 3, (n, 2)), np.zeros((n, 1))], axis=1)
+    goals = init[:, None, :2] + rng.uniform(-1.2, 1.2, (n, 3, 2))
+    ms = np.full(n, 1.6)
+    tracker = FixedWaypointTracker(initial_positions=init[:, :2].copy(), waypoints=goals.copy(), loop=loop)
+    shadow = FixedWaypointTracker(initial_positions=init[:, :2].copy(), waypoints=goals.copy(), loop=loop)   # the dict rule
+    model = ORCAPedestriansModel(0.01, tracker, n, initial_poses=init.copy(), params=ORCAParams(default_max_speed=2.), max_speeds=ms)
+    table = np.concatenate([init[:, None, :2], goals], axis=1)[None]
+    o = orc.OracleOrca(0.01, init[None], table, loop=loop, max_speed=ms[None], default_max_speed=2.0)
+    early = None
+    for k in range(500):
+        model.step()
+        shadow.update_waypoints(model.state.poses)
+        if k == 120:
+            early = model.state                      # evaluated only at the end: must still show step 120's waypoints
+            o.rollout(121)
+            want_early = {i: table[0, i, int(o.wp_index[0, i])] for i in range(n)}
+    o.rollout(500 - 121)
+    p, _ = _ped_arrays(model.state)
+    assert np.array_equal(p[:, :2].astype(np.float32), o.pos[0])
+    idx = {i: int(o.wp_index[0, i]) for i in range(n)}
+    assert sum(idx.values()) > n                     # hand-offs happened
+    st = model.state.waypoints
+    assert st.current_indices == idx == shadow.state.current_indices
+    assert all(np.array_equal(st.current_waypoints[i], table[0, i, idx[i]]) for i in range(n))
+    assert all(np.array_equal(early.waypoints.current_waypoints[i], want_early[i]) for i in range(n))
+
+
 def _orca_host_loop(o, tracker, steps):
     """The reference's ORCAPedestriansModel.step around the ORACLE's rvo2 restatement: doStep, tracker hand-off on the new
     poses, preferred velocities from the tracker's current waypoints (_orca.py:95-112,118-127).  The oracle's own table tracker

@@ -81,12 +81,12 @@ def run_orca(n, steps, warm):
 
 
 if __name__ == "__main__":
-    if "--profile" in sys.argv:          # where the Python side of a tick goes (cProfile, N = 64)
+    if "--profile" in sys.argv:          # where the Python side of a tick goes (cProfile, N = 64); `--profile orca`: the ORCA model
         import cProfile
         import pstats
         pr = cProfile.Profile()
         pr.enable()
-        run(64, 2000, 50)
+        (run_orca if "orca" in sys.argv else run)(64, 2000, 50)
         pr.disable()
         pstats.Stats(pr).sort_stats("tottime").print_stats(22)
         sys.exit(0)
