@@ -118,6 +118,48 @@ __global__ void tick_pack_kernel(size_t n, int W, int words, HsfmArgs a, double 
     if (g < (size_t)W) nonfinite[g] = a.nonfinite[g];
     if (g == 0) *n_events = a.ev_count ? *a.ev_count : 0;
 }
+// pms_sense_tick of a small batch (the drop-in classes: one world) in ONE kernel: the caller's poses and the robot pose are
+// read from the pinned host block (mapped), stored as the handle's state (velocities zero, plain low parts -- what
+// pms_set_ped_state + pms_set_robot_pose would leave), the collision list + detector evaluated like sense_kernel and the
+// reading written into the output part of the same block -- no copies in the chain.  Grid (world, block of 256 pedestrians).
+template <typename ST>
+__global__ void sense_tick_kernel(const __grid_constant__ HsfmArgs a, const double *poses, const double *robot, double2 *vals_out,
+                                  uint32_t *coll_out, uint32_t *det_out, bool keep_lo)
+{
+    const int w = blockIdx.x, i = blockIdx.y * blockDim.x + threadIdx.x;
+    const int N = a.N, words = (N + 31) >> 5;
+    const RobotSlot rb{robot[3 * w], robot[3 * w + 1], robot[3 * w + 2], 0.0, 0.0};
+    if (i < 3 && blockIdx.y == 0) a.robot_pose[3 * w + i] = robot[3 * w + i];
+    SenseOut so{false, false, 0.0, 0.0};
+    const size_t g = (size_t)w * N + i;
+    if (i < N) {
+        using ST2 = typename Vec2<ST>::type;
+        const double px = poses[3 * g], py = poses[3 * g + 1], pt = poses[3 * g + 2];
+        const ST x = (ST)px, y = (ST)py;
+        store_pv(a, g, x, y, (ST)0, (ST)0);
+        ST2 t; t.x = (ST)pt; t.y = (ST)0;
+        reinterpret_cast<ST2 *>(a.th)[g] = t;
+        if constexpr (sizeof(ST) == 4) {       // low parts like pack_state_kernel
+            auto lo = [&](double v) { return keep_lo ? (float)(v - (double)(float)v) : 0.0f; };
+            const float xl = lo(px), yl = lo(py);
+            reinterpret_cast<float4 *>(a.pos_lo)[g] = make_float4(xl, yl, 0.f, 0.f);
+            reinterpret_cast<float2 *>(a.th_lo)[g] = make_float2(lo(pt), 0.f);
+            so = sense_ped<double>(a, rb, (double)x + (double)xl, (double)y + (double)yl, true);
+        } else {
+            so = sense_ped<ST>(a, rb, x, y, true);
+        }
+        const double2 v = a.det_enabled ? make_double2(so.v0, so.v1) : a.det_vals[g];
+        if (a.det_enabled) a.det_vals[g] = v;
+        vals_out[g] = v;
+    }
+    const unsigned dm = __ballot_sync(0xffffffffu, so.det);
+    const unsigned cm = __ballot_sync(0xffffffffu, so.coll);
+    if ((i & 31) == 0 && (i >> 5) < words) {
+        const size_t m = (size_t)w * words + (i >> 5);
+        a.det_mask[m] = dm; a.coll_mask[m] = cm;
+        det_out[m] = dm; coll_out[m] = cm;
+    }
+}
 template <typename ST>
 __global__ void convert_back_kernel(size_t n, const ST *src, double *dst)
 {
@@ -1150,7 +1192,9 @@ int pms_sense_tick(pms_sim *h, const double *poses, const double *robot_pose, do
     const size_t n = (size_t)W * h->N, nm = (size_t)W * h->words;
     // host block: poses (3n doubles) | robot pose (3W) -- then reused for the results: det_vals (2n doubles) | coll | det
     const size_t in_bytes = (n * 3 + (size_t)W * 3) * 8, o_coll = n * 16, o_det = o_coll + nm * 4, out_bytes = o_det + nm * 4;
-    const size_t need = in_bytes > out_bytes ? in_bytes : out_bytes;
+    const size_t o_out = (in_bytes + 15) & ~(size_t)15;      // double2 records: 16-byte aligned
+    const bool direct = o_out + out_bytes <= 262144;         // small tick: one kernel on the mapped host block (outputs behind the inputs)
+    const size_t need = direct ? o_out + out_bytes : (in_bytes > out_bytes ? in_bytes : out_bytes);
     if (need > h->tick_bytes) {
         if (h->tick_dev) cudaFree(h->tick_dev);
         if (h->tick_host) cudaFreeHost(h->tick_host);
@@ -1164,6 +1208,24 @@ int pms_sense_tick(pms_sim *h, const double *poses, const double *robot_pose, do
     std::memcpy(st, poses, n * 24);
     std::memcpy(st + n * 3, robot_pose, (size_t)W * 24);
     a.robot_model = PMS_ROBOT_EXTERNAL; a.robot_radius = robot_radius;
+    if (direct) {
+        fill_consts(a);
+        const dim3 grid(W, (h->Np + 255) / 256);
+        const int threads = h->Np < 256 ? h->Np : 256;
+        unsigned char *o = h->tick_host + o_out;
+        if (h->precision == PMS_FP32)
+            sense_tick_kernel<float><<<grid, threads, 0, h->stream>>>(a, st, st + n * 3, (double2 *)o, (uint32_t *)(o + o_coll), (uint32_t *)(o + o_det), h->compensated);
+        else
+            sense_tick_kernel<double><<<grid, threads, 0, h->stream>>>(a, st, st + n * 3, (double2 *)o, (uint32_t *)(o + o_coll), (uint32_t *)(o + o_det), false);
+        CK(cudaGetLastError());
+        h->large.sorted_valid = false;
+        h->info.kernel_launches++;
+        CK(cudaStreamSynchronize(h->stream));
+        if (det_vals) std::memcpy(det_vals, o, n * 16);
+        if (coll_mask) std::memcpy(coll_mask, o + o_coll, nm * 4);
+        if (det_mask) std::memcpy(det_mask, o + o_det, nm * 4);
+        return PMS_OK;
+    }
     CK(cudaMemcpyAsync(h->stage, st, n * 24, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->stage + n * 3, 0, n * 24, h->stream));
     CK(cudaMemcpyAsync(a.robot_pose, st + n * 3, (size_t)W * 24, cudaMemcpyHostToDevice, h->stream));
@@ -1314,7 +1376,10 @@ int pms_step_tick(pms_sim *h, double dt, int n_steps, const double *robot_pose, 
     }
     int rc = pms_hsfm_step_async(h, dt, n_steps);
     if (rc) return rc;
-    unsigned char *d = h->tick_dev;
+    // small ticks (the drop-in classes: one world): the gather kernel writes straight into the pinned host block (mapped, UVA)
+    // -- no device-to-host copy in the chain; large ones go through the device block and one copy
+    const bool direct = total <= 65536;
+    unsigned char *d = direct ? h->tick_host : h->tick_dev;
     {
         const unsigned nb_ = nblk(n > nm ? n : nm);
         if (h->precision == PMS_FP32)
@@ -1325,7 +1390,7 @@ int pms_step_tick(pms_sim *h, double dt, int n_steps, const double *robot_pose, 
                                                                  (int *)(d + o_idx), (uint32_t *)(d + o_coll), (uint32_t *)(d + o_det), (int *)(d + o_nf), (int *)(d + o_ev));
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->tick_host, d, total, cudaMemcpyDeviceToHost, h->stream));
+    if (!direct) CK(cudaMemcpyAsync(h->tick_host, d, total, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const unsigned char *q = h->tick_host;
     if (poses) std::memcpy(poses, q + o_pose, n * 24);

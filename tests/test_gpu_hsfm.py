@@ -590,3 +590,27 @@ def test_step_tick_and_sense_tick_equal_the_separate_calls(precision):
     assert np.array_equal(det, m) and np.array_equal(coll, b.get_collisions()) and det.any()
     hit = np.array([[(int(m[w, i >> 5]) >> (i & 31)) & 1 for i in range(40)] for w in range(3)], dtype=bool)
     assert np.array_equal(vals[hit], v2[hit])
+    # the state a sense_tick leaves is the uploaded one (velocities zero)
+    p2, v2s = a.get_state()
+    b_p, _ = b.get_state()
+    assert np.array_equal(p2, b_p) and not v2s.any()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_sense_tick_large_batch_takes_the_copy_path(precision):
+    """Ticks beyond 256 KB go through the device block and copies instead of the one-kernel mapped-host path: same reading."""
+    from pyminisim_b200 import _capi as capi
+    sc = make_bench_crowd(300, 40)
+    rng = np.random.default_rng(9)
+    a = make_cuda(sc, precision, det=(6.0, 200.0, 2), robot=0)
+    b = make_cuda(sc, precision, det=(6.0, 200.0, 2), robot=0)
+    pose = np.concatenate([sc.poses[:, 7, :2] + rng.uniform(0.2, 0.6, (300, 2)), rng.uniform(-3, 3, (300, 1))], axis=1)
+    poses = sc.poses + rng.uniform(-0.3, 0.3, sc.poses.shape)
+    coll, det, vals = a.sense_tick(poses, pose, 0.5)
+    b.set_state(poses); b.set_robot(capi.ROBOT_EXTERNAL, pose, velocity=np.zeros((300, 3)), radius=0.5); b.sense()
+    m, v2 = b.get_detector()
+    assert np.array_equal(det, m) and np.array_equal(coll, b.get_collisions()) and det.any() and coll.any()
+    hit = np.unpackbits(m.view(np.uint8), axis=1, bitorder="little")[:, :40].astype(bool)
+    assert np.array_equal(vals[hit], v2[hit])
+    assert np.array_equal(a.get_state()[0], b.get_state()[0])
+
