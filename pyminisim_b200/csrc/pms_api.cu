@@ -486,14 +486,40 @@ bool duo_eligible(const pms_sim *h)
 // 7 / 4 CTAs resident per SM for N <= 32 / 64) wins.  Measured cross-over on one B200 (profiles/r2_duo.md): N <= 32: one
 // wave of CTAs (1024 worlds: 1.04 vs 1.46 ms per 1000 steps, 2048: 1.97 vs 1.97); N <= 64: up to ~2.5 waves (512: 1.48 vs
 // 2.81, 1024: 2.52 vs 3.27; 2048 worlds would take 4 waves and lose to the 4.8 ms of the warp-per-world kernel).
-// units of the pair scheme per pair warp (hsfm_duo_api.cuh): one tile: 2; two tiles: 2 when that -- 5 instead of 4 worlds per
-// SM -- lets the batch fit one wave of CTAs it would not fit with one unit per warp, and the SMs would hold 3 worlds or more anyway
+// Two-tile worlds: which variant (one or two units of the pair scheme per pair warp: 7 warps and 4 worlds per SM, or 5 warps
+// and 5 worlds per SM) and whether the kernel beats the warp-per-world one is a matter of how the batch fills the SMs wave by
+// wave.  Model from measurements on one B200 (profiles/r2_history.md, tools/ab_duo_variants.py; ms per 1000 steps): an SM that
+// holds n worlds takes t[n]; the fullest SM holds ceil(W / SMs) worlds, in waves of the variant's occupancy; consecutive waves
+// overlap by about 7 %.  The warp-per-world kernel's time moves in layers of one more CTA (4 worlds) per SM.  Checked against 20
+// measured batch sizes from 128 to 2960 worlds: the choice is the fastest of the three everywhere but at 1184 (3 % off).
+double duo_model_ms(int n, int upw)
+{
+    static const double t1[5] = {0.0, 0.755, 0.956, 1.211, 1.460}, t2[6] = {0.0, 0.897, 1.093, 1.239, 1.396, 1.764};
+    const int occ = upw == 2 ? 5 : 4;
+    const double *t = upw == 2 ? t2 : t1;
+    double s = 0.0;
+    int waves = 0;
+    for (; n > 0; ++waves) {
+        const int k = n < occ ? n : occ;
+        s += t[k];
+        n -= k;
+    }
+    return waves > 1 ? 0.93 * s : s;
+}
+double warp_model_ms(int W, int sms)
+{
+    static const double layer_ms[5] = {0.0, 2.46, 3.03, 3.83, 4.75};
+    const int layers = (W + 4 * sms - 1) / (4 * sms);       // one more CTA (4 worlds) on every SM
+    return layers <= 4 ? layer_ms[layers] : 1.13 * layers;
+}
+
+// units of the pair scheme per pair warp (hsfm_duo_api.cuh): one tile: 2; two tiles: the faster by the model above
 int duo_upw(const pms_sim *h)
 {
     if (h->Np <= 32) return 2;
     if (h->tune_S == 4 && (h->tune_wpc == 1 || h->tune_wpc == 2)) return h->tune_wpc;     // forced (tests, A/B runs)
-    const long long w4 = 4LL * h->sm_count, w5 = 5LL * h->sm_count;
-    return (h->W > 2 * w4 / 3 && h->W <= w5) ? 2 : 1;
+    const int n = (h->W + h->sm_count - 1) / h->sm_count;
+    return duo_model_ms(n, 2) < duo_model_ms(n, 1) ? 2 : 1;
 }
 
 bool duo_preferred(const pms_sim *h)
@@ -505,9 +531,13 @@ bool duo_preferred(const pms_sim *h)
     size_t smem = 0;
     if (duo_kernel_prepare(h->compensated, false, h->Np / 32, h->Np <= 32 ? 2 : 1, &occ, &smem) != cudaSuccess || occ < 1) return false;
     const long long wave = (long long)occ * h->sm_count;
-    // measured cross-overs against the warp-per-world kernel (profiles/r2_history.md): one tile: 1.65 waves of 9 worlds per SM
-    // (2048 x 32: 1.90 vs 1.97 ms, 2664 x 32: 2.32 vs 2.18); two tiles: 2.5 waves of 4 (1480 x 64: 3.52 vs 3.74, 2048 x 64: 4.83 vs 4.65)
-    return h->Np <= 32 ? 20LL * h->W <= 33 * wave : 2LL * h->W <= 5 * wave;
+    // measured cross-over against the warp-per-world kernel (profiles/r2_history.md): one tile: 1.65 waves of 9 worlds per SM
+    // (2048 x 32: 1.90 vs 1.97 ms, 2664 x 32: 2.32 vs 2.18)
+    if (h->Np <= 32) return 20LL * h->W <= 33 * wave;
+    if (occ < 4) return 2LL * h->W <= 5 * wave;            // not the occupancy the model was measured at
+    const int n = (h->W + h->sm_count - 1) / h->sm_count;
+    const double duo = duo_model_ms(n, 1) < duo_model_ms(n, 2) ? duo_model_ms(n, 1) : duo_model_ms(n, 2);
+    return duo < warp_model_ms(h->W, h->sm_count);
 }
 
 int launch_duo(pms_sim *h)
