@@ -284,9 +284,10 @@ __device__ __forceinline__ void duo_contact(const HsfmArgs &a, const float2 *pl,
     }
 }
 
-// SENS: the instantiation that serves a sensor plan (see warp_robot_block in hsfm_warp.cuh); UPW: units per pair warp
-template <int T, bool COMP, bool SENS, int UPW>
-__global__ void __launch_bounds__(duo_threads(T, UPW), duo_min_blocks(T, UPW)) hsfm_duo_kernel(const __grid_constant__ HsfmArgs a)
+// SENS: the instantiation that serves a sensor plan (see warp_robot_block in hsfm_warp.cuh); UPW: units per pair warp;
+// DENSE (two tiles, two units per warp): compiled for 7 instead of 5 worlds per SM (56 registers per thread, a few more spills)
+template <int T, bool COMP, bool SENS, int UPW, bool DENSE = false>
+__global__ void __launch_bounds__(duo_threads(T, UPW), DENSE ? DUO_DENSE_BLOCKS : duo_min_blocks(T, UPW)) hsfm_duo_kernel(const __grid_constant__ HsfmArgs a)
 {
     using L = DuoSmem<T>;
     constexpr int Np = 32 * T;

@@ -492,11 +492,12 @@ bool duo_eligible(const pms_sim *h)
 // holds n worlds takes t[n]; the fullest SM holds ceil(W / SMs) worlds, in waves of the variant's occupancy; consecutive waves
 // overlap by about 7 %.  The warp-per-world kernel's time moves in layers of one more CTA (4 worlds) per SM.  Checked against 20
 // measured batch sizes from 128 to 2960 worlds: the choice is the fastest of the three everywhere but at 1184 (3 % off).
-double duo_model_ms(int n, int upw)
+double duo_model_ms(int n, int variant)
 {
-    static const double t1[5] = {0.0, 0.755, 0.956, 1.211, 1.460}, t2[6] = {0.0, 0.897, 1.093, 1.239, 1.396, 1.764};
-    const int occ = upw == 2 ? 5 : 4;
-    const double *t = upw == 2 ? t2 : t1;
+    static const double t1[5] = {0.0, 0.755, 0.956, 1.211, 1.460}, t2[6] = {0.0, 0.897, 1.093, 1.239, 1.396, 1.764},
+                        t3[8] = {0.0, 1.039, 1.213, 1.353, 1.468, 1.864, 2.167, 2.282};
+    const int occ = variant == 3 ? 7 : (variant == 2 ? 5 : 4);
+    const double *t = variant == 3 ? t3 : (variant == 2 ? t2 : t1);
     double s = 0.0;
     int waves = 0;
     for (; n > 0; ++waves) {
@@ -504,7 +505,7 @@ double duo_model_ms(int n, int upw)
         s += t[k];
         n -= k;
     }
-    return waves > 1 ? 0.93 * s : s;
+    return waves > 1 ? (variant == 3 ? 0.965 : 0.93) * s : s;
 }
 double warp_model_ms(int W, int sms)
 {
@@ -513,13 +514,20 @@ double warp_model_ms(int W, int sms)
     return layers <= 4 ? layer_ms[layers] : 1.13 * layers;
 }
 
-// units of the pair scheme per pair warp (hsfm_duo_api.cuh): one tile: 2; two tiles: the faster by the model above
+// variant of the kernel (hsfm_duo_api.cuh): one tile: 2; two tiles: the fastest by the model above (forced by j_split 4 +
+// worlds_per_block 1 / 2 / 3: tests, A/B runs)
+int duo_best_variant(int n)
+{
+    int best = 1;
+    for (int v = 2; v <= 3; ++v)
+        if (duo_model_ms(n, v) < duo_model_ms(n, best)) best = v;
+    return best;
+}
 int duo_upw(const pms_sim *h)
 {
     if (h->Np <= 32) return 2;
-    if (h->tune_S == 4 && (h->tune_wpc == 1 || h->tune_wpc == 2)) return h->tune_wpc;     // forced (tests, A/B runs)
-    const int n = (h->W + h->sm_count - 1) / h->sm_count;
-    return duo_model_ms(n, 2) < duo_model_ms(n, 1) ? 2 : 1;
+    if (h->tune_S == 4 && h->tune_wpc >= 1 && h->tune_wpc <= 3) return h->tune_wpc;
+    return duo_best_variant((h->W + h->sm_count - 1) / h->sm_count);
 }
 
 bool duo_preferred(const pms_sim *h)
@@ -536,19 +544,18 @@ bool duo_preferred(const pms_sim *h)
     if (h->Np <= 32) return 20LL * h->W <= 33 * wave;
     if (occ < 4) return 2LL * h->W <= 5 * wave;            // not the occupancy the model was measured at
     const int n = (h->W + h->sm_count - 1) / h->sm_count;
-    const double duo = duo_model_ms(n, 1) < duo_model_ms(n, 2) ? duo_model_ms(n, 1) : duo_model_ms(n, 2);
-    return duo < warp_model_ms(h->W, h->sm_count);
+    return duo_model_ms(n, duo_best_variant(n)) < warp_model_ms(h->W, h->sm_count);
 }
 
 int launch_duo(pms_sim *h)
 {
-    const int T = h->Np / 32, upw = duo_upw(h);
+    const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation (no 7-worlds-per-SM build of it: variant 3 runs as 2)
+    const int T = h->Np / 32, upw = sens && duo_upw(h) == 3 ? 2 : duo_upw(h);
     const bool comp = h->compensated;
     int occ = 0;
     size_t smem = 0;
     h->a.wpc = 1;
     h->a.n_chunks = 1; h->a.chunk_steps = h->a.n_steps;
-    const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation
     CK(duo_kernel_prepare(comp, sens, T, upw, &occ, &smem));
     CK(duo_kernel_launch(comp, sens, T, upw, h->a, h->W, smem, h->stream));
     if (!comp) {        // plain fp32 state: the low parts a set_state left are gone
@@ -557,7 +564,7 @@ int launch_duo(pms_sim *h)
         CK(cudaMemsetAsync(h->a.th_lo, 0, n * 8, h->stream));
     }
     h->info.kernel = 4;
-    h->info.threads_per_block = duo_threads(T, upw);
+    h->info.threads_per_block = duo_threads(T, duo_variant_upw(upw));
     h->info.blocks = h->W;
     h->info.worlds_per_block = 1;
     h->info.j_split = upw;

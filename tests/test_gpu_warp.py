@@ -108,7 +108,8 @@ def test_contact_pass_is_exercised_one_step():
 @pytest.mark.parametrize("precision", ["fp32", "mixed"])
 def test_warp_kernel_tuning_is_bit_identical(precision):
     """Worlds per CTA and the dynamic (chunk, group) scheduler only move work around.  (Pair-warp / owner-warp kernel:
-    worlds_per_block 1 / 2 force one / two units of the pair scheme per pair warp -- bit-identical too.)"""
+    worlds_per_block 1 / 2 / 3 force its variants -- one / two units of the pair scheme per pair warp, two units compiled for 7
+    worlds per SM -- bit-identical too.)"""
     sc = make_bench_crowd(37, 64)
     outs = []
     for wpc, chunks in ((0, 1), (1, 1), (2, 1), (3, 1), (8, 4), (5, 3)):
@@ -119,7 +120,9 @@ def test_warp_kernel_tuning_is_bit_identical(precision):
         # (the pair-warp / owner-warp kernel runs one world per CTA on a static grid: wpc / chunks do not apply)
         assert info["kernel"] == expected_kernel(sim) and info["n_chunks"] == (chunks if info["kernel"] == KERNEL_WARP else 1)
         if info["kernel"] == KERNEL_DUO:
-            assert info["j_split"] == (2 if wpc == 2 else 1)                  # units per pair warp
+            assert info["j_split"] == (wpc if wpc in (2, 3) else 1)           # the variant that ran
+            assert info["threads_per_block"] == (224 if info["j_split"] == 1 else 160)
+            assert info["blocks_per_sm"] == {1: 4, 2: 5, 3: 7}[info["j_split"]]
         outs.append(sim.get_state() + sim.get_detector() + (sim.get_collisions(),) + sim.get_stats() + sim.get_robot())
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
