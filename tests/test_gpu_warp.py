@@ -307,3 +307,26 @@ def test_async_io_pipeline_equals_blocking_calls():
             assert np.array_equal(o["det"], det_ref) and np.array_equal(o["col"], col_ref)
             assert (o["nf"] == 0).all() and (nf_ref == 0).all()   # sync() maps the raw "never" sentinel of the async copy to 0
     sims[1].sync()
+
+
+def test_automatic_kernel_choice_for_two_tile_batches():
+    """pms_api.cu:duo_preferred / duo_upw -- the wave-by-wave model of measured times picks, on a 148-SM
+    B200, the pair-warp / owner-warp kernel's variant 1 / 2 / 3 or the warp-per-world kernel by how the batch fills the SMs."""
+    import torch
+    from pyminisim_b200.batched import BatchedSimulation
+    if torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip("the expectations are those of a 148-SM device")
+    want = {148: (KERNEL_DUO, 1), 444: (KERNEL_DUO, 1), 512: (KERNEL_DUO, 2), 740: (KERNEL_DUO, 2), 1024: (KERNEL_DUO, 3),
+            1480: (KERNEL_DUO, 2), 1776: (KERNEL_WARP, 0), 2048: (KERNEL_DUO, 3), 2368: (KERNEL_WARP, 0), 4096: (KERNEL_WARP, 0)}
+    for W, (kernel, variant) in want.items():
+        sc = make_bench_crowd(W, 64)
+        sim = helpers.make_cuda(sc, "fp32")
+        sim.step(0.01, 2)
+        info = sim.launch_info()
+        assert (info["kernel"], info["j_split"]) == (kernel, variant), (W, info)
+        sim.close()
+    sim = helpers.make_cuda(make_bench_crowd(1024, 32), "fp32")          # one tile: C2 runs the pair-warp / owner-warp kernel
+    sim.step(0.01, 2)
+    assert sim.launch_info()["kernel"] == KERNEL_DUO
+    sim.close()
+
