@@ -12,7 +12,7 @@ constexpr int DUO_MAX_TILES = 2;            // N <= 64
 // registers); which one is fastest depends on how the batch fills the SMs (pms_api.cu: duo_model_ms).
 __host__ __device__ constexpr int duo_pair_warps(int T, int upw) { return 2 * T / upw; }
 __host__ __device__ constexpr int duo_threads(int T, int upw) { return 32 * (duo_pair_warps(T, upw) + T + 1); }   // + T owner warps + 1 service warp
-__host__ __device__ constexpr int duo_min_blocks(int T, int upw) { return T == 1 ? (upw == 2 ? 9 : 7) : (upw == 2 ? 5 : 4); }
+__host__ __device__ constexpr int duo_min_blocks(int T, int upw) { return T == 1 ? (upw == 2 ? 10 : 7) : (upw == 2 ? 5 : 4); }   // one tile: 64 registers (measured 9 / 10 / 12 / 14 worlds per SM: 1.007 / 0.988 / 1.048 / 1.169 ms on 1024 x 32)
 constexpr int DUO_DENSE_BLOCKS = 7;         // variant 3
 __host__ __device__ constexpr int duo_variant_upw(int variant) { return variant == 3 ? 2 : variant; }
 

@@ -483,7 +483,7 @@ bool duo_eligible(const pms_sim *h)
 
 // automatic choice: the warp-per-world kernel brings ONE warp per world to the schedulers; below ~2 warps per scheduler its
 // dependent chain per step is exposed and the pair-warp / owner-warp kernel (3T + 1 warps per world, one world per CTA,
-// 7 / 4 CTAs resident per SM for N <= 32 / 64) wins.  Measured cross-over on one B200 (profiles/r2_duo.md): N <= 32: one
+// 10 / 4 - 7 CTAs resident per SM for N <= 32 / 64) wins.  Measured cross-over on one B200 (profiles/r2_duo.md): N <= 32: one
 // wave of CTAs (1024 worlds: 1.04 vs 1.46 ms per 1000 steps, 2048: 1.97 vs 1.97); N <= 64: up to ~2.5 waves (512: 1.48 vs
 // 2.81, 1024: 2.52 vs 3.27; 2048 worlds would take 4 waves and lose to the 4.8 ms of the warp-per-world kernel).
 // Two-tile worlds: which variant (one or two units of the pair scheme per pair warp: 7 warps and 4 worlds per SM, or 5 warps
@@ -535,12 +535,12 @@ bool duo_preferred(const pms_sim *h)
     if (h->tune_S == 5) return false;                      // forced: warp-per-world kernel
     if (h->tune_S == 4) return true;                       // forced: pair-warp / owner-warp kernel
     if (h->tune_S != 0 || h->tune_wpc > 0 || h->tune_chunks > 0) return false;   // explicit launch knobs of the other kernels
-    int occ = h->Np <= 32 ? 9 : 4;                         // resident CTAs (= worlds) per SM of the instantiation
+    int occ = h->Np <= 32 ? 10 : 4;                        // resident CTAs (= worlds) per SM of the instantiation
     size_t smem = 0;
     if (duo_kernel_prepare(h->compensated, false, h->Np / 32, h->Np <= 32 ? 2 : 1, &occ, &smem) != cudaSuccess || occ < 1) return false;
     const long long wave = (long long)occ * h->sm_count;
-    // measured cross-over against the warp-per-world kernel (profiles/r2_history.md): one tile: 1.65 waves of 9 worlds per SM
-    // (2048 x 32: 1.90 vs 1.97 ms, 2664 x 32: 2.32 vs 2.18)
+    // measured cross-over against the warp-per-world kernel (profiles/r2_history.md): one tile: 1.65 waves of 10 worlds per SM
+    // (2048 x 32: 1.80 vs 1.97 ms, 2664 x 32: 2.23 vs 2.18)
     if (h->Np <= 32) return 20LL * h->W <= 33 * wave;
     if (occ < 4) return 2LL * h->W <= 5 * wave;            // not the occupancy the model was measured at
     const int n = (h->W + h->sm_count - 1) / h->sm_count;
