@@ -325,9 +325,9 @@ int pms_get_launch_info(pms_sim *h, pms_launch_info *out);
  *                    directed-pair kernel (FP64, larger worlds) j_split = 1, 2, 4, 8 is the number of j-slices.
  *                    FP32 batches of up to 64 pedestrians per world that fit about one wave of CTAs (one world per CTA) run the
  *                    pair-warp / owner-warp kernel instead (kernel 4: 3T + 1 warps per world, the pair pass of step t + 1
- *                    overlaps the dynamics of step t); j_split 4 forces it (worlds_per_block 1 / 2 / 3 then also forces the
- *                    variant for two-tile worlds -- one / two units of the pair scheme per pair warp / two units compiled for 7
- *                    worlds per SM: bit-identical results, different speed; pms_launch_info.j_split reports the variant),
+ *                    overlaps the dynamics of step t); j_split 4 forces it (worlds_per_block 1 .. 5 then also forces the
+ *                    variant for two-tile worlds -- one / two units of the pair scheme per pair warp / two units compiled for 7,
+ *                    4, 3 worlds per SM: bit-identical results, different speed; pms_launch_info.j_split reports the variant),
  *                    j_split 5 forces the warp-per-world kernel, and so
  *                    does any explicit worlds_per_block / n_chunks.  The two kernels add the same pair forces in a different
  *                    order: results agree to fp32 rounding, not bit for bit -- pin one of them (4 / 5) when the bits of a world

@@ -13,9 +13,12 @@ template <typename F> cudaError_t dispatch(bool comp, bool sens, int T, int vari
           : (comp ? f(hsfm_duo_kernel<TT, true, false, UU>, DuoSmem<TT>::BYTES, duo_threads(TT, UU))                          \
                   : f(hsfm_duo_kernel<TT, false, false, UU>, DuoSmem<TT>::BYTES, duo_threads(TT, UU))))
     if (T == 1) return PMS_DUO_INST(1, 2);
-    if (T == 2 && variant == 3 && !sens)
-        return comp ? f(hsfm_duo_kernel<2, true, false, 2, true>, DuoSmem<2>::BYTES, duo_threads(2, 2))
-                    : f(hsfm_duo_kernel<2, false, false, 2, true>, DuoSmem<2>::BYTES, duo_threads(2, 2));
+#define PMS_DUO_MINB(MB)                                                                                                      \
+    (comp ? f(hsfm_duo_kernel<2, true, false, 2, MB>, DuoSmem<2>::BYTES, duo_threads(2, 2))                                   \
+          : f(hsfm_duo_kernel<2, false, false, 2, MB>, DuoSmem<2>::BYTES, duo_threads(2, 2)))
+    if (T == 2 && variant >= 3 && !sens)
+        return variant == 3 ? PMS_DUO_MINB(7) : (variant == 4 ? PMS_DUO_MINB(4) : PMS_DUO_MINB(3));
+#undef PMS_DUO_MINB
     if (T == 2) return variant >= 2 ? PMS_DUO_INST(2, 2) : PMS_DUO_INST(2, 1);
 #undef PMS_DUO_INST
     return cudaErrorInvalidValue;

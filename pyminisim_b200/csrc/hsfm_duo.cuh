@@ -285,9 +285,10 @@ __device__ __forceinline__ void duo_contact(const HsfmArgs &a, const float2 *pl,
 }
 
 // SENS: the instantiation that serves a sensor plan (see warp_robot_block in hsfm_warp.cuh); UPW: units per pair warp;
-// DENSE (two tiles, two units per warp): compiled for 7 instead of 5 worlds per SM (56 registers per thread, a few more spills)
-template <int T, bool COMP, bool SENS, int UPW, bool DENSE = false>
-__global__ void __launch_bounds__(duo_threads(T, UPW), DENSE ? DUO_DENSE_BLOCKS : duo_min_blocks(T, UPW)) hsfm_duo_kernel(const __grid_constant__ HsfmArgs a)
+// MINB (two tiles, two units per warp): worlds per SM the kernel is compiled for instead of the default 5 (72 registers) --
+// 7: 56 registers, a few more spills; 4: 96 registers; 3: 127 registers, no spills (hsfm_duo_api.cuh: duo_variant_blocks)
+template <int T, bool COMP, bool SENS, int UPW, int MINB = 0>
+__global__ void __launch_bounds__(duo_threads(T, UPW), MINB ? MINB : duo_min_blocks(T, UPW)) hsfm_duo_kernel(const __grid_constant__ HsfmArgs a)
 {
     using L = DuoSmem<T>;
     constexpr int Np = 32 * T;

@@ -494,15 +494,18 @@ bool duo_eligible(const pms_sim *h)
 // measured batch sizes from 128 to 2960 worlds: the choice is the fastest of the three everywhere but at 1184 (3 % off).
 double duo_model_ms(int n, int variant)
 {
-    static const double t1[5] = {0.0, 0.755, 0.956, 1.211, 1.460}, t2[6] = {0.0, 0.897, 1.093, 1.239, 1.396, 1.764},
-                        t3[8] = {0.0, 1.039, 1.213, 1.353, 1.468, 1.864, 2.167, 2.282};
-    const int occ = variant == 3 ? 7 : (variant == 2 ? 5 : 4);
-    const double *t = variant == 3 ? t3 : (variant == 2 ? t2 : t1);
+    static const double t[DUO_VARIANTS + 1][8] = {{0.0},
+        {0.0, 0.755, 0.956, 1.211, 1.460},                          // 1: one unit per pair warp, 4 worlds per SM
+        {0.0, 0.897, 1.093, 1.239, 1.396, 1.764},                   // 2: two units, 5 per SM
+        {0.0, 1.039, 1.213, 1.353, 1.468, 1.864, 2.167, 2.282},     // 3: two units, 7 per SM
+        {0.0, 0.783, 1.001, 1.161, 1.319},                          // 4: two units, 4 per SM
+        {0.0, 0.734, 0.960, 1.125}};                                // 5: two units, 3 per SM
+    const int occ = duo_variant_blocks(variant);
     double s = 0.0;
     int waves = 0;
     for (; n > 0; ++waves) {
         const int k = n < occ ? n : occ;
-        s += t[k];
+        s += t[variant][k];
         n -= k;
     }
     return waves > 1 ? (variant == 3 ? 0.965 : 0.93) * s : s;
@@ -519,14 +522,14 @@ double warp_model_ms(int W, int sms)
 int duo_best_variant(int n)
 {
     int best = 1;
-    for (int v = 2; v <= 3; ++v)
+    for (int v = 2; v <= DUO_VARIANTS; ++v)
         if (duo_model_ms(n, v) < duo_model_ms(n, best)) best = v;
     return best;
 }
 int duo_upw(const pms_sim *h)
 {
     if (h->Np <= 32) return 2;
-    if (h->tune_S == 4 && h->tune_wpc >= 1 && h->tune_wpc <= 3) return h->tune_wpc;
+    if (h->tune_S == 4 && h->tune_wpc >= 1 && h->tune_wpc <= DUO_VARIANTS) return h->tune_wpc;
     return duo_best_variant((h->W + h->sm_count - 1) / h->sm_count);
 }
 
@@ -549,8 +552,8 @@ bool duo_preferred(const pms_sim *h)
 
 int launch_duo(pms_sim *h)
 {
-    const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation (no 7-worlds-per-SM build of it: variant 3 runs as 2)
-    const int T = h->Np / 32, upw = sens && duo_upw(h) == 3 ? 2 : duo_upw(h);
+    const bool sens = h->a.sp.on != 0;      // sensor plan: its own instantiation (no other-occupancy builds of it: variants 3 .. 5 run as 2)
+    const int T = h->Np / 32, upw = sens && duo_upw(h) >= 3 ? 2 : duo_upw(h);
     const bool comp = h->compensated;
     int occ = 0;
     size_t smem = 0;

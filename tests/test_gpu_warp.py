@@ -108,11 +108,11 @@ def test_contact_pass_is_exercised_one_step():
 @pytest.mark.parametrize("precision", ["fp32", "mixed"])
 def test_warp_kernel_tuning_is_bit_identical(precision):
     """Worlds per CTA and the dynamic (chunk, group) scheduler only move work around.  (Pair-warp / owner-warp kernel:
-    worlds_per_block 1 / 2 / 3 force its variants -- one / two units of the pair scheme per pair warp, two units compiled for 7
-    worlds per SM -- bit-identical too.)"""
+    worlds_per_block 1 .. 5 force its variants -- one / two units of the pair scheme per pair warp, two units compiled for 7 / 4 /
+    3 worlds per SM -- bit-identical too.)"""
     sc = make_bench_crowd(37, 64)
     outs = []
-    for wpc, chunks in ((0, 1), (1, 1), (2, 1), (3, 1), (8, 4), (5, 3)):
+    for wpc, chunks in ((0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (8, 4), (7, 3)):
         sim = make_cuda(sc, precision)
         sim.set_tuning(FORCE["j_split"], wpc, chunks)
         sim.step(0.01, 130)
@@ -120,9 +120,9 @@ def test_warp_kernel_tuning_is_bit_identical(precision):
         # (the pair-warp / owner-warp kernel runs one world per CTA on a static grid: wpc / chunks do not apply)
         assert info["kernel"] == expected_kernel(sim) and info["n_chunks"] == (chunks if info["kernel"] == KERNEL_WARP else 1)
         if info["kernel"] == KERNEL_DUO:
-            assert info["j_split"] == (wpc if wpc in (2, 3) else 1)           # the variant that ran
+            assert info["j_split"] == (wpc if 1 <= wpc <= 5 else 5)           # the variant that ran (37 worlds: the model picks 5)
             assert info["threads_per_block"] == (224 if info["j_split"] == 1 else 160)
-            assert info["blocks_per_sm"] == {1: 4, 2: 5, 3: 7}[info["j_split"]]
+            assert info["blocks_per_sm"] == {1: 4, 2: 5, 3: 7, 4: 4, 5: 3}[info["j_split"]]
         outs.append(sim.get_state() + sim.get_detector() + (sim.get_collisions(),) + sim.get_stats() + sim.get_robot())
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
@@ -311,13 +311,14 @@ def test_async_io_pipeline_equals_blocking_calls():
 
 def test_automatic_kernel_choice_for_two_tile_batches():
     """pms_api.cu:duo_preferred / duo_upw -- the wave-by-wave model of measured times picks, on a 148-SM
-    B200, the pair-warp / owner-warp kernel's variant 1 / 2 / 3 or the warp-per-world kernel by how the batch fills the SMs."""
+    B200, one of the pair-warp / owner-warp kernel's five variants or the warp-per-world kernel by how the batch fills the SMs."""
     import torch
     from pyminisim_b200.batched import BatchedSimulation
     if torch.cuda.get_device_properties(0).multi_processor_count != 148:
         pytest.skip("the expectations are those of a 148-SM device")
-    want = {148: (KERNEL_DUO, 1), 444: (KERNEL_DUO, 1), 512: (KERNEL_DUO, 2), 740: (KERNEL_DUO, 2), 1024: (KERNEL_DUO, 3),
-            1480: (KERNEL_DUO, 2), 1776: (KERNEL_WARP, 0), 2048: (KERNEL_DUO, 3), 2368: (KERNEL_WARP, 0), 4096: (KERNEL_WARP, 0)}
+    want = {148: (KERNEL_DUO, 5), 296: (KERNEL_DUO, 1), 444: (KERNEL_DUO, 5), 512: (KERNEL_DUO, 4), 740: (KERNEL_DUO, 2),
+            1024: (KERNEL_DUO, 3), 1184: (KERNEL_DUO, 4), 1480: (KERNEL_DUO, 2), 2048: (KERNEL_DUO, 3), 2368: (KERNEL_WARP, 0),
+            4096: (KERNEL_WARP, 0)}
     for W, (kernel, variant) in want.items():
         sc = make_bench_crowd(W, 64)
         sim = helpers.make_cuda(sc, "fp32")

@@ -16,7 +16,7 @@ N = 64
 for W in [int(x) for x in sys.argv[1:]]:
     sc = make_bench_crowd(W, N)
     row = []
-    for tune in ((4, 1), (4, 2), (4, 3), (5, 0), (0, 0)):      # the kernel's three variants, warp-per-world kernel, automatic
+    for tune in ((4, 1), (4, 2), (4, 3), (4, 4), (4, 5), (5, 0), (0, 0)):      # the kernel's five variants, warp-per-world kernel, automatic
         sim = BatchedSimulation(W, N, precision="fp32")
         sim.set_state(sc.poses, sc.vels); sim.set_speeds(sc.vmag); sim.set_waypoints_fixed(sc.table, loop=True)
         sim.set_robot(capi.ROBOT_UNICYCLE, sc.robot_pose, control=sc.robot_control)
