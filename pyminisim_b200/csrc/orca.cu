@@ -129,13 +129,16 @@ __global__ void __launch_bounds__(256) orca_kernel(const __grid_constant__ OrcaA
     const bool valid = w < a.W && i < N;
     // per world: positions as two arrays sx | sy (four candidates per LDS.128, packed-FP32 differences), velocities float2 --
     // TWO copies by step parity: step s reads copy s & 1 and publishes the new state to the other one, so ONE barrier per
-    // step is enough (a thread that runs ahead writes the copy nobody reads in this step).  Worlds are independent: the
-    // barrier is the WORLD's (named barrier 1 + local world, or __syncwarp for a one-warp world), not the CTA's -- an agent with
-    // many neighbours (the LP is divergent work) holds up its own world only.
+    // step is enough (a thread that runs ahead writes the copy nobody reads in this step).  Worlds are independent and never
+    // share a barrier: a one-warp world (several per CTA) re-converges with __syncwarp, a larger world is its own CTA and uses
+    // barrier 0.  (Round 2 measured why not named barriers 1 + local world with several worlds per CTA: a barrier id in a
+    // register makes every CTA reserve all 16 hardware barriers, which caps the SM at 5 resident CTAs whatever their size --
+    // C5 with 4 / 2 / 1 worlds per CTA took 2.59 / 3.68 / 6.41 ms that way and takes 2.40 with one world per CTA and barrier 0:
+    // 14 instead of 16 worlds on the fullest SM.)
     float *sbase = reinterpret_cast<float *>(smem_raw) + (size_t)wl * 8 * Np;
     auto world_sync = [&]() {
         if (Np == 32) __syncwarp();
-        else asm volatile("bar.sync %0, %1;" :: "r"(wl + 1), "r"(Np) : "memory");
+        else asm volatile("bar.sync 0;" ::: "memory");
     };
     const size_t g = (size_t)(valid ? w : 0) * N + (valid ? i : 0);
 
@@ -315,7 +318,7 @@ OrcaArgs make_args(const OrcaState &s, int n_steps)
     a.time_horizon = s.time_horizon; a.radius = s.radius; a.goal_threshold = s.goal_threshold; a.reach = s.reach;
     a.pos = s.pos; a.vel = s.vel; a.pref = s.pref; a.max_speed = s.max_speed; a.pref_speed = s.pref_speed;
     a.cur_wp = s.cur_wp; a.table = s.table; a.wp_index = s.wp_index; a.heading = s.heading; a.n_constraints = s.n_constraints;
-    a.wpc = 256 / s.Np > 0 ? 256 / s.Np : 1;
+    a.wpc = s.Np == 32 ? 8 : 1;           // one-warp worlds: 8 per CTA; larger worlds: one CTA each (see world_sync in orca_kernel)
     if (a.wpc > s.W) a.wpc = s.W;
     return a;
 }
