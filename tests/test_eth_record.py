@@ -96,8 +96,16 @@ def test_under_simulation_frames_on_the_device(golden, assets, seq, dt, start, r
     sensors = [PedestrianDetector(config=PedestrianDetectorConfig(max_dist=6.0, fov=np.deg2rad(200.0), return_type="absolute"))]
     sim = Simulation(world_map=EmptyWorld(), robot_model=rm, pedestrians_model=model, sensors=sensors, sim_dt=dt, rt_factor=None)
     rows, got_det, got_coll = _rows(0, model.state), [], []
+    kept = None
     for k in range(1, len(counters)):
+        if k == 31:                     # jump back to the world of step 20: the device frame counter follows (reset_to_state)
+            sim.reset_to_state(kept)
+            for j in range(21, 31):
+                again = sim.step()
+                assert np.array_equal(np.array(_rows(j, again.world.pedestrians)), want[want[:, 0] == j])
         state = sim.step()
+        if k == 20:
+            kept = state.world
         rows += _rows(k, state.world.pedestrians)
         got_det += [[k, ped, *v] for ped, v in state.sensors["pedestrian_detector"].reading.pedestrians.items()]
         got_coll += [[k, ped] for ped in state.world.robot_to_pedestrians_collisions]
