@@ -133,3 +133,36 @@ def test_replay_policy_frame_sequence_matches_reference(golden):
         ReplayPedestriansPolicy(np.zeros((4, 3, 2)), np.zeros((4, 3, 3)))
     with pytest.raises(AssertionError):
         ReplayPedestriansState(-1, {})
+
+
+def test_fixed_tracker_array_path_equals_the_dict_rule():
+    """FixedWaypointTracker.update_from_array (the accelerated models' host mirror: positions as an (N, 2) array, no per-pedestrian
+    objects unless somebody reached a waypoint) against update_waypoints (_fixed_waypoint_tracker.py:68-87) on a random walk that
+    crosses many waypoints, loop and clamp; state_later() shows the waypoints of the step it was taken at."""
+    from pyminisim_b200.pedestrians import FixedWaypointTracker
+    rng = np.random.default_rng(12)
+    n = 11
+    start = rng.uniform(-2, 2, (n, 2))
+    wps = start[:, None, :] + rng.uniform(-1.0, 1.0, (n, 4, 2))
+    for loop in (True, False):
+        a = FixedWaypointTracker(start.copy(), wps.copy(), reach_distance=0.35, loop=loop)
+        b = FixedWaypointTracker(start.copy(), wps.copy(), reach_distance=0.35, loop=loop)
+        pos = start.copy()
+        snaps = []
+        for step in range(400):
+            # walk towards the current waypoint of tracker b with some noise
+            cur = np.stack([b.state.current_waypoints[i] for i in range(n)])
+            pos = pos + 0.08 * (cur - pos) / np.maximum(np.linalg.norm(cur - pos, axis=1, keepdims=True), 1e-9) + rng.normal(0, 0.01, (n, 2))
+            idx = a.update_from_array(pos)
+            b.update_waypoints({i: np.array([pos[i, 0], pos[i, 1], 0.0]) for i in range(n)})
+            assert a.state.current_indices == b.state.current_indices == {i: int(idx[i]) for i in range(n)}
+            if step % 97 == 0:
+                snaps.append((a.state_later(), {i: b.state.current_waypoints[i].copy() for i in range(n)}))
+        assert sum(b.state.current_indices.values()) > n + 5                     # hand-offs happened
+        for later, want in snaps:
+            got = later().current_waypoints
+            assert all(np.array_equal(got[i], want[i]) for i in range(n))
+        # the dict path and the array path share one state: mixing them stays coherent
+        a.update_waypoints({i: np.array([pos[i, 0], pos[i, 1], 0.0]) for i in range(n)})
+        assert np.array_equal(a.update_from_array(pos), np.array([a.state.current_indices[i] for i in range(n)]))
+
